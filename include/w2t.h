@@ -1,0 +1,119 @@
+/*
+ * w2t.h — C-ABI of libw2t.so: the B200 (sm_100a) implementation of the
+ * post-detection box pipeline of xuyuan/waymo_2d_tracking
+ * (soft-NMS ensemble + per-class SORT).
+ *
+ * The reference has no FFI layer: the "operator API" of this path is its Python
+ * call surface.  Each export below replaces the Python call it
+ * cites; the Python drop-ins in waymo_2d_tracking_b200/ bind these symbols with
+ * ctypes (INTEGRATION.md shows the stub).  Plain pointers and sizes only, no
+ * torch types.  Unless stated otherwise pointers are DEVICE pointers, launches
+ * are asynchronous on `stream`, nothing is allocated behind the caller's back
+ * and there is no CPU fallback: without a CUDA device every compute entry
+ * point returns W2T_ERR_CUDA.
+ *
+ * Paths are relative to /root/reference.
+ */
+#ifndef W2T_H
+#define W2T_H
+
+#include "w2t_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *w2t_stream_t; /* == cudaStream_t */
+
+/* ---- library ---------------------------------------------------------- */
+
+const char *w2t_version(void);
+/* message of the last failing call on this host thread ("" if none) */
+const char *w2t_last_error(void);
+/* SM count and compute capability of the current device */
+int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- soft-NMS ensemble ------------------------------------------------- */
+
+/* Replaces the per-image loop of detnet/ensemble.py:145-157, i.e. ensemble()
+ * (:50-64) -> nms_detections() (detnet/nn/tta.py:8-19) -> nms(soft=True)
+ * (detnet/utils/box_utils.py:307-395) for every (image, category) group in one
+ * launch, plus — when problem->score_thr is set — the filters and box
+ * conversion read_data_file()/track_sort() apply to that output before
+ * tracking (tracking/utils.py:79-87,32-35; tracker_sort.py:45).
+ *
+ * max_group_size: largest group_offsets[g+1]-group_offsets[g] (host knows it
+ *                 from the offsets it built).
+ * status:         device int32, set to a W2T_ERR_* code by the kernel if an
+ *                 input is outside what the soft-NMS path supports (negative
+ *                 or NaN score, non-positive box area); must be zeroed by the
+ *                 caller.  May be NULL.
+ * result->img_exists, if given, must be zeroed by the caller. */
+int w2t_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
+                       int32_t *status, w2t_stream_t stream);
+
+/* Largest group the soft-NMS kernel accepts (shared-memory resident). */
+int w2t_softnms_max_group(void);
+
+/* ---- SORT --------------------------------------------------------------- */
+
+/* HOST function.  Sizes the per-sub-stream workspace slabs from the detection
+ * counts (host copies of det_count / img_exists): a tracker alive at image f
+ * was created or last updated by a distinct detection of the previous
+ * max_age+1 images, so the window sum of counts bounds the tracker list
+ * (tracking/sort/sort.py:276-278,292-293).  plan arrays are caller-allocated
+ * host arrays of n_streams*n_classes entries. */
+int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                  const int32_t *det_count, const uint8_t *img_exists, int32_t max_age,
+                  w2t_sort_plan_t *plan);
+
+/* Replaces the loop of tracking/track.py:42-47: track_sort()
+ * (tracking/utils.py:25-60) -> MultiClassTrackerSort.track()
+ * (tracking/sort/tracker_sort.py:22-51) -> Sort.update()
+ * (tracking/sort/sort.py:244-296) for every stream.  One persistent CTA per
+ * (stream, category) sub-stream walks the stream's images in order.
+ * plan holds DEVICE copies of the arrays w2t_sort_plan filled.
+ * Global object ids are not assigned here: every row carries the (group, k)
+ * of its tracker's creation and `created` holds the per-group creation counts;
+ * the id is an exclusive scan of `created` in the reference's processing order
+ * (KalmanBoxTracker.count, sort.py:86,140-141) — see w2t_assign_ids. */
+int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
+                   w2t_sort_result_t *result, void *workspace, int32_t *status, w2t_stream_t stream);
+
+/* HOST function.  Turns (birth group, k) into the reference's global
+ * object_id (= KalmanBoxTracker.id + 1, sort.py:288).  All pointers are host
+ * pointers.  class_rank[n_streams*n_classes] gives, per stream, the position
+ * of each category in the reference's tracker dict (first-appearance order,
+ * tracker_sort.py:32-33,41); pass NULL to rank by (first_img, category id).
+ * id_base is the value of KalmanBoxTracker.count before the call; returns the
+ * count after it through id_next. */
+int w2t_assign_ids(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                   const int32_t *det_start, const int32_t *out_count, const int32_t *created,
+                   const int32_t *first_img, const int32_t *class_rank, const int32_t *out_birth,
+                   int64_t id_base, int64_t *out_id, int64_t *id_next);
+
+/* ---- building blocks (unit-parity entry points) ------------------------- */
+
+/* iou() of sort.py:33-47 for every (detection, tracker) pair, as filled into
+ * the float32 matrix of sort.py:201-205.  out[D,T]. */
+int w2t_iou_matrix(const float *dets, int32_t D, const double *trks, int32_t T, float *out,
+                   w2t_stream_t stream);
+
+/* scikit-learn 0.22.2 linear_assignment (call site sort.py:206) on a float32
+ * [D,T] cost matrix.  pairs[min(D,T),2] sorted by (row, col); *n_pairs =
+ * min(D,T).  workspace: w2t_linear_assignment_workspace(D,T) bytes. */
+size_t w2t_linear_assignment_workspace(int32_t D, int32_t T);
+int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, int32_t *pairs, int32_t *n_pairs,
+                          void *workspace, w2t_stream_t stream);
+
+/* KalmanBoxTracker.__init__/predict/update (sort.py:88-178) on n independent
+ * filters: x[n,7], P[n,49] row-major, dets[n,4] float32 x1,y1,x2,y2;
+ * boxes[n,4] (may be NULL) receives convert_x_to_bbox(x) (sort.py:65-75). */
+int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, w2t_stream_t stream);
+int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2t_stream_t stream);
+int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n, w2t_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2T_H */

@@ -1,0 +1,119 @@
+/*
+ * w2t_types.h — plain-C data layout shared by the CUDA library (include/w2t.h)
+ * and the CPU oracle (oracle/csrc/w2t_oracle.h).  No torch types, no C++.
+ *
+ * Vocabulary follows the reference (xuyuan/waymo_2d_tracking):
+ *   stream     one (segment, camera) sequence            tracking/utils.py:25-31
+ *   image      one camera frame, image_id 'seg/frame/cam' tracking/utils.py:70
+ *   group      one (image, category) set of boxes          detnet/ensemble.py:52-56
+ *   sub-stream one (stream, category) = one reference `Sort` object
+ *                                                          tracking/sort/tracker_sort.py:32-33
+ *
+ * Index spaces
+ *   images of stream s are contiguous and sorted by frame id:
+ *       img in [stream_img_offsets[s], stream_img_offsets[s+1])
+ *   group  g = img * n_classes + (category_id - 1)
+ *   sub-stream q = s * n_classes + (category_id - 1)
+ *   rows (detections / emitted track rows) of group g live at
+ *       [det_start[g], det_start[g] + det_count[g])   (capacity: up to det_start of the next group)
+ */
+#ifndef W2T_TYPES_H
+#define W2T_TYPES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2T_MAX_CLASSES 8
+
+/* status codes returned by every entry point */
+enum {
+  W2T_OK = 0,
+  W2T_ERR_ARG = 1,        /* bad argument (null pointer, negative size, too many classes) */
+  W2T_ERR_CAPACITY = 2,   /* a plan capacity (tracks / detections per frame) was exceeded */
+  W2T_ERR_CUDA = 3,       /* CUDA runtime error; see w2t_last_error() */
+  W2T_ERR_NONFINITE = 4   /* a tracker box became +-inf (unreachable with finite inputs; the
+                             reference mis-indexes its tracker list there, sort.py:261-265) */
+};
+
+/* Per-sub-stream launch plan, computed on the host from the detection counts
+ * (w2t_sort_plan).  All arrays have n_streams * n_classes entries. */
+typedef struct w2t_sort_plan_t {
+  int32_t *order;        /* launch order: sub-stream ids, heaviest first                     */
+  int32_t *track_cap;    /* upper bound on simultaneously live trackers (window sum of dets) */
+  int32_t *det_cap;      /* max detections of that category in any one image of the stream   */
+  int64_t *ws_offset;    /* byte offset of the sub-stream's slab in the workspace            */
+  int64_t  ws_bytes;     /* total workspace size                                             */
+} w2t_sort_plan_t;
+
+/* Inputs of the SORT stage (tracking/utils.py:25-60 for every stream at once).
+ * Pointers are device pointers for the CUDA library and host pointers for the oracle. */
+typedef struct w2t_sort_problem_t {
+  int32_t n_streams;
+  int32_t n_classes;                 /* category ids are 1..n_classes                         */
+  const int32_t *stream_img_offsets; /* [n_streams+1]                                         */
+  const int32_t *det_start;          /* [n_img*n_classes]                                     */
+  const int32_t *det_count;          /* [n_img*n_classes] detections that survived            */
+                                     /*   read_data_file's filters (utils.py:79-87)           */
+  const float   *det_box;            /* [N,4] x1,y1,x2,y2 already rounded to float32          */
+                                     /*   (tracker_sort.py:45)                                */
+  const uint8_t *img_exists;         /* [n_img] or NULL (= every image is present in the      */
+                                     /*   input JSON, utils.py:76-77)                         */
+  const double  *cam_wh;             /* [n_streams,2] IMAGE_SIZES of the camera, utils.py:11  */
+  double  iou_thr[W2T_MAX_CLASSES];  /* --iou-threshold, track.py:25-26                       */
+  int32_t max_age;                   /* track.py:21                                           */
+  int32_t min_hits;                  /* track.py:22                                           */
+} w2t_sort_problem_t;
+
+/* Outputs of the SORT stage.  Row k of group g is at det_start[g] + k. */
+typedef struct w2t_sort_result_t {
+  double  *out_box;      /* [N,4] x1,y1,width,height after clip_xy (utils.py:40-44)           */
+  double  *out_score;    /* [N]   clip(exp(-0.1*mean(P00,P11,P22)),0.2,1) (sort.py:286-287,   */
+                         /*       utils.py:49)                                                */
+  int32_t *out_birth;    /* [N,2] (group, k): the tracker was the k-th one created at that    */
+                         /*       (image, category); see w2t_assign_ids                       */
+  int32_t *out_count;    /* [n_img*n_classes] rows emitted (<= det_count)                     */
+  int32_t *created;      /* [n_img*n_classes] trackers created at this (image, category)      */
+  int32_t *first_img;    /* [n_streams*n_classes] stream-local index of the image where the   */
+                         /*   category first appeared (tracker_sort.py:32-33) or -1           */
+  /* optional (may be NULL): final filter state of every sub-stream, for parity tests */
+  int32_t *final_count;  /* [n_streams*n_classes] live trackers after the last image          */
+  double  *final_state;  /* [n_streams*n_classes, final_cap, 56] x[7] then P[49] row-major     */
+  int32_t  final_cap;
+} w2t_sort_result_t;
+
+/* Inputs of the soft-NMS ensemble stage (detnet/ensemble.py:50-64 for every image). */
+typedef struct w2t_nms_problem_t {
+  int32_t n_groups;
+  const int32_t *group_offsets;  /* [n_groups+1] into rows                                    */
+  const double  *rows;           /* [N,5] score*weight, left, top, width, height              */
+                                 /*   (convert_submission, ensemble.py:44), concatenated over */
+                                 /*   submissions in input-file order (tta.py:9-12)           */
+  double iou_thresh;             /* --iou-thresh   ensemble.py:96                             */
+  double soft_nms_cut;           /* --soft-nms-cut ensemble.py:97                             */
+  double min_score;              /* --min-score    ensemble.py:98 (strict > on output, :60)   */
+  /* optional hand-over to the SORT stage (NULL score_thr = skip) */
+  int32_t n_classes;             /* group g has category (g % n_classes) + 1                  */
+  const double *score_thr;       /* [n_classes] --score-threshold, track.py:23-24 (host ptr)  */
+} w2t_nms_problem_t;
+
+/* Outputs of the ensemble stage.  Row k of group g is at group_offsets[g] + k, in the
+ * reference's output order (descending original score, box_utils.py:344-391). */
+typedef struct w2t_nms_result_t {
+  double  *merged;       /* [N,5] score', cx, cy, w, h = nms_detections() rows (tta.py:19); may be NULL */
+  int32_t *src_index;    /* [N] row index (into rows) each output row came from; may be NULL  */
+  int32_t *ens_count;    /* [n_groups] rows with score' > min_score (ensemble.py:60)          */
+  int32_t *ens_box;      /* [N,4] left,top,width,height truncated to int (ensemble.py:62)     */
+  double  *ens_score;    /* [N] round(score',5) (ensemble.py:62)                              */
+  int32_t *trk_count;    /* [n_groups] rows that also pass read_data_file (utils.py:79-87)    */
+  float   *trk_box;      /* [N,4] x, y, x+w, y+h as float32 (utils.py:32-35, tracker_sort.py:45) */
+  uint8_t *img_exists;   /* [n_groups/n_classes] image has >= 1 ensemble row; may be NULL     */
+} w2t_nms_result_t;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2T_TYPES_H */

@@ -1,0 +1,119 @@
+"""ctypes mirror of ``include/w2t_types.h`` / ``include/w2t.h``.
+
+Only declarations live here: the structs, the status codes and the argument
+types of every exported symbol.  ``_lib.py`` binds them to ``libw2t.so``.
+"""
+import ctypes as C
+
+W2T_MAX_CLASSES = 8
+
+W2T_OK = 0
+W2T_ERR_ARG = 1
+W2T_ERR_CAPACITY = 2
+W2T_ERR_CUDA = 3
+W2T_ERR_NONFINITE = 4
+
+STATUS_NAMES = {
+    W2T_OK: "ok",
+    W2T_ERR_ARG: "bad argument / unsupported input",
+    W2T_ERR_CAPACITY: "plan capacity exceeded",
+    W2T_ERR_CUDA: "CUDA error",
+    W2T_ERR_NONFINITE: "tracker box became infinite",
+}
+
+_p = C.c_void_p
+
+
+class SortPlan(C.Structure):
+    _fields_ = [
+        ("order", _p),
+        ("track_cap", _p),
+        ("det_cap", _p),
+        ("ws_offset", _p),
+        ("ws_bytes", C.c_int64),
+    ]
+
+
+class SortProblem(C.Structure):
+    _fields_ = [
+        ("n_streams", C.c_int32),
+        ("n_classes", C.c_int32),
+        ("stream_img_offsets", _p),
+        ("det_start", _p),
+        ("det_count", _p),
+        ("det_box", _p),
+        ("img_exists", _p),
+        ("cam_wh", _p),
+        ("iou_thr", C.c_double * W2T_MAX_CLASSES),
+        ("max_age", C.c_int32),
+        ("min_hits", C.c_int32),
+    ]
+
+
+class SortResult(C.Structure):
+    _fields_ = [
+        ("out_box", _p),
+        ("out_score", _p),
+        ("out_birth", _p),
+        ("out_count", _p),
+        ("created", _p),
+        ("first_img", _p),
+        ("final_count", _p),
+        ("final_state", _p),
+        ("final_cap", C.c_int32),
+    ]
+
+
+class NmsProblem(C.Structure):
+    _fields_ = [
+        ("n_groups", C.c_int32),
+        ("group_offsets", _p),
+        ("rows", _p),
+        ("iou_thresh", C.c_double),
+        ("soft_nms_cut", C.c_double),
+        ("min_score", C.c_double),
+        ("n_classes", C.c_int32),
+        ("score_thr", _p),
+    ]
+
+
+class NmsResult(C.Structure):
+    _fields_ = [
+        ("merged", _p),
+        ("src_index", _p),
+        ("ens_count", _p),
+        ("ens_box", _p),
+        ("ens_score", _p),
+        ("trk_count", _p),
+        ("trk_box", _p),
+        ("img_exists", _p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/w2t.h declares
+EXPORTS = {
+    "w2t_version": (C.c_char_p, []),
+    "w2t_last_error": (C.c_char_p, []),
+    "w2t_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "w2t_softnms_groups": (C.c_int, [C.POINTER(NmsProblem), C.POINTER(NmsResult), C.c_int, _p, _p]),
+    "w2t_softnms_max_group": (C.c_int, []),
+    "w2t_sort_plan": (C.c_int, [C.c_int32, C.c_int32, _p, _p, _p, C.c_int32, C.POINTER(SortPlan)]),
+    "w2t_sort_track": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortPlan), C.POINTER(SortResult), _p, _p, _p]),
+    "w2t_assign_ids": (C.c_int, [C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p, _p, C.c_int64, _p,
+                                 C.POINTER(C.c_int64)]),
+    "w2t_iou_matrix": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p, _p]),
+    "w2t_linear_assignment_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "w2t_linear_assignment": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p, _p, _p]),
+    "w2t_kf_init": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
+    "w2t_kf_predict": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
+    "w2t_kf_update": (C.c_int, [_p, _p, _p, _p, C.c_int32, _p]),
+}
+
+
+def bind(lib, exports=EXPORTS):
+    """Attach restype/argtypes; raises AttributeError if a symbol is missing."""
+    for name, (restype, argtypes) in exports.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib

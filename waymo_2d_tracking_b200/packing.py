@@ -1,0 +1,241 @@
+"""Host-side packing: the reference's nested dicts <-> the flat arrays of ``include/w2t_types.h``.
+
+The reference keeps detections as ``segment -> camera -> frame -> [dict]``
+(``tracking/utils.py:63-96``) and ``image_id -> category_id -> [[score,x,y,w,h]]``
+(``detnet/ensemble.py:31-47``).  The CUDA library works on CSR-style arrays;
+this module converts both ways and owns the bookkeeping that is order- rather
+than arithmetic-related (stream order, category first-appearance order, global
+object ids).
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+# tracking/utils.py:11-17
+IMAGE_SIZES = {
+    'FRONT': [1920, 1280],
+    'FRONT_LEFT': [1920, 1280],
+    'FRONT_RIGHT': [1920, 1280],
+    'SIDE_LEFT': [1920, 886],
+    'SIDE_RIGHT': [1920, 886],
+}
+
+
+@dataclass
+class PackedTracks:
+    """Input of the SORT stage for a set of streams (host arrays)."""
+    n_streams: int
+    n_classes: int
+    streams: List[Tuple[str, str]]            # (segment_id, camera_id) in processing order
+    frame_ids: np.ndarray                     # [n_img] int64, sorted inside each stream
+    stream_img_offsets: np.ndarray            # [S+1] int32
+    det_start: np.ndarray                     # [n_img*NC] int32
+    det_count: np.ndarray                     # [n_img*NC] int32
+    det_box: np.ndarray                       # [N,4] float32 x1,y1,x2,y2
+    cam_wh: np.ndarray                        # [S,2] float64
+    img_exists: Optional[np.ndarray] = None   # [n_img] uint8 or None
+    class_rank: Optional[np.ndarray] = None   # [S*NC] int32 position in the tracker dict, or None
+    n_rows: int = 0
+    extras: dict = field(default_factory=dict)
+
+    @property
+    def n_img(self):
+        return int(self.stream_img_offsets[-1])
+
+
+def camera_size(camera_id):
+    """``IMAGE_SIZES[camera_id]`` — KeyError for an unknown camera like utils.py:21."""
+    return IMAGE_SIZES[camera_id]
+
+
+def pack_predictions(predictions, n_classes, streams=None):
+    """``predictions`` = output of ``read_data_file``; one stream per (segment, camera).
+
+    Group g = img * n_classes + (category_id - 1); rows of a group keep their
+    order in the frame's list (the order ``MultiClassTrackerSort.track`` sees,
+    tracker_sort.py:29-36).
+    """
+    if streams is None:
+        streams = [(seg, cam) for seg in predictions.keys() for cam in predictions[seg]]
+    NC = int(n_classes)
+    frame_ids, offsets, cam_wh = [], [0], []
+    counts, boxes, ranks = [], [], []
+    for seg, cam in streams:
+        frames = predictions[seg][cam]
+        w, h = camera_size(cam)
+        cam_wh.append((float(w), float(h)))
+        rank = np.full(NC, -1, np.int64)
+        seen = 0
+        for fid in sorted(frames.keys()):
+            per_class = [[] for _ in range(NC)]
+            for e in frames[fid]:
+                cat = e['category_id']
+                if not (1 <= cat <= NC):
+                    # the reference indexes iou_thresholds[category_id - 1] (tracker_sort.py:46)
+                    raise IndexError("category_id %r outside 1..%d" % (cat, NC))
+                b = e['bbox']
+                per_class[cat - 1].append((b[0], b[1], b[0] + b[2], b[1] + b[3]))
+                if rank[cat - 1] < 0:
+                    rank[cat - 1] = seen
+                    seen += 1
+            frame_ids.append(fid)
+            for c in range(NC):
+                counts.append(len(per_class[c]))
+                boxes.extend(per_class[c])
+        for c in range(NC):
+            if rank[c] < 0:
+                rank[c] = seen
+                seen += 1
+        ranks.append(rank)
+        offsets.append(len(frame_ids))
+    det_count = np.asarray(counts, np.int32).reshape(-1)
+    det_start = np.zeros_like(det_count)
+    if len(det_count):
+        det_start[1:] = np.cumsum(det_count[:-1], dtype=np.int64).astype(np.int32)
+    det_box = np.asarray(boxes, dtype=np.float64).reshape(-1, 4).astype(np.float32)
+    return PackedTracks(
+        n_streams=len(streams), n_classes=NC, streams=list(streams),
+        frame_ids=np.asarray(frame_ids, np.int64), stream_img_offsets=np.asarray(offsets, np.int32),
+        det_start=det_start, det_count=det_count, det_box=det_box,
+        cam_wh=np.asarray(cam_wh, np.float64).reshape(-1, 2),
+        class_rank=np.asarray(ranks, np.int32).reshape(-1) if ranks else np.zeros(0, np.int32),
+        n_rows=int(det_box.shape[0]))
+
+
+def default_class_rank(first_img, n_streams, n_classes):
+    """Rank categories of each stream by (first image they appear in, category id).
+
+    Exact whenever no two categories first appear in the same image; with a tie
+    the reference's order is the order inside that frame's detection list —
+    ascending category for anything written by ``detnet.ensemble`` (it emits an
+    image's rows category by category, ensemble.py:52-63).
+    """
+    fi = np.asarray(first_img, np.int64).reshape(n_streams, n_classes)
+    key = np.where(fi < 0, np.iinfo(np.int64).max // 2, fi) * n_classes + np.arange(n_classes)[None, :]
+    order = np.argsort(key, axis=1, kind='stable')
+    rank = np.empty_like(order)
+    np.put_along_axis(rank, order, np.arange(n_classes)[None, :].repeat(n_streams, 0), axis=1)
+    return rank.astype(np.int32).reshape(-1)
+
+
+def assign_ids(stream_img_offsets, n_classes, det_start, out_count, created, first_img, class_rank,
+               out_birth, id_base=0):
+    """NumPy statement of ``w2t_assign_ids`` (used to cross-check the C export).
+
+    The reference numbers trackers with one process-global counter
+    (``KalmanBoxTracker.count``, sort.py:86,140-141) in creation order: streams in
+    order, frames in order, categories in tracker-dict order, new trackers in
+    ``unmatched_dets`` order.  ``object_id = id + 1`` (sort.py:288).
+    """
+    offs = np.asarray(stream_img_offsets, np.int64)
+    S, NC = len(offs) - 1, int(n_classes)
+    n_img = int(offs[-1])
+    created = np.asarray(created, np.int64).reshape(n_img, NC)
+    if class_rank is None:
+        class_rank = default_class_rank(first_img, S, NC)
+    rank = np.asarray(class_rank, np.int64).reshape(S, NC)
+    stream_of_img = np.repeat(np.arange(S), np.diff(offs))
+    # column k of `ordered` = the category processed k-th in that stream
+    cat_at_rank = np.argsort(rank, axis=1, kind='stable')
+    ordered = np.take_along_axis(created, cat_at_rank[stream_of_img], axis=1)
+    flat = ordered.reshape(-1)
+    base_ordered = (np.cumsum(flat) - flat).reshape(n_img, NC) + id_base
+    base = np.empty_like(base_ordered)
+    np.put_along_axis(base, cat_at_rank[stream_of_img], base_ordered, axis=1)
+    base = base.reshape(-1)
+    birth = np.asarray(out_birth, np.int64).reshape(-1, 2)
+    ids = np.zeros(len(birth), np.int64)        # rows outside [det_start, det_start+out_count) stay 0
+    idx, _ = valid_row_index(det_start, out_count)
+    ids[idx] = base[birth[idx, 0]] + birth[idx, 1] + 1
+    return ids, int(id_base + flat.sum())
+
+
+def _ranges(starts, counts):
+    """Concatenate arange(s, s+c) for every (s, c) without a Python loop."""
+    total = int(counts.sum())
+    ends = np.cumsum(counts)
+    out = np.ones(total, np.int64)
+    out[0] = starts[0]
+    out[ends[:-1]] = starts[1:] - (starts[:-1] + counts[:-1] - 1)
+    return np.cumsum(out)
+
+
+def valid_row_index(det_start, out_count):
+    ds = np.asarray(det_start, np.int64)
+    oc = np.asarray(out_count, np.int64)
+    nz = np.nonzero(oc)[0]
+    if len(nz) == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return _ranges(ds[nz], oc[nz]), np.repeat(nz, oc[nz])
+
+
+def unpack_tracks(packed, out_box, out_score, out_count, first_img, ids, class_rank=None):
+    """Emit the reference's list of dicts (utils.py:52-58) in the reference's order:
+    stream, frame, category in tracker-dict order, rows in ``Sort.update`` order."""
+    S, NC = packed.n_streams, packed.n_classes
+    rank = packed.class_rank if class_rank is None else class_rank
+    if rank is None:
+        rank = default_class_rank(first_img, S, NC)
+    rank = np.asarray(rank).reshape(S, NC)
+    first_img = np.asarray(first_img).reshape(S, NC)
+    out = []
+    offs = packed.stream_img_offsets
+    for s, (seg, cam) in enumerate(packed.streams):
+        cats = [int(c) for c in np.argsort(rank[s], kind='stable')]
+        for img in range(int(offs[s]), int(offs[s + 1])):
+            f_local = img - int(offs[s])
+            image_id = '%s/%i/%s' % (seg, packed.frame_ids[img], cam)
+            for c in cats:
+                if first_img[s, c] < 0 or first_img[s, c] > f_local:
+                    continue
+                g = img * NC + c
+                r0 = int(packed.det_start[g])
+                for r in range(r0, r0 + int(out_count[g])):
+                    out.append({
+                        'image_id': image_id,
+                        'bbox': [out_box[r, 0], out_box[r, 1], out_box[r, 2], out_box[r, 3]],
+                        'score': out_score[r],
+                        'category_id': c + 1,
+                        'object_id': '%i' % int(ids[r]),
+                    })
+    return out
+
+
+# ---------------------------------------------------------------------------
+# ensemble side
+# ---------------------------------------------------------------------------
+
+@dataclass
+class PackedGroups:
+    """Input of the soft-NMS stage: one group per (image, category)."""
+    image_ids: list                 # group g belongs to image_ids[g // len(category_ids)]
+    category_ids: list              # iteration order of the reference's category set
+    group_offsets: np.ndarray       # [G+1] int32
+    rows: np.ndarray                # [N,5] float64: score*weight, left, top, width, height
+    max_group: int = 0
+
+
+def pack_submissions(input_detections, image_ids, category_ids):
+    """``input_detections``: one ``convert_submission`` result per input file (ensemble.py:82);
+    rows of a group are concatenated in file order, then JSON order (tta.py:9-12)."""
+    image_ids = list(image_ids)
+    category_ids = list(category_ids)
+    offsets = [0]
+    chunks = []
+    total = 0
+    for image_id in image_ids:
+        per_file = [det.get(image_id) if hasattr(det, 'get') else det[image_id] for det in input_detections]
+        for cat in category_ids:
+            for det in per_file:
+                if det is None:
+                    continue
+                rows = det.get(cat)
+                if rows:
+                    chunks.append(np.asarray(rows, dtype=np.float64).reshape(-1, 5))
+                    total += len(rows)
+            offsets.append(total)
+    rows = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, 5), np.float64)
+    offsets = np.asarray(offsets, np.int64)
+    max_group = int(np.diff(offsets).max()) if len(offsets) > 1 else 0
+    return PackedGroups(image_ids, category_ids, offsets.astype(np.int32), np.ascontiguousarray(rows), max_group)
