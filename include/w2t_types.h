@@ -68,7 +68,9 @@ typedef struct w2t_sort_problem_t {
   int32_t min_hits;                  /* track.py:22                                           */
 } w2t_sort_problem_t;
 
-/* Outputs of the SORT stage.  Row k of group g is at det_start[g] + k. */
+/* Outputs of the SORT stage.  Row k of group g is at det_start[g] + k, in tracker-list
+ * (creation) order; the reference emits a group's rows in the REVERSE of that order
+ * (sort.py:280), which the host layer restores when it builds the output list. */
 typedef struct w2t_sort_result_t {
   double  *out_box;      /* [N,4] x1,y1,width,height after clip_xy (utils.py:40-44)           */
   double  *out_score;    /* [N]   clip(exp(-0.1*mean(P00,P11,P22)),0.2,1) (sort.py:286-287,   */
@@ -81,7 +83,8 @@ typedef struct w2t_sort_result_t {
                          /*   category first appeared (tracker_sort.py:32-33) or -1           */
   /* optional (may be NULL): final filter state of every sub-stream, for parity tests */
   int32_t *final_count;  /* [n_streams*n_classes] live trackers after the last image          */
-  double  *final_state;  /* [n_streams*n_classes, final_cap, 56] x[7] then P[49] row-major     */
+  double  *final_state;  /* [n_streams*n_classes, final_cap, 56] x[7] then P[49] row-major,    */
+                         /*   predicted one step past the last image                          */
   int32_t  final_cap;
 } w2t_sort_result_t;
 

@@ -420,7 +420,7 @@ static int track_substream(const w2t_sort_problem_t *p, w2t_sort_result_t *r, in
   const int q = s * NC + c;
   const int img0 = p->stream_img_offsets[s], img1 = p->stream_img_offsets[s + 1];
   const double W = p->cam_wh[2 * s], H = p->cam_wh[2 * s + 1];
-  int cap = 64, T = 0, created_total = 0, frame_count = 0, started = 0, status = W2T_OK;
+  int cap = 64, T = 0, frame_count = 0, started = 0, status = W2T_OK;
   trk_t *trk = (trk_t *)malloc(sizeof(trk_t) * cap);
   double *boxes = NULL;
   int32_t *match = NULL, *new_order = NULL;
@@ -488,11 +488,12 @@ static int track_substream(const w2t_sort_problem_t *p, w2t_sort_result_t *r, in
       k->birth_k = i;
     }
     T += n_new;
-    created_total += n_new;
     r->created[g] = n_new;
-    /* sort.py:280-293 emission in reversed list order, then utils.py:37-58 */
+    /* sort.py:280-293 + utils.py:37-58.  The reference walks the list in REVERSE; rows are
+     * stored here in list order (same convention as the CUDA library, include/w2t_types.h):
+     * whether a tracker emits a row does not depend on the walk direction. */
     int emitted = 0;
-    for (int t = T - 1; t >= 0; t--) {
+    for (int t = 0; t < T; t++) {
       trk_t *k = &trk[t];
       if (k->tsu < 1 && (k->hit_streak >= p->min_hits || frame_count <= p->min_hits)) {
         double b[4];
@@ -525,10 +526,13 @@ static int track_substream(const w2t_sort_problem_t *p, w2t_sort_result_t *r, in
     T = keep;
   }
   if (r->final_count) {
+    /* state of every live tracker, predicted one step past the last image (the CUDA kernel
+     * runs the next image's predict at the end of the current one) */
     r->final_count[q] = T;
     if (r->final_state)
       for (int t = 0; t < T && t < r->final_cap; t++) {
         double *dst = r->final_state + ((size_t)q * r->final_cap + t) * 56;
+        w2t_oracle_kf_predict(trk[t].x, trk[t].P);
         memcpy(dst, trk[t].x, 7 * sizeof(double));
         memcpy(dst + 7, trk[t].P, 49 * sizeof(double));
       }

@@ -1,0 +1,137 @@
+"""Generate the committed golden fixtures by EXECUTING THE REFERENCE'S OWN FILES.
+
+Run in the dev container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+For every case the inputs are synthetic submissions (``waymo_2d_tracking_b200.synth``,
+seeded) written to JSON exactly as the reference expects them; the outputs are what the
+reference's own code returns for them through ``oracle.ref_shim``:
+
+* tracking cases : ``tracking/utils.py`` read_data_file + track_sort (-> tracker_sort.py,
+  sort.py) with the two absent third-party pieces restated (oracle/munkres.py,
+  oracle/kalman.py — parity unpinned there, see oracle/__init__.py);
+* ensemble cases : ``detnet/ensemble.py`` convert_submission + ensemble (-> tta.py,
+  box_utils.py), 100 % reference code on torch CPU.  ``torch.Tensor.sort`` is forced stable
+  (canonical tie rule); all cases but ``ensemble_ties`` have distinct scores,
+  for which the unpatched reference gives the same result.
+
+Inputs and outputs are stored as exact NumPy arrays (npz), a few hundred KB in total.
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref_shim  # noqa: E402
+from waymo_2d_tracking_b200 import synth  # noqa: E402
+import golden_io  # noqa: E402
+
+SCORE_THR = [0.95, 0.6, 1.0, 0.9]
+IOU_THR = [0.01, 0.01, 1.0, 0.0]
+
+TRACK_CASES = {
+    # README recipe: --max-age=2 --min-hits=0
+    "track_c1_small": dict(cfg=dict(n_segments=1, cameras=("FRONT", "SIDE_LEFT"), n_frames=40, n_submissions=1,
+                                    objects_per_frame=60.0, seed=11), max_age=2, min_hits=0),
+    # upstream SORT defaults exercise the min_hits / hit_streak gate
+    "track_minhits": dict(cfg=dict(n_segments=2, cameras=("FRONT_RIGHT",), n_frames=30, n_submissions=1,
+                                   objects_per_frame=30.0, seed=12), max_age=1, min_hits=3),
+    # cyclist-heavy and sparse: iou_threshold 0.0 keeps zero-IoU assignments, so Munkres ties decide
+    "track_cyclist_ties": dict(cfg=dict(n_segments=1, cameras=("SIDE_RIGHT", "FRONT_LEFT"), n_frames=40,
+                                        n_submissions=1, objects_per_frame=25.0, class_mix=(0.1, 0.1, 0.1, 0.7),
+                                        mean_life=6.0, p_miss=0.3, seed=13), max_age=2, min_hits=0),
+    # dense: more detections than trackers and vice versa, larger assignment problems
+    "track_dense": dict(cfg=dict(n_segments=1, cameras=("FRONT",), n_frames=16, n_submissions=1,
+                                 objects_per_frame=260.0, size_range=(12.0, 80.0), mean_life=10.0, p_miss=0.25,
+                                 seed=14), max_age=2, min_hits=0),
+}
+
+ENSEMBLE_CASES = {
+    "ensemble_c2_small": dict(cfg=dict(n_segments=1, cameras=("FRONT", "SIDE_LEFT"), n_frames=8, n_submissions=3,
+                                       objects_per_frame=45.0, seed=21),
+                              min_score=0.01, iou_thresh=0.5, cut=0.9, weights=None),
+    "ensemble_weighted": dict(cfg=dict(n_segments=1, cameras=("FRONT_LEFT",), n_frames=6, n_submissions=4,
+                                       objects_per_frame=30.0, seed=22),
+                              min_score=0.05, iou_thresh=0.4, cut=1.0, weights=[2, 1, 4, 3]),
+    "ensemble_ties": dict(cfg=dict(n_segments=1, cameras=("FRONT",), n_frames=4, n_submissions=3,
+                                   objects_per_frame=40.0, seed=23),
+                          min_score=0.01, iou_thresh=0.5, cut=0.9, weights=None, round_scores=2),
+}
+
+
+def scene_inputs(scene):
+    d = {"image_ids": np.asarray(scene.image_ids()), "n_sub": np.int64(len(scene.submissions))}
+    for k, sub in enumerate(scene.submissions):
+        d["s%d_img" % k] = sub.image_index
+        d["s%d_cat" % k] = sub.category
+        d["s%d_bbox" % k] = sub.bbox
+        d["s%d_score" % k] = sub.score
+    return d
+
+
+def run_reference_tracking(dets, max_age, min_hits):
+    ref_utils, ref_sort, _ = ref_shim.load_tracking()
+    with tempfile.NamedTemporaryFile("wt", suffix=".json", delete=False) as fp:
+        json.dump(dets, fp)
+        path = fp.name
+    try:
+        predictions = ref_utils.read_data_file(path, SCORE_THR)
+    finally:
+        os.unlink(path)
+    return ref_shim.ref_track_all(predictions, IOU_THR, max_age, min_hits)
+
+
+def main():
+    assert ref_shim.available(), "reference not mounted at %s" % ref_shim.REF_ROOT
+    for name, case in TRACK_CASES.items():
+        scene = synth.make_scene(synth.SynthConfig(**case["cfg"]))
+        dets = synth.to_json_list(scene, scene.submissions[0])
+        rows = run_reference_tracking(dets, case["max_age"], case["min_hits"])
+        out = scene_inputs(scene)
+        out.update({"out_" + k: v for k, v in golden_io.tracks_to_arrays(rows, scene.image_ids()).items()})
+        out["max_age"], out["min_hits"] = np.int64(case["max_age"]), np.int64(case["min_hits"])
+        out["cfg"] = np.asarray(json.dumps(case["cfg"]))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "dets", len(dets), "rows", len(rows), "ids", out["out_oid"].max() if len(rows) else 0)
+
+    for name, case in ENSEMBLE_CASES.items():
+        scene = synth.make_scene(synth.SynthConfig(**case["cfg"]))
+        if case.get("round_scores"):
+            for sub in scene.submissions:
+                sub.score[:] = np.maximum(np.round(sub.score, case["round_scores"]), 0.01)
+        subs = [synth.to_json_list(scene, s) for s in scene.submissions]
+        rows = ref_shim.ref_ensemble_all(subs, case["weights"], case["min_score"], case["iou_thresh"], case["cut"])
+        out = scene_inputs(scene)
+        out.update({"out_" + k: v for k, v in golden_io.dets_to_arrays(rows, scene.image_ids()).items()})
+        out["min_score"], out["iou_thresh"], out["cut"] = (np.float64(case["min_score"]),
+                                                           np.float64(case["iou_thresh"]), np.float64(case["cut"]))
+        out["weights"] = np.asarray(case["weights"] if case["weights"] else [1] * len(subs), np.float64)
+        out["cfg"] = np.asarray(json.dumps(case["cfg"]))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "in", sum(len(s) for s in subs), "out", len(rows))
+
+    # end to end: ensemble JSON -> tracker, both through the reference's own code
+    case = ENSEMBLE_CASES["ensemble_c2_small"]
+    cfg = dict(case["cfg"], n_frames=24, seed=31)
+    scene = synth.make_scene(synth.SynthConfig(**cfg))
+    subs = [synth.to_json_list(scene, s) for s in scene.submissions]
+    ens = ref_shim.ref_ensemble_all(subs, None, 0.01, 0.5, 0.9)   # images in sorted image_id order
+    rows = run_reference_tracking(ens, 2, 0)
+    out = scene_inputs(scene)
+    out.update({"ens_" + k: v for k, v in golden_io.dets_to_arrays(ens, scene.image_ids()).items()})
+    out.update({"out_" + k: v for k, v in golden_io.tracks_to_arrays(rows, scene.image_ids()).items()})
+    out["cfg"] = np.asarray(json.dumps(cfg))
+    np.savez_compressed(os.path.join(HERE, "pipeline_small.npz"), **out)
+    print("pipeline_small ens", len(ens), "rows", len(rows))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/w2t.h declares; host-only entry points (plan, id assignment) are exercised; compute
+entry points must fail loudly without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from waymo_2d_tracking_b200 import _abi, _lib, packing, runtime
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "w2t.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(w2t_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_abi.EXPORTS) == names          # the ctypes mirror binds exactly the header
+
+
+def test_version_and_struct_sizes():
+    lib = _lib.lib()
+    assert b"sm_100a" in lib.w2t_version()
+    assert ctypes.sizeof(_abi.SortProblem) == 8 + 6 * 8 + 8 * 8 + 8
+    assert ctypes.sizeof(_abi.SortPlan) == 5 * 8
+
+
+def test_sort_plan_bounds_and_order():
+    offs = np.array([0, 4, 8], np.int32)
+    cnt = np.zeros((8, 2), np.int32)
+    cnt[:4, 0] = [3, 5, 2, 7]
+    cnt[4:, 1] = [1, 1, 9, 1]
+    plan = runtime.make_plan(2, 2, offs, cnt.reshape(-1), None, max_age=1)
+    # window = max_age + 2 = 3 images
+    assert plan["track_cap"].tolist() == [14, 1, 1, 11]
+    assert plan["det_cap"].tolist() == [7, 1, 1, 9]
+    assert plan["order"].tolist()[:2] == [0, 3]
+    assert plan["ws_offset"][0] == 0 and np.all(np.diff(plan["ws_offset"]) > 0) and plan["ws_bytes"] > 0
+
+
+def test_assign_ids_c_matches_numpy_statement():
+    rng = np.random.default_rng(0)
+    S, NC, F = 3, 4, 5
+    offs = (np.arange(S + 1) * F).astype(np.int32)
+    cnt = rng.integers(0, 4, S * F * NC).astype(np.int32)
+    start = (np.cumsum(cnt) - cnt).astype(np.int32)
+    created = np.minimum(cnt, rng.integers(0, 3, len(cnt))).astype(np.int32)
+    out_count = cnt.copy()
+    birth = np.zeros((int(cnt.sum()), 2), np.int32)
+    for g in range(len(cnt)):
+        for k in range(cnt[g]):
+            # any earlier-or-equal group of the same sub-stream that created something
+            s, c = (g // NC) // F, g % NC
+            cands = [h for h in range(s * F * NC + c, g + 1, NC) if created[h] > 0]
+            if cands:
+                h = cands[rng.integers(len(cands))]
+                birth[start[g] + k] = (h, rng.integers(created[h]))
+            else:
+                out_count[g] = 0
+    first = np.full(S * NC, -1, np.int32)
+    for s in range(S):
+        for c in range(NC):
+            nz = np.nonzero(cnt.reshape(S, F, NC)[s, :, c])[0]
+            if len(nz):
+                first[s * NC + c] = nz[0]
+    rank = packing.default_class_rank(first, S, NC)
+    a, na = packing.assign_ids(offs, NC, start, out_count, created, first, rank, birth, id_base=7)
+    b, nb = runtime.assign_ids(S, NC, offs, start, out_count, created, first, rank, birth, id_base=7)
+    np.testing.assert_array_equal(a, b)
+    c, nc = runtime.assign_ids(S, NC, offs, start, out_count, created, first, None, birth, id_base=7)
+    np.testing.assert_array_equal(a, c)
+    assert na == nb == nc == 7 + created.sum()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_gpu():
+    with pytest.raises(_lib.W2TError):
+        runtime.softnms_groups(np.array([0, 1], np.int32), np.zeros((1, 5)))
+    with pytest.raises(_lib.W2TError):
+        runtime.iou_matrix(np.zeros((1, 4), np.float32), np.zeros((1, 4)))

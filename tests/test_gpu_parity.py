@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libw2t.so) against the oracle on the
+same inputs and against the committed golden fixtures (outputs of the reference's own code).
+
+Bars (BASELINE.json north_star): track ids, assignments and kept-box sets bit-exact; Kalman
+states and decayed scores within 1e-9 relative (they are in fact bit-identical to the C oracle,
+which these tests demand wherever no transcendental function is involved)."""
+import numpy as np
+import pytest
+
+import golden_io
+import helpers
+from oracle import c_oracle
+from waymo_2d_tracking_b200 import packing, runtime, synth
+
+pytestmark = pytest.mark.gpu
+
+TRACK_CASES = ["track_c1_small", "track_minhits", "track_cyclist_ties", "track_dense"]
+ENS_CASES = ["ensemble_c2_small", "ensemble_weighted", "ensemble_ties"]
+
+
+def rand_boxes(rng, n, lo=0, hi=800, smin=2, smax=250):
+    xy = rng.uniform(lo, hi, (n, 2))
+    return np.c_[xy, xy + rng.uniform(smin, smax, (n, 2))]
+
+
+# ---- building blocks ------------------------------------------------------------------------
+
+def test_kalman_bit_exact_vs_c_oracle():
+    rng = np.random.default_rng(0)
+    n = 257
+    dets = rand_boxes(rng, n).astype(np.float32)
+    x, P = runtime.kf_init(dets)
+    ox = np.zeros_like(x)
+    oP = np.zeros_like(P)
+    for i in range(n):
+        ox[i], oP[i] = c_oracle.kf_init(dets[i])
+    np.testing.assert_array_equal(x, ox)
+    np.testing.assert_array_equal(P, oP)
+    for step in range(12):
+        x, P, boxes = runtime.kf_predict(x, P)
+        for i in range(n):
+            ox[i], oP[i] = c_oracle.kf_predict(ox[i], oP[i])
+        np.testing.assert_array_equal(x, ox)
+        np.testing.assert_array_equal(P, oP)
+        np.testing.assert_array_equal(boxes, np.stack([c_oracle.x_to_bbox(v) for v in ox]))
+        dets = (dets + rng.normal(0, 3, dets.shape)).astype(np.float32)
+        dets[:, 2:] = np.maximum(dets[:, 2:], dets[:, :2] + 1)
+        x, P, _ = runtime.kf_update(x, P, dets)
+        for i in range(n):
+            ox[i], oP[i] = c_oracle.kf_update(ox[i], oP[i], dets[i])
+        np.testing.assert_array_equal(x, ox)                     # bit-exact, far inside the 1e-9 bar
+        np.testing.assert_array_equal(P, oP)
+
+
+def test_kalman_negative_scale_gives_nan_box_like_reference():
+    x = np.array([[10., 10., -4., 1., 0., 0., 1.], [10., 10., 4., 1., 0., 0., -9.]])
+    P = np.tile(np.eye(7), (2, 1, 1))
+    x2, _, boxes = runtime.kf_predict(x, P)
+    assert np.isnan(boxes[0]).all()
+    assert x2[1, 6] == 0.0 and x2[1, 2] == 4.0
+
+
+def test_iou_matrix_bit_exact():
+    rng = np.random.default_rng(1)
+    for D, T in [(1, 1), (7, 3), (64, 50), (130, 257)]:
+        dets = rand_boxes(rng, D).astype(np.float32)
+        trks = rand_boxes(rng, T)
+        trks[: T // 3] = dets[rng.integers(0, D, T // 3)] + rng.normal(0, 2, (T // 3, 4))
+        np.testing.assert_array_equal(runtime.iou_matrix(dets, trks), c_oracle.iou_matrix(dets, trks))
+
+
+def test_linear_assignment_bit_exact_including_ties():
+    rng = np.random.default_rng(2)
+    shapes = [(1, 1), (1, 9), (9, 1), (5, 5), (17, 40), (40, 17), (33, 33), (64, 65), (70, 200), (150, 90)]
+    for trial, (D, T) in enumerate(shapes * 4):
+        kind = trial % 5
+        if kind == 0:
+            M = rng.random((D, T))
+        elif kind == 1:
+            M = (rng.random((D, T)) < 0.1) * rng.random((D, T))
+        elif kind == 2:
+            M = np.round(rng.random((D, T)) * 3) / 3
+        elif kind == 3:
+            M = np.zeros((D, T))
+        else:
+            M = (rng.random((D, T)) < 0.3).astype(float)
+        cost = (-M).astype(np.float32)
+        np.testing.assert_array_equal(runtime.linear_assignment(cost), c_oracle.linear_assignment(cost))
+
+
+def test_linear_assignment_large_crowded():
+    # IoU-like matrix of a crowded scene (C4 sizes): many step-6 rounds
+    rng = np.random.default_rng(3)
+    dets = rand_boxes(rng, 450, 0, 1500, 20, 120).astype(np.float32)
+    trks = np.r_[dets[:380] + rng.normal(0, 6, (380, 4)), rand_boxes(rng, 140, 0, 1500, 20, 120)]
+    cost = -c_oracle.iou_matrix(dets, trks)
+    np.testing.assert_array_equal(runtime.linear_assignment(cost), c_oracle.linear_assignment(cost))
+    np.testing.assert_array_equal(runtime.linear_assignment(cost.T.copy()), c_oracle.linear_assignment(cost.T.copy()))
+
+
+# ---- SORT stage -------------------------------------------------------------------------------
+
+def compare_sort(packed, iou_thr, max_age, min_hits, final_cap=0):
+    got = runtime.sort_track(packed, iou_thr, max_age, min_hits, final_cap=final_cap)
+    want = c_oracle.sort_track(packed, iou_thr, max_age, min_hits, final_cap=final_cap)
+    assert want["status"] == 0
+    np.testing.assert_array_equal(got["out_count"], want["out_count"])
+    np.testing.assert_array_equal(got["created"], want["created"])
+    np.testing.assert_array_equal(got["first_img"], want["first_img"])
+    rows, _ = packing.valid_row_index(packed.det_start, want["out_count"])
+    np.testing.assert_array_equal(got["out_birth"][rows], want["out_birth"][rows])   # assignments
+    np.testing.assert_array_equal(got["out_box"][rows], want["out_box"][rows])       # states -> boxes: bit-exact
+    np.testing.assert_allclose(got["out_score"][rows], want["out_score"][rows], rtol=1e-9, atol=0)
+    ids, nxt = packing.assign_ids(packed.stream_img_offsets, packed.n_classes, packed.det_start, want["out_count"],
+                                  want["created"], want["first_img"], packed.class_rank, want["out_birth"])
+    np.testing.assert_array_equal(got["ids"], ids)
+    assert got["id_next"] == nxt
+    if final_cap:
+        np.testing.assert_array_equal(got["final_count"], want["final_count"])
+        for q, t in enumerate(want["final_count"]):
+            t = min(int(t), final_cap)
+            np.testing.assert_array_equal(got["final_state"][q, :t], want["final_state"][q, :t])
+    return got
+
+
+@pytest.mark.parametrize("name", TRACK_CASES)
+def test_sort_matches_reference_golden(name):
+    g = golden_io.load(name)
+    scene = helpers.golden_scene(g)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    res = compare_sort(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), final_cap=64)
+    got = helpers.track_rows_as_arrays(packed, res, scene.image_ids(), ids=res["ids"])
+    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)
+
+
+@pytest.mark.parametrize("seed,max_age,min_hits", [(101, 2, 0), (102, 1, 3), (103, 0, 0), (104, 5, 1)])
+def test_sort_seeded_vs_oracle(seed, max_age, min_hits):
+    cfg = synth.SynthConfig(n_segments=2, n_frames=50, n_submissions=1, objects_per_frame=70.0, seed=seed)
+    scene = synth.make_scene(cfg)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    compare_sort(packed, helpers.IOU_THR, max_age, min_hits, final_cap=160)
+
+
+def test_sort_ragged_and_empty_streams():
+    # empty stream, a stream whose detections are all filtered, missing images, a late-starting category
+    cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT", "SIDE_LEFT", "SIDE_RIGHT"), n_frames=25,
+                            n_submissions=1, objects_per_frame=20.0, seed=5)
+    scene = synth.make_scene(cfg)
+    sub = scene.submissions[0]
+    keep = np.ones(len(sub.score), bool)
+    F = cfg.n_frames
+    keep[sub.image_index // F == 1] = False                        # stream 1: no detections at all
+    keep[(sub.image_index % F) % 7 == 3] = False                   # images absent from the JSON
+    keep[(sub.category == 2) & (sub.image_index % F < 12)] = False  # pedestrians appear late
+    sub2 = synth.Submission(sub.image_index[keep], sub.category[keep], sub.bbox[keep], sub.score[keep].copy())
+    sub2.score[(sub2.image_index // F == 2)] = 0.011               # stream 2: everything below threshold
+    packed = synth.tracks_from_submission(scene, sub2, helpers.SCORE_THR)
+    assert packed.img_exists.min() == 0
+    res = compare_sort(packed, helpers.IOU_THR, 2, 0, final_cap=64)
+    assert res["out_count"].reshape(-1, 4)[F:2 * F].sum() == 0
+    # no streams at all
+    empty = packing.PackedTracks(0, 4, [], np.zeros(0, np.int64), np.zeros(1, np.int32), np.zeros(0, np.int32),
+                                 np.zeros(0, np.int32), np.zeros((0, 4), np.float32), np.zeros((0, 2)), None,
+                                 np.zeros(0, np.int32), 0)
+    out = runtime.sort_track(empty, helpers.IOU_THR, 2, 0)
+    assert out["id_next"] == 0 and len(out["ids"]) == 0
+
+
+def test_sort_crowded_matches_oracle():
+    # C4-shaped miniature: ~1000 dets/frame, hundreds of live tracks per category
+    cfg = synth.preset("c4", cameras=("FRONT",), n_frames=8, seed=9)
+    scene = synth.make_scene(cfg)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    assert packed.det_count.max() > 300
+    compare_sort(packed, helpers.IOU_THR, 2, 0)
+
+
+def test_sort_is_invariant_to_sharding():
+    # tracking a subset of streams alone gives the same rows; ids differ only by the scan base
+    cfg = synth.SynthConfig(n_segments=2, cameras=("FRONT", "SIDE_LEFT"), n_frames=30, n_submissions=1,
+                            objects_per_frame=40.0, seed=6)
+    scene = synth.make_scene(cfg)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    full = runtime.sort_track(packed, helpers.IOU_THR, 2, 0)
+    F, NC = cfg.n_frames, 4
+    base = 0
+    for s in range(packed.n_streams):
+        g0, g1 = s * F * NC, (s + 1) * F * NC
+        r0 = int(packed.det_start[g0])
+        r1 = int(packed.det_start[g1]) if g1 < len(packed.det_start) else packed.n_rows
+        part = packing.PackedTracks(1, NC, [packed.streams[s]], packed.frame_ids[s * F:(s + 1) * F],
+                                    np.array([0, F], np.int32), packed.det_start[g0:g1] - r0,
+                                    packed.det_count[g0:g1], packed.det_box[r0:r1], packed.cam_wh[s:s + 1],
+                                    packed.img_exists[s * F:(s + 1) * F], packed.class_rank[s * NC:(s + 1) * NC],
+                                    r1 - r0)
+        one = runtime.sort_track(part, helpers.IOU_THR, 2, 0, id_base=base)
+        base = one["id_next"]
+        np.testing.assert_array_equal(one["out_count"], full["out_count"][g0:g1])
+        rows, _ = packing.valid_row_index(part.det_start, one["out_count"])
+        np.testing.assert_array_equal(one["out_box"][rows], full["out_box"][r0:r1][rows])
+        np.testing.assert_array_equal(one["ids"][rows], full["ids"][r0:r1][rows])
+    assert base == full["id_next"]
+
+
+# ---- soft-NMS ensemble stage --------------------------------------------------------------------
+
+def compare_nms(groups, iou_thresh, cut, min_score):
+    got = runtime.softnms_groups(groups.group_offsets, groups.rows, iou_thresh, cut, min_score, 4,
+                                 helpers.SCORE_THR, max_group=groups.max_group)
+    want = c_oracle.softnms_groups(groups.group_offsets, groups.rows, iou_thresh, cut, min_score, 4,
+                                   helpers.SCORE_THR)
+    np.testing.assert_array_equal(got["merged"], want["merged"])          # decayed scores: bit-exact
+    np.testing.assert_array_equal(got["src_index"], want["src_index"])    # kept-box order
+    np.testing.assert_array_equal(got["ens_count"], want["ens_count"])
+    np.testing.assert_array_equal(got["trk_count"], want["trk_count"])
+    np.testing.assert_array_equal(got["img_exists"], want["img_exists"])
+    off = groups.group_offsets.astype(np.int64)
+    rows, _ = packing.valid_row_index(off[:-1], want["ens_count"])
+    np.testing.assert_array_equal(got["ens_box"][rows], want["ens_box"][rows])
+    np.testing.assert_array_equal(got["ens_score"][rows], want["ens_score"][rows])
+    rows, _ = packing.valid_row_index(off[:-1], want["trk_count"])
+    np.testing.assert_array_equal(got["trk_box"][rows], want["trk_box"][rows])
+    return got
+
+
+@pytest.mark.parametrize("name", ENS_CASES)
+def test_softnms_matches_reference_golden(name):
+    g = golden_io.load(name)
+    scene = helpers.golden_scene(g)
+    groups = synth.groups_from_scene(scene, list(g["weights"]), float(g["min_score"]))
+    res = compare_nms(groups, float(g["iou_thresh"]), float(g["cut"]), float(g["min_score"]))
+    got = helpers.ensemble_rows_as_arrays(groups.group_offsets, res, scene.n_img,
+                                          image_order=helpers.sorted_image_order(scene.image_ids()))
+    for k in ("img", "cat", "bbox", "score"):
+        np.testing.assert_array_equal(got[k], g["out_" + k])
+
+
+def test_softnms_edge_groups():
+    # n = 0, 1, 2; identical boxes (IoU 1 -> weight 0); disjoint boxes; IoU >= cut
+    rows = np.array([
+        [0.9, 10, 10, 20, 20],                               # group 1: single box
+        [0.9, 10, 10, 20, 20], [0.8, 10, 10, 20, 20],        # group 2: identical boxes
+        [0.9, 0, 0, 10, 10], [0.8, 100, 100, 10, 10],        # group 3: disjoint
+        [0.9, 0, 0, 100, 100], [0.8, 2, 2, 100, 100], [0.7, 50, 0, 100, 100], [0.3, 1, 1, 99, 99],
+    ], np.float64)
+    offsets = np.array([0, 0, 1, 3, 5, 9, 9, 9, 9], np.int32)   # 8 groups = 2 images x 4 categories
+    groups = packing.PackedGroups(None, [1, 2, 3, 4], offsets, rows, 4)
+    res = compare_nms(groups, 0.5, 0.9, 0.0)
+    assert res["ens_count"].tolist() == [0, 1, 1, 2, 3, 0, 0, 0]
+    assert res["merged"][2, 0] == 0.0 and res["merged"][1, 0] == 0.9
+
+
+def test_softnms_large_group_tta_shaped():
+    # C5-shaped: 5 submissions, thousands of boxes per image
+    cfg = synth.preset("c5", cameras=("FRONT",), n_frames=2, seed=4)
+    scene = synth.make_scene(cfg)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    assert groups.max_group > 1000
+    compare_nms(groups, 0.5, 0.9, 0.01)
+
+
+def test_softnms_rejects_unsupported_scores_loudly():
+    rows = np.array([[-0.5, 0, 0, 10, 10], [0.5, 0, 0, 10, 10]], np.float64)
+    with pytest.raises(Exception):
+        runtime.softnms_groups(np.array([0, 2], np.int32), rows, 0.5, 0.9, 0.0)
+
+
+# ---- ensemble -> SORT on the device ----------------------------------------------------------------
+
+def test_pipeline_matches_reference_golden_end_to_end():
+    import test_oracle as T
+    g = golden_io.load("pipeline_small")
+    scene = helpers.golden_scene(g)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    res = runtime.ensemble_and_track(groups.group_offsets, groups.rows, scene.stream_img_offsets, scene.cam_wh(), 4,
+                                     0.5, 0.9, 0.01, helpers.SCORE_THR, helpers.IOU_THR, 2, 0,
+                                     max_group=groups.max_group)
+    ens = helpers.ensemble_rows_as_arrays(groups.group_offsets, res, scene.n_img,
+                                          image_order=helpers.sorted_image_order(scene.image_ids()))
+    for k in ("img", "cat", "bbox", "score"):
+        np.testing.assert_array_equal(ens[k], g["ens_" + k])
+    packed = packing.PackedTracks(
+        n_streams=scene.n_streams, n_classes=4, streams=scene.streams(), frame_ids=scene.frame_ids,
+        stream_img_offsets=scene.stream_img_offsets, det_start=res["det_start"], det_count=res["trk_count"],
+        det_box=np.zeros((len(groups.rows), 4), np.float32), cam_wh=scene.cam_wh(), img_exists=res["img_exists"],
+        class_rank=None, n_rows=len(groups.rows))
+    order = T.stream_order_of_sorted_images(scene)
+    got = T.rows_in_stream_order(packed, res, scene, order)
+    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)

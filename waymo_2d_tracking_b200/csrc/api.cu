@@ -1,0 +1,38 @@
+// api.cu — library-level entry points and error plumbing.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace w2t {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+  set_last_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return W2T_ERR_CUDA;
+}
+
+}  // namespace w2t
+
+extern "C" const char *w2t_version(void) { return "w2t 0.1 (sm_100a)"; }
+
+extern "C" const char *w2t_last_error(void) { return w2t::g_last_error; }
+
+extern "C" int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+  int dev = 0;
+  W2T_CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  W2T_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return W2T_OK;
+}

@@ -1,0 +1,127 @@
+// sort.cu — host entry points of the SORT stage: plan, launch, id assignment.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "sort_kernel.cuh"
+
+using namespace w2t;
+
+extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                             const int32_t *det_count, const uint8_t *img_exists, int32_t max_age,
+                             w2t_sort_plan_t *plan) {
+  if (!stream_img_offsets || !det_count || !plan || !plan->order || !plan->track_cap || !plan->det_cap ||
+      !plan->ws_offset || n_streams < 0 || n_classes < 1 || n_classes > W2T_MAX_CLASSES || max_age < 0) {
+    set_last_error("w2t_sort_plan: bad argument");
+    return W2T_ERR_ARG;
+  }
+  const int NC = n_classes;
+  const int nq = n_streams * NC;
+  const int window = max_age + 2;  // images whose detections can still own a live tracker
+  std::vector<int64_t> work(nq, 0);
+  std::vector<int> ring(window);
+  for (int s = 0; s < n_streams; s++) {
+    for (int c = 0; c < NC; c++) {
+      const int q = s * NC + c;
+      std::fill(ring.begin(), ring.end(), 0);
+      int64_t sum = 0, best = 0, w = 0;
+      int dmax = 0, pos = 0;
+      for (int img = stream_img_offsets[s]; img < stream_img_offsets[s + 1]; img++) {
+        if (img_exists && !img_exists[img]) continue;
+        const int d = det_count[(size_t)img * NC + c];
+        sum += d - ring[pos];
+        ring[pos] = d;
+        pos = (pos + 1) % window;
+        best = std::max(best, sum);
+        dmax = std::max(dmax, d);
+        w += (int64_t)d * d + d;
+      }
+      plan->track_cap[q] = (int32_t)std::max<int64_t>(best, 1);
+      plan->det_cap[q] = std::max(dmax, 1);
+      work[q] = w;
+    }
+  }
+  std::iota(plan->order, plan->order + nq, 0);
+  std::stable_sort(plan->order, plan->order + nq, [&](int a, int b) { return work[a] > work[b]; });
+  int64_t off = 0;
+  for (int q = 0; q < nq; q++) {
+    plan->ws_offset[q] = off;
+    off += (int64_t)slab_layout(plan->track_cap[q], plan->det_cap[q]).total;
+  }
+  plan->ws_bytes = off;
+  return W2T_OK;
+}
+
+extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
+                              w2t_sort_result_t *result, void *workspace, int32_t *status, w2t_stream_t stream) {
+  if (!problem || !plan || !result || !status || problem->n_classes < 1 ||
+      problem->n_classes > W2T_MAX_CLASSES || problem->n_streams < 0) {
+    set_last_error("w2t_sort_track: bad argument");
+    return W2T_ERR_ARG;
+  }
+  const int nq = problem->n_streams * problem->n_classes;
+  if (nq == 0) return W2T_OK;
+  if (!workspace || !result->out_box || !result->out_score || !result->out_birth || !result->out_count ||
+      !result->created || !result->first_img) {
+    set_last_error("w2t_sort_track: null buffer");
+    return W2T_ERR_ARG;
+  }
+  SortParams P;
+  P.p = *problem;
+  P.r = *result;
+  P.order = plan->order;
+  P.track_cap = plan->track_cap;
+  P.det_cap = plan->det_cap;
+  P.ws_offset = plan->ws_offset;
+  P.ws = static_cast<char *>(workspace);
+  P.status = status;
+  sort_track_kernel<kSortBlock><<<nq, kSortBlock, 0, (cudaStream_t)stream>>>(P);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
+
+extern "C" int w2t_assign_ids(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                              const int32_t *det_start, const int32_t *out_count, const int32_t *created,
+                              const int32_t *first_img, const int32_t *class_rank, const int32_t *out_birth,
+                              int64_t id_base, int64_t *out_id, int64_t *id_next) {
+  if (!stream_img_offsets || !det_start || !out_count || !created || !out_birth || !out_id ||
+      (!first_img && !class_rank) || n_classes < 1 || n_classes > W2T_MAX_CLASSES) {
+    set_last_error("w2t_assign_ids: bad argument");
+    return W2T_ERR_ARG;
+  }
+  const int NC = n_classes;
+  const int n_img = stream_img_offsets[n_streams];
+  std::vector<int64_t> base((size_t)n_img * NC);
+  int64_t next = id_base;
+  for (int s = 0; s < n_streams; s++) {
+    // categories in the order the reference's tracker dict holds them
+    int cats[W2T_MAX_CLASSES];
+    std::iota(cats, cats + NC, 0);
+    if (class_rank) {
+      const int32_t *rk = class_rank + (size_t)s * NC;
+      std::stable_sort(cats, cats + NC, [&](int a, int b) { return rk[a] < rk[b]; });
+    } else {
+      const int32_t *fi = first_img + (size_t)s * NC;
+      std::stable_sort(cats, cats + NC, [&](int a, int b) {
+        const int64_t fa = fi[a] < 0 ? INT64_MAX : fi[a], fb = fi[b] < 0 ? INT64_MAX : fi[b];
+        return fa < fb;
+      });
+    }
+    for (int img = stream_img_offsets[s]; img < stream_img_offsets[s + 1]; img++)
+      for (int k = 0; k < NC; k++) {
+        const size_t g = (size_t)img * NC + cats[k];
+        base[g] = next;
+        next += created[g];
+      }
+  }
+  for (size_t g = 0; g < (size_t)n_img * NC; g++) {
+    const size_t r0 = (size_t)det_start[g];
+    for (int k = 0; k < out_count[g]; k++) {
+      const size_t r = r0 + k;
+      out_id[r] = base[out_birth[2 * r]] + out_birth[2 * r + 1] + 1;  // id + 1, sort.py:288
+    }
+  }
+  if (id_next) *id_next = next;
+  return W2T_OK;
+}

@@ -1,0 +1,385 @@
+// sort_kernel.cuh — the persistent SORT kernel: one CTA per (stream, category) sub-stream.
+//
+// Replaces, for every stream at once, the loop of tracking/track.py:42-47:
+//   track_sort (tracking/utils.py:25-60) -> MultiClassTrackerSort.track
+//   (tracking/sort/tracker_sort.py:22-51) -> Sort.update (tracking/sort/sort.py:244-296)
+//   -> KalmanBoxTracker / associate_detections_to_trackers / iou (sort.py:33-230).
+//
+// A reference `Sort` object only ever sees the detections of one category of one stream, and
+// the only thing sub-streams share is the global id counter (sort.py:86), which never feeds
+// back into the dynamics.  So each sub-stream is an independent sequential recurrence over
+// the stream's images and gets one CTA that walks them in order; ids are resolved afterwards
+// from per-group creation counts (w2t_assign_ids).
+//
+// Per image the CTA runs:
+//   A. association: -IoU cost matrix (warp per row, coalesced) -> Munkres (munkres.cuh) ->
+//      matched / rejected / unassigned detections -> order of new trackers (sort.py:208-222);
+//   B. one pass over the tracker list, one thread per tracker: Kalman update with the matched
+//      detection or creation from an unmatched one, emission of the output row
+//      (sort.py:280-289 + utils.py:37-58), age test (sort.py:292) and — for survivors — the
+//      predict step of the NEXT image (sort.py:255-262), so a tracker's 56 doubles are read
+//      and written once per image;
+//   C. stable compaction of the tracker list.
+//
+// Tracker state lives in a per-sub-stream slab of global memory (struct-of-arrays, one slot
+// per tracker, L1/L2 resident while the CTA runs).  The tracker LIST is an array of slot
+// numbers: its first T entries are the live trackers in creation order (the reference's list
+// order), the rest are free slots, so removal moves 4-byte slot numbers, never filter state.
+#pragma once
+
+#include "kalman.cuh"
+#include "munkres.cuh"
+
+namespace w2t {
+
+constexpr int kSortBlock = 128;
+constexpr int kStateDoubles = 60;  // x[7], P[49], predicted box[4]
+
+struct SlabLayout {
+  size_t st, tsu, hs, bg, bk, list, tmp, flag, dstat, newdet, C, Z, rstar, cstar, rprime, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline SlabLayout slab_layout(int Tcap, int Dcap) {
+  SlabLayout L;
+  const size_t T = (size_t)Tcap, D = (size_t)Dcap;
+  const size_t n = T < D ? T : D, m = T < D ? D : T;
+  const size_t mcap = m < (size_t)kMunkresMaxDim ? m : (size_t)kMunkresMaxDim;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+  L.st = take(sizeof(double) * kStateDoubles * T);
+  L.tsu = take(4 * T);
+  L.hs = take(4 * T);
+  L.bg = take(4 * T);
+  L.bk = take(4 * T);
+  L.list = take(4 * T);
+  L.tmp = take(4 * m);
+  L.flag = take(4 * T);
+  L.dstat = take(4 * D);
+  L.newdet = take(4 * D);
+  L.C = take(4 * n * m);
+  L.Z = take(4 * n * (size_t)munkres_zstride((int)mcap));
+  L.rstar = take(4 * n);
+  L.cstar = take(4 * m);
+  L.rprime = take(4 * n);
+  L.total = align_up(o, 256);
+  return L;
+}
+
+struct SortParams {
+  w2t_sort_problem_t p;
+  w2t_sort_result_t r;
+  const int32_t *order, *track_cap, *det_cap;
+  const int64_t *ws_offset;
+  char *ws;
+  int32_t *status;
+};
+
+// iou() of sort.py:33-47 as numba compiles it for (float32[:], float64[:]): the detection's
+// own area is a float32 product, everything else float64; the result is stored as float32.
+__device__ __forceinline__ float iou_pair(const float4 d, const double t0, const double t1, const double t2,
+                                          const double t3) {
+  const double xx1 = (double)d.x > t0 ? (double)d.x : t0;
+  const double yy1 = (double)d.y > t1 ? (double)d.y : t1;
+  const double xx2 = (double)d.z < t2 ? (double)d.z : t2;
+  const double yy2 = (double)d.w < t3 ? (double)d.w : t3;
+  double w = xx2 - xx1;
+  if (!(w > 0.)) w = 0.;
+  double h = yy2 - yy1;
+  if (!(h > 0.)) h = 0.;
+  const double wh = w * h;
+  const float ad = (d.z - d.x) * (d.w - d.y);
+  const double at = (t2 - t0) * (t3 - t1);
+  const double den = ((double)ad + at) - wh;
+  if (wh == 0. && den > 0.) return 0.0f;  // 0/den exactly; skips the FP64 divide for disjoint boxes
+  return (float)(wh / den);
+}
+
+__device__ __forceinline__ double clipd(double v, double lo, double hi) {
+  // numpy.clip: minimum(maximum(v, lo), hi), NaN propagates
+  if (v < lo) v = lo;
+  if (v > hi) v = hi;
+  return v;
+}
+
+// Stable partition of the values val(i), i < n: those with fa(i) go to dst[0..na) and those
+// with fb(i) to dst[na..na+nb), both in order.  dst may be the array val reads from.
+template <int BLOCK, class VAL, class FA, class FB>
+__device__ void partition3(int n, VAL val, FA fa, FB fb, int *dst, int *tmp, int *scratch, int &na, int &nb) {
+  int ca = 0, cb = 0;
+  for (int i0 = 0; i0 < n; i0 += BLOCK) {
+    const int i = i0 + threadIdx.x;
+    bool a = false, b = false;
+    int v = 0;
+    if (i < n) { v = val(i); a = fa(i); b = fb(i); }
+    int ea, eb, ta, tb;
+    block_scan2<BLOCK>(a, b, scratch, ea, eb, ta, tb);
+    if (a) dst[ca + ea] = v;
+    if (b) tmp[cb + eb] = v;
+    ca += ta;
+    cb += tb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cb; i += BLOCK) dst[ca + i] = tmp[i];
+  __syncthreads();
+  na = ca;
+  nb = cb;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
+  constexpr int NW = BLOCK / 32;
+  __shared__ MunkresShared ms;
+  __shared__ int s_scan[2 * NW];
+  __shared__ int s_nan;
+
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int q = P.order[blockIdx.x];
+  const int NC = P.p.n_classes;
+  const int s = q / NC, c = q % NC;
+  const int Tcap = P.track_cap[q], Dcap = P.det_cap[q];
+  char *slab = P.ws + P.ws_offset[q];
+  const SlabLayout L = slab_layout(Tcap, Dcap);
+  double *st = reinterpret_cast<double *>(slab + L.st);
+  int *tsuA = reinterpret_cast<int *>(slab + L.tsu);
+  int *hsA = reinterpret_cast<int *>(slab + L.hs);
+  int *bgA = reinterpret_cast<int *>(slab + L.bg);
+  int *bkA = reinterpret_cast<int *>(slab + L.bk);
+  int *list = reinterpret_cast<int *>(slab + L.list);
+  int *tmp = reinterpret_cast<int *>(slab + L.tmp);
+  int *flag = reinterpret_cast<int *>(slab + L.flag);   // per list position: matched det, then survivor flag
+  int *dstat = reinterpret_cast<int *>(slab + L.dstat);
+  int *newdet = reinterpret_cast<int *>(slab + L.newdet);
+
+  Munkres<BLOCK> mk;
+  mk.s = &ms;
+  mk.g.C = reinterpret_cast<float *>(slab + L.C);
+  mk.g.Z = reinterpret_cast<uint32_t *>(slab + L.Z);
+  mk.g.row_star = reinterpret_cast<int *>(slab + L.rstar);
+  mk.g.col_star = reinterpret_cast<int *>(slab + L.cstar);
+  mk.g.row_prime = reinterpret_cast<int *>(slab + L.rprime);
+
+  const int img0 = P.p.stream_img_offsets[s], img1 = P.p.stream_img_offsets[s + 1];
+  const double camW = P.p.cam_wh[2 * s], camH = P.p.cam_wh[2 * s + 1];
+  const float thr_f = (float)P.p.iou_thr[c];  // NEP 50: the python float adopts float32 (sort.py:220)
+  const int max_age = P.p.max_age, min_hits = P.p.min_hits;
+  const float4 *det_box = reinterpret_cast<const float4 *>(P.p.det_box);
+
+  for (int i = tid; i < Tcap; i += BLOCK) list[i] = i;
+  if (tid == 0) { P.r.first_img[q] = -1; s_nan = 0; }
+  __syncthreads();
+
+  int T = 0, frame_count = 0, err = 0;
+  bool started = false;
+
+  for (int img = img0; img < img1; ++img) {
+    const int g = img * NC + c;
+    bool skip = (P.p.img_exists != nullptr) && (P.p.img_exists[img] == 0);
+    const int D = skip ? 0 : P.p.det_count[g];
+    if (!skip && !started) {
+      if (D == 0) skip = true;  // no Sort object for this category yet (tracker_sort.py:32-33)
+      else {
+        started = true;
+        if (tid == 0) P.r.first_img[q] = img - img0;
+      }
+    }
+    if (!skip && !err && (D > Dcap || D > kMunkresMaxDim || T > kMunkresMaxDim)) err = W2T_ERR_CAPACITY;
+    if (skip || err) {
+      if (tid == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
+      continue;
+    }
+    frame_count++;
+    const int base = P.p.det_start[g];
+    const float4 *dets = det_box + base;
+
+    // ---- trackers whose predicted box is NaN are dropped before association (sort.py:261-265)
+    if (s_nan) {
+      int na, nb;
+      partition3<BLOCK>(
+          T, [&](int i) { return list[i]; },
+          [&](int i) {
+            const int sl = list[i];
+            return !(isnan(st[56 * Tcap + sl]) || isnan(st[57 * Tcap + sl]) || isnan(st[58 * Tcap + sl]) ||
+                     isnan(st[59 * Tcap + sl]));
+          },
+          [&](int i) {
+            const int sl = list[i];
+            return isnan(st[56 * Tcap + sl]) || isnan(st[57 * Tcap + sl]) || isnan(st[58 * Tcap + sl]) ||
+                   isnan(st[59 * Tcap + sl]);
+          },
+          list, tmp, s_scan, na, nb);
+      T = na;
+      if (tid == 0) s_nan = 0;
+      __syncthreads();
+    }
+
+    // ---- A. association ------------------------------------------------------------------
+    for (int t = tid; t < T; t += BLOCK) flag[t] = -1;
+    if (T > 0 && D > 0) {
+      const bool flipped = D > T;  // the solver transposes when there are more rows than columns
+      const int n = flipped ? T : D, m = flipped ? D : T;
+      mk.n = n;
+      mk.m = m;
+      mk.mw = munkres_words(m);
+      mk.zs = munkres_zstride(m);
+      for (int r = warp; r < n; r += NW) {
+        float *row = mk.g.C + (size_t)r * m;
+        if (!flipped) {
+          const float4 d = dets[r];
+          for (int cc = lane; cc < m; cc += 32) {
+            const int sl = list[cc];
+            row[cc] = -iou_pair(d, st[56 * Tcap + sl], st[57 * Tcap + sl], st[58 * Tcap + sl], st[59 * Tcap + sl]);
+          }
+        } else {
+          const int sl = list[r];
+          const double t0 = st[56 * Tcap + sl], t1 = st[57 * Tcap + sl], t2 = st[58 * Tcap + sl],
+                       t3 = st[59 * Tcap + sl];
+          for (int cc = lane; cc < m; cc += 32) row[cc] = -iou_pair(dets[cc], t0, t1, t2, t3);
+        }
+      }
+      __syncthreads();
+      if (mk.solve() != 0) err = W2T_ERR_ARG;
+      for (int d = tid; d < D; d += BLOCK) {
+        const int t = flipped ? mk.g.col_star[d] : mk.g.row_star[d];
+        int stt = 0;
+        if (t >= 0) {
+          const int sl = list[t];
+          const float o = iou_pair(dets[d], st[56 * Tcap + sl], st[57 * Tcap + sl], st[58 * Tcap + sl],
+                                   st[59 * Tcap + sl]);
+          if (o < thr_f) stt = 2;  // assigned but rejected: becomes a new tracker AFTER the unassigned ones
+          else { stt = 1; flag[t] = d; }
+        }
+        dstat[d] = stt;
+      }
+    } else {
+      for (int d = tid; d < D; d += BLOCK) dstat[d] = 0;
+    }
+    __syncthreads();
+    int n_un, n_rej;
+    partition3<BLOCK>(
+        D, [&](int i) { return i; }, [&](int i) { return dstat[i] == 0; }, [&](int i) { return dstat[i] == 2; },
+        newdet, tmp, s_scan, n_un, n_rej);
+    const int n_new = n_un + n_rej;
+    const int Ttot = T + n_new;
+    if (Ttot > Tcap) err = W2T_ERR_CAPACITY;
+    if (err) {
+      if (tid == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
+      continue;
+    }
+
+    // ---- B. one pass over the tracker list --------------------------------------------------
+    int emitted = 0;
+    for (int t0 = 0; t0 < Ttot; t0 += BLOCK) {
+      const int t = t0 + tid;
+      bool ok = false;
+      double ob0 = 0, ob1 = 0, ob2 = 0, ob3 = 0, oconf = 0;
+      int obg = 0, obk = 0;
+      if (t < Ttot) {
+        const int sl = list[t];
+        double x[7], Pm[49];
+        int tsu, hs;
+        if (t >= T) {  // sort.py:276-278
+          const float4 d4 = dets[newdet[t - T]];
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+          kf_init(dd, x, Pm);
+          tsu = 0;
+          hs = 0;
+          obg = g;
+          obk = t - T;
+          bgA[sl] = obg;
+          bkA[sl] = obk;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 7; k++) x[k] = st[k * Tcap + sl];
+#pragma unroll
+          for (int k = 0; k < 49; k++) Pm[k] = st[(7 + k) * Tcap + sl];
+          tsu = tsuA[sl];
+          hs = hsA[sl];
+          obg = bgA[sl];
+          obk = bkA[sl];
+          const int md = flag[t];
+          if (md >= 0) {  // sort.py:270-273, :153-164
+            const float4 d4 = dets[md];
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            kf_update(x, Pm, dd);
+            tsu = 0;
+            hs += 1;
+          }
+        }
+        // sort.py:281-289 and utils.py:37-49
+        if (tsu < 1 && (hs >= min_hits || frame_count <= min_hits)) {
+          double b[4];
+          x_to_bbox(x, b);
+          const double e = ((Pm[0] + Pm[8]) + Pm[16]) / 3.0;
+          const double conf = exp(-e * 0.1);
+          const double x1 = clipd(b[0], 0., camW), y1 = clipd(b[1], 0., camH);
+          const double x2 = clipd(b[2], 0., camW), y2 = clipd(b[3], 0., camH);
+          const double wd = x2 - x1, ht = y2 - y1;
+          if (!(wd < 1 || ht < 1)) {
+            ok = true;
+            ob0 = x1; ob1 = y1; ob2 = wd; ob3 = ht;
+            oconf = clipd(conf, 0.2, 1.0);
+          }
+        }
+        const bool surv = !(tsu > max_age);  // sort.py:292
+        if (surv) {
+          // predict of the next image (sort.py:166-178)
+          kf_predict(x, Pm);
+          if (tsu > 0) hs = 0;
+          tsu += 1;
+          double b[4];
+          x_to_bbox(x, b);
+          if (isnan(b[0]) || isnan(b[1]) || isnan(b[2]) || isnan(b[3])) s_nan = 1;
+          else if (isinf(b[0]) || isinf(b[1]) || isinf(b[2]) || isinf(b[3])) atomicMax(P.status, W2T_ERR_NONFINITE);
+#pragma unroll
+          for (int k = 0; k < 7; k++) st[k * Tcap + sl] = x[k];
+#pragma unroll
+          for (int k = 0; k < 49; k++) st[(7 + k) * Tcap + sl] = Pm[k];
+#pragma unroll
+          for (int k = 0; k < 4; k++) st[(56 + k) * Tcap + sl] = b[k];
+          tsuA[sl] = tsu;
+          hsA[sl] = hs;
+        }
+        flag[t] = surv ? 1 : 0;
+      }
+      int ex, exb, tot, totb;
+      block_scan2<BLOCK>(ok, false, s_scan, ex, exb, tot, totb);
+      if (ok) {
+        const size_t o = (size_t)base + emitted + ex;
+        double *ob = P.r.out_box + 4 * o;
+        ob[0] = ob0; ob[1] = ob1; ob[2] = ob2; ob[3] = ob3;
+        P.r.out_score[o] = oconf;
+        P.r.out_birth[2 * o + 0] = obg;
+        P.r.out_birth[2 * o + 1] = obk;
+      }
+      emitted += tot;
+    }
+    if (tid == 0) { P.r.out_count[g] = emitted; P.r.created[g] = n_new; }
+    __syncthreads();
+
+    // ---- C. drop dead trackers, keep the list order (sort.py:292-293) --------------------------
+    int n_live, n_dead;
+    partition3<BLOCK>(
+        Ttot, [&](int i) { return list[i]; }, [&](int i) { return flag[i] != 0; },
+        [&](int i) { return flag[i] == 0; }, list, tmp, s_scan, n_live, n_dead);
+    T = n_live;
+  }
+
+  if (err && tid == 0) atomicMax(P.status, err);
+
+  // optional: filter state of every live tracker, already predicted one step past the last image
+  if (P.r.final_count != nullptr) {
+    if (tid == 0) P.r.final_count[q] = T;
+    if (P.r.final_state != nullptr) {
+      const int cap = P.r.final_cap;
+      for (int t = tid; t < T && t < cap; t += BLOCK) {
+        const int sl = list[t];
+        double *dst = P.r.final_state + ((size_t)q * cap + t) * 56;
+        for (int k = 0; k < 56; k++) dst[k] = st[k * Tcap + sl];
+      }
+    }
+  }
+}
+
+}  // namespace w2t

@@ -1,0 +1,178 @@
+// units.cu — building-block entry points (unit parity against the oracle).
+//
+// The same device functions the persistent SORT kernel uses (kalman.cuh, munkres.cuh,
+// iou_pair) exposed one operation at a time.
+#include "sort_kernel.cuh"
+
+using namespace w2t;
+
+namespace {
+
+__global__ void iou_matrix_kernel(const float4 *dets, int D, const double *trks, int T, float *out) {
+  const size_t total = (size_t)D * T;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i / T), t = (int)(i % T);
+    const double *b = trks + 4 * (size_t)t;
+    out[i] = iou_pair(dets[d], b[0], b[1], b[2], b[3]);
+  }
+}
+
+struct LapLayout { size_t C, Z, rstar, cstar, rprime, total; };
+
+__host__ __device__ inline LapLayout lap_layout(int D, int T) {
+  const size_t n = D < T ? D : T, m = D < T ? T : D;
+  LapLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+  L.C = take(4 * n * m);
+  L.Z = take(4 * n * (size_t)munkres_zstride((int)m));
+  L.rstar = take(4 * n);
+  L.cstar = take(4 * m);
+  L.rprime = take(4 * n);
+  L.total = align_up(o + 16, 256);
+  return L;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) lap_kernel(const float *cost, int D, int T, int32_t *pairs, int32_t *n_pairs,
+                                                   char *ws) {
+  __shared__ MunkresShared ms;
+  const bool flipped = T < D;
+  const int n = flipped ? T : D, m = flipped ? D : T;
+  const LapLayout L = lap_layout(D, T);
+  Munkres<BLOCK> mk;
+  mk.s = &ms;
+  mk.n = n; mk.m = m; mk.mw = munkres_words(m); mk.zs = munkres_zstride(m);
+  mk.g.C = reinterpret_cast<float *>(ws + L.C);
+  mk.g.Z = reinterpret_cast<uint32_t *>(ws + L.Z);
+  mk.g.row_star = reinterpret_cast<int *>(ws + L.rstar);
+  mk.g.col_star = reinterpret_cast<int *>(ws + L.cstar);
+  mk.g.row_prime = reinterpret_cast<int *>(ws + L.rprime);
+  for (size_t i = threadIdx.x; i < (size_t)n * m; i += BLOCK) {
+    const int r = (int)(i / m), c = (int)(i % m);
+    mk.g.C[i] = flipped ? cost[(size_t)c * T + r] : cost[(size_t)r * T + c];
+  }
+  __syncthreads();
+  const int act = mk.solve();
+  if (threadIdx.x == 0) {
+    int k = 0;
+    if (act == 0) {
+      if (!flipped) {
+        for (int r = 0; r < n; r++) { pairs[2 * k] = r; pairs[2 * k + 1] = mk.g.row_star[r]; k++; }
+      } else {
+        for (int c = 0; c < m; c++)
+          if (mk.g.col_star[c] >= 0) { pairs[2 * k] = c; pairs[2 * k + 1] = mk.g.col_star[c]; k++; }
+      }
+    }
+    *n_pairs = (act == 0) ? k : -1;
+  }
+}
+
+__global__ void kf_init_kernel(double *x, double *P, const float4 *dets, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 d4 = dets[i];
+  const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+  double xv[7], Pv[49];
+  kf_init(dd, xv, Pv);
+  for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
+  for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
+}
+
+__global__ void kf_predict_kernel(double *x, double *P, double *boxes, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xv[7], Pv[49];
+  for (int k = 0; k < 7; k++) xv[k] = x[7 * (size_t)i + k];
+  for (int k = 0; k < 49; k++) Pv[k] = P[49 * (size_t)i + k];
+  kf_predict(xv, Pv);
+  for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
+  for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
+  if (boxes) {
+    double b[4];
+    x_to_bbox(xv, b);
+    for (int k = 0; k < 4; k++) boxes[4 * (size_t)i + k] = b[k];
+  }
+}
+
+__global__ void kf_update_kernel(double *x, double *P, const float4 *dets, double *boxes, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 d4 = dets[i];
+  const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+  double xv[7], Pv[49];
+  for (int k = 0; k < 7; k++) xv[k] = x[7 * (size_t)i + k];
+  for (int k = 0; k < 49; k++) Pv[k] = P[49 * (size_t)i + k];
+  kf_update(xv, Pv, dd);
+  for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
+  for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
+  if (boxes) {
+    double b[4];
+    x_to_bbox(xv, b);
+    for (int k = 0; k < 4; k++) boxes[4 * (size_t)i + k] = b[k];
+  }
+}
+
+}  // namespace
+
+extern "C" int w2t_iou_matrix(const float *dets, int32_t D, const double *trks, int32_t T, float *out,
+                              w2t_stream_t stream) {
+  if (D < 0 || T < 0) return W2T_ERR_ARG;
+  if (D == 0 || T == 0) return W2T_OK;
+  if (!dets || !trks || !out) return W2T_ERR_ARG;
+  const size_t total = (size_t)D * T;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  iou_matrix_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(dets), D, trks, T, out);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
+
+extern "C" size_t w2t_linear_assignment_workspace(int32_t D, int32_t T) {
+  if (D <= 0 || T <= 0) return 256;
+  return lap_layout(D, T).total;
+}
+
+extern "C" int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, int32_t *pairs, int32_t *n_pairs,
+                                     void *workspace, w2t_stream_t stream) {
+  if (D < 0 || T < 0 || !n_pairs) return W2T_ERR_ARG;
+  if (D == 0 || T == 0) {
+    W2T_CUDA_TRY(cudaMemsetAsync(n_pairs, 0, sizeof(int32_t), (cudaStream_t)stream));
+    return W2T_OK;
+  }
+  if (!cost || !pairs || !workspace) return W2T_ERR_ARG;
+  if (std::max(D, T) > kMunkresMaxDim) {
+    set_last_error("w2t_linear_assignment: max(D,T)=%d exceeds %d", std::max(D, T), kMunkresMaxDim);
+    return W2T_ERR_CAPACITY;
+  }
+  lap_kernel<256><<<1, 256, 0, (cudaStream_t)stream>>>(cost, D, T, pairs, n_pairs, static_cast<char *>(workspace));
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
+
+extern "C" int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, w2t_stream_t stream) {
+  if (n < 0) return W2T_ERR_ARG;
+  if (n == 0) return W2T_OK;
+  if (!x || !P || !dets) return W2T_ERR_ARG;
+  kf_init_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), n);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
+
+extern "C" int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2t_stream_t stream) {
+  if (n < 0) return W2T_ERR_ARG;
+  if (n == 0) return W2T_OK;
+  if (!x || !P) return W2T_ERR_ARG;
+  kf_predict_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, boxes, n);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
+
+extern "C" int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n,
+                             w2t_stream_t stream) {
+  if (n < 0) return W2T_ERR_ARG;
+  if (n == 0) return W2T_OK;
+  if (!x || !P || !dets) return W2T_ERR_ARG;
+  kf_update_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), boxes, n);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}

@@ -191,7 +191,7 @@ def unpack_tracks(packed, out_box, out_score, out_count, first_img, ids, class_r
                     continue
                 g = img * NC + c
                 r0 = int(packed.det_start[g])
-                for r in range(r0, r0 + int(out_count[g])):
+                for r in range(r0 + int(out_count[g]) - 1, r0 - 1, -1):   # reference walks the list reversed
                     out.append({
                         'image_id': image_id,
                         'bbox': [out_box[r, 0], out_box[r, 1], out_box[r, 2], out_box[r, 3]],

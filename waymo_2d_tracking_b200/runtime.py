@@ -1,0 +1,338 @@
+"""Host runtime: torch owns device memory and streams, ``libw2t.so`` does the work.
+
+Three entry points, all over the packed arrays of ``include/w2t_types.h``:
+
+* :func:`softnms_groups` — the soft-NMS ensemble stage (``detnet/ensemble.py:145-157``);
+* :func:`sort_track`     — the SORT stage (``tracking/track.py:42-47``);
+* :func:`ensemble_and_track` — both, with the ensemble output handed to the tracker on the
+  device (the int / 5-decimal rounding the reference applies when it writes the JSON in
+  between is part of the data flow and is applied on the device).
+
+Inputs may be NumPy arrays, CPU tensors (pinned ones are copied asynchronously) or CUDA
+tensors.  There is no CPU fallback: without a CUDA device these functions raise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._lib import W2TError, check, check_device_status, lib
+
+_NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+         np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.uint8): torch.uint8}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise W2TError("no CUDA device visible: the box pipeline runs on sm_100a only (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dev(a, dtype, device):
+    """NumPy / CPU tensor / CUDA tensor -> contiguous CUDA tensor of ``dtype``."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+    if a.dtype != _NP2T[np.dtype(dtype)]:
+        a = a.to(_NP2T[np.dtype(dtype)])
+    return a.to(device, non_blocking=True).contiguous()
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _host(t, pinned=True):
+    """Device tensor -> NumPy array through a pinned buffer (async copy + one sync by the caller)."""
+    if t is None:
+        return None
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=pinned)
+    buf.copy_(t, non_blocking=True)
+    return buf
+
+
+def _np(t):
+    return None if t is None else t.numpy()
+
+
+# ---------------------------------------------------------------------------
+# soft-NMS ensemble
+# ---------------------------------------------------------------------------
+
+def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
+                          n_classes=0, score_thr=None, want_merged=True):
+    """Launch on device tensors; returns device tensors (no synchronisation)."""
+    device = d_rows.device
+    N = int(d_rows.shape[0])
+    out = {
+        "merged": torch.empty((N, 5), dtype=torch.float64, device=device) if want_merged else None,
+        "src_index": torch.empty(N, dtype=torch.int32, device=device) if want_merged else None,
+        "ens_count": torch.empty(n_groups, dtype=torch.int32, device=device),
+        "ens_box": torch.empty((N, 4), dtype=torch.int32, device=device),
+        "ens_score": torch.empty(N, dtype=torch.float64, device=device),
+        "trk_count": None, "trk_box": None, "img_exists": None,
+        "status": torch.zeros(1, dtype=torch.int32, device=device),
+    }
+    thr = None
+    if score_thr is not None:
+        if n_classes < 1:
+            raise W2TError("score_thr needs n_classes")
+        thr = (C.c_double * n_classes)(*[float(v) for v in score_thr[:n_classes]])
+        out["trk_count"] = torch.empty(n_groups, dtype=torch.int32, device=device)
+        out["trk_box"] = torch.empty((N, 4), dtype=torch.float32, device=device)
+        out["img_exists"] = torch.zeros(max(n_groups // n_classes, 1), dtype=torch.uint8, device=device)
+    prob = _abi.NmsProblem()
+    prob.n_groups = int(n_groups)
+    prob.group_offsets = _ptr(d_offsets)
+    prob.rows = _ptr(d_rows)
+    prob.iou_thresh, prob.soft_nms_cut, prob.min_score = float(iou_thresh), float(soft_nms_cut), float(min_score)
+    prob.n_classes = int(n_classes)
+    prob.score_thr = C.cast(thr, C.c_void_p) if thr is not None else None
+    res = _abi.NmsResult()
+    for k in ("merged", "src_index", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box", "img_exists"):
+        setattr(res, k, _ptr(out[k]))
+    check(lib().w2t_softnms_groups(C.byref(prob), C.byref(res), int(max_group), _ptr(out["status"]), _stream()),
+          "w2t_softnms_groups")
+    return out
+
+
+def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_score=0.0, n_classes=0,
+                   score_thr=None, max_group=None, want_merged=True):
+    """Soft-NMS merge of every (image, category) group; NumPy in, NumPy out."""
+    device = require_cuda()
+    offs_np = group_offsets if isinstance(group_offsets, np.ndarray) else None
+    n_groups = int(group_offsets.shape[0]) - 1
+    if max_group is None:
+        if offs_np is None:
+            offs_np = torch.as_tensor(group_offsets).cpu().numpy()
+        max_group = int(np.diff(offs_np).max()) if n_groups > 0 else 0
+    d_offsets = _dev(group_offsets, np.int32, device)
+    d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
+    out = softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
+                                n_classes, score_thr, want_merged)
+    host = {k: _host(v) for k, v in out.items()}
+    torch.cuda.current_stream().synchronize()
+    check_device_status(int(host["status"][0]), "soft-NMS")
+    return {k: _np(v) for k, v in host.items()}
+
+
+# ---------------------------------------------------------------------------
+# SORT
+# ---------------------------------------------------------------------------
+
+def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age):
+    nq = n_streams * n_classes
+    arrays = dict(order=np.zeros(nq, np.int32), track_cap=np.zeros(nq, np.int32),
+                  det_cap=np.zeros(nq, np.int32), ws_offset=np.zeros(nq, np.int64))
+    plan = _abi.SortPlan()
+    for k, v in arrays.items():
+        setattr(plan, k, v.ctypes.data_as(C.c_void_p))
+    h_offsets = np.ascontiguousarray(h_offsets, np.int32)
+    h_count = np.ascontiguousarray(h_count, np.int32)
+    h_exists = None if h_exists is None else np.ascontiguousarray(h_exists, np.uint8)
+    check(lib().w2t_sort_plan(int(n_streams), int(n_classes), h_offsets.ctypes.data_as(C.c_void_p),
+                              h_count.ctypes.data_as(C.c_void_p),
+                              None if h_exists is None else h_exists.ctypes.data_as(C.c_void_p),
+                              int(max_age), C.byref(plan)), "w2t_sort_plan")
+    arrays["ws_bytes"] = int(plan.ws_bytes)
+    return arrays
+
+
+def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, d_exists, d_cam,
+                      iou_thresholds, max_age, min_hits, plan, final_cap=0):
+    """Launch on device tensors; ``plan`` = host arrays from :func:`make_plan`.  No synchronisation."""
+    device = d_box.device
+    NC = int(n_classes)
+    if len(iou_thresholds) < NC:
+        raise IndexError("iou_thresholds has %d entries for %d categories" % (len(iou_thresholds), NC))
+    n_groups = int(d_start.shape[0])
+    N = int(d_box.shape[0])
+    nq = n_streams * NC
+    out = {
+        "out_box": torch.empty((N, 4), dtype=torch.float64, device=device),
+        "out_score": torch.empty(N, dtype=torch.float64, device=device),
+        "out_birth": torch.empty((N, 2), dtype=torch.int32, device=device),
+        "out_count": torch.empty(n_groups, dtype=torch.int32, device=device),
+        "created": torch.empty(n_groups, dtype=torch.int32, device=device),
+        "first_img": torch.empty(nq, dtype=torch.int32, device=device),
+        "final_count": torch.empty(nq, dtype=torch.int32, device=device) if final_cap else None,
+        "final_state": torch.zeros((nq, final_cap, 56), dtype=torch.float64, device=device) if final_cap else None,
+        "status": torch.zeros(1, dtype=torch.int32, device=device),
+    }
+    d_plan = {k: _dev(plan[k], np.int64 if k == "ws_offset" else np.int32, device)
+              for k in ("order", "track_cap", "det_cap", "ws_offset")}
+    workspace = torch.empty(max(plan["ws_bytes"], 256), dtype=torch.uint8, device=device)
+    prob = _abi.SortProblem()
+    prob.n_streams, prob.n_classes = int(n_streams), NC
+    prob.stream_img_offsets = _ptr(d_offsets)
+    prob.det_start, prob.det_count, prob.det_box = _ptr(d_start), _ptr(d_count), _ptr(d_box)
+    prob.img_exists = _ptr(d_exists)
+    prob.cam_wh = _ptr(d_cam)
+    for i in range(NC):
+        prob.iou_thr[i] = float(iou_thresholds[i])
+    prob.max_age, prob.min_hits = int(max_age), int(min_hits)
+    cplan = _abi.SortPlan()
+    for k in ("order", "track_cap", "det_cap", "ws_offset"):
+        setattr(cplan, k, _ptr(d_plan[k]))
+    cplan.ws_bytes = plan["ws_bytes"]
+    res = _abi.SortResult()
+    for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img", "final_count", "final_state"):
+        setattr(res, k, _ptr(out[k]))
+    res.final_cap = int(final_cap)
+    check(lib().w2t_sort_track(C.byref(prob), C.byref(cplan), C.byref(res), _ptr(workspace), _ptr(out["status"]),
+                               _stream()), "w2t_sort_track")
+    out["_keepalive"] = (d_plan, workspace)
+    return out
+
+
+def assign_ids(n_streams, n_classes, h_offsets, h_start, h_out_count, h_created, h_first_img, class_rank,
+               h_out_birth, id_base=0):
+    """``w2t_assign_ids`` on host arrays -> (ids[int64, N], next id base)."""
+    def p(a, dt):
+        return None if a is None else np.ascontiguousarray(a, dt)
+    offs, start, cnt = p(h_offsets, np.int32), p(h_start, np.int32), p(h_out_count, np.int32)
+    created, first, rank, birth = p(h_created, np.int32), p(h_first_img, np.int32), p(class_rank, np.int32), \
+        p(h_out_birth, np.int32)
+    ids = np.zeros(birth.shape[0], np.int64)
+    nxt = C.c_int64(0)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    check(lib().w2t_assign_ids(int(n_streams), int(n_classes), vp(offs), vp(start), vp(cnt), vp(created), vp(first),
+                               vp(rank), vp(birth), int(id_base), vp(ids), C.byref(nxt)), "w2t_assign_ids")
+    return ids, int(nxt.value)
+
+
+def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0):
+    """SORT over every stream of ``packed`` (``packing.PackedTracks``); NumPy out, ids included."""
+    device = require_cuda()
+    S, NC = packed.n_streams, packed.n_classes
+    plan = make_plan(S, NC, packed.stream_img_offsets, packed.det_count, packed.img_exists, max_age)
+    out = sort_track_device(
+        S, NC, _dev(packed.stream_img_offsets, np.int32, device), _dev(packed.det_start, np.int32, device),
+        _dev(packed.det_count, np.int32, device), _dev(packed.det_box, np.float32, device).reshape(-1, 4),
+        _dev(packed.img_exists, np.uint8, device), _dev(packed.cam_wh, np.float64, device),
+        iou_thresholds, max_age, min_hits, plan, final_cap)
+    host = {k: _host(v) for k, v in out.items() if k != "_keepalive"}
+    torch.cuda.current_stream().synchronize()
+    check_device_status(int(host["status"][0]), "SORT")
+    res = {k: _np(v) for k, v in host.items()}
+    res["ids"], res["id_next"] = assign_ids(S, NC, packed.stream_img_offsets, packed.det_start, res["out_count"],
+                                            res["created"], res["first_img"], packed.class_rank, res["out_birth"],
+                                            id_base)
+    return res
+
+
+# ---------------------------------------------------------------------------
+# ensemble -> SORT without leaving the device
+# ---------------------------------------------------------------------------
+
+def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh, soft_nms_cut,
+                       min_score, score_thr, iou_thresholds, max_age, min_hits, max_group=None,
+                       want_ensemble=True, id_base=0):
+    """Groups must be laid out as g = img * n_classes + (category - 1) with the images of a
+    stream contiguous and in frame order (``synth.groups_from_scene`` / ``packing``)."""
+    device = require_cuda()
+    NC = int(n_classes)
+    h_offsets = np.ascontiguousarray(stream_img_offsets, np.int32)
+    S = len(h_offsets) - 1
+    n_groups = int(group_offsets.shape[0]) - 1
+    if n_groups != int(h_offsets[-1]) * NC:
+        raise W2TError("group layout does not match stream_img_offsets * n_classes")
+    if max_group is None:
+        go = group_offsets if isinstance(group_offsets, np.ndarray) else torch.as_tensor(group_offsets).cpu().numpy()
+        max_group = int(np.diff(go).max()) if n_groups else 0
+    d_goff = _dev(group_offsets, np.int32, device)
+    d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
+    nms = softnms_groups_device(d_goff, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, NC,
+                                score_thr, want_merged=False)
+    # the plan needs the surviving counts on the host: one small D2H between the stages
+    h_cnt, h_exists = _host(nms["trk_count"]), _host(nms["img_exists"])
+    torch.cuda.current_stream().synchronize()
+    plan = make_plan(S, NC, h_offsets, h_cnt.numpy(), h_exists.numpy(), max_age)
+    d_start = d_goff[:-1]
+    trk = sort_track_device(S, NC, _dev(h_offsets, np.int32, device), d_start, nms["trk_count"], nms["trk_box"],
+                            nms["img_exists"], _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits,
+                            plan)
+    keys = ["out_box", "out_score", "out_birth", "out_count", "created", "first_img", "status"]
+    host = {k: _host(trk[k]) for k in keys}
+    ens_host = {}
+    if want_ensemble:
+        ens_host = {k: _host(nms[k]) for k in ("ens_count", "ens_box", "ens_score")}
+    nms_status = _host(nms["status"])
+    torch.cuda.current_stream().synchronize()
+    check_device_status(int(nms_status[0]), "soft-NMS")
+    check_device_status(int(host["status"][0]), "SORT")
+    res = {k: _np(v) for k, v in host.items()}
+    res.update({k: _np(v) for k, v in ens_host.items()})
+    res["trk_count"], res["img_exists"] = h_cnt.numpy(), h_exists.numpy()
+    go_np = group_offsets if isinstance(group_offsets, np.ndarray) else torch.as_tensor(group_offsets).cpu().numpy()
+    res["det_start"] = np.ascontiguousarray(go_np[:-1], np.int32)
+    res["ids"], res["id_next"] = assign_ids(S, NC, h_offsets, res["det_start"], res["out_count"], res["created"],
+                                            res["first_img"], None, res["out_birth"], id_base)
+    return res
+
+
+# ---------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------
+
+def iou_matrix(dets, trks):
+    device = require_cuda()
+    d = _dev(np.asarray(dets, np.float32).reshape(-1, 4), np.float32, device)
+    t = _dev(np.asarray(trks, np.float64).reshape(-1, 4), np.float64, device)
+    out = torch.zeros((d.shape[0], t.shape[0]), dtype=torch.float32, device=device)
+    check(lib().w2t_iou_matrix(_ptr(d), int(d.shape[0]), _ptr(t), int(t.shape[0]), _ptr(out), _stream()),
+          "w2t_iou_matrix")
+    return out.cpu().numpy()
+
+
+def linear_assignment(cost):
+    device = require_cuda()
+    cost = np.ascontiguousarray(cost, np.float32)
+    D, T = cost.shape
+    c = _dev(cost, np.float32, device)
+    pairs = torch.zeros((max(min(D, T), 1), 2), dtype=torch.int32, device=device)
+    n_pairs = torch.zeros(1, dtype=torch.int32, device=device)
+    ws = torch.empty(int(lib().w2t_linear_assignment_workspace(D, T)), dtype=torch.uint8, device=device)
+    check(lib().w2t_linear_assignment(_ptr(c), D, T, _ptr(pairs), _ptr(n_pairs), _ptr(ws), _stream()),
+          "w2t_linear_assignment")
+    k = int(n_pairs.cpu()[0])
+    if k < 0:
+        raise W2TError("w2t_linear_assignment: iteration budget exhausted (NaN costs?)")
+    return pairs[:k].cpu().numpy().astype(int).reshape(-1, 2)
+
+
+def kf_init(dets):
+    device = require_cuda()
+    d = _dev(np.asarray(dets, np.float32).reshape(-1, 4), np.float32, device)
+    n = int(d.shape[0])
+    x = torch.zeros((n, 7), dtype=torch.float64, device=device)
+    P = torch.zeros((n, 49), dtype=torch.float64, device=device)
+    check(lib().w2t_kf_init(_ptr(x), _ptr(P), _ptr(d), n, _stream()), "w2t_kf_init")
+    return x.cpu().numpy(), P.cpu().numpy().reshape(n, 7, 7)
+
+
+def kf_predict(x, P):
+    device = require_cuda()
+    xd = _dev(np.asarray(x, np.float64).reshape(-1, 7), np.float64, device).clone()
+    n = int(xd.shape[0])
+    Pd = _dev(np.asarray(P, np.float64).reshape(n, 49), np.float64, device).clone()
+    boxes = torch.zeros((n, 4), dtype=torch.float64, device=device)
+    check(lib().w2t_kf_predict(_ptr(xd), _ptr(Pd), _ptr(boxes), n, _stream()), "w2t_kf_predict")
+    return xd.cpu().numpy(), Pd.cpu().numpy().reshape(n, 7, 7), boxes.cpu().numpy()
+
+
+def kf_update(x, P, dets):
+    device = require_cuda()
+    xd = _dev(np.asarray(x, np.float64).reshape(-1, 7), np.float64, device).clone()
+    n = int(xd.shape[0])
+    Pd = _dev(np.asarray(P, np.float64).reshape(n, 49), np.float64, device).clone()
+    d = _dev(np.asarray(dets, np.float32).reshape(n, 4), np.float32, device)
+    boxes = torch.zeros((n, 4), dtype=torch.float64, device=device)
+    check(lib().w2t_kf_update(_ptr(xd), _ptr(Pd), _ptr(d), _ptr(boxes), n, _stream()), "w2t_kf_update")
+    return xd.cpu().numpy(), Pd.cpu().numpy().reshape(n, 7, 7), boxes.cpu().numpy()
