@@ -80,6 +80,17 @@ int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t *stream_im
 int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
                    w2t_sort_result_t *result, void *workspace, int32_t *status, w2t_stream_t stream);
 
+/* Device-side id assignment + dense output list (finalize.cu): object ids by an exclusive
+ * scan of `created` in the reference's processing order (KalmanBoxTracker.count,
+ * sort.py:86,140-141), rows gathered into the order tracking/utils.py:37-58 appends them.
+ * class_rank: DEVICE [n_streams*n_classes] position of each category in the stream's tracker
+ * dict, or NULL to rank by (first_img, category id).  workspace:
+ * w2t_sort_finalize_workspace() bytes.  n_groups = n_img * n_classes. */
+size_t w2t_sort_finalize_workspace(int32_t n_streams, int32_t n_classes, int64_t n_groups);
+int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_sort_result_t *result,
+                      const int32_t *class_rank, int64_t id_base, int64_t n_groups, void *workspace,
+                      w2t_rows_t *rows, w2t_stream_t stream);
+
 /* HOST function.  Turns (birth group, k) into the reference's global
  * object_id (= KalmanBoxTracker.id + 1, sort.py:288).  All pointers are host
  * pointers.  class_rank[n_streams*n_classes] gives, per stream, the position

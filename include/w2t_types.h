@@ -88,6 +88,19 @@ typedef struct w2t_sort_result_t {
   int32_t  final_cap;
 } w2t_sort_result_t;
 
+/* Dense output list of the SORT stage (w2t_sort_finalize): the rows the reference's
+ * track.py writes (tracking/utils.py:52-58), in the reference's order for the streams as
+ * given.  capacity = rows the arrays can hold (sum of det_count is always enough). */
+typedef struct w2t_rows_t {
+  double  *box;        /* [capacity,4] x1, y1, width, height                                  */
+  double  *score;      /* [capacity]                                                          */
+  int64_t *object_id;  /* [capacity] KalmanBoxTracker.id + 1 (sort.py:288)                    */
+  int32_t *image;      /* [capacity] image index                                              */
+  int32_t *category;   /* [capacity] category_id                                              */
+  int64_t *totals;     /* [2] device: trackers created (next id = id_base + totals[0]), rows  */
+  int64_t  capacity;
+} w2t_rows_t;
+
 /* Inputs of the soft-NMS ensemble stage (detnet/ensemble.py:50-64 for every image). */
 typedef struct w2t_nms_problem_t {
   int32_t n_groups;

@@ -115,6 +115,18 @@ def compare_sort(packed, iou_thr, max_age, min_hits, final_cap=0):
                                   want["created"], want["first_img"], packed.class_rank, want["out_birth"])
     np.testing.assert_array_equal(got["ids"], ids)
     assert got["id_next"] == nxt
+    # dense list built on the device == the host construction from the per-slot arrays
+    dense = packing.unpack_tracks(packed, want["out_box"], want["out_score"], want["out_count"], want["first_img"],
+                                  ids)
+    assert got["n_rows"] == len(dense)
+    np.testing.assert_array_equal(got["rows_id"], np.array([int(r["object_id"]) for r in dense], np.int64))
+    np.testing.assert_array_equal(got["rows_cat"], np.array([r["category_id"] for r in dense], np.int32))
+    np.testing.assert_array_equal(got["rows_box"], np.array([r["bbox"] for r in dense], np.float64).reshape(-1, 4))
+    iid = {}
+    for s_, (seg, cam) in enumerate(packed.streams):
+        for img in range(int(packed.stream_img_offsets[s_]), int(packed.stream_img_offsets[s_ + 1])):
+            iid['%s/%i/%s' % (seg, packed.frame_ids[img], cam)] = img
+    np.testing.assert_array_equal(got["rows_img"], np.array([iid[r["image_id"]] for r in dense], np.int32))
     if final_cap:
         np.testing.assert_array_equal(got["final_count"], want["final_count"])
         for q, t in enumerate(want["final_count"]):
@@ -247,7 +259,7 @@ def test_softnms_edge_groups():
     offsets = np.array([0, 0, 1, 3, 5, 9, 9, 9, 9], np.int32)   # 8 groups = 2 images x 4 categories
     groups = packing.PackedGroups(None, [1, 2, 3, 4], offsets, rows, 4)
     res = compare_nms(groups, 0.5, 0.9, 0.0)
-    assert res["ens_count"].tolist() == [0, 1, 1, 2, 3, 0, 0, 0]
+    assert res["ens_count"].tolist() == [0, 1, 1, 2, 2, 0, 0, 0]   # IoU >= cut zeroes two boxes
     assert res["merged"][2, 0] == 0.0 and res["merged"][1, 0] == 0.9
 
 

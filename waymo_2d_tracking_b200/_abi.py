@@ -64,6 +64,18 @@ class SortResult(C.Structure):
     ]
 
 
+class Rows(C.Structure):
+    _fields_ = [
+        ("box", _p),
+        ("score", _p),
+        ("object_id", _p),
+        ("image", _p),
+        ("category", _p),
+        ("totals", _p),
+        ("capacity", C.c_int64),
+    ]
+
+
 class NmsProblem(C.Structure):
     _fields_ = [
         ("n_groups", C.c_int32),
@@ -99,6 +111,9 @@ EXPORTS = {
     "w2t_softnms_max_group": (C.c_int, []),
     "w2t_sort_plan": (C.c_int, [C.c_int32, C.c_int32, _p, _p, _p, C.c_int32, C.POINTER(SortPlan)]),
     "w2t_sort_track": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortPlan), C.POINTER(SortResult), _p, _p, _p]),
+    "w2t_sort_finalize_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "w2t_sort_finalize": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortResult), _p, C.c_int64, C.c_int64, _p,
+                                    C.POINTER(Rows), _p]),
     "w2t_assign_ids": (C.c_int, [C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p, _p, C.c_int64, _p,
                                  C.POINTER(C.c_int64)]),
     "w2t_iou_matrix": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p, _p]),

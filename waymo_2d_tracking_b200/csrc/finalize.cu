@@ -1,0 +1,175 @@
+// finalize.cu — global object ids and the dense output list of the SORT stage, on the device.
+//
+// The reference numbers trackers with one process-global counter (KalmanBoxTracker.count,
+// tracking/sort/sort.py:86,140-141) in creation order — streams in order, images in order,
+// categories in tracker-dict order (tracker_sort.py:32-33,41), new trackers in unmatched
+// order — and appends output rows in the same nesting, each (image, category) block walked
+// in reverse list order (sort.py:280; tracking/utils.py:37-58).  Both are exclusive scans
+// over per-(image, category) counts taken in that processing order:
+//   1. order kernel : per stream, rank the categories and permute the `created` and
+//                     `out_count` arrays into processing order;
+//   2. two scans    : id base per group, dense row offset per group;
+//   3. rows kernel  : one warp per group copies its rows to their dense position (reversed)
+//                     and resolves object_id = base[birth group] + k + 1 (sort.py:288).
+#include "common.cuh"
+
+using namespace w2t;
+
+namespace {
+
+struct FinParams {
+  int32_t n_streams, n_classes;
+  const int32_t *stream_img_offsets, *det_start, *out_count, *created, *first_img, *class_rank;
+  const double *out_box, *out_score;
+  const int32_t *out_birth;
+  int64_t id_base;
+  int32_t *perm_created, *perm_count, *scan_created, *scan_count, *stream_rank;
+  int64_t *totals;  // [0] ids created, [1] dense rows
+  double *rows_box, *rows_score;
+  int64_t *rows_id;
+  int32_t *rows_img, *rows_cat;
+  int64_t rows_cap;
+};
+
+// One block per stream.
+__global__ void order_kernel(const FinParams P) {
+  const int s = blockIdx.x, NC = P.n_classes;
+  int rank[W2T_MAX_CLASSES];
+  for (int c = 0; c < NC; c++) {
+    int r = 0;
+    if (P.class_rank) {
+      r = P.class_rank[s * NC + c];
+    } else {
+      // position in the tracker dict = order of first appearance; same image -> category order
+      // (what detnet.ensemble's output gives: it emits an image's rows category by category)
+      const long long fc = P.first_img[s * NC + c] < 0 ? (1ll << 40) : P.first_img[s * NC + c];
+      for (int o = 0; o < NC; o++) {
+        if (o == c) continue;
+        const long long fo = P.first_img[s * NC + o] < 0 ? (1ll << 40) : P.first_img[s * NC + o];
+        r += (fo < fc || (fo == fc && o < c)) ? 1 : 0;
+      }
+    }
+    rank[c] = r;
+    if (threadIdx.x == 0) P.stream_rank[s * NC + c] = r;
+  }
+  const int img0 = P.stream_img_offsets[s], img1 = P.stream_img_offsets[s + 1];
+  for (int i = img0 * NC + threadIdx.x; i < img1 * NC; i += blockDim.x) {
+    const int img = i / NC, c = i % NC;
+    P.perm_created[img * NC + rank[c]] = P.created[i];
+    P.perm_count[img * NC + rank[c]] = P.out_count[i];
+  }
+}
+
+// Exclusive scan of n int32 by ONE block: contiguous chunk per thread, block scan of chunk sums.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) scan_kernel(const int32_t *in, int32_t *out, int64_t n, int64_t *total) {
+  __shared__ int64_t s_sum[BLOCK];
+  const int64_t chunk = (n + BLOCK - 1) / BLOCK;
+  const int64_t lo = min((int64_t)threadIdx.x * chunk, n), hi = min(lo + chunk, n);
+  int64_t sum = 0;
+  for (int64_t i = lo; i < hi; i++) sum += in[i];
+  s_sum[threadIdx.x] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the chunk sums
+  for (int o = 1; o < BLOCK; o <<= 1) {
+    const int64_t v = (threadIdx.x >= o) ? s_sum[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_sum[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int64_t run = s_sum[threadIdx.x] - sum;
+  for (int64_t i = lo; i < hi; i++) {
+    const int32_t v = in[i];
+    out[i] = (int32_t)run;
+    run += v;
+  }
+  if (threadIdx.x == BLOCK - 1 && total) *total = s_sum[BLOCK - 1];
+}
+
+// One block per stream, one warp per (image, category) group at a time.
+__global__ void rows_kernel(const FinParams P) {
+  const int s = blockIdx.x, NC = P.n_classes;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int img0 = P.stream_img_offsets[s], img1 = P.stream_img_offsets[s + 1];
+  for (int g = img0 * NC + warp; g < img1 * NC; g += nwarp) {
+    const int cnt = P.out_count[g];
+    if (cnt == 0) continue;
+    const int img = g / NC, c = g % NC;
+    const int k = P.stream_rank[s * NC + c];
+    const int64_t off = P.scan_count[img * NC + k];
+    const int64_t r0 = P.det_start[g];
+    for (int j = lane; j < cnt; j += 32) {
+      const int64_t src = r0 + j;
+      const int64_t dst = off + (cnt - 1 - j);  // the reference walks the tracker list reversed
+      if (dst >= P.rows_cap) continue;
+      const double4 b = reinterpret_cast<const double4 *>(P.out_box)[src];
+      reinterpret_cast<double4 *>(P.rows_box)[dst] = b;
+      P.rows_score[dst] = P.out_score[src];
+      const int bg = P.out_birth[2 * src], bk = P.out_birth[2 * src + 1];
+      P.rows_id[dst] = P.id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
+      P.rows_img[dst] = img;
+      P.rows_cat[dst] = c + 1;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" size_t w2t_sort_finalize_workspace(int32_t n_streams, int32_t n_classes, int64_t n_groups) {
+  return (size_t)(4 * n_groups + (int64_t)n_streams * n_classes) * sizeof(int32_t) + 256;
+}
+
+extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_sort_result_t *result,
+                                 const int32_t *class_rank, int64_t id_base, int64_t n_groups, void *workspace,
+                                 w2t_rows_t *rows, w2t_stream_t stream) {
+  if (!problem || !result || !rows || problem->n_classes < 1 || problem->n_classes > W2T_MAX_CLASSES ||
+      problem->n_streams < 0 || n_groups < 0) {
+    set_last_error("w2t_sort_finalize: bad argument");
+    return W2T_ERR_ARG;
+  }
+  if (!rows->totals) {
+    set_last_error("w2t_sort_finalize: rows->totals is required");
+    return W2T_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (problem->n_streams == 0 || n_groups == 0) {
+    W2T_CUDA_TRY(cudaMemsetAsync(rows->totals, 0, 2 * sizeof(int64_t), st));
+    return W2T_OK;
+  }
+  if (!workspace || !rows->box || !rows->score || !rows->object_id || !rows->image || !rows->category) {
+    set_last_error("w2t_sort_finalize: null buffer");
+    return W2T_ERR_ARG;
+  }
+  FinParams P;
+  P.n_streams = problem->n_streams;
+  P.n_classes = problem->n_classes;
+  P.stream_img_offsets = problem->stream_img_offsets;
+  P.det_start = problem->det_start;
+  P.out_count = result->out_count;
+  P.created = result->created;
+  P.first_img = result->first_img;
+  P.class_rank = class_rank;
+  P.out_box = result->out_box;
+  P.out_score = result->out_score;
+  P.out_birth = result->out_birth;
+  P.id_base = id_base;
+  int32_t *w = static_cast<int32_t *>(workspace);
+  P.perm_created = w;
+  P.perm_count = w + n_groups;
+  P.scan_created = w + 2 * n_groups;
+  P.scan_count = w + 3 * n_groups;
+  P.stream_rank = w + 4 * n_groups;
+  P.totals = rows->totals;
+  P.rows_box = rows->box;
+  P.rows_score = rows->score;
+  P.rows_id = rows->object_id;
+  P.rows_img = rows->image;
+  P.rows_cat = rows->category;
+  P.rows_cap = rows->capacity;
+  order_kernel<<<P.n_streams, 256, 0, st>>>(P);
+  scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_created, P.scan_created, n_groups, P.totals);
+  scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_count, P.scan_count, n_groups, P.totals + 1);
+  rows_kernel<<<P.n_streams, 256, 0, st>>>(P);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}

@@ -23,6 +23,36 @@ _NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float3
          np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.uint8): torch.uint8}
 
 
+# When set to a list, every kernel launch through this module is bracketed by CUDA events on
+# the launching stream: (kernel name, start, end).  bench.py uses it for the roofline numbers.
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.end.record()
+            PROFILE.append((self.name, self.start, self.end))
+
+
+def collect_profile():
+    """Average device milliseconds per launch of each kernel recorded in PROFILE."""
+    torch.cuda.synchronize()
+    acc = {}
+    for name, a, b in PROFILE or []:
+        acc.setdefault(name, []).append(a.elapsed_time(b))
+    return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise W2TError("no CUDA device visible: the box pipeline runs on sm_100a only (no CPU fallback)")
@@ -97,8 +127,9 @@ def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, so
     res = _abi.NmsResult()
     for k in ("merged", "src_index", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box", "img_exists"):
         setattr(res, k, _ptr(out[k]))
-    check(lib().w2t_softnms_groups(C.byref(prob), C.byref(res), int(max_group), _ptr(out["status"]), _stream()),
-          "w2t_softnms_groups")
+    with _timed("softnms_kernel"):
+        check(lib().w2t_softnms_groups(C.byref(prob), C.byref(res), int(max_group), _ptr(out["status"]), _stream()),
+              "w2t_softnms_groups")
     return out
 
 
@@ -185,8 +216,9 @@ def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, 
     for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img", "final_count", "final_state"):
         setattr(res, k, _ptr(out[k]))
     res.final_cap = int(final_cap)
-    check(lib().w2t_sort_track(C.byref(prob), C.byref(cplan), C.byref(res), _ptr(workspace), _ptr(out["status"]),
-                               _stream()), "w2t_sort_track")
+    with _timed("sort_track_kernel"):
+        check(lib().w2t_sort_track(C.byref(prob), C.byref(cplan), C.byref(res), _ptr(workspace), _ptr(out["status"]),
+                                   _stream()), "w2t_sort_track")
     out["_keepalive"] = (d_plan, workspace)
     return out
 
@@ -207,23 +239,86 @@ def assign_ids(n_streams, n_classes, h_offsets, h_start, h_out_count, h_created,
     return ids, int(nxt.value)
 
 
-def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0):
-    """SORT over every stream of ``packed`` (``packing.PackedTracks``); NumPy out, ids included."""
+def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank, id_base, rows_cap):
+    """Device-side ids + dense rows (``w2t_sort_finalize``) on the tensors ``sort_track_device`` returned."""
+    device = trk["out_box"].device
+    NC = int(n_classes)
+    n_groups = int(d_start.shape[0])
+    cap = max(int(rows_cap), 1)
+    rows = {
+        "rows_box": torch.empty((cap, 4), dtype=torch.float64, device=device),
+        "rows_score": torch.empty(cap, dtype=torch.float64, device=device),
+        "rows_id": torch.empty(cap, dtype=torch.int64, device=device),
+        "rows_img": torch.empty(cap, dtype=torch.int32, device=device),
+        "rows_cat": torch.empty(cap, dtype=torch.int32, device=device),
+        "totals": torch.zeros(2, dtype=torch.int64, device=device),
+    }
+    ws = torch.empty(int(lib().w2t_sort_finalize_workspace(int(n_streams), NC, n_groups)), dtype=torch.uint8,
+                     device=device)
+    prob = _abi.SortProblem()
+    prob.n_streams, prob.n_classes = int(n_streams), NC
+    prob.stream_img_offsets, prob.det_start = _ptr(d_offsets), _ptr(d_start)
+    res = _abi.SortResult()
+    for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img"):
+        setattr(res, k, _ptr(trk[k]))
+    crows = _abi.Rows()
+    crows.box, crows.score, crows.object_id = _ptr(rows["rows_box"]), _ptr(rows["rows_score"]), _ptr(rows["rows_id"])
+    crows.image, crows.category, crows.totals = _ptr(rows["rows_img"]), _ptr(rows["rows_cat"]), _ptr(rows["totals"])
+    crows.capacity = cap
+    with _timed("finalize_kernels"):
+        check(lib().w2t_sort_finalize(C.byref(prob), C.byref(res), _ptr(d_class_rank), int(id_base), n_groups,
+                                      _ptr(ws), C.byref(crows), _stream()), "w2t_sort_finalize")
+    rows["_keepalive"] = ws
+    return rows
+
+
+_ROW_KEYS = ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat", "totals")
+_RAW_KEYS = ("out_box", "out_score", "out_birth", "out_count", "created", "first_img", "final_count", "final_state")
+
+
+def _collect(trk, rows, raw, extra=None):
+    """Copy the requested device results to pinned host buffers, sync once, check the status."""
+    host = {k: _host(rows[k]) for k in _ROW_KEYS}
+    host["status"] = _host(trk["status"])
+    if raw:
+        host.update({k: _host(trk[k]) for k in _RAW_KEYS if trk.get(k) is not None})
+    for k, v in (extra or {}).items():
+        host[k] = _host(v)
+    torch.cuda.current_stream().synchronize()
+    check_device_status(int(host["status"][0]), "SORT")
+    d2h = sum(v.numel() * v.element_size() for v in host.values() if v is not None)
+    res = {k: _np(v) for k, v in host.items()}
+    res["d2h_bytes"] = d2h
+    n_rows = int(res["totals"][1])
+    for k in _ROW_KEYS[:-1]:
+        res[k] = res[k][:n_rows]
+    res["n_rows"] = n_rows
+    return res
+
+
+def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0, raw=True):
+    """SORT over every stream of ``packed`` (``packing.PackedTracks``).
+
+    Returns the dense output list (``rows_box/score/id/img/cat`` in the reference's order, ids
+    assigned on the device) and, with ``raw``, the per-slot arrays of ``w2t_sort_result_t``.
+    """
     device = require_cuda()
     S, NC = packed.n_streams, packed.n_classes
     plan = make_plan(S, NC, packed.stream_img_offsets, packed.det_count, packed.img_exists, max_age)
-    out = sort_track_device(
-        S, NC, _dev(packed.stream_img_offsets, np.int32, device), _dev(packed.det_start, np.int32, device),
-        _dev(packed.det_count, np.int32, device), _dev(packed.det_box, np.float32, device).reshape(-1, 4),
-        _dev(packed.img_exists, np.uint8, device), _dev(packed.cam_wh, np.float64, device),
-        iou_thresholds, max_age, min_hits, plan, final_cap)
-    host = {k: _host(v) for k, v in out.items() if k != "_keepalive"}
-    torch.cuda.current_stream().synchronize()
-    check_device_status(int(host["status"][0]), "SORT")
-    res = {k: _np(v) for k, v in host.items()}
-    res["ids"], res["id_next"] = assign_ids(S, NC, packed.stream_img_offsets, packed.det_start, res["out_count"],
-                                            res["created"], res["first_img"], packed.class_rank, res["out_birth"],
-                                            id_base)
+    d_offsets = _dev(packed.stream_img_offsets, np.int32, device)
+    d_start = _dev(packed.det_start, np.int32, device)
+    trk = sort_track_device(
+        S, NC, d_offsets, d_start, _dev(packed.det_count, np.int32, device),
+        _dev(packed.det_box, np.float32, device).reshape(-1, 4), _dev(packed.img_exists, np.uint8, device),
+        _dev(packed.cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan, final_cap)
+    rows = finalize_device(S, NC, d_offsets, d_start, trk, _dev(packed.class_rank, np.int32, device), id_base,
+                           int(np.asarray(packed.det_count, np.int64).sum()))
+    res = _collect(trk, rows, raw)
+    res["id_next"] = int(id_base + res["totals"][0])
+    if raw:
+        res["ids"], nxt = assign_ids(S, NC, packed.stream_img_offsets, packed.det_start, res["out_count"],
+                                     res["created"], res["first_img"], packed.class_rank, res["out_birth"], id_base)
+        assert nxt == res["id_next"], "host and device id scans disagree"
     return res
 
 
@@ -233,9 +328,11 @@ def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_ba
 
 def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh, soft_nms_cut,
                        min_score, score_thr, iou_thresholds, max_age, min_hits, max_group=None,
-                       want_ensemble=True, id_base=0):
+                       want_ensemble=True, id_base=0, raw=True, to_host=True):
     """Groups must be laid out as g = img * n_classes + (category - 1) with the images of a
-    stream contiguous and in frame order (``synth.groups_from_scene`` / ``packing``)."""
+    stream contiguous and in frame order (``synth.groups_from_scene`` / ``packing``).
+
+    ``group_offsets`` / ``rows`` may be NumPy, CPU (ideally pinned) or CUDA tensors."""
     device = require_cuda()
     NC = int(n_classes)
     h_offsets = np.ascontiguousarray(stream_img_offsets, np.int32)
@@ -251,29 +348,31 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     nms = softnms_groups_device(d_goff, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, NC,
                                 score_thr, want_merged=False)
     # the plan needs the surviving counts on the host: one small D2H between the stages
-    h_cnt, h_exists = _host(nms["trk_count"]), _host(nms["img_exists"])
+    h_cnt, h_exists, h_nms_status = _host(nms["trk_count"]), _host(nms["img_exists"]), _host(nms["status"])
     torch.cuda.current_stream().synchronize()
+    check_device_status(int(h_nms_status[0]), "soft-NMS")
     plan = make_plan(S, NC, h_offsets, h_cnt.numpy(), h_exists.numpy(), max_age)
+    d_offsets = _dev(h_offsets, np.int32, device)
     d_start = d_goff[:-1]
-    trk = sort_track_device(S, NC, _dev(h_offsets, np.int32, device), d_start, nms["trk_count"], nms["trk_box"],
-                            nms["img_exists"], _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits,
-                            plan)
-    keys = ["out_box", "out_score", "out_birth", "out_count", "created", "first_img", "status"]
-    host = {k: _host(trk[k]) for k in keys}
-    ens_host = {}
-    if want_ensemble:
-        ens_host = {k: _host(nms[k]) for k in ("ens_count", "ens_box", "ens_score")}
-    nms_status = _host(nms["status"])
-    torch.cuda.current_stream().synchronize()
-    check_device_status(int(nms_status[0]), "soft-NMS")
-    check_device_status(int(host["status"][0]), "SORT")
-    res = {k: _np(v) for k, v in host.items()}
-    res.update({k: _np(v) for k, v in ens_host.items()})
+    trk = sort_track_device(S, NC, d_offsets, d_start, nms["trk_count"], nms["trk_box"], nms["img_exists"],
+                            _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan)
+    out_rows = finalize_device(S, NC, d_offsets, d_start, trk, None, id_base, int(h_cnt.numpy().sum(dtype=np.int64)))
+    n_trk = int(h_cnt.numpy().sum(dtype=np.int64))
+    if not to_host:
+        # results stay in HBM (bench.py's device-resident leg); 1 soft-NMS + 1 SORT + 4 finalize kernels
+        dev = {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": n_trk, "launches": 6}
+        return dev
+    extra = {k: nms[k] for k in ("ens_count", "ens_box", "ens_score")} if want_ensemble else {}
+    res = _collect(trk, out_rows, raw, extra)
+    res["d2h_bytes"] += h_cnt.numel() * 4 + h_exists.numel() + 4
+    res["n_trk"], res["launches"] = n_trk, 6
     res["trk_count"], res["img_exists"] = h_cnt.numpy(), h_exists.numpy()
-    go_np = group_offsets if isinstance(group_offsets, np.ndarray) else torch.as_tensor(group_offsets).cpu().numpy()
-    res["det_start"] = np.ascontiguousarray(go_np[:-1], np.int32)
-    res["ids"], res["id_next"] = assign_ids(S, NC, h_offsets, res["det_start"], res["out_count"], res["created"],
-                                            res["first_img"], None, res["out_birth"], id_base)
+    res["id_next"] = int(id_base + res["totals"][0])
+    if raw:
+        go_np = group_offsets if isinstance(group_offsets, np.ndarray) else torch.as_tensor(group_offsets).cpu().numpy()
+        res["det_start"] = np.ascontiguousarray(go_np[:-1], np.int32)
+        res["ids"], _ = assign_ids(S, NC, h_offsets, res["det_start"], res["out_count"], res["created"],
+                                   res["first_img"], None, res["out_birth"], id_base)
     return res
 
 
