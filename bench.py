@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--segments", type=int, default=150, help="segments per GPU (150 = configuration C3)")
     ap.add_argument("--seed", type=int, default=1000)
-    ap.add_argument("--cpu-sample-frames", type=int, default=40)
+    ap.add_argument("--cpu-sample-frames", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -254,7 +254,7 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dominant = max(kernel_ms, key=lambda k: kernel_ms[k]) if kernel_ms else None
+    dominant = max(alg, key=lambda k: kernel_ms.get(k, 0.0)) if kernel_ms else None
     roofline = None
     if dominant:
         traffic = None

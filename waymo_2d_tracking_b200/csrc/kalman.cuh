@@ -226,4 +226,119 @@ __device__ __forceinline__ void kf_update(double (&x)[7], double (&P)[49], const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block form used by the tracker kernel.
+//
+// With the reference's constants — F couples only (x,vx), (y,vy), (s,vs) (sort.py:104-106), H
+// selects x,y,s,r (sort.py:120-121), Q, R and P0 are diagonal (sort.py:111-134) — every entry
+// of P outside the three 2x2 blocks {a, a+4} (a = 0,1,2) and P[3][3] is an exact zero, and it
+// stays an exact zero through the FMA chains above (fma(0, v, acc) == acc, 0 + 0 == 0; checked
+// against NumPy/OpenBLAS and the C oracle).  Dropping those terms from the sums leaves, for
+// every remaining entry, exactly the operations listed above in exactly the same order, so
+// the 13 live entries are bit-identical to the 49-entry computation at ~1/20 of the work:
+//   S is diagonal -> LAPACK's LU does no pivoting and inv(S) = diag(fl(1/S_kk));
+//   K[i][k] = fl(P[i][k] * SI_k);  x_i += fl(K[i][k] * y_k);  A = I - K;
+//   M = A P (+P), N = M A' (+M), P = N + (K R) K'  restricted to each block.
+// p[4a+0] = P[a][a], p[4a+1] = P[a][a+4], p[4a+2] = P[a+4][a], p[4a+3] = P[a+4][a+4], p[12] = P[3][3].
+constexpr int kBlockP = 13;
+
+__device__ __forceinline__ void kfb_init(const float (&det)[4], double (&x)[7], double (&p)[kBlockP]) {
+  float z[4];
+  bbox_to_z(det, z);
+#pragma unroll
+  for (int i = 0; i < 4; i++) x[i] = (double)z[i];
+  x[4] = x[5] = x[6] = 0.;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    p[4 * a + 0] = 10.;
+    p[4 * a + 1] = 0.;
+    p[4 * a + 2] = 0.;
+    p[4 * a + 3] = 10000.;
+  }
+  p[12] = 10.;
+}
+
+__device__ __forceinline__ void kfb_predict(double (&x)[7], double (&p)[kBlockP]) {
+  if (x[6] + x[2] <= 0) x[6] *= 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    x[a] = x[a] + x[a + 4];
+    // F P : row a += row a+4
+    const double aa = p[4 * a + 0] + p[4 * a + 2];
+    const double ab = p[4 * a + 1] + p[4 * a + 3];
+    // (F P) F' : column a += column a+4, then + Q
+    p[4 * a + 0] = (aa + ab) + q_diag(a);
+    p[4 * a + 1] = ab + 0.0;
+    p[4 * a + 2] = (p[4 * a + 2] + p[4 * a + 3]) + 0.0;
+    p[4 * a + 3] = p[4 * a + 3] + q_diag(a + 4);
+  }
+  p[12] = p[12] + q_diag(3);
+}
+
+__device__ __forceinline__ void kfb_update(double (&x)[7], double (&p)[kBlockP], const float (&det)[4]) {
+  float zf[4];
+  bbox_to_z(det, zf);
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const double y = (double)zf[a] - x[a];
+    const double P00 = p[4 * a + 0], P01 = p[4 * a + 1], P10 = p[4 * a + 2], P11 = p[4 * a + 3];
+    const double si = 1.0 * (1.0 / (P00 + r_diag(a)));
+    const double k0 = P00 * si, k1 = P10 * si;
+    x[a] = x[a] + k0 * y;
+    x[a + 4] = x[a + 4] + k1 * y;
+    const double a0 = 1.0 - k0, a1 = 0.0 - k1;
+    const double m00 = a0 * P00, m01 = a0 * P01;
+    const double m10 = a1 * P00 + P10, m11 = a1 * P01 + P11;
+    const double kr0 = k0 * r_diag(a), kr1 = k1 * r_diag(a);
+    p[4 * a + 0] = (m00 * a0) + (kr0 * k0);
+    p[4 * a + 1] = ((m00 * a1) + m01) + (kr0 * k1);
+    p[4 * a + 2] = (m10 * a0) + (kr1 * k0);
+    p[4 * a + 3] = ((m10 * a1) + m11) + (kr1 * k1);
+  }
+  {
+    const double y = (double)zf[3] - x[3];
+    const double P33 = p[12];
+    const double si = 1.0 * (1.0 / (P33 + r_diag(3)));
+    const double k = P33 * si;
+    x[3] = x[3] + k * y;
+    const double a3 = 1.0 - k;
+    const double m = a3 * P33;
+    p[12] = (m * a3) + ((k * r_diag(3)) * k);
+  }
+}
+
+// scatter / gather between the block form and the dense 7x7 (unit entry points, debug dumps)
+__device__ __forceinline__ void kfb_to_dense(const double (&p)[kBlockP], double (&P)[49]) {
+#pragma unroll
+  for (int i = 0; i < 49; i++) P[i] = 0.;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    P[a * 7 + a] = p[4 * a + 0];
+    P[a * 7 + a + 4] = p[4 * a + 1];
+    P[(a + 4) * 7 + a] = p[4 * a + 2];
+    P[(a + 4) * 7 + a + 4] = p[4 * a + 3];
+  }
+  P[3 * 7 + 3] = p[12];
+}
+
+__device__ __forceinline__ bool kfb_from_dense(const double (&P)[49], double (&p)[kBlockP]) {
+  bool structured = true;
+#pragma unroll
+  for (int i = 0; i < 7; i++)
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const bool live = (i == j) || (i < 3 && j == i + 4) || (j < 3 && i == j + 4);
+      if (!live && P[i * 7 + j] != 0.) structured = false;
+    }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    p[4 * a + 0] = P[a * 7 + a];
+    p[4 * a + 1] = P[a * 7 + a + 4];
+    p[4 * a + 2] = P[(a + 4) * 7 + a];
+    p[4 * a + 3] = P[(a + 4) * 7 + a + 4];
+  }
+  p[12] = P[3 * 7 + 3];
+  return structured;
+}
+
 }  // namespace w2t

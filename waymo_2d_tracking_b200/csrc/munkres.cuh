@@ -12,14 +12,29 @@
 // Representation.  The reference keeps an n x m `marked` matrix; a row holds at most one
 // star and one prime and a column at most one star, so three index arrays carry the same
 // state.  Zeros of the cost matrix are mirrored in a bit matrix Z (one 32-bit word per 32
-// columns) that is rebuilt only when the costs change (step 1 and step 6); with the column
+// columns) that is updated only when the costs change (step 1 and step 6); with the column
 // cover kept as a bit mask too, "first uncovered zero of a row" is an AND + find-first-set
 // per word instead of a scan over floats.
 //
-// Work split.  Steps 3-5 are a serial state machine: warp 0 runs them (lanes own words of
-// the masks, rows are scanned 32 at a time) while the other warps wait at the CTA barrier.
-// Step 1 and step 6 touch the whole matrix and are done by all warps, one warp per row,
-// coalesced, with the Z words produced by __ballot_sync.
+// The serial parts are restructured so that their length is the number of CONFLICTS, not the
+// number of rows, without changing any decision the reference makes:
+//   * step 2 (greedy stars in row-major order): 32 rows at a time propose their first free
+//     zero; the longest prefix of rows whose proposals are pairwise distinct is exactly what
+//     the sequential loop would star, so it commits at once (__match_any_sync finds the
+//     first clash), and only the clashing rows go around again;
+//   * step 4 ("first uncovered zero"): a bit mask of rows that currently own an uncovered
+//     zero is kept up to date — inside a step-4 run columns only get uncovered and rows only
+//     get covered, so a row can only ENTER the set when a column holding one of its zeros is
+//     uncovered — and the search is a find-first-set;
+//   * step 6 only changes covered rows (+min) and uncovered columns (-min) and its minimum
+//     only looks at uncovered rows x uncovered columns; warp 0 compacts both index lists
+//     from the cover masks and the CTA touches just those cells.
+// Steps 3-5 run in warp 0 while the other warps wait at the CTA barrier; step 1 and step 6
+// use the whole CTA.
+//
+// Storage.  All arrays are reached through plain pointers: the caller points them at shared
+// memory when the problem fits and at its global workspace otherwise.  `ldc` (the row pitch
+// of C) and `zs` are odd so that "one thread per row" accesses are bank-conflict free.
 #pragma once
 
 #include "common.cuh"
@@ -33,35 +48,68 @@ struct MunkresShared {
   uint32_t colcov[kMunkresMaxWords];
   uint32_t rowcov[kMunkresMaxWords];
   uint32_t starcols[kMunkresMaxWords];
+  uint32_t rowhas[kMunkresMaxWords];  // rows that own an uncovered zero (step 4)
   float red[32];
-  int ctl[4];  // 0: next action (0 done, 6 shift, 9 error)  1: stars  2: resume step  3: unused
+  int ctl[4];  // 0: next action (0 done, 6 shift, 9 error)  1: #uncovered cols  2: #covered rows (step 6)
 };
 
 struct MunkresGlobal {
-  float *C;         // [n*m] cost, n <= m, row-major
+  float *C;         // [n*ldc] cost, n <= m, row-major with pitch ldc
   uint32_t *Z;      // [n*zs] zero bit matrix
   int *row_star;    // [n] column of the row's star or -1
   int *col_star;    // [m] row of the column's star or -1
   int *row_prime;   // [n] column of the row's prime (valid for rows primed in the current phase)
+  int *ucols;       // [m] scratch: uncovered columns (step 6)
+  int *crows;       // [n] scratch: covered rows (step 6)
 };
 
+__host__ __device__ inline int munkres_pitch(int m) { return m | 1; }
 __host__ __device__ inline int munkres_words(int m) { return (m + 31) >> 5; }
 __host__ __device__ inline int munkres_zstride(int m) { return munkres_words(m) | 1; }
 
-template <int BLOCK>
+template <int BLOCK, bool TIMERS = false>
 struct Munkres {
   static constexpr int NW = BLOCK / 32;
-  int n, m, mw, zs;
+  int n, m, mw, zs, ldc;
+  bool rowwise;  // arrays are in shared memory: one thread per row is the fast layout for step 1
   MunkresGlobal g;
   MunkresShared *s;
+  long long *ph;  // phase cycle counters (debug aid, TIMERS only): [3] reduce [4] greedy [5] drive [6] shift
+  long long t_last;
+
+  __device__ __forceinline__ void tick(int i) {
+    if (TIMERS && threadIdx.x == 0) {
+      const long long now = clock64();
+      ph[i] += now - t_last;
+      t_last = now;
+    }
+  }
 
   __device__ __forceinline__ bool row_covered(int r) const { return (s->rowcov[r >> 5] >> (r & 31)) & 1u; }
 
   // ---- step 1: subtract the row minimum, build Z ------------------------------------------
   __device__ void reduce_rows() {
+    if (rowwise) {
+      for (int r = threadIdx.x; r < n; r += BLOCK) {
+        float *row = g.C + (size_t)r * ldc;
+        float mn = row[0];
+        for (int c = 1; c < m; c++) mn = fminf(mn, row[c]);
+        for (int k = 0; k < mw; k++) {
+          uint32_t word = 0u;
+          const int c1 = min(32, m - k * 32);
+          for (int b = 0; b < c1; b++) {
+            const float v = row[k * 32 + b] - mn;
+            row[k * 32 + b] = v;
+            word |= (v == 0.0f) ? (1u << b) : 0u;
+          }
+          g.Z[(size_t)r * zs + k] = word;
+        }
+      }
+      return;
+    }
     const int lane = lane_id();
     for (int r = warp_id(); r < n; r += NW) {
-      float *row = g.C + (size_t)r * m;
+      float *row = g.C + (size_t)r * ldc;
       float mn = row[0];
       for (int c = lane; c < m; c += 32) mn = fminf(mn, row[c]);
 #pragma unroll
@@ -80,48 +128,55 @@ struct Munkres {
     }
   }
 
+  // first zero of row r that is not in the column cover, or -1 (one lane per row)
+  __device__ __forceinline__ int first_free_zero_lane(int r) const {
+    const uint32_t *zr = g.Z + (size_t)r * zs;
+    for (int w = 0; w < mw; w++) {
+      const uint32_t v = zr[w] & ~s->colcov[w];
+      if (v) return w * 32 + (__ffs(v) - 1);
+    }
+    return -1;
+  }
+
   // ---- step 2: star zeros greedily in row-major order (warp 0) ---------------------------------
+  // s->colcov is used as the running column cover; on return it equals s->starcols.
   __device__ int greedy_stars() {
     const int lane = lane_id();
-    uint32_t cov0 = 0, cov1 = 0;  // words lane and lane+32 of the column cover
+    const unsigned lt = (1u << lane) - 1u;
+    for (int w = lane; w < kMunkresMaxWords; w += 32) s->colcov[w] = 0u;
+    __syncwarp();
     int stars = 0;
-    for (int r = 0; r < n; r++) {
-      const uint32_t *zr = g.Z + (size_t)r * zs;
-      uint32_t v0 = (lane < mw) ? (zr[lane] & ~cov0) : 0u;
-      unsigned b = __ballot_sync(0xffffffffu, v0 != 0u);
-      int wsel = -1;
-      uint32_t vsel = 0;
-      if (b) {
-        const int src = __ffs(b) - 1;
-        vsel = __shfl_sync(0xffffffffu, v0, src);
-        wsel = src;
-        if (lane == src) cov0 |= (vsel & (0u - vsel));
-      } else if (mw > 32) {
-        uint32_t v1 = (lane + 32 < mw) ? (zr[lane + 32] & ~cov1) : 0u;
-        b = __ballot_sync(0xffffffffu, v1 != 0u);
-        if (b) {
-          const int src = __ffs(b) - 1;
-          vsel = __shfl_sync(0xffffffffu, v1, src);
-          wsel = src + 32;
-          if (lane == src) cov1 |= (vsel & (0u - vsel));
+    for (int rb = 0; rb < n; rb += 32) {
+      const int r = rb + lane;
+      bool pending = r < n;
+      for (;;) {
+        int cand = -1;
+        if (pending) {
+          cand = first_free_zero_lane(r);
+          if (cand < 0) pending = false;  // every zero of the row is taken: no star, like the reference
         }
-      }
-      if (wsel >= 0) {
-        const int c = wsel * 32 + (__ffs(vsel) - 1);
-        if (lane == 0) {
-          g.row_star[r] = c;
-          g.col_star[c] = r;
+        if (!__ballot_sync(0xffffffffu, pending)) break;
+        // rows whose proposal equals that of an earlier pending row must wait for the next round
+        const unsigned peers = __match_any_sync(0xffffffffu, pending ? cand : (-2 - lane));
+        const unsigned clash = __ballot_sync(0xffffffffu, pending && (peers & lt) != 0u);
+        const int first_clash = clash ? (__ffs(clash) - 1) : 32;
+        const bool commit = pending && lane < first_clash;
+        if (commit) {
+          g.row_star[r] = cand;
+          g.col_star[cand] = r;
+          atomicOr(&s->colcov[cand >> 5], 1u << (cand & 31));
+          pending = false;
         }
-        stars++;
+        stars += __popc(__ballot_sync(0xffffffffu, commit));
+        __syncwarp();
       }
     }
-    if (lane < mw) s->starcols[lane] = cov0;
-    if (lane + 32 < mw) s->starcols[lane + 32] = cov1;
+    for (int w = lane; w < kMunkresMaxWords; w += 32) s->starcols[w] = s->colcov[w];
     __syncwarp();
     return stars;
   }
 
-  // first uncovered zero of row r: column index or -1 (warp 0, all lanes)
+  // first uncovered zero of row r: column index or -1 (warp 0, all lanes cooperate)
   __device__ __forceinline__ int first_open_zero(int r) {
     const int lane = lane_id();
     const uint32_t *zr = g.Z + (size_t)r * zs;
@@ -138,76 +193,128 @@ struct Munkres {
     return -1;
   }
 
+  // rowhas from scratch (warp 0): uncovered rows with a zero in an uncovered column
+  __device__ void compute_rowhas() {
+    const int lane = lane_id();
+    for (int rb = 0; rb < n; rb += 32) {
+      const int r = rb + lane;
+      const bool any = (r < n) && !row_covered(r) && (first_free_zero_lane(r) >= 0);
+      const unsigned b = __ballot_sync(0xffffffffu, any);
+      if (lane == 0) s->rowhas[rb >> 5] = b;
+    }
+    __syncwarp();
+  }
+
+  // warp 0: compact the uncovered columns and the covered rows into index lists (step 6 prologue)
+  __device__ void build_step6_lists() {
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    int nu = 0, nc = 0;
+    for (int w = 0; w < mw; w++) {
+      const int c = w * 32 + lane;
+      const bool open = (c < m) && !((s->colcov[w] >> lane) & 1u);
+      const unsigned b = __ballot_sync(0xffffffffu, open);
+      if (open) g.ucols[nu + __popc(b & lt)] = c;
+      nu += __popc(b);
+    }
+    const int nwr = munkres_words(n);
+    for (int w = 0; w < nwr; w++) {
+      const int r = w * 32 + lane;
+      const bool cov = (r < n) && ((s->rowcov[w] >> lane) & 1u);
+      const unsigned b = __ballot_sync(0xffffffffu, cov);
+      if (cov) g.crows[nc + __popc(b & lt)] = r;
+      nc += __popc(b);
+    }
+    if (lane == 0) { s->ctl[1] = nu; s->ctl[2] = nc; }
+  }
+
   // ---- steps 3, 4, 5 (warp 0): returns 0 when n stars exist, 6 when the costs must shift -----
   __device__ int drive(int step, int &stars, int &budget) {
     const int lane = lane_id();
+    const int nwr = munkres_words(n);
     for (;;) {
       if (step == 3) {
+        // cover every starred column, uncover all rows
         for (int w = lane; w < kMunkresMaxWords; w += 32) {
           s->rowcov[w] = 0u;
           s->colcov[w] = (w < mw) ? s->starcols[w] : 0u;
         }
         __syncwarp();
         if (stars >= n) return 0;
-        step = 4;
       }
-      // step 4: first uncovered zero in row-major order
-      if (--budget < 0) return 9;
-      int fr = -1;
-      for (int rb = 0; rb < n; rb += 32) {
-        const int r = rb + lane;
-        bool any = false;
-        if (r < n && !row_covered(r)) {
-          const uint32_t *zr = g.Z + (size_t)r * zs;
-          for (int w = 0; w < mw; w++)
-            if (zr[w] & ~s->colcov[w]) { any = true; break; }
+      compute_rowhas();  // entering step 4: after a cover reset (step 3) or a cost shift (step 6)
+      for (;;) {
+        // step 4: first uncovered zero in row-major order
+        if (--budget < 0) return 9;
+        int fr = -1;
+        for (int w0 = 0; w0 < nwr; w0 += 32) {
+          const int w = w0 + lane;
+          const uint32_t v = (w < nwr) ? s->rowhas[w] : 0u;
+          const unsigned b = __ballot_sync(0xffffffffu, v != 0u);
+          if (b) {
+            const int src = __ffs(b) - 1;
+            const uint32_t vv = __shfl_sync(0xffffffffu, v, src);
+            fr = (w0 + src) * 32 + (__ffs(vv) - 1);
+            break;
+          }
         }
-        const unsigned b = __ballot_sync(0xffffffffu, any);
-        if (b) { fr = rb + __ffs(b) - 1; break; }
-      }
-      if (fr < 0) return 6;
-      const int fc = first_open_zero(fr);
-      const int sc = g.row_star[fr];
-      if (sc >= 0) {
+        if (fr < 0) {
+          build_step6_lists();
+          return 6;
+        }
+        const int fc = first_open_zero(fr);
+        const int sc = g.row_star[fr];
+        if (sc < 0) {
+          // step 5: augment along the alternating path that starts at the primed zero (fr, fc)
+          if (lane == 0) {
+            int r = fr, c = fc;
+            for (;;) {
+              const int rs = g.col_star[c];
+              g.row_star[r] = c;
+              g.col_star[c] = r;
+              if (rs < 0) {
+                s->starcols[c >> 5] |= (1u << (c & 31));
+                break;
+              }
+              r = rs;
+              c = g.row_prime[r];
+            }
+          }
+          __syncwarp();
+          stars++;
+          step = 3;
+          break;
+        }
         // the row has a star: prime the zero, cover the row, uncover the star's column
         if (lane == 0) {
           g.row_prime[fr] = fc;
           s->rowcov[fr >> 5] |= (1u << (fr & 31));
           s->colcov[sc >> 5] &= ~(1u << (sc & 31));
+          s->rowhas[fr >> 5] &= ~(1u << (fr & 31));
         }
         __syncwarp();
-        continue;
-      }
-      // step 5: augment along the alternating path that starts at the primed zero (fr, fc)
-      if (lane == 0) {
-        int r = fr, c = fc;
-        for (;;) {
-          const int rs = g.col_star[c];
-          g.row_star[r] = c;
-          g.col_star[c] = r;
-          if (rs < 0) {
-            s->starcols[c >> 5] |= (1u << (c & 31));
-            break;
-          }
-          r = rs;
-          c = g.row_prime[r];
+        // uncovered rows with a zero in the newly uncovered column now own an uncovered zero
+        for (int rb = 0; rb < n; rb += 32) {
+          const int r = rb + lane;
+          const bool has = (r < n) && !row_covered(r) && ((g.Z[(size_t)r * zs + (sc >> 5)] >> (sc & 31)) & 1u);
+          const unsigned b = __ballot_sync(0xffffffffu, has);
+          if (lane == 0 && b) s->rowhas[rb >> 5] |= b;
         }
+        __syncwarp();
       }
-      __syncwarp();
-      stars++;
-      step = 3;
     }
   }
 
-  // ---- step 6 (all threads): shift by the smallest uncovered value, rebuild Z --------------
+  // ---- step 6 (all threads): C[covered rows] += min ; C[:, uncovered cols] -= min ------------
+  // min over uncovered rows x uncovered columns.  Only those cells are visited.
   __device__ void shift_by_min() {
     const int lane = lane_id(), warp = warp_id();
+    const int nu = s->ctl[1], nc = s->ctl[2];
     float mn = INFINITY;
-    for (int r = warp; r < n; r += NW) {
+    for (int r = threadIdx.x; r < n; r += BLOCK) {
       if (row_covered(r)) continue;
-      const float *row = g.C + (size_t)r * m;
-      for (int c = lane; c < m; c += 32)
-        if (!((s->colcov[c >> 5] >> (c & 31)) & 1u)) mn = fminf(mn, row[c]);
+      const float *row = g.C + (size_t)r * ldc;
+      for (int u = 0; u < nu; u++) mn = fminf(mn, row[g.ucols[u]]);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -217,22 +324,35 @@ struct Munkres {
 #pragma unroll
     for (int i = 1; i < NW; i++) mn = fminf(mn, s->red[i]);
     if (mn == INFINITY) return;  // nothing uncovered: the reference leaves the matrix alone
-    for (int r = warp; r < n; r += NW) {
-      const bool rc = row_covered(r);
-      float *row = g.C + (size_t)r * m;
+    // covered rows: every column gets +min, the uncovered ones then -min (two float32 roundings)
+    for (int i = warp; i < nc; i += NW) {
+      const int r = g.crows[i];
+      float *row = g.C + (size_t)r * ldc;
       for (int k = 0; k < mw; k++) {
         const int c = k * 32 + lane;
         bool z = false;
         if (c < m) {
-          const bool cu = !((s->colcov[k] >> lane) & 1u);
-          float v = row[c];
-          if (rc) v = v + mn;
-          if (cu) v = v - mn;
-          if (rc || cu) row[c] = v;
+          float v = row[c] + mn;
+          if (!((s->colcov[k] >> lane) & 1u)) v = v - mn;
+          row[c] = v;
           z = (v == 0.0f);
         }
         const unsigned word = __ballot_sync(0xffffffffu, z);
         if (lane == 0) g.Z[(size_t)r * zs + k] = word;
+      }
+    }
+    // uncovered rows: only the uncovered columns change (-min); one thread owns a row's Z words
+    for (int r = threadIdx.x; r < n; r += BLOCK) {
+      if (row_covered(r)) continue;
+      float *row = g.C + (size_t)r * ldc;
+      uint32_t *zr = g.Z + (size_t)r * zs;
+      for (int u = 0; u < nu; u++) {
+        const int c = g.ucols[u];
+        const float v = row[c] - mn;
+        row[c] = v;
+        const uint32_t bit = 1u << (c & 31);
+        const uint32_t zw = zr[c >> 5];
+        zr[c >> 5] = (v == 0.0f) ? (zw | bit) : (zw & ~bit);
       }
     }
   }
@@ -244,9 +364,11 @@ struct Munkres {
     for (int i = threadIdx.x; i < m; i += BLOCK) g.col_star[i] = -1;
     reduce_rows();
     __syncthreads();
+    tick(3);
     int stars = 0, step = 3;
     int budget = 4 * n * n + 64 * (n + m) + 1024;
     if (warp_id() == 0) stars = greedy_stars();
+    tick(4);
     for (;;) {
       if (warp_id() == 0) {
         const int act = drive(step, stars, budget);
@@ -254,10 +376,12 @@ struct Munkres {
         step = 4;
       }
       __syncthreads();
+      tick(5);
       const int act = s->ctl[0];
       if (act != 6) return act;
       shift_by_min();
       __syncthreads();
+      tick(6);
     }
   }
 };

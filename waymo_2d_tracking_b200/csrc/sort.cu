@@ -1,5 +1,6 @@
 // sort.cu — host entry points of the SORT stage: plan, launch, id assignment.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -76,7 +77,15 @@ extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_
   P.ws_offset = plan->ws_offset;
   P.ws = static_cast<char *>(workspace);
   P.status = status;
-  sort_track_kernel<kSortBlock><<<nq, kSortBlock, 0, (cudaStream_t)stream>>>(P);
+  // debug aid: W2T_SORT_TIMERS=<device pointer as decimal> receives [n_substreams,16] phase cycle
+  // counters from an instrumented instantiation of the same kernel (scripts/phase_timers.py)
+  P.timers = getenv("W2T_SORT_TIMERS") ? reinterpret_cast<long long *>(strtoull(getenv("W2T_SORT_TIMERS"), nullptr, 10))
+                                        : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (P.timers != nullptr)
+    sort_track_kernel<kSortBlock, kSortMinBlocks, true><<<nq, kSortBlock, 0, st>>>(P);
+  else
+    sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq, kSortBlock, 0, st>>>(P);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
 }

@@ -18,7 +18,7 @@
 //      detection or creation from an unmatched one, emission of the output row
 //      (sort.py:280-289 + utils.py:37-58), age test (sort.py:292) and — for survivors — the
 //      predict step of the NEXT image (sort.py:255-262), so a tracker's 56 doubles are read
-//      and written once per image;
+//      and written once per image (20 of them: the filter is kept in block form, kalman.cuh);
 //   C. stable compaction of the tracker list.
 //
 // Tracker state lives in a per-sub-stream slab of global memory (struct-of-arrays, one slot
@@ -33,11 +33,21 @@
 namespace w2t {
 
 constexpr int kSortBlock = 128;
-constexpr int kStateDoubles = 60;  // x[7], P[49], predicted box[4]
+constexpr int kSortMinBlocks = 4;   // CTAs per SM the register budget is capped for
+constexpr int kStateDoubles = 24;  // x[7], block-form P[13] (kalman.cuh), predicted box[4]
+constexpr int kBoxAt = 20;         // first of the 4 box components
 
 struct SlabLayout {
-  size_t st, tsu, hs, bg, bk, list, tmp, flag, dstat, newdet, C, Z, rstar, cstar, rprime, total;
+  size_t st, tsu, hs, bg, bk, list, tmp, flag, dstat, newdet, C, Z, rstar, cstar, rprime, ucols, crows, total;
 };
+
+// Shared-memory home of the per-image association problem.  Anything larger (crowded scenes)
+// runs out of the global slab through the same pointers.
+constexpr int kSmemC = 6144;     // floats: cost matrix incl. pitch (e.g. 76 x 80)
+constexpr int kSmemZ = 512;      // words : zero bit matrix
+constexpr int kSmemN = 128;      // rows
+constexpr int kSmemM = 256;      // columns
+constexpr int kSmemBox = 256;    // predicted tracker boxes staged per image
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -58,11 +68,13 @@ __host__ __device__ inline SlabLayout slab_layout(int Tcap, int Dcap) {
   L.flag = take(4 * T);
   L.dstat = take(4 * D);
   L.newdet = take(4 * D);
-  L.C = take(4 * n * m);
+  L.C = take(4 * n * (size_t)munkres_pitch((int)m));
   L.Z = take(4 * n * (size_t)munkres_zstride((int)mcap));
   L.rstar = take(4 * n);
   L.cstar = take(4 * m);
   L.rprime = take(4 * n);
+  L.ucols = take(4 * m);
+  L.crows = take(4 * n);
   L.total = align_up(o, 256);
   return L;
 }
@@ -74,6 +86,7 @@ struct SortParams {
   const int64_t *ws_offset;
   char *ws;
   int32_t *status;
+  long long *timers;  // optional [n_substreams,16] phase cycle counters (debug aid, may be NULL)
 };
 
 // iou() of sort.py:33-47 as numba compiles it for (float32[:], float64[:]): the detection's
@@ -127,12 +140,17 @@ __device__ void partition3(int n, VAL val, FA fa, FB fb, int *dst, int *tmp, int
   nb = cb;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
+template <int BLOCK, int MINB, bool TIMERS>
+__global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParams P) {
   constexpr int NW = BLOCK / 32;
   __shared__ MunkresShared ms;
   __shared__ int s_scan[2 * NW];
   __shared__ int s_nan;
+  __shared__ __align__(16) float s_C[kSmemC];
+  __shared__ uint32_t s_Z[kSmemZ];
+  __shared__ int s_rstar[kSmemN], s_rprime[kSmemN], s_crows[kSmemN];
+  __shared__ int s_cstar[kSmemM], s_ucols[kSmemM];
+  __shared__ double s_box[5][kSmemBox];  // x1, y1, x2, y2, area (NaN when the box is inverted)
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int q = P.order[blockIdx.x];
@@ -152,13 +170,25 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
   int *dstat = reinterpret_cast<int *>(slab + L.dstat);
   int *newdet = reinterpret_cast<int *>(slab + L.newdet);
 
-  Munkres<BLOCK> mk;
+  Munkres<BLOCK, TIMERS> mk;
   mk.s = &ms;
-  mk.g.C = reinterpret_cast<float *>(slab + L.C);
-  mk.g.Z = reinterpret_cast<uint32_t *>(slab + L.Z);
-  mk.g.row_star = reinterpret_cast<int *>(slab + L.rstar);
-  mk.g.col_star = reinterpret_cast<int *>(slab + L.cstar);
-  mk.g.row_prime = reinterpret_cast<int *>(slab + L.rprime);
+  mk.ph = nullptr;
+  mk.t_last = 0;
+  MunkresGlobal g_glob, g_smem;
+  g_glob.C = reinterpret_cast<float *>(slab + L.C);
+  g_glob.Z = reinterpret_cast<uint32_t *>(slab + L.Z);
+  g_glob.row_star = reinterpret_cast<int *>(slab + L.rstar);
+  g_glob.col_star = reinterpret_cast<int *>(slab + L.cstar);
+  g_glob.row_prime = reinterpret_cast<int *>(slab + L.rprime);
+  g_glob.ucols = reinterpret_cast<int *>(slab + L.ucols);
+  g_glob.crows = reinterpret_cast<int *>(slab + L.crows);
+  g_smem.C = s_C;
+  g_smem.Z = s_Z;
+  g_smem.row_star = s_rstar;
+  g_smem.col_star = s_cstar;
+  g_smem.row_prime = s_rprime;
+  g_smem.ucols = s_ucols;
+  g_smem.crows = s_crows;
 
   const int img0 = P.p.stream_img_offsets[s], img1 = P.p.stream_img_offsets[s + 1];
   const double camW = P.p.cam_wh[2 * s], camH = P.p.cam_wh[2 * s + 1];
@@ -172,6 +202,14 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
 
   int T = 0, frame_count = 0, err = 0;
   bool started = false;
+  long long ph[TIMERS ? 16 : 1];
+  if (TIMERS) {
+#pragma unroll
+    for (int i = 0; i < (TIMERS ? 16 : 1); i++) ph[i] = 0;
+    mk.ph = ph;
+    mk.t_last = clock64();
+  }
+#define W2T_TICK(i) mk.tick(i)
 
   for (int img = img0; img < img1; ++img) {
     const int g = img * NC + c;
@@ -200,13 +238,13 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
           T, [&](int i) { return list[i]; },
           [&](int i) {
             const int sl = list[i];
-            return !(isnan(st[56 * Tcap + sl]) || isnan(st[57 * Tcap + sl]) || isnan(st[58 * Tcap + sl]) ||
-                     isnan(st[59 * Tcap + sl]));
+            return !(isnan(st[(kBoxAt + 0) * Tcap + sl]) || isnan(st[(kBoxAt + 1) * Tcap + sl]) || isnan(st[(kBoxAt + 2) * Tcap + sl]) ||
+                     isnan(st[(kBoxAt + 3) * Tcap + sl]));
           },
           [&](int i) {
             const int sl = list[i];
-            return isnan(st[56 * Tcap + sl]) || isnan(st[57 * Tcap + sl]) || isnan(st[58 * Tcap + sl]) ||
-                   isnan(st[59 * Tcap + sl]);
+            return isnan(st[(kBoxAt + 0) * Tcap + sl]) || isnan(st[(kBoxAt + 1) * Tcap + sl]) || isnan(st[(kBoxAt + 2) * Tcap + sl]) ||
+                   isnan(st[(kBoxAt + 3) * Tcap + sl]);
           },
           list, tmp, s_scan, na, nb);
       T = na;
@@ -214,6 +252,7 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
       __syncthreads();
     }
 
+    W2T_TICK(1);
     // ---- A. association ------------------------------------------------------------------
     for (int t = tid; t < T; t += BLOCK) flag[t] = -1;
     if (T > 0 && D > 0) {
@@ -223,30 +262,68 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
       mk.m = m;
       mk.mw = munkres_words(m);
       mk.zs = munkres_zstride(m);
+      mk.ldc = munkres_pitch(m);
+      const bool fits = (n * mk.ldc <= kSmemC) && (n * mk.zs <= kSmemZ) && (n <= kSmemN) && (m <= kSmemM);
+      mk.g = fits ? g_smem : g_glob;
+      mk.rowwise = fits;
+      // predicted boxes of the live trackers, by list position
+      const bool boxes_staged = T <= kSmemBox;
+      if (boxes_staged) {
+        for (int t = tid; t < T; t += BLOCK) {
+          const int sl = list[t];
+          double b[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { b[k] = st[(kBoxAt + k) * Tcap + sl]; s_box[k][t] = b[k]; }
+          s_box[4][t] = (b[2] > b[0] && b[3] > b[1]) ? (b[2] - b[0]) * (b[3] - b[1]) : NAN;
+        }
+        __syncthreads();
+      }
+      auto tbox = [&](int t, double &t0, double &t1, double &t2, double &t3, double &at) {
+        if (boxes_staged) {
+          t0 = s_box[0][t]; t1 = s_box[1][t]; t2 = s_box[2][t]; t3 = s_box[3][t]; at = s_box[4][t];
+        } else {
+          const int sl = list[t];
+          t0 = st[(kBoxAt + 0) * Tcap + sl]; t1 = st[(kBoxAt + 1) * Tcap + sl];
+          t2 = st[(kBoxAt + 2) * Tcap + sl]; t3 = st[(kBoxAt + 3) * Tcap + sl];
+          at = (t2 > t0 && t3 > t1) ? (t2 - t0) * (t3 - t1) : NAN;
+        }
+      };
+      // -IoU.  Disjoint boxes (the vast majority) are settled by four compares: their IoU is
+      // 0 / (area_det + area_trk - 0) = +0 whenever that denominator is positive; anything
+      // unusual (NaN, inverted box, non-positive denominator) takes the full iou_pair path.
+      auto neg_iou = [&](const float4 d, double t0, double t1, double t2, double t3, double at) -> float {
+        const bool apart = !((double)d.z > t0 && t2 > (double)d.x && (double)d.w > t1 && t3 > (double)d.y);
+        if (apart && d.z > d.x && d.w > d.y) {
+          const float ad = (d.z - d.x) * (d.w - d.y);
+          if ((double)ad + at > 0.) return -0.0f;
+        }
+        return -iou_pair(d, t0, t1, t2, t3);
+      };
       for (int r = warp; r < n; r += NW) {
-        float *row = mk.g.C + (size_t)r * m;
+        float *row = mk.g.C + (size_t)r * mk.ldc;
         if (!flipped) {
           const float4 d = dets[r];
           for (int cc = lane; cc < m; cc += 32) {
-            const int sl = list[cc];
-            row[cc] = -iou_pair(d, st[56 * Tcap + sl], st[57 * Tcap + sl], st[58 * Tcap + sl], st[59 * Tcap + sl]);
+            double t0, t1, t2, t3, at;
+            tbox(cc, t0, t1, t2, t3, at);
+            row[cc] = neg_iou(d, t0, t1, t2, t3, at);
           }
         } else {
-          const int sl = list[r];
-          const double t0 = st[56 * Tcap + sl], t1 = st[57 * Tcap + sl], t2 = st[58 * Tcap + sl],
-                       t3 = st[59 * Tcap + sl];
-          for (int cc = lane; cc < m; cc += 32) row[cc] = -iou_pair(dets[cc], t0, t1, t2, t3);
+          double t0, t1, t2, t3, at;
+          tbox(r, t0, t1, t2, t3, at);
+          for (int cc = lane; cc < m; cc += 32) row[cc] = neg_iou(dets[cc], t0, t1, t2, t3, at);
         }
       }
       __syncthreads();
+      W2T_TICK(2);
       if (mk.solve() != 0) err = W2T_ERR_ARG;
       for (int d = tid; d < D; d += BLOCK) {
         const int t = flipped ? mk.g.col_star[d] : mk.g.row_star[d];
         int stt = 0;
         if (t >= 0) {
-          const int sl = list[t];
-          const float o = iou_pair(dets[d], st[56 * Tcap + sl], st[57 * Tcap + sl], st[58 * Tcap + sl],
-                                   st[59 * Tcap + sl]);
+          double t0, t1, t2, t3, at;
+          tbox(t, t0, t1, t2, t3, at);
+          const float o = iou_pair(dets[d], t0, t1, t2, t3);
           if (o < thr_f) stt = 2;  // assigned but rejected: becomes a new tracker AFTER the unassigned ones
           else { stt = 1; flag[t] = d; }
         }
@@ -256,10 +333,12 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
       for (int d = tid; d < D; d += BLOCK) dstat[d] = 0;
     }
     __syncthreads();
+    W2T_TICK(7);
     int n_un, n_rej;
     partition3<BLOCK>(
         D, [&](int i) { return i; }, [&](int i) { return dstat[i] == 0; }, [&](int i) { return dstat[i] == 2; },
         newdet, tmp, s_scan, n_un, n_rej);
+    W2T_TICK(8);
     const int n_new = n_un + n_rej;
     const int Ttot = T + n_new;
     if (Ttot > Tcap) err = W2T_ERR_CAPACITY;
@@ -277,12 +356,12 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
       int obg = 0, obk = 0;
       if (t < Ttot) {
         const int sl = list[t];
-        double x[7], Pm[49];
+        double x[7], Pm[kBlockP];
         int tsu, hs;
         if (t >= T) {  // sort.py:276-278
           const float4 d4 = dets[newdet[t - T]];
           const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-          kf_init(dd, x, Pm);
+          kfb_init(dd, x, Pm);
           tsu = 0;
           hs = 0;
           obg = g;
@@ -293,7 +372,7 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
 #pragma unroll
           for (int k = 0; k < 7; k++) x[k] = st[k * Tcap + sl];
 #pragma unroll
-          for (int k = 0; k < 49; k++) Pm[k] = st[(7 + k) * Tcap + sl];
+          for (int k = 0; k < kBlockP; k++) Pm[k] = st[(7 + k) * Tcap + sl];
           tsu = tsuA[sl];
           hs = hsA[sl];
           obg = bgA[sl];
@@ -302,7 +381,7 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
           if (md >= 0) {  // sort.py:270-273, :153-164
             const float4 d4 = dets[md];
             const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            kf_update(x, Pm, dd);
+            kfb_update(x, Pm, dd);
             tsu = 0;
             hs += 1;
           }
@@ -311,7 +390,7 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
         if (tsu < 1 && (hs >= min_hits || frame_count <= min_hits)) {
           double b[4];
           x_to_bbox(x, b);
-          const double e = ((Pm[0] + Pm[8]) + Pm[16]) / 3.0;
+          const double e = ((Pm[0] + Pm[4]) + Pm[8]) / 3.0;  // mean(P00, P11, P22), sort.py:190
           const double conf = exp(-e * 0.1);
           const double x1 = clipd(b[0], 0., camW), y1 = clipd(b[1], 0., camH);
           const double x2 = clipd(b[2], 0., camW), y2 = clipd(b[3], 0., camH);
@@ -325,7 +404,7 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
         const bool surv = !(tsu > max_age);  // sort.py:292
         if (surv) {
           // predict of the next image (sort.py:166-178)
-          kf_predict(x, Pm);
+          kfb_predict(x, Pm);
           if (tsu > 0) hs = 0;
           tsu += 1;
           double b[4];
@@ -335,9 +414,9 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
 #pragma unroll
           for (int k = 0; k < 7; k++) st[k * Tcap + sl] = x[k];
 #pragma unroll
-          for (int k = 0; k < 49; k++) st[(7 + k) * Tcap + sl] = Pm[k];
+          for (int k = 0; k < kBlockP; k++) st[(7 + k) * Tcap + sl] = Pm[k];
 #pragma unroll
-          for (int k = 0; k < 4; k++) st[(56 + k) * Tcap + sl] = b[k];
+          for (int k = 0; k < 4; k++) st[(kBoxAt + k) * Tcap + sl] = b[k];
           tsuA[sl] = tsu;
           hsA[sl] = hs;
         }
@@ -357,6 +436,7 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
     }
     if (tid == 0) { P.r.out_count[g] = emitted; P.r.created[g] = n_new; }
     __syncthreads();
+    W2T_TICK(9);
 
     // ---- C. drop dead trackers, keep the list order (sort.py:292-293) --------------------------
     int n_live, n_dead;
@@ -364,7 +444,13 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
         Ttot, [&](int i) { return list[i]; }, [&](int i) { return flag[i] != 0; },
         [&](int i) { return flag[i] == 0; }, list, tmp, s_scan, n_live, n_dead);
     T = n_live;
+    W2T_TICK(10);
   }
+  if (TIMERS && P.timers != nullptr && tid == 0) {
+    ph[0] = frame_count;
+    for (int i = 0; i < (TIMERS ? 16 : 1); i++) P.timers[(size_t)q * 16 + i] = ph[i];
+  }
+#undef W2T_TICK
 
   if (err && tid == 0) atomicMax(P.status, err);
 
@@ -376,7 +462,11 @@ __global__ void __launch_bounds__(BLOCK) sort_track_kernel(const SortParams P) {
       for (int t = tid; t < T && t < cap; t += BLOCK) {
         const int sl = list[t];
         double *dst = P.r.final_state + ((size_t)q * cap + t) * 56;
-        for (int k = 0; k < 56; k++) dst[k] = st[k * Tcap + sl];
+        double pb[kBlockP], Pd[49];
+        for (int k = 0; k < 7; k++) dst[k] = st[k * Tcap + sl];
+        for (int k = 0; k < kBlockP; k++) pb[k] = st[(7 + k) * Tcap + sl];
+        kfb_to_dense(pb, Pd);
+        for (int k = 0; k < 49; k++) dst[7 + k] = Pd[k];
       }
     }
   }

@@ -17,18 +17,20 @@ __global__ void iou_matrix_kernel(const float4 *dets, int D, const double *trks,
   }
 }
 
-struct LapLayout { size_t C, Z, rstar, cstar, rprime, total; };
+struct LapLayout { size_t C, Z, rstar, cstar, rprime, ucols, crows, total; };
 
 __host__ __device__ inline LapLayout lap_layout(int D, int T) {
   const size_t n = D < T ? D : T, m = D < T ? T : D;
   LapLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
-  L.C = take(4 * n * m);
+  L.C = take(4 * n * (size_t)munkres_pitch((int)m));
   L.Z = take(4 * n * (size_t)munkres_zstride((int)m));
   L.rstar = take(4 * n);
   L.cstar = take(4 * m);
   L.rprime = take(4 * n);
+  L.ucols = take(4 * m);
+  L.crows = take(4 * n);
   L.total = align_up(o + 16, 256);
   return L;
 }
@@ -42,15 +44,20 @@ __global__ void __launch_bounds__(BLOCK) lap_kernel(const float *cost, int D, in
   const LapLayout L = lap_layout(D, T);
   Munkres<BLOCK> mk;
   mk.s = &ms;
-  mk.n = n; mk.m = m; mk.mw = munkres_words(m); mk.zs = munkres_zstride(m);
+  mk.ph = nullptr;
+  mk.t_last = 0;
+  mk.rowwise = false;
+  mk.n = n; mk.m = m; mk.mw = munkres_words(m); mk.zs = munkres_zstride(m); mk.ldc = munkres_pitch(m);
   mk.g.C = reinterpret_cast<float *>(ws + L.C);
   mk.g.Z = reinterpret_cast<uint32_t *>(ws + L.Z);
   mk.g.row_star = reinterpret_cast<int *>(ws + L.rstar);
   mk.g.col_star = reinterpret_cast<int *>(ws + L.cstar);
   mk.g.row_prime = reinterpret_cast<int *>(ws + L.rprime);
+  mk.g.ucols = reinterpret_cast<int *>(ws + L.ucols);
+  mk.g.crows = reinterpret_cast<int *>(ws + L.crows);
   for (size_t i = threadIdx.x; i < (size_t)n * m; i += BLOCK) {
     const int r = (int)(i / m), c = (int)(i % m);
-    mk.g.C[i] = flipped ? cost[(size_t)c * T + r] : cost[(size_t)r * T + c];
+    mk.g.C[(size_t)r * mk.ldc + c] = flipped ? cost[(size_t)c * T + r] : cost[(size_t)r * T + c];
   }
   __syncthreads();
   const int act = mk.solve();
@@ -85,7 +92,13 @@ __global__ void kf_predict_kernel(double *x, double *P, double *boxes, int n) {
   double xv[7], Pv[49];
   for (int k = 0; k < 7; k++) xv[k] = x[7 * (size_t)i + k];
   for (int k = 0; k < 49; k++) Pv[k] = P[49 * (size_t)i + k];
-  kf_predict(xv, Pv);
+  double pb[kBlockP];
+  if (kfb_from_dense(Pv, pb)) {  // the tracker's path: block form
+    kfb_predict(xv, pb);
+    kfb_to_dense(pb, Pv);
+  } else {
+    kf_predict(xv, Pv);
+  }
   for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
   for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
   if (boxes) {
@@ -103,7 +116,13 @@ __global__ void kf_update_kernel(double *x, double *P, const float4 *dets, doubl
   double xv[7], Pv[49];
   for (int k = 0; k < 7; k++) xv[k] = x[7 * (size_t)i + k];
   for (int k = 0; k < 49; k++) Pv[k] = P[49 * (size_t)i + k];
-  kf_update(xv, Pv, dd);
+  double pb[kBlockP];
+  if (kfb_from_dense(Pv, pb)) {  // the tracker's path: block form
+    kfb_update(xv, pb, dd);
+    kfb_to_dense(pb, Pv);
+  } else {
+    kf_update(xv, Pv, dd);
+  }
   for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
   for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
   if (boxes) {

@@ -78,11 +78,26 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _host(t, pinned=True):
-    """Device tensor -> NumPy array through a pinned buffer (async copy + one sync by the caller)."""
+# Pinned staging buffers are expensive to allocate (cudaHostAlloc), so they are kept and reused:
+# one buffer per (tag, dtype), grown on demand.  A result returned to the caller is a view of such
+# a buffer and is overwritten by the next call that uses the same tag.
+_PINNED = {}
+
+
+def _host(t, tag=None):
+    """Device tensor -> pinned host tensor (async copy; the caller synchronises once)."""
     if t is None:
         return None
-    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=pinned)
+    n = t.numel()
+    if tag is None:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    else:
+        key = (tag, t.dtype)
+        pool = _PINNED.get(key)
+        if pool is None or pool.numel() < n:
+            pool = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
+            _PINNED[key] = pool
+        buf = pool[:n].view(t.shape)
     buf.copy_(t, non_blocking=True)
     return buf
 
@@ -278,12 +293,12 @@ _RAW_KEYS = ("out_box", "out_score", "out_birth", "out_count", "created", "first
 
 def _collect(trk, rows, raw, extra=None):
     """Copy the requested device results to pinned host buffers, sync once, check the status."""
-    host = {k: _host(rows[k]) for k in _ROW_KEYS}
-    host["status"] = _host(trk["status"])
+    host = {k: _host(rows[k], k) for k in _ROW_KEYS}
+    host["status"] = _host(trk["status"], "status")
     if raw:
-        host.update({k: _host(trk[k]) for k in _RAW_KEYS if trk.get(k) is not None})
+        host.update({k: _host(trk[k], k) for k in _RAW_KEYS if trk.get(k) is not None})
     for k, v in (extra or {}).items():
-        host[k] = _host(v)
+        host[k] = _host(v, k)
     torch.cuda.current_stream().synchronize()
     check_device_status(int(host["status"][0]), "SORT")
     d2h = sum(v.numel() * v.element_size() for v in host.values() if v is not None)
@@ -348,7 +363,8 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     nms = softnms_groups_device(d_goff, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, NC,
                                 score_thr, want_merged=False)
     # the plan needs the surviving counts on the host: one small D2H between the stages
-    h_cnt, h_exists, h_nms_status = _host(nms["trk_count"]), _host(nms["img_exists"]), _host(nms["status"])
+    h_cnt, h_exists, h_nms_status = _host(nms["trk_count"], "trk_count"), _host(nms["img_exists"], "img_exists"), \
+        _host(nms["status"], "nms_status")
     torch.cuda.current_stream().synchronize()
     check_device_status(int(h_nms_status[0]), "soft-NMS")
     plan = make_plan(S, NC, h_offsets, h_cnt.numpy(), h_exists.numpy(), max_age)
