@@ -268,7 +268,7 @@ struct Munkres {
           // step 5: augment along the alternating path that starts at the primed zero (fr, fc)
           if (lane == 0) {
             int r = fr, c = fc;
-            for (;;) {
+            for (int hops = 0;; hops++) {
               const int rs = g.col_star[c];
               g.row_star[r] = c;
               g.col_star[c] = r;
@@ -278,9 +278,12 @@ struct Munkres {
               }
               r = rs;
               c = g.row_prime[r];
+              if (c < 0 || hops > n + m) { budget = -1; break; }  // cannot happen in a valid state
             }
           }
           __syncwarp();
+          budget = __shfl_sync(0xffffffffu, budget, 0);
+          if (budget < 0) return 9;
           stars++;
           step = 3;
           break;
@@ -357,9 +360,211 @@ struct Munkres {
     }
   }
 
+  // =============================================================================================
+  // Small problems (n <= m <= 64): every mask is one 64-bit word.
+  //
+  // Step 1 uses the CTA (one thread per row); everything else runs in warp 0 with NO
+  // intra-warp communication on the serial path: covers, the "rows owning an uncovered zero"
+  // set and the star count live in registers and all 32 lanes execute the same scalar
+  // instructions on the same values, so one step-4 iteration is two dependent shared-memory
+  // loads plus a dozen integer ops (no ballot, shuffle or barrier).  Zr[r] / Zc[c] are the
+  // zero bit matrix by row and by column (g.Z reinterpreted: 64 + 64 words of 64 bits);
+  // uncovering column sc adds Zc[sc] & ~rowcov to the row set.  Lanes spread over rows /
+  // columns only where the data is wide: the initial row set and step 6.
+  // =============================================================================================
+  typedef unsigned long long u64;
+
+  __device__ __forceinline__ static u64 low_mask(int k) { return k >= 64 ? ~0ull : ((1ull << k) - 1ull); }
+
+  __device__ int solve_small() {
+    u64 *Zr = reinterpret_cast<u64 *>(g.Z), *Zc = Zr + 64;
+    const int lane = lane_id();
+    // ---- step 1 (CTA): row minimum, subtract, zero masks by row (one thread per row) ...
+    for (int c = threadIdx.x; c < m; c += BLOCK) g.col_star[c] = -1;
+    for (int r = threadIdx.x; r < n; r += BLOCK) {
+      float *row = g.C + (size_t)r * ldc;
+      float mn = row[0];
+      for (int c = 1; c < m; c++) mn = fminf(mn, row[c]);
+      u64 zr = 0ull;
+      for (int c = 0; c < m; c++) {
+        const float v = row[c] - mn;
+        row[c] = v;
+        zr |= (v == 0.0f) ? (1ull << c) : 0ull;
+      }
+      Zr[r] = zr;
+      g.row_star[r] = -1;
+      g.row_prime[r] = -1;
+    }
+    __syncthreads();
+    // ... and by column (one thread per column; consecutive threads read consecutive floats)
+    for (int c = threadIdx.x; c < m; c += BLOCK) {
+      u64 zc = 0ull;
+      for (int r = 0; r < n; r++) zc |= (g.C[(size_t)r * ldc + c] == 0.0f) ? (1ull << r) : 0ull;
+      Zc[c] = zc;
+    }
+    __syncthreads();
+    tick(3);
+    if (warp_id() == 0) {
+      const u64 nmask = low_mask(n), mmask = low_mask(m);
+      // ---- step 2: greedy stars in row-major order.  Lane L keeps rows L and L+32 in registers;
+      // the serial loop gets row r by shuffle, so its only loop-carried chain is the cover word.
+      u64 starcols = 0ull;
+      int stars = 0;
+      {
+        const u64 z0 = (lane < n) ? Zr[lane] : 0ull, z1 = (lane + 32 < n) ? Zr[lane + 32] : 0ull;
+        int rs0 = -1, rs1 = -1;  // star column of rows lane, lane+32
+        int cs0 = -1, cs1 = -1;  // star row of columns lane, lane+32
+        for (int r = 0; r < n; r++) {
+          const u64 zr = __shfl_sync(0xffffffffu, (r < 32) ? z0 : z1, r & 31);
+          const u64 v = zr & ~starcols;
+          if (v) {
+            const int c = __ffsll((long long)v) - 1;
+            if (lane == (r & 31)) { if (r < 32) rs0 = c; else rs1 = c; }
+            if (lane == (c & 31)) { if (c < 32) cs0 = r; else cs1 = r; }
+            starcols |= 1ull << c;
+            stars++;
+          }
+        }
+        if (lane < n) g.row_star[lane] = rs0;
+        if (lane + 32 < n) g.row_star[lane + 32] = rs1;
+        if (lane < m) g.col_star[lane] = cs0;
+        if (lane + 32 < m) g.col_star[lane + 32] = cs1;
+      }
+      // Every lane executes the scalar state machine redundantly on identical values; lanes are
+      // re-aligned (and their shared-memory accesses ordered) wherever one lane could otherwise
+      // overwrite a word another lane has yet to read.
+      __syncwarp();
+      tick(4);
+      int act = 0;
+      int budget = 4 * n * n + 64 * (n + m) + 1024;
+      while (stars < n) {
+        // ---- step 3: cover the starred columns, uncover all rows
+        u64 rowcov = 0ull, colcov = starcols;
+        for (;;) {
+          // rows that own an uncovered zero, from scratch (entering step 4 / after a cost shift)
+          u64 rowhas;
+          {
+            const int r0 = lane, r1 = lane + 32;
+            const bool h0 = (r0 < n) && !((rowcov >> r0) & 1ull) && (Zr[r0] & ~colcov) != 0ull;
+            const bool h1 = (r1 < n) && !((rowcov >> r1) & 1ull) && (Zr[r1] & ~colcov) != 0ull;
+            const unsigned lo = __ballot_sync(0xffffffffu, h0), hi = __ballot_sync(0xffffffffu, h1);
+            rowhas = (u64)lo | ((u64)hi << 32);
+          }
+          bool augmented = false;
+          // ---- step 4: prime uncovered zeros in row-major order
+          while (rowhas) {
+            if (--budget < 0) { act = 9; break; }
+            const int fr = __ffsll((long long)rowhas) - 1;
+            const int sc = g.row_star[fr];
+            const int fc = __ffsll((long long)(Zr[fr] & ~colcov)) - 1;
+            if (sc < 0) {
+              // ---- step 5: flip stars along the alternating path from the primed zero (fr, fc)
+              int r = fr, c = fc;
+              __syncwarp();
+              for (int hops = 0;; hops++) {
+                const int rs = g.col_star[c];
+                __syncwarp();  // all lanes have read the old star before any lane replaces it
+                g.row_star[r] = c;
+                g.col_star[c] = r;
+                if (rs < 0) {
+                  starcols |= 1ull << c;
+                  break;
+                }
+                r = rs;
+                c = g.row_prime[r];
+                if (c < 0 || hops > n + m) { act = 9; break; }  // cannot happen in a valid state
+              }
+              __syncwarp();
+              stars++;
+              augmented = true;
+              break;
+            }
+            g.row_prime[fr] = fc;
+            rowcov |= 1ull << fr;
+            colcov &= ~(1ull << sc);
+            rowhas = (rowhas & ~(1ull << fr)) | (Zc[sc] & ~rowcov & nmask);
+          }
+          if (augmented || act) break;
+          __syncwarp();
+          tick(5);
+          // ---- step 6: min over uncovered rows x uncovered columns; covered rows += min,
+          //      uncovered columns -= min (float32, in that order)
+          if (--budget < 0) { act = 9; break; }
+          const u64 ucols = ~colcov & mmask, urows = ~rowcov & nmask;
+          float mn = INFINITY;
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int r = lane + 32 * half;
+            if ((urows >> r) & 1ull) {
+              const float *row = g.C + (size_t)r * ldc;
+              for (u64 rem = ucols; rem; rem &= rem - 1ull) mn = fminf(mn, row[__ffsll((long long)rem) - 1]);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          if (mn == INFINITY) { act = 9; break; }
+          for (u64 rem = rowcov & nmask; rem; rem &= rem - 1ull) {
+            const int r = __ffsll((long long)rem) - 1;
+            float *row = g.C + (size_t)r * ldc;
+            u64 zbits = 0ull;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+              const int c = lane + 32 * half;
+              bool z = false;
+              if (c < m) {
+                float v = row[c] + mn;
+                if ((ucols >> c) & 1ull) v = v - mn;
+                row[c] = v;
+                z = (v == 0.0f);
+                Zc[c] = (Zc[c] & ~(1ull << r)) | ((u64)z << r);
+              }
+              zbits |= (u64)__ballot_sync(0xffffffffu, z) << (32 * half);
+            }
+            Zr[r] = zbits;
+          }
+          __syncwarp();  // Zc words written by their owning lanes above are read by every lane below
+          {
+            const int r0 = lane, r1 = lane + 32;
+            const bool a0 = (urows >> r0) & 1ull, a1 = (urows >> r1) & 1ull;
+            float *row0 = g.C + (size_t)r0 * ldc, *row1 = g.C + (size_t)r1 * ldc;
+            u64 zr0 = a0 ? Zr[r0] : 0ull, zr1 = a1 ? Zr[r1] : 0ull;
+            for (u64 rem = ucols; rem; rem &= rem - 1ull) {
+              const int c = __ffsll((long long)rem) - 1;
+              bool f0 = false, f1 = false;
+              if (a0) {
+                const float v = row0[c] - mn;
+                row0[c] = v;
+                f0 = (v == 0.0f);
+                zr0 = (zr0 & ~(1ull << c)) | ((u64)f0 << c);
+              }
+              if (a1) {
+                const float v = row1[c] - mn;
+                row1[c] = v;
+                f1 = (v == 0.0f);
+                zr1 = (zr1 & ~(1ull << c)) | ((u64)f1 << c);
+              }
+              const u64 colbits = (u64)__ballot_sync(0xffffffffu, f0) | ((u64)__ballot_sync(0xffffffffu, f1) << 32);
+              Zc[c] = (Zc[c] & ~urows) | colbits;
+            }
+            if (a0) Zr[r0] = zr0;
+            if (a1) Zr[r1] = zr1;
+          }
+          __syncwarp();
+          tick(6);
+        }
+        if (act) break;
+      }
+      tick(5);
+      if (lane == 0) s->ctl[0] = act;
+    }
+    __syncthreads();
+    return s->ctl[0];
+  }
+
   // Whole solve.  Precondition: g.C holds the n x m costs (n <= m).  All threads call it.
   // Returns 0, or 9 if the iteration budget ran out (malformed input such as NaN costs).
   __device__ int solve() {
+    if (rowwise && m <= 64) return solve_small();
     for (int i = threadIdx.x; i < n; i += BLOCK) { g.row_star[i] = -1; g.row_prime[i] = -1; }
     for (int i = threadIdx.x; i < m; i += BLOCK) g.col_star[i] = -1;
     reduce_rows();

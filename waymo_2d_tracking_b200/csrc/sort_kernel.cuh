@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   __shared__ int s_scan[2 * NW];
   __shared__ int s_nan;
   __shared__ __align__(16) float s_C[kSmemC];
-  __shared__ uint32_t s_Z[kSmemZ];
+  __shared__ __align__(16) uint32_t s_Z[kSmemZ];
   __shared__ int s_rstar[kSmemN], s_rprime[kSmemN], s_crows[kSmemN];
   __shared__ int s_cstar[kSmemM], s_ucols[kSmemM];
   __shared__ double s_box[5][kSmemBox];  // x1, y1, x2, y2, area (NaN when the box is inverted)
