@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box call: parity tests, the bench line, the ncu launch list and full captures of the two kernels.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_round.sh <tag>
+tag=${1:-r01}
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_gpu.txt 2>&1
+nproc >> $out/${tag}_gpu.txt; grep -m1 "model name" /proc/cpuinfo >> $out/${tag}_gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log
+tail -3 $out/${tag}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log
+timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"; cat $out/${tag}_bench.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err; cat $out/${tag}_bench_ref.json
+# launch list of the same command (shares, not absolutes)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_bench_under_ncu.log 2>&1
+# full captures (smaller batch: ncu replays each launch ~40 times)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sort_track_kernel -s 1 -c 1 -f -o $out/${tag}_prof_sort \
+    python bench.py --segments 30 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_sort.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:softnms_kernel -s 1 -c 1 -f -o $out/${tag}_prof_nms \
+    python bench.py --segments 30 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_nms.log 2>&1
+ls -la $out
