@@ -42,6 +42,10 @@ int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * conversion read_data_file()/track_sort() apply to that output before
  * tracking (tracking/utils.py:79-87,32-35; tracker_sort.py:45).
  *
+ * problem->box_format / top_k / conf_thresh open the general signature of nms()
+ * (box_utils.py:307) to the drop-ins of nms() and nms_detections(); the ensemble CLI leaves
+ * them 0.  With top_k or conf_thresh a group keeps fewer rows than it has: result->kept_count.
+ *
  * max_group_size: largest group_offsets[g+1]-group_offsets[g] (host knows it
  *                 from the offsets it built).
  * status:         device int32, set to a W2T_ERR_* code by the kernel if an
@@ -52,7 +56,28 @@ int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int w2t_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
                        int32_t *status, w2t_stream_t stream);
 
-/* Largest group the soft-NMS kernel accepts (shared-memory resident). */
+/* The same for the hard branch of nms() (box_utils.py:329-333: torchvision.ops.nms on the
+ * ascending-sorted boxes) behind `python -m detnet.ensemble -m nms` (ensemble.py:139-140):
+ * greedy suppression of lower ranked boxes with IoU > iou_thresh, scores unchanged.
+ * soft_nms_cut and conf_thresh are ignored; everything else as above. */
+int w2t_hardnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
+                       int32_t *status, w2t_stream_t stream);
+
+/* Confidence-weighted box fusion of every group: merge_detections() (detnet/nn/tta.py:22-66,
+ * with jaccard_bbox, detnet/utils/box_utils.py:72-140), the reference CLI's default method
+ * (`-m weighted_fusion`, ensemble.py:94,138).  The submissions of a group are folded into a
+ * running result list in input-file order, so the kernel needs to know where each submission's
+ * rows end: sub_counts[n_groups, n_sub] (device) = rows of group g that come from input file k
+ * (rows of a group are concatenated in file order; n_sub = number of input files, the divisor
+ * of tta.py:34).  problem->iou_thresh is nms_thresh; box_format W2T_BOX_LTWH or W2T_BOX_CXCYWH;
+ * soft_nms_cut / top_k / conf_thresh are ignored.  result->merged rows and the ensemble rows are
+ * in result-list order (first file's boxes, then the unmatched boxes of each later file);
+ * result->kept_count[g] = length of the result list; src_index is not written. */
+int w2t_fusion_groups(const w2t_nms_problem_t *problem, const int32_t *sub_counts, int32_t n_sub,
+                      w2t_nms_result_t *result, int max_group_size, int32_t *status, w2t_stream_t stream);
+int w2t_fusion_max_group(void);
+
+/* Largest group the NMS kernels accept (shared-memory resident). */
 int w2t_softnms_max_group(void);
 
 /* ---- SORT --------------------------------------------------------------- */
@@ -123,6 +148,14 @@ int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, int32_t *pair
 int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, w2t_stream_t stream);
 int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2t_stream_t stream);
 int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n, w2t_stream_t stream);
+
+/* convert_bbox_to_z (sort.py:50-62) of n float32 rows x1,y1,x2,y2 -> z[n,4] = x, y, s, r, every
+ * component float32 (NumPy 2 / NEP 50 semantics). */
+int w2t_bbox_to_z(const float *dets, float *z, int32_t n, w2t_stream_t stream);
+
+/* convert_x_to_bbox (sort.py:65-75) of n states: row i is x[i*ldx .. i*ldx+3] = x, y, s, r (ldx >= 4);
+ * boxes[n,4] = x1, y1, x2, y2. */
+int w2t_x_to_bbox(const double *x, int32_t ldx, double *boxes, int32_t n, w2t_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,14 @@ typedef struct w2t_rows_t {
   int64_t  capacity;
 } w2t_rows_t;
 
+/* layout of the four box columns of w2t_nms_problem_t.rows */
+enum {
+  W2T_BOX_LTWH = 0,    /* left, top, width, height: rows of convert_submission (ensemble.py:44);  */
+                       /*   lxly2cxcy (ensemble.py:19-22) and point_form are applied on the device */
+  W2T_BOX_CXCYWH = 1,  /* centre x, centre y, width, height: input of nms_detections (tta.py:8-13) */
+  W2T_BOX_XYXY = 2     /* x1, y1, x2, y2: input of nms (box_utils.py:307)                          */
+};
+
 /* Inputs of the soft-NMS ensemble stage (detnet/ensemble.py:50-64 for every image). */
 typedef struct w2t_nms_problem_t {
   int32_t n_groups;
@@ -114,6 +122,13 @@ typedef struct w2t_nms_problem_t {
   /* optional hand-over to the SORT stage (NULL score_thr = skip) */
   int32_t n_classes;             /* group g has category (g % n_classes) + 1                  */
   const double *score_thr;       /* [n_classes] --score-threshold, track.py:23-24 (host ptr)  */
+  /* general nms() API (detnet/utils/box_utils.py:307); all zero for the ensemble CLI          */
+  int32_t box_format;            /* W2T_BOX_* : what rows[.,1:5] hold                         */
+  int32_t top_k;                 /* > 0: only the top_k best scored boxes of a group take     */
+                                 /*   part (box_utils.py:325-327)                             */
+  double conf_thresh;            /* > 0: a box whose running score drops below it is removed  */
+                                 /*   and neither output nor suppresses later ones            */
+                                 /*   (box_utils.py:379-381)                                  */
 } w2t_nms_problem_t;
 
 /* Outputs of the ensemble stage.  Row k of group g is at group_offsets[g] + k, in the
@@ -121,6 +136,8 @@ typedef struct w2t_nms_problem_t {
 typedef struct w2t_nms_result_t {
   double  *merged;       /* [N,5] score', cx, cy, w, h = nms_detections() rows (tta.py:19); may be NULL */
   int32_t *src_index;    /* [N] row index (into rows) each output row came from; may be NULL  */
+  int32_t *kept_count;   /* [n_groups] rows of merged/src_index that are valid (= group size  */
+                         /*   unless top_k / conf_thresh removed boxes); may be NULL          */
   int32_t *ens_count;    /* [n_groups] rows with score' > min_score (ensemble.py:60)          */
   int32_t *ens_box;      /* [N,4] left,top,width,height truncated to int (ensemble.py:62)     */
   double  *ens_score;    /* [N] round(score',5) (ensemble.py:62)                              */

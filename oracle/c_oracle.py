@@ -29,6 +29,10 @@ _EXPORTS = {
     "w2t_oracle_associate": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_double, _p, _p]),
     "w2t_oracle_sort_track": (C.c_int, [C.POINTER(_abi.SortProblem), C.POINTER(_abi.SortResult)]),
     "w2t_oracle_softnms_groups": (C.c_int, [C.POINTER(_abi.NmsProblem), C.POINTER(_abi.NmsResult)]),
+    "w2t_oracle_merge_detections": (C.c_int, [_p, _p, C.c_int, C.c_double, _p]),
+    "w2t_oracle_fusion_groups": (C.c_int, [C.POINTER(_abi.NmsProblem), _p, C.c_int, C.POINTER(_abi.NmsResult)]),
+    "w2t_oracle_hardnms_groups": (C.c_int, [C.POINTER(_abi.NmsProblem), C.POINTER(_abi.NmsResult)]),
+    "w2t_oracle_hard_nms": (C.c_int, [_p, _p, C.c_int, C.c_double, C.c_int, _p]),
     "w2t_oracle_soft_nms": (C.c_int, [_p, _p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _p, _p]),
 }
 
@@ -121,6 +125,49 @@ def soft_nms(boxes, scores, overlap=0.5, top_k=0, conf_thresh=0.0, soft_nms_cut=
     return keep[:k].tolist(), ns[:k].copy()
 
 
+def hard_nms(boxes, scores, overlap=0.5, top_k=0):
+    boxes = _c(boxes, np.float64).reshape(-1, 4)
+    scores = _c(scores, np.float64).reshape(-1)
+    n = len(scores)
+    keep = np.zeros(n, np.int32)
+    k = lib().w2t_oracle_hard_nms(_ptr(boxes), _ptr(scores), n, overlap, top_k, _ptr(keep))
+    return keep[:k].tolist()
+
+
+def merge_detections(detections, nms_thresh=0.5):
+    """tta.py:22-66 on a list of [n_k,5] arrays (inputs are not modified)."""
+    stacked = [_c(d, np.float64).reshape(-1, 5) for d in detections]
+    rows = _c(np.vstack(stacked), np.float64)
+    counts = np.asarray([len(d) for d in stacked], np.int32)
+    out = np.zeros((max(len(rows), 1), 5))
+    k = lib().w2t_oracle_merge_detections(_ptr(rows), _ptr(counts), len(counts), float(nms_thresh), _ptr(out))
+    return out[:k].copy()
+
+
+def fusion_groups(group_offsets, rows, sub_counts, iou_thresh, min_score, n_classes=0, score_thr=None, box_format=0):
+    group_offsets = _c(group_offsets, np.int32)
+    rows = _c(rows, np.float64).reshape(-1, 5)
+    G, N = len(group_offsets) - 1, len(rows)
+    sub_counts = _c(sub_counts, np.int32).reshape(G, -1)
+    prob = _abi.NmsProblem()
+    prob.n_groups = G
+    prob.group_offsets, prob.rows = _ptr(group_offsets), _ptr(rows)
+    prob.iou_thresh, prob.soft_nms_cut, prob.min_score = float(iou_thresh), 1.0, float(min_score)
+    prob.n_classes = int(n_classes)
+    thr = None if score_thr is None else _c(score_thr, np.float64)
+    prob.score_thr = _ptr(thr)
+    prob.box_format = int(box_format)
+    out = dict(
+        merged=np.zeros((N, 5)), kept_count=np.zeros(G, np.int32), ens_count=np.zeros(G, np.int32),
+        ens_box=np.zeros((N, 4), np.int32), ens_score=np.zeros(N), trk_count=np.zeros(G, np.int32),
+        trk_box=np.zeros((N, 4), np.float32), img_exists=np.zeros(G // n_classes, np.uint8) if n_classes else None)
+    res = _abi.NmsResult()
+    for k in ("merged", "kept_count", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box", "img_exists"):
+        setattr(res, k, _ptr(out[k]))
+    out["status"] = lib().w2t_oracle_fusion_groups(C.byref(prob), _ptr(sub_counts), sub_counts.shape[1], C.byref(res))
+    return out
+
+
 # ---- packed stages ----------------------------------------------------------
 
 def sort_track(packed, iou_thresholds, max_age, min_hits, final_cap=0):
@@ -158,7 +205,8 @@ def sort_track(packed, iou_thresholds, max_age, min_hits, final_cap=0):
     return out
 
 
-def softnms_groups(group_offsets, rows, iou_thresh, soft_nms_cut, min_score, n_classes=0, score_thr=None):
+def softnms_groups(group_offsets, rows, iou_thresh, soft_nms_cut, min_score, n_classes=0, score_thr=None,
+                   box_format=0, top_k=0, conf_thresh=0.0, hard=False):
     group_offsets = _c(group_offsets, np.int32)
     rows = _c(rows, np.float64).reshape(-1, 5)
     G, N = len(group_offsets) - 1, len(rows)
@@ -170,14 +218,18 @@ def softnms_groups(group_offsets, rows, iou_thresh, soft_nms_cut, min_score, n_c
     prob.n_classes = int(n_classes)
     thr = None if score_thr is None else _c(score_thr, np.float64)
     prob.score_thr = _ptr(thr)
+    prob.box_format, prob.top_k, prob.conf_thresh = int(box_format), int(top_k), float(conf_thresh)
     out = dict(
-        merged=np.zeros((N, 5)), src_index=np.zeros(N, np.int32), ens_count=np.zeros(G, np.int32),
+        merged=np.zeros((N, 5)), src_index=np.zeros(N, np.int32), kept_count=np.zeros(G, np.int32),
+        ens_count=np.zeros(G, np.int32),
         ens_box=np.zeros((N, 4), np.int32), ens_score=np.zeros(N), trk_count=np.zeros(G, np.int32),
         trk_box=np.zeros((N, 4), np.float32),
         img_exists=np.zeros(G // n_classes, np.uint8) if n_classes else None)
     res = _abi.NmsResult()
-    for k in ("merged", "src_index", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box", "img_exists"):
+    for k in ("merged", "src_index", "kept_count", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box",
+              "img_exists"):
         setattr(res, k, _ptr(out[k]))
-    status = lib().w2t_oracle_softnms_groups(C.byref(prob), C.byref(res))
+    fn = lib().w2t_oracle_hardnms_groups if hard else lib().w2t_oracle_softnms_groups
+    status = fn(C.byref(prob), C.byref(res))
     out["status"] = status
     return out

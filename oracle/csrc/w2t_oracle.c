@@ -623,7 +623,62 @@ int w2t_oracle_soft_nms(const double *boxes, const double *scores, int n, double
   return kept;
 }
 
-int w2t_oracle_softnms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r) {
+static int hk_cmp(const void *a, const void *b) {
+  /* reference: stable ascending scores.sort(0) (box_utils.py:324, canonical tie rule), then
+   * torchvision's stable DESCENDING sort of that array: descending score, smaller index first */
+  const sk_t *x = (const sk_t *)a, *y = (const sk_t *)b;
+  if (x->s > y->s) return -1;
+  if (x->s < y->s) return 1;
+  return (x->i < y->i) ? -1 : (x->i > y->i);
+}
+
+/* nms(soft=False), box_utils.py:329-333 -> torchvision.ops.nms (third-party, torchvision/csrc/ops/cpu/
+ * nms_kernel.cpp nms_kernel_impl): greedy, suppress j when inter / (area_i + area_j - inter) > overlap. */
+int w2t_oracle_hard_nms(const double *boxes, const double *scores, int n, double overlap, int top_k,
+                        int32_t *keep) {
+  if (n <= 0) return 0;
+  sk_t *order = (sk_t *)malloc(sizeof(sk_t) * n);
+  unsigned char *dead = (unsigned char *)calloc(n, 1);
+  for (int i = 0; i < n; i++) { order[i].s = scores[i]; order[i].i = i; }
+  qsort(order, n, sizeof(sk_t), hk_cmp);
+  int m = n;
+  if (top_k > 0 && top_k < n) {
+    /* idx[-top_k:] of the stable ASCENDING sort keeps, among equal scores at the cut, the later boxes */
+    qsort(order, n, sizeof(sk_t), sk_cmp);
+    m = top_k;
+    qsort(order, m, sizeof(sk_t), hk_cmp);
+  }
+  int kept = 0;
+  for (int a = 0; a < m; a++) {
+    if (dead[a]) continue;
+    const double *bi = boxes + 4 * order[a].i;
+    const double iarea = (bi[2] - bi[0]) * (bi[3] - bi[1]);
+    keep[kept++] = order[a].i;
+    for (int b = a + 1; b < m; b++) {
+      if (dead[b]) continue;
+      const double *bj = boxes + 4 * order[b].i;
+      double xx1 = bi[0] > bj[0] ? bi[0] : bj[0];
+      double yy1 = bi[1] > bj[1] ? bi[1] : bj[1];
+      double xx2 = bi[2] < bj[2] ? bi[2] : bj[2];
+      double yy2 = bi[3] < bj[3] ? bi[3] : bj[3];
+      double w = xx2 - xx1; if (!(w > 0.)) w = 0.;
+      double h = yy2 - yy1; if (!(h > 0.)) h = 0.;
+      double inter = w * h;
+      double jarea = (bj[2] - bj[0]) * (bj[3] - bj[1]);
+      double ovr = inter / ((iarea + jarea) - inter);
+      if (ovr > overlap) dead[b] = 1;
+    }
+  }
+  free(order); free(dead);
+  return kept;
+}
+
+static int nms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r, int hard);
+
+int w2t_oracle_softnms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r) { return nms_groups(p, r, 0); }
+int w2t_oracle_hardnms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r) { return nms_groups(p, r, 1); }
+
+static int nms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r, int hard) {
   if (!p || !r || p->n_groups < 0) return W2T_ERR_ARG;
   const int NC = p->n_classes > 0 ? p->n_classes : 1;
   if (r->img_exists && p->n_classes > 0)
@@ -643,16 +698,28 @@ int w2t_oracle_softnms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r) {
     const double *rows = p->rows + 5 * (size_t)base;
     for (int i = 0; i < n; i++) {
       const double *rw = rows + 5 * i;
-      /* ensemble.py:19-22 then box_utils.py:32-35 */
-      double cx = rw[1] + rw[3] / 2, cy = rw[2] + rw[4] / 2;
-      double hw = rw[3] * 0.5, hh = rw[4] * 0.5;
-      pf[4 * i + 0] = cx - hw;
-      pf[4 * i + 1] = cy - hh;
-      pf[4 * i + 2] = cx + hw;
-      pf[4 * i + 3] = cy + hh;
+      if (p->box_format == W2T_BOX_XYXY) {
+        for (int k = 0; k < 4; k++) pf[4 * i + k] = rw[1 + k];
+      } else {
+        /* ensemble.py:19-22 (rows of convert_submission only) then box_utils.py:32-35 */
+        double cx = rw[1], cy = rw[2];
+        if (p->box_format == W2T_BOX_LTWH) { cx = cx + rw[3] / 2; cy = cy + rw[4] / 2; }
+        double hw = rw[3] * 0.5, hh = rw[4] * 0.5;
+        pf[4 * i + 0] = cx - hw;
+        pf[4 * i + 1] = cy - hh;
+        pf[4 * i + 2] = cx + hw;
+        pf[4 * i + 3] = cy + hh;
+      }
       sc[i] = rw[0];
     }
-    int kept = w2t_oracle_soft_nms(pf, sc, n, p->iou_thresh, 0, 0.0, p->soft_nms_cut, keep, ns);
+    int kept;
+    if (hard) {
+      kept = w2t_oracle_hard_nms(pf, sc, n, p->iou_thresh, p->top_k, keep);
+      for (int k = 0; k < kept; k++) ns[k] = sc[keep[k]];
+    } else {
+      kept = w2t_oracle_soft_nms(pf, sc, n, p->iou_thresh, p->top_k, p->conf_thresh, p->soft_nms_cut, keep, ns);
+    }
+    if (r->kept_count) r->kept_count[g] = kept;
     int n_ens = 0, n_trk = 0;
     const int c = g % NC;
     for (int k = 0; k < kept; k++) {
@@ -671,11 +738,13 @@ int w2t_oracle_softnms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r) {
         long bx = (long)left, by = (long)top, bw = (long)w, bh = (long)h; /* astype(int) */
         double rs = rint(ns[k] * 1e5) / 1e5;                              /* round(np.float64, 5) */
         size_t e = (size_t)base + n_ens;
-        r->ens_box[4 * e + 0] = (int32_t)bx;
-        r->ens_box[4 * e + 1] = (int32_t)by;
-        r->ens_box[4 * e + 2] = (int32_t)bw;
-        r->ens_box[4 * e + 3] = (int32_t)bh;
-        r->ens_score[e] = rs;
+        if (r->ens_box) {
+          r->ens_box[4 * e + 0] = (int32_t)bx;
+          r->ens_box[4 * e + 1] = (int32_t)by;
+          r->ens_box[4 * e + 2] = (int32_t)bw;
+          r->ens_box[4 * e + 3] = (int32_t)bh;
+          r->ens_score[e] = rs;
+        }
         n_ens++;
         if (p->score_thr && r->trk_box) {
           /* utils.py:79-87 then :32-35 and tracker_sort.py:45 */
@@ -695,5 +764,150 @@ int w2t_oracle_softnms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r) {
     if (r->img_exists && p->n_classes > 0 && n_ens > 0) r->img_exists[g / NC] = 1;
   }
   free(pf); free(sc); free(ns); free(keep);
+  return W2T_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* weighted box fusion                                                 */
+/* ------------------------------------------------------------------ */
+
+/* merge_detections, detnet/nn/tta.py:22-66, with jaccard_bbox (detnet/utils/box_utils.py:72-140).
+ * rows[n,5] = score, cx, cy, w, h of all submissions concatenated; counts[n_sub] rows per submission.
+ * out[n,5] receives the result list; returns its length. */
+int w2t_oracle_merge_detections(const double *rows, const int32_t *counts, int n_sub, double nms_thresh,
+                                double *out) {
+  int n = 0;
+  for (int k = 0; k < n_sub; k++) n += counts[k];
+  if (n == 0) return 0;
+  double *acc = out;                                   /* the running results, weighted rows */
+  double *box = (double *)malloc(sizeof(double) * 5 * n); /* de-weighted point form + area */
+  int *last = (int *)malloc(sizeof(int) * n);
+  int *fresh = (int *)malloc(sizeof(int) * n);
+  const double N = (double)n_sub;
+  int R = 0, row0 = 0;
+  for (int k = 0; k < n_sub; k++) {
+    const int nk = counts[k];
+    if (nk == 0) continue;                             /* tta.py:38 (and an empty first submission) */
+    const double *oth = rows + 5 * (size_t)row0;
+    if (R == 0) {
+      for (int o = 0; o < nk; o++) {
+        const double s = oth[5 * o] / N;               /* tta.py:34-35 / :39-40 */
+        acc[5 * o] = s;
+        for (int i = 1; i < 5; i++) acc[5 * o + i] = oth[5 * o + i] * s;
+      }
+      R = nk;
+      row0 += nk;
+      continue;
+    }
+    for (int r = 0; r < R; r++) {                      /* tta.py:43, box_utils.py:32-35,123-128 */
+      const double s = acc[5 * r];
+      const double cx = acc[5 * r + 1] / s, cy = acc[5 * r + 2] / s, w = acc[5 * r + 3] / s, h = acc[5 * r + 4] / s;
+      box[5 * r + 0] = cx - w * 0.5; box[5 * r + 1] = cy - h * 0.5;
+      box[5 * r + 2] = cx + w * 0.5; box[5 * r + 3] = cy + h * 0.5;
+      box[5 * r + 4] = w * h;
+      last[r] = -1;
+    }
+    int n_fresh = 0;
+    for (int o = 0; o < nk; o++) {
+      const double s = oth[5 * o] / N;
+      const double wc[4] = {oth[5 * o + 1] * s, oth[5 * o + 2] * s, oth[5 * o + 3] * s, oth[5 * o + 4] * s};
+      const double cx = wc[0] / s, cy = wc[1] / s, w = wc[2] / s, h = wc[3] / s;   /* tta.py:44 */
+      const double x1 = cx - w * 0.5, y1 = cy - h * 0.5, x2 = cx + w * 0.5, y2 = cy + h * 0.5;
+      const double area = w * h;
+      double best = -1.0;
+      int arg = 0;
+      for (int r = 0; r < R; r++) {                    /* box_utils.py:72-92,113-121 */
+        double iw = (box[5 * r + 2] < x2 ? box[5 * r + 2] : x2) - (box[5 * r + 0] > x1 ? box[5 * r + 0] : x1);
+        double ih = (box[5 * r + 3] < y2 ? box[5 * r + 3] : y2) - (box[5 * r + 1] > y1 ? box[5 * r + 1] : y1);
+        if (iw < 0.) iw = 0.;
+        if (ih < 0.) ih = 0.;
+        const double inter = iw * ih;
+        const double iou = inter / ((box[5 * r + 4] + area) - inter);
+        if (iou > best) { best = iou; arg = r; }       /* overlaps.max(0): first maximum */
+      }
+      if (best >= nms_thresh) last[arg] = o;           /* fancy-index +=: the last duplicate wins */
+      else if (best < nms_thresh) fresh[n_fresh++] = o;
+    }
+    for (int r = 0; r < R; r++) {
+      const int o = last[r];
+      if (o < 0) continue;
+      const double s = oth[5 * o] / N;
+      acc[5 * r] = acc[5 * r] + s;
+      for (int i = 1; i < 5; i++) acc[5 * r + i] = acc[5 * r + i] + oth[5 * o + i] * s;
+    }
+    for (int f = 0; f < n_fresh; f++) {                /* tta.py:56-58 */
+      const int o = fresh[f];
+      const double s = oth[5 * o] / N;
+      acc[5 * R] = s;
+      for (int i = 1; i < 5; i++) acc[5 * R + i] = oth[5 * o + i] * s;
+      R++;
+    }
+    row0 += nk;
+  }
+  for (int r = 0; r < R; r++)                          /* tta.py:67 */
+    for (int i = 1; i < 5; i++) acc[5 * r + i] = acc[5 * r + i] / acc[5 * r];
+  free(box); free(last); free(fresh);
+  return R;
+}
+
+/* detnet/ensemble.py:50-64 with merge_func = merge_detections, for all groups (host pointers). */
+int w2t_oracle_fusion_groups(const w2t_nms_problem_t *p, const int32_t *sub_counts, int n_sub,
+                             w2t_nms_result_t *r) {
+  if (!p || !r || !sub_counts || p->n_groups < 0 || n_sub < 1) return W2T_ERR_ARG;
+  const int NC = p->n_classes > 0 ? p->n_classes : 1;
+  if (r->img_exists && p->n_classes > 0) memset(r->img_exists, 0, (size_t)(p->n_groups / NC));
+  int maxn = 0;
+  for (int g = 0; g < p->n_groups; g++) {
+    int n = p->group_offsets[g + 1] - p->group_offsets[g];
+    if (n > maxn) maxn = n;
+  }
+  double *in = (double *)malloc(sizeof(double) * 5 * (maxn + 1));
+  double *out = (double *)malloc(sizeof(double) * 5 * (maxn + 1));
+  for (int g = 0; g < p->n_groups; g++) {
+    const int base = p->group_offsets[g];
+    const int n = p->group_offsets[g + 1] - base;
+    for (int i = 0; i < n; i++) {
+      const double *rw = p->rows + 5 * ((size_t)base + i);
+      in[5 * i] = rw[0];
+      in[5 * i + 1] = rw[1]; in[5 * i + 2] = rw[2]; in[5 * i + 3] = rw[3]; in[5 * i + 4] = rw[4];
+      if (p->box_format == W2T_BOX_LTWH) {             /* lxly2cxcy, ensemble.py:19-22 */
+        in[5 * i + 1] = rw[1] + rw[3] / 2;
+        in[5 * i + 2] = rw[2] + rw[4] / 2;
+      }
+    }
+    const int R = w2t_oracle_merge_detections(in, sub_counts + (size_t)g * n_sub, n_sub, p->iou_thresh, out);
+    if (r->kept_count) r->kept_count[g] = R;
+    int n_ens = 0, n_trk = 0;
+    const int c = g % NC;
+    for (int k = 0; k < R; k++) {
+      const double s = out[5 * k], cx = out[5 * k + 1], cy = out[5 * k + 2], w = out[5 * k + 3], h = out[5 * k + 4];
+      if (r->merged) {
+        double *mr = r->merged + 5 * ((size_t)base + k);
+        mr[0] = s; mr[1] = cx; mr[2] = cy; mr[3] = w; mr[4] = h;
+      }
+      if (s > p->min_score) {
+        double left = cx - w / 2, top = cy - h / 2;
+        long bx = (long)left, by = (long)top, bw = (long)w, bh = (long)h;
+        double rs = rint(s * 1e5) / 1e5;
+        size_t e = (size_t)base + n_ens;
+        if (r->ens_box) {
+          r->ens_box[4 * e + 0] = (int32_t)bx; r->ens_box[4 * e + 1] = (int32_t)by;
+          r->ens_box[4 * e + 2] = (int32_t)bw; r->ens_box[4 * e + 3] = (int32_t)bh;
+          r->ens_score[e] = rs;
+        }
+        n_ens++;
+        if (p->score_thr && r->trk_box && !(bw < 1 || bh < 1) && !(rs < p->score_thr[c])) {
+          size_t t = (size_t)base + n_trk;
+          r->trk_box[4 * t + 0] = (float)bx; r->trk_box[4 * t + 1] = (float)by;
+          r->trk_box[4 * t + 2] = (float)(bx + bw); r->trk_box[4 * t + 3] = (float)(by + bh);
+          n_trk++;
+        }
+      }
+    }
+    r->ens_count[g] = n_ens;
+    if (r->trk_count) r->trk_count[g] = n_trk;
+    if (r->img_exists && p->n_classes > 0 && n_ens > 0) r->img_exists[g / NC] = 1;
+  }
+  free(in); free(out);
   return W2T_OK;
 }

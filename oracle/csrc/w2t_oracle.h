@@ -59,6 +59,19 @@ int w2t_oracle_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t
 int w2t_oracle_soft_nms(const double *boxes, const double *scores, int n, double overlap, int top_k,
                         double conf_thresh, double soft_nms_cut, int32_t *keep, double *new_scores);
 
+/* box_utils.py:329-333 (hard branch): torchvision.ops.nms on the ascending-sorted boxes.
+ * Returns the number of kept boxes; keep[n] in descending score order. */
+int w2t_oracle_hard_nms(const double *boxes, const double *scores, int n, double overlap, int top_k,
+                        int32_t *keep);
+int w2t_oracle_hardnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result);
+
+/* detnet/nn/tta.py:22-66 merge_detections: rows[n,5] = score,cx,cy,w,h of all submissions
+ * concatenated, counts[n_sub]; out[n,5]; returns the length of the result list. */
+int w2t_oracle_merge_detections(const double *rows, const int32_t *counts, int n_sub, double nms_thresh,
+                                double *out);
+int w2t_oracle_fusion_groups(const w2t_nms_problem_t *problem, const int32_t *sub_counts, int n_sub,
+                             w2t_nms_result_t *result);
+
 #ifdef __cplusplus
 }
 #endif

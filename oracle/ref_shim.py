@@ -155,15 +155,21 @@ def ref_track_all(predictions, iou_thresholds, max_age, min_hits):
     return out
 
 
-def ref_ensemble_all(submissions, weights=None, min_score=0.0, iou_thresh=0.5, soft_nms_cut=1.0, image_order=None):
-    """detnet/ensemble.py:123-149 (soft_nms method) executed with the reference's own modules."""
+def ref_ensemble_all(submissions, weights=None, min_score=0.0, iou_thresh=0.5, soft_nms_cut=1.0, image_order=None,
+                     method="soft_nms"):
+    """detnet/ensemble.py:123-149 executed with the reference's own modules (any of its three methods)."""
     ens, tta, _ = load_ensemble()
     if weights is None:
         weights = [1] * len(submissions)
     top = max(weights)
     weights = [w / top for w in weights]
     ens.args = Namespace(min_score=min_score)
-    ens.merge_func = partial(tta.nms_detections, iou_thresh=iou_thresh, soft=True, soft_nms_cut=soft_nms_cut)
+    if method == "soft_nms":
+        ens.merge_func = partial(tta.nms_detections, iou_thresh=iou_thresh, soft=True, soft_nms_cut=soft_nms_cut)
+    elif method == "nms":
+        ens.merge_func = partial(tta.nms_detections, iou_thresh=iou_thresh)
+    else:
+        ens.merge_func = partial(tta.merge_detections, nms_thresh=iou_thresh)
     category_ids = set(sum([[d['category_id'] for d in det] for det in submissions], []))
     grouped = [ens.convert_submission(d, w, min_score) for d, w in zip(submissions, weights)]
     if image_order is None:

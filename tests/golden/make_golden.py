@@ -67,6 +67,47 @@ ENSEMBLE_CASES = {
 }
 
 
+# the CLI's other two methods (ensemble.py:94,138-140), same generator
+METHOD_CASES = {
+    "ensemble_nms": dict(cfg=dict(n_segments=1, cameras=("FRONT", "SIDE_RIGHT"), n_frames=6, n_submissions=3,
+                                  objects_per_frame=45.0, seed=24),
+                         method="nms", min_score=0.01, iou_thresh=0.5, cut=1.0, weights=None),
+    "ensemble_fusion": dict(cfg=dict(n_segments=1, cameras=("FRONT", "SIDE_LEFT"), n_frames=6, n_submissions=4,
+                                     objects_per_frame=45.0, seed=25),
+                            method="weighted_fusion", min_score=0.0, iou_thresh=0.5, cut=1.0, weights=[3, 1, 2, 2]),
+    "ensemble_fusion_default": dict(cfg=dict(n_segments=1, cameras=("FRONT_LEFT",), n_frames=5, n_submissions=2,
+                                             objects_per_frame=60.0, seed=26),
+                                    method="weighted_fusion", min_score=0.05, iou_thresh=0.6, cut=1.0, weights=None),
+}
+
+
+def nms_api_cases():
+    """The general signature of box_utils.nms (top_k, conf_thresh, soft / hard) on random box sets,
+    ties included; outputs of the reference's own function (torch + torchvision CPU)."""
+    import torch
+    _, _, bu = ref_shim.load_ensemble()
+    rng = np.random.default_rng(77)
+    out = {}
+    n_cases = 0
+    for trial in range(48):
+        n = int(rng.integers(1, 70))
+        xy = rng.uniform(0, 300, (n, 2))
+        boxes = np.c_[xy, xy + rng.uniform(8, 150, (n, 2))]
+        scores = np.round(rng.uniform(0.02, 1, n), 1 if trial % 3 == 0 else 5)
+        kw = dict(overlap=[0.5, 0.3, 0.7][trial % 3], top_k=[0, 0, 7, 500][trial % 4], soft=bool(trial % 2),
+                  conf_thresh=[0.0, 0.25, 0.05][(trial // 2) % 3], soft_nms_cut=[1.0, 0.9][(trial // 4) % 2])
+        with ref_shim.stable_torch_sort():
+            keep, sc = bu.nms(torch.from_numpy(boxes), torch.from_numpy(scores), **kw)
+        p = "c%d_" % n_cases
+        out[p + "boxes"], out[p + "scores"] = boxes, scores
+        out[p + "args"] = np.asarray([kw["overlap"], kw["top_k"], float(kw["soft"]), kw["conf_thresh"], kw["soft_nms_cut"]])
+        out[p + "keep"] = np.asarray([int(k) for k in keep], np.int64)
+        out[p + "out_scores"] = np.asarray(sc, np.float64)
+        n_cases += 1
+    out["n_cases"] = np.int64(n_cases)
+    return out
+
+
 def scene_inputs(scene):
     d = {"image_ids": np.asarray(scene.image_ids()), "n_sub": np.int64(len(scene.submissions))}
     for k, sub in enumerate(scene.submissions):
@@ -89,8 +130,37 @@ def run_reference_tracking(dets, max_age, min_hits):
     return ref_shim.ref_track_all(predictions, IOU_THR, max_age, min_hits)
 
 
+def main_methods():
+    """Fixtures added after the first batch: written only where the file does not exist yet."""
+    for name, case in METHOD_CASES.items():
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path):
+            continue
+        scene = synth.make_scene(synth.SynthConfig(**case["cfg"]))
+        subs = [synth.to_json_list(scene, s) for s in scene.submissions]
+        rows = ref_shim.ref_ensemble_all(subs, case["weights"], case["min_score"], case["iou_thresh"], case["cut"],
+                                         method=case["method"])
+        out = scene_inputs(scene)
+        out.update({"out_" + k: v for k, v in golden_io.dets_to_arrays(rows, scene.image_ids()).items()})
+        out["min_score"], out["iou_thresh"], out["cut"] = (np.float64(case["min_score"]),
+                                                           np.float64(case["iou_thresh"]), np.float64(case["cut"]))
+        out["weights"] = np.asarray(case["weights"] if case["weights"] else [1] * len(subs), np.float64)
+        out["method"] = np.asarray(case["method"])
+        out["cfg"] = np.asarray(json.dumps(case["cfg"]))
+        np.savez_compressed(path, **out)
+        print(name, "in", sum(len(s) for s in subs), "out", len(rows))
+    path = os.path.join(HERE, "nms_api.npz")
+    if not os.path.exists(path):
+        out = nms_api_cases()
+        np.savez_compressed(path, **out)
+        print("nms_api", int(out["n_cases"]), "cases")
+
+
 def main():
     assert ref_shim.available(), "reference not mounted at %s" % ref_shim.REF_ROOT
+    if "--new-only" in sys.argv:
+        return main_methods()
+    main_methods()
     for name, case in TRACK_CASES.items():
         scene = synth.make_scene(synth.SynthConfig(**case["cfg"]))
         dets = synth.to_json_list(scene, scene.submissions[0])

@@ -258,3 +258,39 @@ def test_reference_itself_agrees_with_ports_on_a_fresh_seed():
     for x, y in zip(a, b):
         assert x["image_id"] == y["image_id"] and x["object_id"] == y["object_id"]
         assert [float(v) for v in x["bbox"]] == [float(v) for v in y["bbox"]] and float(x["score"]) == float(y["score"])
+
+
+# ---- the CLI's other two methods and the general nms() signature -------------------------------
+
+METHOD_CASES = ["ensemble_nms", "ensemble_fusion", "ensemble_fusion_default"]
+
+
+@pytest.mark.parametrize("name", METHOD_CASES)
+def test_c_oracle_other_methods_match_reference_golden(name):
+    g = golden_io.load(name)
+    scene = helpers.golden_scene(g)
+    groups = synth.groups_from_scene(scene, list(g["weights"]), float(g["min_score"]))
+    if str(g["method"]) == "nms":
+        res = c_oracle.softnms_groups(groups.group_offsets, groups.rows, float(g["iou_thresh"]), 1.0,
+                                      float(g["min_score"]), hard=True)
+    else:
+        res = c_oracle.fusion_groups(groups.group_offsets, groups.rows, groups.sub_counts, float(g["iou_thresh"]),
+                                     float(g["min_score"]))
+    got = helpers.ensemble_rows_as_arrays(groups.group_offsets, res, scene.n_img,
+                                          image_order=helpers.sorted_image_order(scene.image_ids()))
+    for k in ("img", "cat", "bbox", "score"):
+        np.testing.assert_array_equal(got[k], g["out_" + k])
+
+
+def test_c_oracle_nms_api_matches_reference_golden():
+    g = golden_io.load("nms_api")
+    for i in range(int(g["n_cases"])):
+        p = "c%d_" % i
+        overlap, top_k, soft, conf, cut = g[p + "args"]
+        if soft:
+            keep, sc = c_oracle.soft_nms(g[p + "boxes"], g[p + "scores"], overlap, int(top_k), conf, cut)
+        else:
+            keep = c_oracle.hard_nms(g[p + "boxes"], g[p + "scores"], overlap, int(top_k))
+            sc = g[p + "scores"][keep]
+        assert keep == g[p + "keep"].tolist(), i
+        np.testing.assert_array_equal(sc, g[p + "out_scores"])

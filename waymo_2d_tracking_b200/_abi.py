@@ -86,13 +86,20 @@ class NmsProblem(C.Structure):
         ("min_score", C.c_double),
         ("n_classes", C.c_int32),
         ("score_thr", _p),
+        ("box_format", C.c_int32),
+        ("top_k", C.c_int32),
+        ("conf_thresh", C.c_double),
     ]
+
+
+W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY = 0, 1, 2
 
 
 class NmsResult(C.Structure):
     _fields_ = [
         ("merged", _p),
         ("src_index", _p),
+        ("kept_count", _p),
         ("ens_count", _p),
         ("ens_box", _p),
         ("ens_score", _p),
@@ -108,7 +115,10 @@ EXPORTS = {
     "w2t_last_error": (C.c_char_p, []),
     "w2t_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "w2t_softnms_groups": (C.c_int, [C.POINTER(NmsProblem), C.POINTER(NmsResult), C.c_int, _p, _p]),
+    "w2t_hardnms_groups": (C.c_int, [C.POINTER(NmsProblem), C.POINTER(NmsResult), C.c_int, _p, _p]),
     "w2t_softnms_max_group": (C.c_int, []),
+    "w2t_fusion_groups": (C.c_int, [C.POINTER(NmsProblem), _p, C.c_int32, C.POINTER(NmsResult), C.c_int, _p, _p]),
+    "w2t_fusion_max_group": (C.c_int, []),
     "w2t_sort_plan": (C.c_int, [C.c_int32, C.c_int32, _p, _p, _p, C.c_int32, C.POINTER(SortPlan)]),
     "w2t_sort_track": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortPlan), C.POINTER(SortResult), _p, _p, _p]),
     "w2t_sort_finalize_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
@@ -122,6 +132,8 @@ EXPORTS = {
     "w2t_kf_init": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
     "w2t_kf_predict": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
     "w2t_kf_update": (C.c_int, [_p, _p, _p, _p, C.c_int32, _p]),
+    "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, _p]),
+    "w2t_x_to_bbox": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
 }
 
 

@@ -37,7 +37,10 @@ struct NmsParams {
   int32_t *status;
 };
 
-template <int BLOCK>
+// HARD = false: the soft branch (box_utils.py:335-391).  HARD = true: the hard branch
+// (box_utils.py:329-333), i.e. torchvision.ops.nms on the ascending-sorted boxes: greedy
+// suppression of every lower ranked box with IoU > overlap, scores untouched.
+template <int BLOCK, bool HARD>
 __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_scan[2 * (BLOCK / 32)];
@@ -56,35 +59,64 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
       if (P.status) atomicMax(P.status, W2T_ERR_CAPACITY);
       P.r.ens_count[g] = 0;
       if (P.r.trk_count) P.r.trk_count[g] = 0;
+      if (P.r.kept_count) P.r.kept_count[g] = 0;
     }
     return;
   }
   const double *rows = P.p.rows + 5 * (size_t)base;
 
   // 1. scores to shared memory
+  const double conf = P.p.conf_thresh;
+  // removals make the result order-dependent (box_utils.py:379-381; always for hard NMS)
+  const bool sequential = HARD || conf > 0.;
   bool bad = false;
   for (int i = tid; i < n; i += BLOCK) {
     const double sc = rows[5 * i];
     raw[i] = sc;
-    if (!(sc >= 0.)) bad = true;  // the reference would drop it at `ge(conf_thresh)` (box_utils.py:379)
+    // without removals the reference keeps every box only if no score ever fails `ge(conf_thresh)`
+    if (!HARD && !sequential && !(sc >= (conf < 0. ? conf : 0.))) bad = true;
+    if (sc != sc) bad = true;
   }
   __syncthreads();
 
-  // 2. rank by counting, scatter the point-form box into rank order
+  // 2. rank by counting, scatter the point-form box into rank order; with top_k only the best
+  //    top_k boxes take part (box_utils.py:325-327)
+  const int m = (P.p.top_k > 0 && P.p.top_k < n) ? P.p.top_k : n;
+  const int fmt = P.p.box_format;
   for (int i = tid; i < n; i += BLOCK) {
     const double si = raw[i];
-    int rank = 0;
+    // G boxes score higher; of the equal ones L come earlier and H later in the input.
+    int G = 0, L = 0, H = 0;
     for (int k = 0; k < n; k++) {
       const double sk = raw[k];
-      rank += (sk > si || (sk == si && k > i)) ? 1 : 0;
+      G += (sk > si) ? 1 : 0;
+      L += (sk == si && k < i) ? 1 : 0;
+      H += (sk == si && k > i) ? 1 : 0;
+    }
+    // The reference sorts ascending (stable, canonical rule) and consumes from the end, so among
+    // equal scores the later box ranks higher; top_k cuts that order (box_utils.py:324-327).
+    if (G + H >= m) continue;
+    int rank = G + H;
+    if (HARD) {
+      // torchvision's own stable descending sort of the ascending array then puts the EARLIER of
+      // two equal boxes first; equal boxes cut off by top_k are the earliest ones
+      const int E = L + H + 1;
+      const int sel = E < m - G ? E : m - G;
+      rank = G + L - (E - sel);
     }
     const double *rw = rows + 5 * i;
-    const double w = rw[3], h = rw[4];
-    const double cx = rw[1] + w / 2, cy = rw[2] + h / 2;  // lxly2cxcy, ensemble.py:19-22
-    const double hw = w * 0.5, hh = h * 0.5;              // point_form, box_utils.py:32-35
-    const double x1 = cx - hw, y1 = cy - hh, x2 = cx + hw, y2 = cy + hh;
+    double x1, y1, x2, y2;
+    if (fmt == W2T_BOX_XYXY) {
+      x1 = rw[1]; y1 = rw[2]; x2 = rw[3]; y2 = rw[4];
+    } else {
+      const double w = rw[3], h = rw[4];
+      double cx = rw[1], cy = rw[2];
+      if (fmt == W2T_BOX_LTWH) { cx = cx + w / 2; cy = cy + h / 2; }  // lxly2cxcy, ensemble.py:19-22
+      const double hw = w * 0.5, hh = h * 0.5;                         // point_form, box_utils.py:32-35
+      x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+    }
     const double area = (x2 - x1) * (y2 - y1);            // box_utils.py:342
-    if (!(area > 0.)) bad = true;
+    if (!HARD && !(area > 0.)) bad = true;  // 0/0 weights: the reference would drop the box as NaN
     sx1[rank] = x1; sy1[rank] = y1; sx2[rank] = x2; sy2[rank] = y2;
     sar[rank] = area;
     ssc[rank] = si;
@@ -93,47 +125,106 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   if (bad && P.status) atomicMax(P.status, W2T_ERR_ARG);
   __syncthreads();
 
-  // 3. triangular decay + outputs, chunk by chunk in rank order
+  // 3. decay
   const double cut = P.p.soft_nms_cut;
   const double denom = cut - P.p.iou_thresh;
   double wt0 = (cut - 0.0) / denom;  // weight of a pair with IoU = +0
   if (wt0 < 0.) wt0 = 0.;
   if (wt0 > 1.) wt0 = 1.;
   const bool skip_disjoint = (wt0 == 1.0);
-  const int cls = (P.p.n_classes > 0) ? (g % P.p.n_classes) : 0;
-  int n_ens = 0, n_trk = 0;
-  for (int j0 = 0; j0 < n; j0 += BLOCK) {
-    const int j = j0 + tid;
-    bool f_ens = false, f_trk = false;
-    int bx = 0, by = 0, bw = 0, bh = 0;
-    double rs = 0.;
-    if (j < n) {
+  // weight box i (kept, higher ranked) applies to box j; box_utils.py:349-370
+  auto pair_weight = [&](int i, double x1, double y1, double x2, double y2, double area, bool &one) -> double {
+    const double ix1 = sx1[i], iy1 = sy1[i], ix2 = sx2[i], iy2 = sy2[i];
+    const double xx1 = x1 > ix1 ? x1 : ix1;
+    const double yy1 = y1 > iy1 ? y1 : iy1;
+    const double xx2 = x2 < ix2 ? x2 : ix2;
+    const double yy2 = y2 < iy2 ? y2 : iy2;
+    double w = xx2 - xx1;
+    double h = yy2 - yy1;
+    if (w < 0.) w = 0.;
+    if (h < 0.) h = 0.;
+    const double inter = w * h;
+    if (inter == 0. && skip_disjoint) { one = true; return 1.0; }  // IoU = +0 (areas are positive), weight 1.0
+    one = false;
+    const double uni = (area - inter) + sar[i];
+    const double iou = inter / uni;
+    double wt = (cut - iou) / denom;
+    if (wt < 0.) wt = 0.;
+    if (wt > 1.) wt = 1.;
+    return wt;
+  };
+  int *alive = reinterpret_cast<int *>(raw);  // the input-order scores are no longer needed
+  if (!sequential) {
+    // fixed-order triangular product: thread j multiplies the weights of every i ranked above it
+    for (int j = tid; j < m; j += BLOCK) {
       const double x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j], area = sar[j];
       double live = ssc[j];
       for (int i = 0; i < j; i++) {
-        // box i is the kept (higher ranked) one; box_utils.py:349-370
-        const double ix1 = sx1[i], iy1 = sy1[i], ix2 = sx2[i], iy2 = sy2[i];
-        const double xx1 = x1 > ix1 ? x1 : ix1;
-        const double yy1 = y1 > iy1 ? y1 : iy1;
-        const double xx2 = x2 < ix2 ? x2 : ix2;
-        const double yy2 = y2 < iy2 ? y2 : iy2;
-        double w = xx2 - xx1;
-        double h = yy2 - yy1;
-        if (w < 0.) w = 0.;
-        if (h < 0.) h = 0.;
-        const double inter = w * h;
-        if (inter == 0. && skip_disjoint) continue;  // IoU = +0 (areas are positive), weight 1.0
-        const double uni = (area - inter) + sar[i];
-        const double iou = inter / uni;
-        double wt = (cut - iou) / denom;
-        if (wt < 0.) wt = 0.;
-        if (wt > 1.) wt = 1.;
-        live = live * wt;
+        bool one;
+        const double wt = pair_weight(i, x1, y1, x2, y2, area, one);
+        if (!one) live = live * wt;
       }
+      ssc[j] = live;
+    }
+  } else {
+    // one block-wide pass per surviving rank: decay every lower ranked survivor, drop those that
+    // fall below conf_thresh (also the ones the pass did not touch, like `sorted_scores.ge`)
+    __syncthreads();
+    for (int j = tid; j < m; j += BLOCK) alive[j] = 1;
+    __syncthreads();
+    for (int k = 0; k + 1 < m; k++) {
+      if (!alive[k]) continue;  // uniform: shared memory, barrier-ordered
+      for (int j = k + 1 + tid; j < m; j += BLOCK) {
+        if (!alive[j]) continue;
+        if (HARD) {
+          // torchvision nms_kernel_impl: ovr = inter / (iarea + areas[j] - inter); suppress if > thr
+          const double kx1 = sx1[k], ky1 = sy1[k], kx2 = sx2[k], ky2 = sy2[k];
+          const double xx1 = kx1 > sx1[j] ? kx1 : sx1[j];
+          const double yy1 = ky1 > sy1[j] ? ky1 : sy1[j];
+          const double xx2 = kx2 < sx2[j] ? kx2 : sx2[j];
+          const double yy2 = ky2 < sy2[j] ? ky2 : sy2[j];
+          double w = xx2 - xx1, h = yy2 - yy1;
+          if (!(w > 0.)) w = 0.;   // std::max(0, w): a NaN difference yields 0
+          if (!(h > 0.)) h = 0.;
+          const double inter = w * h;
+          const double ovr = inter / ((sar[k] + sar[j]) - inter);
+          if (ovr > P.p.iou_thresh) alive[j] = 0;
+        } else {
+          bool one;
+          const double wt = pair_weight(k, sx1[j], sy1[j], sx2[j], sy2[j], sar[j], one);
+          const double live = one ? ssc[j] : ssc[j] * wt;
+          ssc[j] = live;
+          if (!(live >= conf)) alive[j] = 0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  // 4. outputs, chunk by chunk in rank order
+  const int cls = (P.p.n_classes > 0) ? (g % P.p.n_classes) : 0;
+  int n_kept = 0, n_ens = 0, n_trk = 0;
+  for (int j0 = 0; j0 < m; j0 += BLOCK) {
+    const int j = j0 + tid;
+    const bool f_keep = (j < m) && (!sequential || alive[j] != 0);
+    int pos = j;
+    if (sequential) {
+      int ek, eu, tk, tu;
+      block_scan2<BLOCK>(f_keep, false, s_scan, ek, eu, tk, tu);
+      pos = n_kept + ek;
+      n_kept += tk;
+    }
+    bool f_ens = false, f_trk = false;
+    int bx = 0, by = 0, bw = 0, bh = 0;
+    double rs = 0.;
+    if (f_keep) {
+      const double x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j];
+      const double live = ssc[j];
       // center_size (box_utils.py:57-69) then cxcy2lxly (ensemble.py:25-28)
       const double cx = (x1 + x2) * 0.5, cy = (y1 + y2) * 0.5;
       const double w = x2 - x1, h = y2 - y1;
-      const size_t o = (size_t)base + j;
+      const size_t o = (size_t)base + pos;
       if (P.r.merged) {
         double *mr = P.r.merged + 5 * o;
         mr[0] = live; mr[1] = cx; mr[2] = cy; mr[3] = w; mr[4] = h;
@@ -150,7 +241,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     }
     int ee, et, te, tt;
     block_scan2<BLOCK>(f_ens, f_trk, s_scan, ee, et, te, tt);
-    if (f_ens) {
+    if (f_ens && P.r.ens_box) {
       const size_t e = (size_t)base + n_ens + ee;
       int32_t *eb = P.r.ens_box + 4 * e;
       eb[0] = bx; eb[1] = by; eb[2] = bw; eb[3] = bh;
@@ -164,6 +255,8 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     n_ens += te;
     n_trk += tt;
   }
+  if (!sequential) n_kept = m;
+  if (tid == 0 && P.r.kept_count) P.r.kept_count[g] = n_kept;
   if (tid == 0) {
     P.r.ens_count[g] = n_ens;
     if (P.r.trk_count) P.r.trk_count[g] = n_trk;
@@ -171,37 +264,36 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   }
 }
 
-template <int BLOCK>
+template <int BLOCK, bool HARD>
 int launch(const NmsParams &P, int n_groups, size_t smem, cudaStream_t stream) {
   if (smem > 48 * 1024)
-    W2T_CUDA_TRY(cudaFuncSetAttribute(softnms_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  softnms_kernel<BLOCK><<<n_groups, BLOCK, smem, stream>>>(P);
+    W2T_CUDA_TRY(cudaFuncSetAttribute(softnms_kernel<BLOCK, HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  softnms_kernel<BLOCK, HARD><<<n_groups, BLOCK, smem, stream>>>(P);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
 }
 
-}  // namespace
-
-extern "C" int w2t_softnms_max_group(void) { return (kMaxSmem - 1024) / kBytesPerBox; }
-
-extern "C" int w2t_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
-                                  int32_t *status, w2t_stream_t stream) {
+template <bool HARD>
+int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size, int32_t *status,
+               cudaStream_t stream, const char *who) {
   if (!problem || !result || problem->n_groups < 0 || problem->n_classes < 0 ||
       problem->n_classes > W2T_MAX_CLASSES || max_group_size < 0) {
-    set_last_error("w2t_softnms_groups: bad argument");
+    set_last_error("%s: bad argument", who);
     return W2T_ERR_ARG;
   }
   if (problem->n_groups == 0) return W2T_OK;
-  if (!problem->group_offsets || !problem->rows || !result->ens_count || !result->ens_box || !result->ens_score) {
-    set_last_error("w2t_softnms_groups: null buffer");
+  if (!problem->group_offsets || !problem->rows || !result->ens_count || (result->ens_box && !result->ens_score) ||
+      problem->box_format < W2T_BOX_LTWH || problem->box_format > W2T_BOX_XYXY || problem->top_k < 0) {
+    set_last_error("%s: null buffer or bad box_format / top_k", who);
     return W2T_ERR_ARG;
   }
   if (problem->score_thr && (!result->trk_count || !result->trk_box || problem->n_classes < 1)) {
-    set_last_error("w2t_softnms_groups: score_thr given without trk_count/trk_box/n_classes");
+    set_last_error("%s: score_thr given without trk_count/trk_box/n_classes", who);
     return W2T_ERR_ARG;
   }
   if (max_group_size > w2t_softnms_max_group()) {
-    set_last_error("w2t_softnms_groups: group of %d boxes exceeds the shared-memory limit of %d", max_group_size,
+    set_last_error("%s: group of %d boxes exceeds the shared-memory limit of %d", who, max_group_size,
                    w2t_softnms_max_group());
     return W2T_ERR_CAPACITY;
   }
@@ -215,7 +307,21 @@ extern "C" int w2t_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_resu
   P.cap = (std::max(max_group_size, 1) + 1) & ~1;  // even: keeps the int array 8-byte aligned
   P.status = status;
   const size_t smem = (size_t)P.cap * kBytesPerBox;
-  if (max_group_size <= 96) return launch<64>(P, problem->n_groups, smem, (cudaStream_t)stream);
-  if (max_group_size <= 768) return launch<128>(P, problem->n_groups, smem, (cudaStream_t)stream);
-  return launch<256>(P, problem->n_groups, smem, (cudaStream_t)stream);
+  if (max_group_size <= 96) return launch<64, HARD>(P, problem->n_groups, smem, stream);
+  if (max_group_size <= 768) return launch<128, HARD>(P, problem->n_groups, smem, stream);
+  return launch<256, HARD>(P, problem->n_groups, smem, stream);
+}
+
+}  // namespace
+
+extern "C" int w2t_softnms_max_group(void) { return (kMaxSmem - 1024) / kBytesPerBox; }
+
+extern "C" int w2t_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
+                                  int32_t *status, w2t_stream_t stream) {
+  return run_groups<false>(problem, result, max_group_size, status, (cudaStream_t)stream, "w2t_softnms_groups");
+}
+
+extern "C" int w2t_hardnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
+                                  int32_t *status, w2t_stream_t stream) {
+  return run_groups<true>(problem, result, max_group_size, status, (cudaStream_t)stream, "w2t_hardnms_groups");
 }

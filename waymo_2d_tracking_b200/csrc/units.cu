@@ -140,7 +140,45 @@ __global__ void kf_update_kernel(double *x, double *P, const float4 *dets, doubl
   }
 }
 
+__global__ void bbox_to_z_kernel(const float4 *dets, float4 *z, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 d4 = dets[i];
+  const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+  float zz[4];
+  bbox_to_z(dd, zz);
+  z[i] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+}
+
+__global__ void x_to_bbox_kernel(const double *x, int ldx, double *boxes, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xv[7] = {0., 0., 0., 0., 0., 0., 0.}, b[4];
+  for (int k = 0; k < 4; k++) xv[k] = x[(size_t)ldx * i + k];
+  x_to_bbox(xv, b);
+  for (int k = 0; k < 4; k++) boxes[4 * (size_t)i + k] = b[k];
+}
+
 }  // namespace
+
+extern "C" int w2t_bbox_to_z(const float *dets, float *z, int32_t n, w2t_stream_t stream) {
+  if (n < 0) return W2T_ERR_ARG;
+  if (n == 0) return W2T_OK;
+  if (!dets || !z) return W2T_ERR_ARG;
+  bbox_to_z_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(dets),
+                                                                    reinterpret_cast<float4 *>(z), n);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
+
+extern "C" int w2t_x_to_bbox(const double *x, int32_t ldx, double *boxes, int32_t n, w2t_stream_t stream) {
+  if (n < 0 || ldx < 4) return W2T_ERR_ARG;
+  if (n == 0) return W2T_OK;
+  if (!x || !boxes) return W2T_ERR_ARG;
+  x_to_bbox_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, ldx, boxes, n);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
 
 extern "C" int w2t_iou_matrix(const float *dets, int32_t D, const double *trks, int32_t T, float *out,
                               w2t_stream_t stream) {

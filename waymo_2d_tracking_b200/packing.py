@@ -214,6 +214,7 @@ class PackedGroups:
     group_offsets: np.ndarray       # [G+1] int32
     rows: np.ndarray                # [N,5] float64: score*weight, left, top, width, height
     max_group: int = 0
+    sub_counts: Optional[np.ndarray] = None   # [G,K] int32: rows of each group per input file (fusion only)
 
 
 def pack_submissions(input_detections, image_ids, category_ids):
@@ -223,14 +224,14 @@ def pack_submissions(input_detections, image_ids, category_ids):
     category_ids = list(category_ids)
     offsets = [0]
     chunks = []
+    sub_counts = []
     total = 0
     for image_id in image_ids:
         per_file = [det.get(image_id) if hasattr(det, 'get') else det[image_id] for det in input_detections]
         for cat in category_ids:
             for det in per_file:
-                if det is None:
-                    continue
-                rows = det.get(cat)
+                rows = None if det is None else det.get(cat)
+                sub_counts.append(len(rows) if rows else 0)
                 if rows:
                     chunks.append(np.asarray(rows, dtype=np.float64).reshape(-1, 5))
                     total += len(rows)
@@ -238,4 +239,28 @@ def pack_submissions(input_detections, image_ids, category_ids):
     rows = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, 5), np.float64)
     offsets = np.asarray(offsets, np.int64)
     max_group = int(np.diff(offsets).max()) if len(offsets) > 1 else 0
-    return PackedGroups(image_ids, category_ids, offsets.astype(np.int32), np.ascontiguousarray(rows), max_group)
+    return PackedGroups(image_ids, category_ids, offsets.astype(np.int32), np.ascontiguousarray(rows), max_group,
+                        np.asarray(sub_counts, np.int32).reshape(len(offsets) - 1, max(len(input_detections), 1)))
+
+
+def image_id_strings(packed):
+    """``'%s/%i/%s' % (segment, frame, camera)`` for every image of ``packed`` (utils.py:51)."""
+    out = []
+    offs = packed.stream_img_offsets
+    for s, (seg, cam) in enumerate(packed.streams):
+        for img in range(int(offs[s]), int(offs[s + 1])):
+            out.append('%s/%i/%s' % (seg, packed.frame_ids[img], cam))
+    return out
+
+
+def rows_to_dicts(packed, res):
+    """Dense device-built output list (``w2t_rows_t``: rows_box/score/id/img/cat, already in the
+    reference's order) -> the list of dicts ``track_sort`` returns (utils.py:52-58)."""
+    ids = image_id_strings(packed)
+    box = np.asarray(res["rows_box"]).tolist()
+    score = np.asarray(res["rows_score"]).tolist()
+    oid = np.asarray(res["rows_id"]).tolist()
+    img = np.asarray(res["rows_img"]).tolist()
+    cat = np.asarray(res["rows_cat"]).tolist()
+    return [{'image_id': ids[i], 'bbox': b, 'score': s, 'category_id': c, 'object_id': '%i' % o}
+            for i, b, s, c, o in zip(img, box, score, cat, oid)]

@@ -111,16 +111,19 @@ def _np(t):
 # ---------------------------------------------------------------------------
 
 def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
-                          n_classes=0, score_thr=None, want_merged=True):
-    """Launch on device tensors; returns device tensors (no synchronisation)."""
+                          n_classes=0, score_thr=None, want_merged=True, box_format=_abi.W2T_BOX_LTWH, top_k=0,
+                          conf_thresh=0.0, want_ensemble=True, hard=False):
+    """Launch on device tensors; returns device tensors (no synchronisation).
+    ``hard`` selects ``w2t_hardnms_groups`` (the ``-m nms`` method) instead of the soft branch."""
     device = d_rows.device
     N = int(d_rows.shape[0])
     out = {
         "merged": torch.empty((N, 5), dtype=torch.float64, device=device) if want_merged else None,
         "src_index": torch.empty(N, dtype=torch.int32, device=device) if want_merged else None,
+        "kept_count": torch.empty(n_groups, dtype=torch.int32, device=device) if want_merged else None,
         "ens_count": torch.empty(n_groups, dtype=torch.int32, device=device),
-        "ens_box": torch.empty((N, 4), dtype=torch.int32, device=device),
-        "ens_score": torch.empty(N, dtype=torch.float64, device=device),
+        "ens_box": torch.empty((N, 4), dtype=torch.int32, device=device) if want_ensemble else None,
+        "ens_score": torch.empty(N, dtype=torch.float64, device=device) if want_ensemble else None,
         "trk_count": None, "trk_box": None, "img_exists": None,
         "status": torch.zeros(1, dtype=torch.int32, device=device),
     }
@@ -139,18 +142,22 @@ def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, so
     prob.iou_thresh, prob.soft_nms_cut, prob.min_score = float(iou_thresh), float(soft_nms_cut), float(min_score)
     prob.n_classes = int(n_classes)
     prob.score_thr = C.cast(thr, C.c_void_p) if thr is not None else None
+    prob.box_format, prob.top_k, prob.conf_thresh = int(box_format), int(top_k), float(conf_thresh)
     res = _abi.NmsResult()
-    for k in ("merged", "src_index", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box", "img_exists"):
+    for k in ("merged", "src_index", "kept_count", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box",
+              "img_exists"):
         setattr(res, k, _ptr(out[k]))
+    entry = lib().w2t_hardnms_groups if hard else lib().w2t_softnms_groups
     with _timed("softnms_kernel"):
-        check(lib().w2t_softnms_groups(C.byref(prob), C.byref(res), int(max_group), _ptr(out["status"]), _stream()),
-              "w2t_softnms_groups")
+        check(entry(C.byref(prob), C.byref(res), int(max_group), _ptr(out["status"]), _stream()),
+              "w2t_hardnms_groups" if hard else "w2t_softnms_groups")
     return out
 
 
 def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_score=0.0, n_classes=0,
-                   score_thr=None, max_group=None, want_merged=True):
-    """Soft-NMS merge of every (image, category) group; NumPy in, NumPy out."""
+                   score_thr=None, max_group=None, want_merged=True, box_format=_abi.W2T_BOX_LTWH, top_k=0,
+                   conf_thresh=0.0, want_ensemble=True, hard=False):
+    """Soft-NMS (or, with ``hard``, plain NMS) merge of every (image, category) group; NumPy in, NumPy out."""
     device = require_cuda()
     offs_np = group_offsets if isinstance(group_offsets, np.ndarray) else None
     n_groups = int(group_offsets.shape[0]) - 1
@@ -161,11 +168,80 @@ def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_sc
     d_offsets = _dev(group_offsets, np.int32, device)
     d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
     out = softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
-                                n_classes, score_thr, want_merged)
+                                n_classes, score_thr, want_merged, box_format, top_k, conf_thresh, want_ensemble,
+                                hard)
     host = {k: _host(v) for k, v in out.items()}
     torch.cuda.current_stream().synchronize()
     check_device_status(int(host["status"][0]), "soft-NMS")
     return {k: _np(v) for k, v in host.items()}
+
+
+def fusion_groups_device(d_offsets, d_rows, d_sub_counts, n_sub, n_groups, max_group, iou_thresh, min_score,
+                         n_classes=0, score_thr=None, want_merged=True, box_format=_abi.W2T_BOX_LTWH,
+                         want_ensemble=True):
+    """``w2t_fusion_groups`` on device tensors; returns device tensors (no synchronisation)."""
+    device = d_rows.device
+    N = int(d_rows.shape[0])
+    out = {
+        "merged": torch.empty((N, 5), dtype=torch.float64, device=device) if want_merged else None,
+        "kept_count": torch.empty(n_groups, dtype=torch.int32, device=device),
+        "ens_count": torch.empty(n_groups, dtype=torch.int32, device=device),
+        "ens_box": torch.empty((N, 4), dtype=torch.int32, device=device) if want_ensemble else None,
+        "ens_score": torch.empty(N, dtype=torch.float64, device=device) if want_ensemble else None,
+        "trk_count": None, "trk_box": None, "img_exists": None,
+        "status": torch.zeros(1, dtype=torch.int32, device=device),
+    }
+    thr = None
+    if score_thr is not None:
+        if n_classes < 1:
+            raise W2TError("score_thr needs n_classes")
+        thr = (C.c_double * n_classes)(*[float(v) for v in score_thr[:n_classes]])
+        out["trk_count"] = torch.empty(n_groups, dtype=torch.int32, device=device)
+        out["trk_box"] = torch.empty((N, 4), dtype=torch.float32, device=device)
+        out["img_exists"] = torch.zeros(max(n_groups // n_classes, 1), dtype=torch.uint8, device=device)
+    prob = _abi.NmsProblem()
+    prob.n_groups = int(n_groups)
+    prob.group_offsets, prob.rows = _ptr(d_offsets), _ptr(d_rows)
+    prob.iou_thresh, prob.soft_nms_cut, prob.min_score = float(iou_thresh), 1.0, float(min_score)
+    prob.n_classes = int(n_classes)
+    prob.score_thr = C.cast(thr, C.c_void_p) if thr is not None else None
+    prob.box_format = int(box_format)
+    res = _abi.NmsResult()
+    for k in ("merged", "kept_count", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box", "img_exists"):
+        setattr(res, k, _ptr(out[k]))
+    with _timed("fusion_kernel"):
+        check(lib().w2t_fusion_groups(C.byref(prob), _ptr(d_sub_counts), int(n_sub), C.byref(res), int(max_group),
+                                      _ptr(out["status"]), _stream()), "w2t_fusion_groups")
+    return out
+
+
+def fusion_groups(group_offsets, rows, sub_counts, iou_thresh=0.5, min_score=0.0, n_classes=0, score_thr=None,
+                  max_group=None, box_format=_abi.W2T_BOX_LTWH):
+    """Weighted box fusion (``merge_detections``) of every group; NumPy in, NumPy out.
+    ``sub_counts[G, K]``: rows of each group that come from each of the K input files."""
+    device = require_cuda()
+    n_groups = int(group_offsets.shape[0]) - 1
+    sub_counts = np.ascontiguousarray(sub_counts, np.int32).reshape(n_groups, -1)
+    if max_group is None:
+        max_group = int(np.diff(np.asarray(group_offsets, np.int64)).max()) if n_groups > 0 else 0
+    out = fusion_groups_device(_dev(group_offsets, np.int32, device), _dev(rows, np.float64, device).reshape(-1, 5),
+                               _dev(sub_counts, np.int32, device), sub_counts.shape[1], n_groups, max_group,
+                               iou_thresh, min_score, n_classes, score_thr, True, box_format)
+    host = {k: _host(v) for k, v in out.items()}
+    torch.cuda.current_stream().synchronize()
+    check_device_status(int(host["status"][0]), "box fusion")
+    return {k: _np(v) for k, v in host.items()}
+
+
+def hardnms_groups(group_offsets, rows, iou_thresh=0.5, top_k=0, max_group=None, box_format=_abi.W2T_BOX_XYXY):
+    """``nms(soft=False)`` of every group: ``keep`` holds, per group from its first row on, the kept
+    input rows (group-local indices) in descending score order; ``kept_count`` how many."""
+    res = softnms_groups(group_offsets, rows, iou_thresh, 1.0, -np.inf, max_group=max_group, box_format=box_format,
+                         top_k=top_k, want_ensemble=False, hard=True)
+    offs = np.asarray(group_offsets, np.int64)
+    local = res["src_index"].astype(np.int64) - np.repeat(offs[:-1], np.diff(offs))
+    res["keep"] = local
+    return res
 
 
 # ---------------------------------------------------------------------------
@@ -361,7 +437,7 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     d_goff = _dev(group_offsets, np.int32, device)
     d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
     nms = softnms_groups_device(d_goff, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, NC,
-                                score_thr, want_merged=False)
+                                score_thr, want_merged=False, want_ensemble=want_ensemble)
     # the plan needs the surviving counts on the host: one small D2H between the stages
     h_cnt, h_exists, h_nms_status = _host(nms["trk_count"], "trk_count"), _host(nms["img_exists"], "img_exists"), \
         _host(nms["status"], "nms_status")
@@ -451,3 +527,23 @@ def kf_update(x, P, dets):
     boxes = torch.zeros((n, 4), dtype=torch.float64, device=device)
     check(lib().w2t_kf_update(_ptr(xd), _ptr(Pd), _ptr(d), _ptr(boxes), n, _stream()), "w2t_kf_update")
     return xd.cpu().numpy(), Pd.cpu().numpy().reshape(n, 7, 7), boxes.cpu().numpy()
+
+
+def bbox_to_z(dets):
+    """``convert_bbox_to_z`` (sort.py:50-62) of n float32 boxes -> float32 [n,4]."""
+    device = require_cuda()
+    d = _dev(np.asarray(dets, np.float32).reshape(-1, 4), np.float32, device)
+    z = torch.zeros_like(d)
+    check(lib().w2t_bbox_to_z(_ptr(d), _ptr(z), int(d.shape[0]), _stream()), "w2t_bbox_to_z")
+    return z.cpu().numpy()
+
+
+def x_to_bbox(x):
+    """``convert_x_to_bbox`` (sort.py:65-75) of n states [n,>=4] -> float64 [n,4]."""
+    device = require_cuda()
+    x = np.ascontiguousarray(x, np.float64)
+    x = x.reshape(-1, x.shape[-1])
+    xd = _dev(x, np.float64, device)
+    boxes = torch.zeros((xd.shape[0], 4), dtype=torch.float64, device=device)
+    check(lib().w2t_x_to_bbox(_ptr(xd), int(xd.shape[1]), _ptr(boxes), int(xd.shape[0]), _stream()), "w2t_x_to_bbox")
+    return boxes.cpu().numpy()

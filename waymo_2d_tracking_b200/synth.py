@@ -262,6 +262,7 @@ def groups_from_scene(scene: Scene, weights: Optional[Sequence[float]] = None, m
         r[:, 1:] = sub.bbox[ok]
         rows.append(r)
         keys.append(sub.image_index[ok].astype(np.int64) * N_CLASSES + (sub.category[ok] - 1))
+    per_file_keys = list(keys)
     rows = np.concatenate(rows) if rows else np.zeros((0, 5))
     keys = np.concatenate(keys) if keys else np.zeros(0, np.int64)
     order = np.argsort(keys, kind='stable')          # stable: keeps (submission, JSON) order inside a group
@@ -270,7 +271,9 @@ def groups_from_scene(scene: Scene, weights: Optional[Sequence[float]] = None, m
     offsets = np.zeros(G + 1, np.int64)
     np.cumsum(counts, out=offsets[1:])
     return PackedGroups(image_ids=None, category_ids=[1, 2, 3, 4], group_offsets=offsets.astype(np.int32),
-                        rows=np.ascontiguousarray(rows[order]), max_group=int(counts.max()) if G else 0)
+                        rows=np.ascontiguousarray(rows[order]), max_group=int(counts.max()) if G else 0,
+                        sub_counts=np.stack([np.bincount(k, minlength=G) for k in per_file_keys], axis=1).astype(np.int32)
+                        if per_file_keys else None)
 
 
 def tracks_from_submission(scene: Scene, sub: Submission, score_thr=DEFAULT_SCORE_THR) -> PackedTracks:

@@ -1,0 +1,72 @@
+"""Drop-in for ``tracking/track.py`` (the SORT CLI, README.md:54):
+
+    python -m waymo_2d_tracking_b200.tracking.track --ground-truth GT/images.json --input ENS.json \\
+           --output tracks.json --max-age=2 --min-hits=0 --score-threshold=0.95,0.6,1.0,0.9
+
+Same flags, same input / output JSON, same prints (the parsed args, every segment id, the
+duration of the tracking loop) as ``track.py:13-50``.  The reference tracks one (segment, camera)
+stream after the other in Python; here all streams are tracked by one launch of the persistent
+CUDA kernel, so the per-segment prints precede the single call.  The ground-truth file is loaded
+(and must exist) like in the reference although its content is not used (``track.py:32-35``).
+"""
+import argparse
+import json
+import time
+import warnings
+from os.path import dirname, join
+
+try:
+    from .utils import read_data_file, track_all
+except ImportError:                     # run as a script from inside tracking/, like the reference
+    from utils import read_data_file, track_all
+
+warnings.simplefilter(action='ignore', category=FutureWarning)
+
+
+def _floats(text):
+    return [float(item) for item in text.split(',')]
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    parser.add_argument("--ground-truth", type=str, default='/data/waymo/det2d/validation/images.json',
+                        help='ground-truth json')
+    parser.add_argument("--input", type=str, default='submission_12545.json', help='submission.json')
+    parser.add_argument("--output", type=str, default='tracker_predictions.json',
+                        help='file to save the tracker predictions')
+    parser.add_argument("--max-age", type=int, default=1, help='SORT max-age')
+    parser.add_argument("--min-hits", type=int, default=0, help='SORT min-hits')
+    parser.add_argument("--score-threshold", type=_floats, default=[0.95, 0.6, 1.0, 0.9],
+                        help='score threshold to track')
+    parser.add_argument("--iou-threshold", type=_floats, default=[0.01, 0.01, 1.0, 0.0],
+                        help='IOU threshold for tracking')
+    parser.add_argument("--segment-id", type=str, help='track only a single segment')
+    return parser
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    print(args)
+
+    predictions = read_data_file(args.input, args.score_threshold)
+    image_id2path = {}
+    ground_truth_dir = dirname(args.ground_truth)
+    with open(args.ground_truth) as fp:
+        for image in json.load(fp):
+            image_id2path[image['id']] = join(ground_truth_dir, image['file_name'])
+
+    if args.segment_id:
+        predictions = {k: v for k, v in predictions.items() if k == args.segment_id}
+
+    start_time = time.time()
+    for segment_id in predictions.keys():
+        print(segment_id)
+    tracked_predictions = track_all(predictions, args.iou_threshold, args.max_age, args.min_hits)
+    print("duration: %.2fs" % (time.time() - start_time))
+    with open(args.output, 'wt') as fp:
+        json.dump(tracked_predictions, fp)
+    return tracked_predictions
+
+
+if __name__ == '__main__':
+    main()
