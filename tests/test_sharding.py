@@ -1,0 +1,93 @@
+"""Multi-process tests of the N > 1 path on CPU (gloo, world_size 2): segment sharding, the id
+rebase by exclusive scan and the host gather reproduce the single-process result exactly.  The
+tracker itself is the oracle port here (no GPU in this container); the GPU variant of the same
+check is ``test_sort_is_invariant_to_sharding`` in test_gpu_parity.py."""
+import json
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+import helpers
+from waymo_2d_tracking_b200 import sharding, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def oracle_track(pred, iou_thr, max_age, min_hits):
+    from oracle import sort_port
+    rows = sort_port.track_all(pred, iou_thr, max_age, min_hits, reset_ids=True)
+    return rows, sort_port.BoxTracker.count
+
+
+def oracle_merge(subs, weights, method, iou_thresh, cut, min_score):
+    from oracle import ensemble_port
+    return ensemble_port.ensemble_all(subs, weights, min_score, iou_thresh, cut) if any(len(s) for s in subs) else []
+
+
+def make_inputs():
+    cfg = synth.SynthConfig(n_segments=3, cameras=("FRONT", "SIDE_LEFT"), n_frames=10, n_submissions=2,
+                            objects_per_frame=18.0, seed=41)
+    scene = synth.make_scene(cfg)
+    return scene, [synth.to_json_list(scene, s) for s in scene.submissions]
+
+
+def worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import sort_port
+    scene, subs = make_inputs()
+    pred = sort_port.group_entries(subs[0], helpers.SCORE_THR)
+    rows, nxt = sharding.track_all_sharded(pred, helpers.IOU_THR, 2, 0, track_fn=oracle_track)
+    ens = sharding.ensemble_sharded(subs, [2, 1], "soft_nms", 0.5, 0.9, 0.01, merge_fn=oracle_merge)
+    before, total = sharding.exclusive_scan_int(rank + 5)
+    assert (before, total) == (sum(r + 5 for r in range(rank)), sum(r + 5 for r in range(world)))
+    if rank == 0:
+        with open(out_path, "w") as fp:
+            json.dump({"rows": [[r['image_id'], r['object_id'], r['category_id'], [float(v) for v in r['bbox']],
+                                 float(r['score'])] for r in rows], "next": nxt, "ens": ens}, fp)
+    else:
+        assert rows is None and ens is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_partition_is_contiguous_and_balanced():
+    for n in (0, 1, 5, 150, 151):
+        for world in (1, 2, 4, 8):
+            blocks = [sharding.block(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_sharded_tracking_and_ensemble_equal_single_process(tmp_path):
+    out = tmp_path / "rank0.json"
+    mp.spawn(worker, args=(2, free_port(), str(out)), nprocs=2, join=True)
+    got = json.loads(out.read_text())
+    from oracle import ensemble_port, sort_port
+    scene, subs = make_inputs()
+    pred = sort_port.group_entries(subs[0], helpers.SCORE_THR)
+    want = sort_port.track_all(pred, helpers.IOU_THR, 2, 0, reset_ids=True)
+    assert got["next"] == sort_port.BoxTracker.count
+    assert len(got["rows"]) == len(want)
+    for a, b in zip(got["rows"], want):
+        assert a[0] == b['image_id'] and a[1] == b['object_id'] and a[2] == b['category_id']
+        assert a[3] == [float(v) for v in b['bbox']] and a[4] == float(b['score'])
+    assert got["ens"] == json.loads(json.dumps(ensemble_port.ensemble_all(subs, [2, 1], 0.01, 0.5, 0.9)))

@@ -31,7 +31,13 @@ from pathlib import Path
 
 import numpy as np
 
-from .. import _abi, packing, runtime
+try:
+    from .. import _abi, packing, runtime, sharding
+except ImportError:                     # imported as top-level `detnet` (PYTHONPATH=.../waymo_2d_tracking_b200)
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
+    from waymo_2d_tracking_b200 import _abi, packing, runtime, sharding
 from .nn.tta import merge_detections, nms_detections
 from .trainer.utils import get_num_workers
 
@@ -254,6 +260,16 @@ def main(argv=None):
         merge_func = partial(nms_detections, iou_thresh=args.iou_thresh, soft=True, soft_nms_cut=args.soft_nms_cut)
 
     submissions = [json.load(Path(f).open()) for f in input_files]
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # launched by torchrun: images sharded over the ranks / GPUs, rank 0 gathers and writes
+        sharding.init_from_env()
+        output_json = sharding.ensemble_sharded(submissions, list(input_weights), args.method, args.iou_thresh,
+                                                args.soft_nms_cut, args.min_score)
+        if output_json is not None:
+            with output_file.open('wt') as fp:
+                json.dump(output_json, fp)
+        return output_json
     groups = pack_submission_lists(submissions, input_weights, args.min_score)
     print('No. Images:', len(groups.image_ids))
     print('No. categories:', len(groups.category_ids))

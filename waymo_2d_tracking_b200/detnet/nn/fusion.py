@@ -3,7 +3,13 @@ the default ``-m weighted_fusion`` of the ensemble CLI).  The arithmetic runs in
 ``csrc/fusion.cu`` (``w2t_fusion_groups``); no CPU fallback."""
 import numpy as np
 
-from ... import _abi, runtime
+try:
+    from ... import _abi, runtime
+except ImportError:                     # imported as top-level `detnet` (PYTHONPATH=.../waymo_2d_tracking_b200)
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))))
+    from waymo_2d_tracking_b200 import _abi, runtime
 
 
 def merge_detections(detections, nms_thresh=0.5):

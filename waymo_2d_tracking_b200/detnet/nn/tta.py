@@ -10,7 +10,13 @@ forward pass and is out of scope.
 """
 import numpy as np
 
-from ... import _abi, runtime
+try:
+    from ... import _abi, runtime
+except ImportError:                     # imported as top-level `detnet` (PYTHONPATH=.../waymo_2d_tracking_b200)
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))))
+    from waymo_2d_tracking_b200 import _abi, runtime
 
 
 def nms_detections(detections, iou_thresh=0.5, soft=False, soft_nms_cut=1):

@@ -15,7 +15,13 @@ ascending sort consumed from the end: of two equal scores the later box is proce
 import numpy as np
 import torch
 
-from ... import _abi, runtime
+try:
+    from ... import _abi, runtime
+except ImportError:                     # imported as top-level `detnet` (PYTHONPATH=.../waymo_2d_tracking_b200)
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))))
+    from waymo_2d_tracking_b200 import _abi, runtime
 
 
 def point_form(boxes):

@@ -1,0 +1,120 @@
+"""Multi-GPU sharding: one process per GPU, streams sharded by segment, no data-path collective.
+
+(segment, camera) streams are independent (a fresh ``MultiClassTrackerSort`` per stream,
+``tracking/utils.py:29``) and so are the (image, category) groups of the ensemble
+(``detnet/ensemble.py:50-58``).  The only thing ranks share is the reference's process-global
+track id counter (``KalmanBoxTracker.count``, ``tracking/sort/sort.py:86``), which never feeds back
+into the dynamics: every rank tracks its contiguous block of segments with local ids and the ids
+are rebased by an exclusive scan of the per-rank creation totals — one int64 per rank, the only
+exchange.  Results are gathered to rank 0 on the host (north star: no NCCL on the data path;
+``torch.distributed`` is used for the rendezvous, the scan and the gather, over gloo or NCCL).
+"""
+import os
+
+import torch.distributed as dist
+
+
+def block(n_items, rank, world):
+    """Contiguous block [lo, hi) of ``n_items`` for ``rank``; sizes differ by at most one."""
+    q, r = divmod(int(n_items), int(world))
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def shard_segments(predictions, rank, world):
+    """This rank's segments of a ``read_data_file`` result, in the file's first-appearance order."""
+    segments = list(predictions.keys())
+    lo, hi = block(len(segments), rank, world)
+    return {seg: predictions[seg] for seg in segments[lo:hi]}
+
+
+def exclusive_scan_int(value, group=None):
+    """Sum of ``value`` over the lower ranks (and the grand total): ``all_gather`` of one int per rank."""
+    world = dist.get_world_size(group)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, int(value), group=group)
+    rank = dist.get_rank(group)
+    return sum(gathered[:rank]), sum(gathered)
+
+
+def init_from_env():
+    """Join the process group ``torchrun`` describes (RANK / WORLD_SIZE / MASTER_*); returns (rank, world).
+    NCCL when a GPU is visible (one rank per GPU, LOCAL_RANK selects it), gloo otherwise."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    if not dist.is_initialized():
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    return dist.get_rank(), dist.get_world_size()
+
+
+def _device_track(predictions, iou_thresholds, max_age, min_hits):
+    """Track a shard on this rank's GPU with ids counted from 0; returns (rows, trackers created)."""
+    from .tracking import utils as trk_utils
+    from .tracking.sort import sort as sort_mod
+    saved = sort_mod.KalmanBoxTracker.count
+    sort_mod.KalmanBoxTracker.count = 0
+    try:
+        rows = trk_utils.track_all(predictions, iou_thresholds, max_age, min_hits)
+        created = sort_mod.KalmanBoxTracker.count
+    finally:
+        sort_mod.KalmanBoxTracker.count = saved
+    return rows, created
+
+
+def track_all_sharded(predictions, iou_thresholds, max_age, min_hits, track_fn=None, group=None, id_base=0):
+    """``tracking.utils.track_all`` over all ranks of ``group``.
+
+    Every rank passes the same ``predictions``; rank r tracks its block of segments
+    (``track_fn(shard, iou_thresholds, max_age, min_hits) -> (rows, n_created)`` with object ids
+    counted from 1, default: the CUDA path), ids are rebased by the exclusive scan of ``n_created``
+    and the rows are gathered in rank order.  Returns ``(rows, next_id_base)`` on rank 0 and
+    ``(None, next_id_base)`` elsewhere; the rows are identical to a single-process run."""
+    if track_fn is None:
+        track_fn = _device_track
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rows, created = track_fn(shard_segments(predictions, rank, world), iou_thresholds, max_age, min_hits)
+    before, total = exclusive_scan_int(created, group)
+    shift = id_base + before
+    if shift:
+        for row in rows:
+            row['object_id'] = '%i' % (int(row['object_id']) + shift)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(rows, gathered, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None, id_base + total
+    merged = []
+    for part in gathered:
+        merged += part
+    return merged, id_base + total
+
+
+def ensemble_sharded(submissions, weights, method, iou_thresh, soft_nms_cut, min_score, merge_fn=None, group=None):
+    """``detnet.ensemble.ensemble_submissions`` over all ranks: images are sharded in sorted order
+    (contiguous blocks, so a segment's images stay together), merged independently and gathered to
+    rank 0 in rank order — the same list a single process produces."""
+    if merge_fn is None:
+        from .detnet import ensemble as ens
+        merge_fn = ens.ensemble_submissions
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    image_ids = sorted(set(d['image_id'] for sub in submissions for d in sub))
+    lo, hi = block(len(image_ids), rank, world)
+    mine = set(image_ids[lo:hi])
+    # the weight normalisation (ensemble.py:125-126) must see all weights; the category set only
+    # matters for output order, which is ascending category either way
+    part = [[d for d in sub if d['image_id'] in mine] for sub in submissions]
+    rows = merge_fn(part, weights, method, iou_thresh, soft_nms_cut, min_score)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(rows, gathered, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+    merged = []
+    for part_rows in gathered:
+        merged += part_rows
+    return merged

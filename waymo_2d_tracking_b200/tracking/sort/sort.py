@@ -21,7 +21,10 @@ import numpy as np
 
 try:
     from ... import runtime
-except ImportError:                     # script-style import with tracking/ on sys.path
+except ImportError:                     # imported as top-level `tracking` / `sort` (reference-style sys.path)
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))))
     from waymo_2d_tracking_b200 import runtime
 
 

@@ -6,19 +6,21 @@
 Same flags, same input / output JSON, same prints (the parsed args, every segment id, the
 duration of the tracking loop) as ``track.py:13-50``.  The reference tracks one (segment, camera)
 stream after the other in Python; here all streams are tracked by one launch of the persistent
-CUDA kernel, so the per-segment prints precede the single call.  The ground-truth file is loaded
+CUDA kernel, so the per-segment prints precede the single call.  Under ``torchrun`` (WORLD_SIZE > 1)
+segments are sharded over the ranks / GPUs and rank 0 writes the output (``sharding.py``).  The ground-truth file is loaded
 (and must exist) like in the reference although its content is not used (``track.py:32-35``).
 """
 import argparse
 import json
+import os
 import time
 import warnings
 from os.path import dirname, join
 
 try:
-    from .utils import read_data_file, track_all
+    from .utils import read_data_file, track_all, sharding
 except ImportError:                     # run as a script from inside tracking/, like the reference
-    from utils import read_data_file, track_all
+    from utils import read_data_file, track_all, sharding
 
 warnings.simplefilter(action='ignore', category=FutureWarning)
 
@@ -61,7 +63,15 @@ def main(argv=None):
     start_time = time.time()
     for segment_id in predictions.keys():
         print(segment_id)
-    tracked_predictions = track_all(predictions, args.iou_threshold, args.max_age, args.min_hits)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # launched by torchrun: one rank per GPU, segments sharded, rank 0 gathers and writes
+        sharding.init_from_env()
+        tracked_predictions, _ = sharding.track_all_sharded(predictions, args.iou_threshold, args.max_age,
+                                                            args.min_hits)
+        if tracked_predictions is None:
+            return None
+    else:
+        tracked_predictions = track_all(predictions, args.iou_threshold, args.max_age, args.min_hits)
     print("duration: %.2fs" % (time.time() - start_time))
     with open(args.output, 'wt') as fp:
         json.dump(tracked_predictions, fp)

@@ -12,13 +12,13 @@ import warnings
 import numpy as np
 
 try:                                    # package import (python -m waymo_2d_tracking_b200.tracking.track)
-    from .. import packing, runtime
+    from .. import packing, runtime, sharding
     from .sort import sort as _sort
-except ImportError:                     # script-style import (python track.py inside tracking/)
-    import os
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-    from waymo_2d_tracking_b200 import packing, runtime
+except ImportError:                     # `python track.py` inside tracking/, or top-level `tracking` package
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
+    from waymo_2d_tracking_b200 import packing, runtime, sharding
     from waymo_2d_tracking_b200.tracking.sort import sort as _sort
 
 warnings.simplefilter(action='ignore', category=FutureWarning)
