@@ -14,7 +14,8 @@ A "step" is one pass of the hot path over that batch:
   value : inputs resident in HBM -> soft-NMS kernel -> (counts to host, launch plan) ->
           SORT kernel -> id scan + dense rows, all outputs left in HBM;
   e2e   : the same through the public API with HOST buffers: pinned host arrays -> H2D ->
-          the same kernels -> D2H of the dense output rows and ids, every step.
+          the same kernels -> D2H of the dense output rows and ids, every step; the streams are
+          cut into --chunks blocks so that copies and kernels of successive blocks overlap.
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -48,6 +49,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--cpu-sample-frames", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=6, help="pipeline depth of the end-to-end leg")
     return ap.parse_args()
 
 
@@ -203,10 +205,13 @@ def main():
               iou_thresholds=IOU_THR, max_age=MAX_AGE, min_hits=MIN_HITS, max_group=groups.max_group, **NMS)
 
     def step_device():
-        return runtime.ensemble_and_track(d_offs, d_rows, to_host=False, want_ensemble=False, raw=False, **kw)
+        # inputs resident in HBM, outputs left in HBM, no host round trip inside the step
+        return runtime.ensemble_and_track(d_offs, d_rows, to_host=False, want_ensemble=False, raw=False,
+                                          host_group_offsets=groups.group_offsets, **kw)
 
     def step_e2e():
-        return runtime.ensemble_and_track(h_offs, h_rows, to_host=True, want_ensemble=False, raw=False, **kw)
+        # public API with HOST buffers: chunked so that H2D, kernels and D2H overlap (runtime.py)
+        return runtime.ensemble_and_track_pipelined(h_offs, h_rows, n_chunks=args.chunks, **kw)
 
     def timed(fn, steps):
         barrier()
@@ -243,7 +248,13 @@ def main():
     value = total_frames * K / (ms_dev / 1e3)
     e2e_value = total_frames * K / (ms_e2e / 1e3)
     n_in = int(groups.rows.shape[0])
-    n_trk = int(out["n_trk"])
+    torch.cuda.synchronize()
+    for stage in ("nms", "trk"):
+        if int(out[stage]["status"].item()) != 0:
+            raise SystemExit("bench.py: %s kernel reported status %d" % (stage, int(out[stage]["status"].item())))
+    n_trk = int(out["nms"]["trk_count"].sum().item())
+    if int(out["rows"]["totals"][1].item()) != int(out_e2e["n_rows"]):
+        raise SystemExit("bench.py: device-resident and end-to-end legs disagree on the number of rows")
     n_out = int(out_e2e["n_rows"])
     h2d = int(h_rows.numel() * 8 + h_offs.numel() * 4)
     d2h = int(out_e2e["d2h_bytes"])

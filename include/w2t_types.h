@@ -99,6 +99,8 @@ typedef struct w2t_rows_t {
   int32_t *category;   /* [capacity] category_id                                              */
   int64_t *totals;     /* [2] device: trackers created (next id = id_base + totals[0]), rows  */
   int64_t  capacity;
+  int32_t  image_base; /* added to every image index written: lets a caller finalize a shard   */
+                       /*   (chunk of streams with shard-local image indices) of a larger job   */
 } w2t_rows_t;
 
 /* layout of the four box columns of w2t_nms_problem_t.rows */

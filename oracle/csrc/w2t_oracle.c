@@ -220,6 +220,15 @@ typedef struct {
   int *path; /* (n+m) x 2 */
 } hung_t;
 
+/* debug counters (scripts/munkres_stats.py): per size bucket of m — calls, step-4 iterations,
+ * augmentations, step-6 rounds, sum of n*m, stars after the greedy step */
+static long long g_stats[8][6];
+static int g_bucket = 0;
+void w2t_oracle_munkres_stats(long long *out, int reset) {
+  if (out) memcpy(out, g_stats, sizeof(g_stats));
+  if (reset) memset(g_stats, 0, sizeof(g_stats));
+}
+
 static int hung_step3(hung_t *s) {
   int stars = 0;
   for (int r = 0; r < s->n; r++)
@@ -239,6 +248,7 @@ static int hung_step4(hung_t *s) {
         if (row[c] == 0.0f && s->col_unc[c]) { fr = r; fc = c; break; }
     }
     if (fr < 0) return 6;
+    g_stats[g_bucket][1]++;
     s->mark[(size_t)fr * m + fc] = 2;
     int sc = -1;
     for (int c = 0; c < m; c++)
@@ -275,6 +285,7 @@ static int hung_step5(hung_t *s) {
   memset(s->col_unc, 1, m);
   for (size_t i = 0; i < (size_t)n * m; i++)
     if (s->mark[i] == 2) s->mark[i] = 0;
+  g_stats[g_bucket][2]++;
   return 3;
 }
 
@@ -283,6 +294,7 @@ static int hung_step6(hung_t *s) {
   int any_r = 0, any_c = 0;
   for (int r = 0; r < n; r++) any_r |= s->row_unc[r];
   for (int c = 0; c < m; c++) any_c |= s->col_unc[c];
+  g_stats[g_bucket][3]++;
   if (any_r && any_c) {
     float minval = INFINITY;
     for (int r = 0; r < n; r++) {
@@ -340,6 +352,10 @@ int w2t_oracle_linear_assignment(const float *cost, int D, int T, int32_t *pairs
       }
   memset(s.row_unc, 1, n);
   memset(s.col_unc, 1, m);
+  g_bucket = m <= 16 ? 0 : m <= 32 ? 1 : m <= 64 ? 2 : m <= 128 ? 3 : m <= 256 ? 4 : m <= 512 ? 5 : 6;
+  g_stats[g_bucket][0]++;
+  g_stats[g_bucket][4] += (long long)n * m;
+  for (size_t i = 0; i < (size_t)n * m; i++) g_stats[g_bucket][5] += (s.mark[i] == 1);
   int step = 3;
   while (step) {
     switch (step) {

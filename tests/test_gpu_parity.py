@@ -301,3 +301,21 @@ def test_pipeline_matches_reference_golden_end_to_end():
     got = T.rows_in_stream_order(packed, res, scene, order)
     want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
     helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)
+
+
+def test_pipelined_chunks_equal_the_single_pass():
+    # chunked H2D / kernels / D2H overlap (runtime.ensemble_and_track_pipelined) changes nothing in the result
+    cfg = synth.SynthConfig(n_segments=3, cameras=("FRONT", "SIDE_LEFT", "SIDE_RIGHT"), n_frames=30, n_submissions=3,
+                            objects_per_frame=40.0, seed=44)
+    scene = synth.make_scene(cfg)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    args = (groups.group_offsets, groups.rows, scene.stream_img_offsets, scene.cam_wh(), 4, 0.5, 0.9, 0.01,
+            helpers.SCORE_THR, helpers.IOU_THR, 2, 0)
+    want = runtime.ensemble_and_track(*args, max_group=groups.max_group, want_ensemble=False, raw=False, id_base=7)
+    want = {k: np.array(want[k]) for k in ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat")} | \
+        {"n_rows": want["n_rows"], "id_next": want["id_next"]}
+    for n_chunks in (1, 2, 4, 9, 50):
+        got = runtime.ensemble_and_track_pipelined(*args, max_group=groups.max_group, id_base=7, n_chunks=n_chunks)
+        assert got["n_rows"] == want["n_rows"] and got["id_next"] == want["id_next"]
+        for k in ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat"):
+            np.testing.assert_array_equal(got[k], want[k])

@@ -73,6 +73,7 @@ class Rows(C.Structure):
         ("category", _p),
         ("totals", _p),
         ("capacity", C.c_int64),
+        ("image_base", C.c_int32),
     ]
 
 

@@ -29,6 +29,7 @@ struct FinParams {
   int64_t *rows_id;
   int32_t *rows_img, *rows_cat;
   int64_t rows_cap;
+  int32_t image_base;
 };
 
 // One block per stream.
@@ -107,7 +108,7 @@ __global__ void rows_kernel(const FinParams P) {
       P.rows_score[dst] = P.out_score[src];
       const int bg = P.out_birth[2 * src], bk = P.out_birth[2 * src + 1];
       P.rows_id[dst] = P.id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
-      P.rows_img[dst] = img;
+      P.rows_img[dst] = img + P.image_base;
       P.rows_cat[dst] = c + 1;
     }
   }
@@ -166,6 +167,7 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
   P.rows_img = rows->image;
   P.rows_cat = rows->category;
   P.rows_cap = rows->capacity;
+  P.image_base = rows->image_base;
   order_kernel<<<P.n_streams, 256, 0, st>>>(P);
   scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_created, P.scan_created, n_groups, P.totals);
   scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_count, P.scan_count, n_groups, P.totals + 1);

@@ -112,11 +112,17 @@ def _np(t):
 
 def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
                           n_classes=0, score_thr=None, want_merged=True, box_format=_abi.W2T_BOX_LTWH, top_k=0,
-                          conf_thresh=0.0, want_ensemble=True, hard=False):
+                          conf_thresh=0.0, want_ensemble=True, hard=False, out=None):
     """Launch on device tensors; returns device tensors (no synchronisation).
-    ``hard`` selects ``w2t_hardnms_groups`` (the ``-m nms`` method) instead of the soft branch."""
+    ``hard`` selects ``w2t_hardnms_groups`` (the ``-m nms`` method) instead of the soft branch.
+    ``out``: preallocated result tensors to write into (all keys below; rows are indexed by the
+    values of ``d_offsets``, so ``d_rows`` and the row outputs may be full arrays of a larger job
+    while ``d_offsets`` and the per-group outputs are a chunk's slices)."""
     device = d_rows.device
     N = int(d_rows.shape[0])
+    if out is not None:
+        return _launch_nms(dict(out), d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
+                           n_classes, score_thr, box_format, top_k, conf_thresh, hard)
     out = {
         "merged": torch.empty((N, 5), dtype=torch.float64, device=device) if want_merged else None,
         "src_index": torch.empty(N, dtype=torch.int32, device=device) if want_merged else None,
@@ -127,14 +133,21 @@ def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, so
         "trk_count": None, "trk_box": None, "img_exists": None,
         "status": torch.zeros(1, dtype=torch.int32, device=device),
     }
-    thr = None
     if score_thr is not None:
         if n_classes < 1:
             raise W2TError("score_thr needs n_classes")
-        thr = (C.c_double * n_classes)(*[float(v) for v in score_thr[:n_classes]])
         out["trk_count"] = torch.empty(n_groups, dtype=torch.int32, device=device)
         out["trk_box"] = torch.empty((N, 4), dtype=torch.float32, device=device)
         out["img_exists"] = torch.zeros(max(n_groups // n_classes, 1), dtype=torch.uint8, device=device)
+    return _launch_nms(out, d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, n_classes,
+                       score_thr, box_format, top_k, conf_thresh, hard)
+
+
+def _launch_nms(out, d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, n_classes,
+                score_thr, box_format, top_k, conf_thresh, hard):
+    thr = None
+    if score_thr is not None:
+        thr = (C.c_double * n_classes)(*[float(v) for v in score_thr[:n_classes]])
     prob = _abi.NmsProblem()
     prob.n_groups = int(n_groups)
     prob.group_offsets = _ptr(d_offsets)
@@ -146,7 +159,7 @@ def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, so
     res = _abi.NmsResult()
     for k in ("merged", "src_index", "kept_count", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box",
               "img_exists"):
-        setattr(res, k, _ptr(out[k]))
+        setattr(res, k, _ptr(out.get(k)))
     entry = lib().w2t_hardnms_groups if hard else lib().w2t_softnms_groups
     with _timed("softnms_kernel"):
         check(entry(C.byref(prob), C.byref(res), int(max_group), _ptr(out["status"]), _stream()),
@@ -267,8 +280,9 @@ def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age):
 
 
 def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, d_exists, d_cam,
-                      iou_thresholds, max_age, min_hits, plan, final_cap=0):
-    """Launch on device tensors; ``plan`` = host arrays from :func:`make_plan`.  No synchronisation."""
+                      iou_thresholds, max_age, min_hits, plan, final_cap=0, out=None):
+    """Launch on device tensors; ``plan`` = host arrays from :func:`make_plan`.  No synchronisation.
+    ``out``: preallocated result tensors (keys of ``w2t_sort_result_t`` + ``status``) to write into."""
     device = d_box.device
     NC = int(n_classes)
     if len(iou_thresholds) < NC:
@@ -276,7 +290,7 @@ def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, 
     n_groups = int(d_start.shape[0])
     N = int(d_box.shape[0])
     nq = n_streams * NC
-    out = {
+    out = dict(out) if out is not None else {
         "out_box": torch.empty((N, 4), dtype=torch.float64, device=device),
         "out_score": torch.empty(N, dtype=torch.float64, device=device),
         "out_birth": torch.empty((N, 2), dtype=torch.int32, device=device),
@@ -305,7 +319,7 @@ def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, 
     cplan.ws_bytes = plan["ws_bytes"]
     res = _abi.SortResult()
     for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img", "final_count", "final_state"):
-        setattr(res, k, _ptr(out[k]))
+        setattr(res, k, _ptr(out.get(k)))
     res.final_cap = int(final_cap)
     with _timed("sort_track_kernel"):
         check(lib().w2t_sort_track(C.byref(prob), C.byref(cplan), C.byref(res), _ptr(workspace), _ptr(out["status"]),
@@ -330,13 +344,15 @@ def assign_ids(n_streams, n_classes, h_offsets, h_start, h_out_count, h_created,
     return ids, int(nxt.value)
 
 
-def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank, id_base, rows_cap):
-    """Device-side ids + dense rows (``w2t_sort_finalize``) on the tensors ``sort_track_device`` returned."""
+def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank, id_base, rows_cap, image_base=0,
+                    rows=None):
+    """Device-side ids + dense rows (``w2t_sort_finalize``) on the tensors ``sort_track_device`` returned.
+    ``rows``: preallocated output tensors (same keys) to write into instead of allocating."""
     device = trk["out_box"].device
     NC = int(n_classes)
     n_groups = int(d_start.shape[0])
     cap = max(int(rows_cap), 1)
-    rows = {
+    rows = rows if rows is not None else {
         "rows_box": torch.empty((cap, 4), dtype=torch.float64, device=device),
         "rows_score": torch.empty(cap, dtype=torch.float64, device=device),
         "rows_id": torch.empty(cap, dtype=torch.int64, device=device),
@@ -356,6 +372,7 @@ def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank,
     crows.box, crows.score, crows.object_id = _ptr(rows["rows_box"]), _ptr(rows["rows_score"]), _ptr(rows["rows_id"])
     crows.image, crows.category, crows.totals = _ptr(rows["rows_img"]), _ptr(rows["rows_cat"]), _ptr(rows["totals"])
     crows.capacity = cap
+    crows.image_base = int(image_base)
     with _timed("finalize_kernels"):
         check(lib().w2t_sort_finalize(C.byref(prob), C.byref(res), _ptr(d_class_rank), int(id_base), n_groups,
                                       _ptr(ws), C.byref(crows), _stream()), "w2t_sort_finalize")
@@ -419,11 +436,14 @@ def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_ba
 
 def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh, soft_nms_cut,
                        min_score, score_thr, iou_thresholds, max_age, min_hits, max_group=None,
-                       want_ensemble=True, id_base=0, raw=True, to_host=True):
+                       want_ensemble=True, id_base=0, raw=True, to_host=True, host_group_offsets=None):
     """Groups must be laid out as g = img * n_classes + (category - 1) with the images of a
     stream contiguous and in frame order (``synth.groups_from_scene`` / ``packing``).
 
-    ``group_offsets`` / ``rows`` may be NumPy, CPU (ideally pinned) or CUDA tensors."""
+    ``group_offsets`` / ``rows`` may be NumPy, CPU (ideally pinned) or CUDA tensors.
+    ``host_group_offsets``: host copy of ``group_offsets`` when those live on the device; with it
+    (``to_host=False`` only) the SORT launch plan is computed from the INPUT group sizes — an upper
+    bound of what survives the ensemble — and the call never synchronises with the device."""
     device = require_cuda()
     NC = int(n_classes)
     h_offsets = np.ascontiguousarray(stream_img_offsets, np.int32)
@@ -438,14 +458,24 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
     nms = softnms_groups_device(d_goff, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, NC,
                                 score_thr, want_merged=False, want_ensemble=want_ensemble)
+    d_offsets = _dev(h_offsets, np.int32, device)
+    d_start = d_goff[:-1]
+    if host_group_offsets is not None and not to_host and n_groups:
+        # no round trip: capacities from the input sizes; W2T_ERR_CAPACITY (only possible when the
+        # ensemble drops every box of an image) is left in trk["status"] for the caller to check
+        sizes = np.diff(np.asarray(host_group_offsets)).astype(np.int32)
+        exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
+        plan = make_plan(S, NC, h_offsets, sizes, exists_ub, max_age)
+        trk = sort_track_device(S, NC, d_offsets, d_start, nms["trk_count"], nms["trk_box"], nms["img_exists"],
+                                _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan)
+        out_rows = finalize_device(S, NC, d_offsets, d_start, trk, None, id_base, int(d_rows.shape[0]))
+        return {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": None, "launches": 6}
     # the plan needs the surviving counts on the host: one small D2H between the stages
     h_cnt, h_exists, h_nms_status = _host(nms["trk_count"], "trk_count"), _host(nms["img_exists"], "img_exists"), \
         _host(nms["status"], "nms_status")
     torch.cuda.current_stream().synchronize()
     check_device_status(int(h_nms_status[0]), "soft-NMS")
     plan = make_plan(S, NC, h_offsets, h_cnt.numpy(), h_exists.numpy(), max_age)
-    d_offsets = _dev(h_offsets, np.int32, device)
-    d_start = d_goff[:-1]
     trk = sort_track_device(S, NC, d_offsets, d_start, nms["trk_count"], nms["trk_box"], nms["img_exists"],
                             _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan)
     out_rows = finalize_device(S, NC, d_offsets, d_start, trk, None, id_base, int(h_cnt.numpy().sum(dtype=np.int64)))
@@ -465,6 +495,195 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
         res["det_start"] = np.ascontiguousarray(go_np[:-1], np.int32)
         res["ids"], _ = assign_ids(S, NC, h_offsets, res["det_start"], res["out_count"], res["created"],
                                    res["first_img"], None, res["out_birth"], id_base)
+    return res
+
+
+# ---------------------------------------------------------------------------
+# ensemble -> SORT, chunked and pipelined: H2D, kernels and D2H of successive chunks overlap
+# ---------------------------------------------------------------------------
+
+def _pinned_pool(tag, dtype, n, keep=0, quiesce=None):
+    """Persistent pinned buffer of at least ``n`` elements; the first ``keep`` survive a regrow
+    (``quiesce`` is called first so that no copy into the old buffer is still in flight)."""
+    key = (tag, dtype)
+    pool = _PINNED.get(key)
+    if pool is None or pool.numel() < n:
+        grown = torch.empty(max(int(n * 1.25), 1), dtype=dtype, pin_memory=True)
+        if pool is not None and keep:
+            if quiesce is not None:
+                quiesce()
+            grown[:keep].copy_(pool[:keep])
+        _PINNED[key] = pool = grown
+    return pool
+
+
+_STREAMS = {}
+
+
+def _side_streams(device):
+    key = (device.index, "io")
+    if key not in _STREAMS:
+        _STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return _STREAMS[key]
+
+
+def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
+    """Split the streams into at most ``n_chunks`` contiguous blocks with about equal input rows."""
+    S = len(h_offsets) - 1
+    rows_at_stream = group_offsets_np[np.asarray(h_offsets, np.int64) * NC].astype(np.int64)
+    total = int(rows_at_stream[-1])
+    n_chunks = max(1, min(int(n_chunks), S))
+    cuts = [0]
+    for k in range(1, n_chunks):
+        s = int(np.searchsorted(rows_at_stream, total * k / n_chunks, side="left"))
+        s = min(max(s, cuts[-1] + 1), S - (n_chunks - k))
+        cuts.append(s)
+    cuts.append(S)
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh,
+                                 soft_nms_cut, min_score, score_thr, iou_thresholds, max_age, min_hits,
+                                 max_group=None, id_base=0, n_chunks=6):
+    """Host buffers in, dense host rows out (``rows_box/score/id/img/cat``), the same result as
+    :func:`ensemble_and_track` — with the streams cut into chunks so that the host->device copy of
+    chunk k+1, the kernels of chunk k and the device->host copy of chunk k-1 run concurrently
+    (three CUDA streams; PCIe is full duplex).
+
+    No mid-pipeline round trip: the launch plan of the SORT stage (slab capacities) is computed on
+    the host from the INPUT group sizes, an upper bound of what survives the ensemble.  (An image
+    all of whose boxes the ensemble drops is treated by the tracker as absent, which can lengthen
+    the window the bound assumes; the kernel then reports W2T_ERR_CAPACITY and the call falls back
+    to the exact, unpipelined path.)"""
+    device = require_cuda()
+    NC = int(n_classes)
+    h_offsets = np.ascontiguousarray(stream_img_offsets, np.int32)
+    S = len(h_offsets) - 1
+    t_goff = group_offsets if torch.is_tensor(group_offsets) else torch.from_numpy(np.ascontiguousarray(group_offsets, np.int32))
+    t_rows = rows if torch.is_tensor(rows) else torch.from_numpy(np.ascontiguousarray(rows, np.float64))
+    t_rows = t_rows.reshape(-1, 5)
+    go_np = t_goff.numpy()
+    G = int(go_np.shape[0]) - 1
+    N = int(t_rows.shape[0])
+    if G != int(h_offsets[-1]) * NC:
+        raise W2TError("group layout does not match stream_img_offsets * n_classes")
+    if S == 0 or G == 0:
+        return ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, NC, iou_thresh, soft_nms_cut,
+                                  min_score, score_thr, iou_thresholds, max_age, min_hits, max_group, False, id_base,
+                                  raw=False)
+    sizes = np.diff(go_np).astype(np.int32)
+    if max_group is None:
+        max_group = int(sizes.max())
+    exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
+    chunks = _chunk_bounds(h_offsets, go_np, NC, n_chunks)
+    cam = np.ascontiguousarray(cam_wh, np.float64).reshape(S, 2)
+
+    main = torch.cuda.current_stream()
+    s_in, s_out = _side_streams(device)
+    i32, f64 = torch.int32, torch.float64
+    n_img = int(h_offsets[-1])
+    d_goff = torch.empty(G + 1, dtype=i32, device=device)
+    d_rows = torch.empty((N, 5), dtype=f64, device=device)
+    nms_out = {"ens_count": torch.empty(G, dtype=i32, device=device),
+               "trk_count": torch.empty(G, dtype=i32, device=device),
+               "trk_box": torch.empty((N, 4), dtype=torch.float32, device=device),
+               "img_exists": torch.zeros(n_img, dtype=torch.uint8, device=device),
+               "status": torch.zeros(1, dtype=i32, device=device)}
+    trk_out = {"out_box": torch.empty((N, 4), dtype=f64, device=device), "out_score": torch.empty(N, dtype=f64, device=device),
+               "out_birth": torch.empty((N, 2), dtype=i32, device=device), "out_count": torch.empty(G, dtype=i32, device=device),
+               "created": torch.empty(G, dtype=i32, device=device), "first_img": torch.empty(S * NC, dtype=i32, device=device),
+               "status": torch.zeros(1, dtype=i32, device=device)}
+    d_cam = _dev(cam, np.float64, device)
+    for t in (d_goff, d_rows):
+        t.record_stream(s_in)
+
+    # 1. all host->device copies are queued up front on the copy-in stream, chunk by chunk
+    h2d_done = []
+    with torch.cuda.stream(s_in):
+        s_in.wait_stream(main)
+        for (s0, s1) in chunks:
+            g0, g1 = int(h_offsets[s0]) * NC, int(h_offsets[s1]) * NC
+            r0, r1 = int(go_np[g0]), int(go_np[g1])
+            d_goff[g0:g1 + 1].copy_(t_goff[g0:g1 + 1], non_blocking=True)
+            d_rows[r0:r1].copy_(t_rows[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+            h2d_done.append(ev)
+
+    # 2. kernels per chunk on the main stream; results of chunk k-1 go home while chunk k computes
+    pending = None            # (chunk index, dense rows, totals on host, event)
+    host = {}
+    n_rows_total, created_total, n_trk_rows = 0, 0, 0
+    keep_alive = []
+    d2h_bytes = 0
+
+    def drain(p):
+        nonlocal n_rows_total, created_total, d2h_bytes
+        rows_k, h_tot, ev = p
+        ev.synchronize()
+        created_k, n_k = int(h_tot[0]), int(h_tot[1])
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev)
+            for key in _ROW_KEYS[:-1]:
+                src = rows_k[key][:n_k]
+                width = src.shape[1] if src.dim() > 1 else 1
+                pool = _pinned_pool("pipe_" + key, src.dtype, (n_rows_total + n_k) * width, n_rows_total * width,
+                                    quiesce=s_out.synchronize)
+                dst = pool[n_rows_total * width:(n_rows_total + n_k) * width].view(src.shape)
+                dst.copy_(src, non_blocking=True)
+                src.record_stream(s_out)
+                d2h_bytes += src.numel() * src.element_size()
+        n_rows_total += n_k
+        created_total += created_k
+        return created_k
+
+    for k, (s0, s1) in enumerate(chunks):
+        img0, img1 = int(h_offsets[s0]), int(h_offsets[s1])
+        g0, g1 = img0 * NC, img1 * NC
+        ns = s1 - s0
+        loc_offsets = (h_offsets[s0:s1 + 1] - h_offsets[s0]).astype(np.int32)
+        plan = make_plan(ns, NC, loc_offsets, sizes[g0:g1], exists_ub[img0:img1], max_age)
+        main.wait_event(h2d_done[k])
+        nms_k = {"ens_count": nms_out["ens_count"][g0:g1], "trk_count": nms_out["trk_count"][g0:g1],
+                 "trk_box": nms_out["trk_box"], "img_exists": nms_out["img_exists"][img0:img1],
+                 "status": nms_out["status"]}
+        softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score, NC,
+                              score_thr, out=nms_k)
+        trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"], "out_birth": trk_out["out_birth"],
+                 "out_count": trk_out["out_count"][g0:g1], "created": trk_out["created"][g0:g1],
+                 "first_img": trk_out["first_img"][s0 * NC:s1 * NC], "status": trk_out["status"]}
+        d_loc = _dev(loc_offsets, np.int32, device)
+        trk = sort_track_device(ns, NC, d_loc, d_goff[g0:g1], nms_k["trk_count"], nms_out["trk_box"],
+                                nms_k["img_exists"], d_cam[s0:s1], iou_thresholds, max_age, min_hits, plan, out=trk_k)
+        keep_alive.append(trk["_keepalive"])
+        if pending is not None:            # ids of this chunk continue after the previous chunk's
+            drain(pending)
+        rows_cap = int(go_np[g1] - go_np[g0])
+        rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk, None, id_base + created_total, rows_cap,
+                                 image_base=img0)
+        keep_alive.append(rows_k["_keepalive"])
+        h_tot = _pinned_pool("pipe_totals", torch.int64, 2 * len(chunks))[2 * k:2 * k + 2]
+        h_tot.copy_(rows_k["totals"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        pending = (rows_k, h_tot, ev)
+    drain(pending)
+    h_status = _host(torch.stack([nms_out["status"][0], trk_out["status"][0]]), "pipe_status")
+    main.wait_stream(s_out)
+    main.synchronize()
+    if int(h_status[1]) == _abi.W2T_ERR_CAPACITY:
+        return ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, NC, iou_thresh, soft_nms_cut,
+                                  min_score, score_thr, iou_thresholds, max_age, min_hits, max_group, False, id_base,
+                                  raw=False)
+    check_device_status(int(h_status[0]), "soft-NMS")
+    check_device_status(int(h_status[1]), "SORT")
+    res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 16 * len(chunks) + 8,
+           "launches": 6 * len(chunks), "n_chunks": len(chunks)}
+    for key in _ROW_KEYS[:-1]:
+        pool = _PINNED[("pipe_" + key, {"rows_box": f64, "rows_score": f64, "rows_id": torch.int64,
+                                         "rows_img": i32, "rows_cat": i32}[key])]
+        width = 4 if key == "rows_box" else 1
+        res[key] = pool[:n_rows_total * width].view((n_rows_total, 4) if width == 4 else (n_rows_total,)).numpy()
     return res
 
 
