@@ -97,7 +97,11 @@ typedef struct w2t_rows_t {
   int64_t *object_id;  /* [capacity] KalmanBoxTracker.id + 1 (sort.py:288)                    */
   int32_t *image;      /* [capacity] image index                                              */
   int32_t *category;   /* [capacity] category_id                                              */
-  int64_t *totals;     /* [2] device: trackers created (next id = id_base + totals[0]), rows  */
+  int64_t *totals;     /* [3] device: trackers created, rows written, next id base            */
+                       /*   (= id_base + *id_base_device + created)                           */
+  const int64_t *id_base_device; /* optional device int64 added to id_base: chains the ids of  */
+                       /*   successive calls (pass the previous call's totals + 2) without a   */
+                       /*   host round trip                                                    */
   int64_t  capacity;
   int32_t  image_base; /* added to every image index written: lets a caller finalize a shard   */
                        /*   (chunk of streams with shard-local image indices) of a larger job   */

@@ -20,3 +20,5 @@ for c, cname in enumerate(["vehicle", "pedestrian", "sign", "cyclist"]):
     tot = tc[:, 1:11].sum(1).mean()
     print("%-10s frames %.0f  total %.0f kcyc/substream = %.1f us/frame @1.9GHz" % (cname, frames, tot / 1e3, tot / max(frames, 1) / 1900))
     print("   " + "  ".join("%s %.1f%%" % (names[i], 100 * tc[:, i].mean() / tot) for i in range(1, 11)))
+    print("   per frame: step-6 rounds %.2f  step-4 iterations %.2f  solves %.2f" % (
+        tc[:, 11].mean() / max(frames, 1), tc[:, 12].mean() / max(frames, 1), tc[:, 13].mean() / max(frames, 1)))

@@ -72,6 +72,7 @@ class Rows(C.Structure):
         ("image", _p),
         ("category", _p),
         ("totals", _p),
+        ("id_base_device", _p),
         ("capacity", C.c_int64),
         ("image_base", C.c_int32),
     ]

@@ -23,8 +23,9 @@ struct FinParams {
   const double *out_box, *out_score;
   const int32_t *out_birth;
   int64_t id_base;
+  const int64_t *id_base_dev;
   int32_t *perm_created, *perm_count, *scan_created, *scan_count, *stream_rank;
-  int64_t *totals;  // [0] ids created, [1] dense rows
+  int64_t *totals;  // [0] ids created, [1] dense rows, [2] next id base
   double *rows_box, *rows_score;
   int64_t *rows_id;
   int32_t *rows_img, *rows_cat;
@@ -92,6 +93,8 @@ __global__ void rows_kernel(const FinParams P) {
   const int s = blockIdx.x, NC = P.n_classes;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int img0 = P.stream_img_offsets[s], img1 = P.stream_img_offsets[s + 1];
+  const int64_t id_base = P.id_base + (P.id_base_dev ? *P.id_base_dev : 0);
+  if (s == 0 && threadIdx.x == 0) P.totals[2] = id_base + P.totals[0];
   for (int g = img0 * NC + warp; g < img1 * NC; g += nwarp) {
     const int cnt = P.out_count[g];
     if (cnt == 0) continue;
@@ -107,7 +110,7 @@ __global__ void rows_kernel(const FinParams P) {
       reinterpret_cast<double4 *>(P.rows_box)[dst] = b;
       P.rows_score[dst] = P.out_score[src];
       const int bg = P.out_birth[2 * src], bk = P.out_birth[2 * src + 1];
-      P.rows_id[dst] = P.id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
+      P.rows_id[dst] = id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
       P.rows_img[dst] = img + P.image_base;
       P.rows_cat[dst] = c + 1;
     }
@@ -134,7 +137,12 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (problem->n_streams == 0 || n_groups == 0) {
+    // nothing created: the next id base is the incoming one
     W2T_CUDA_TRY(cudaMemsetAsync(rows->totals, 0, 2 * sizeof(int64_t), st));
+    if (rows->id_base_device)
+      W2T_CUDA_TRY(cudaMemcpyAsync(rows->totals + 2, rows->id_base_device, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    else
+      W2T_CUDA_TRY(cudaMemcpyAsync(rows->totals + 2, &id_base, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     return W2T_OK;
   }
   if (!workspace || !rows->box || !rows->score || !rows->object_id || !rows->image || !rows->category) {
@@ -154,6 +162,7 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
   P.out_score = result->out_score;
   P.out_birth = result->out_birth;
   P.id_base = id_base;
+  P.id_base_dev = rows->id_base_device;
   int32_t *w = static_cast<int32_t *>(workspace);
   P.perm_created = w;
   P.perm_count = w + n_groups;

@@ -361,210 +361,353 @@ struct Munkres {
   }
 
   // =============================================================================================
-  // Small problems (n <= m <= 64): every mask is one 64-bit word.
+  // Problems up to 128 x 128 whose arrays live in shared memory (the common case).
   //
-  // Step 1 uses the CTA (one thread per row); everything else runs in warp 0 with NO
-  // intra-warp communication on the serial path: covers, the "rows owning an uncovered zero"
-  // set and the star count live in registers and all 32 lanes execute the same scalar
-  // instructions on the same values, so one step-4 iteration is two dependent shared-memory
-  // loads plus a dozen integer ops (no ballot, shuffle or barrier).  Zr[r] / Zc[c] are the
-  // zero bit matrix by row and by column (g.Z reinterpreted: 64 + 64 words of 64 bits);
-  // uncovering column sc adds Zc[sc] & ~rowcov to the row set.  Lanes spread over rows /
-  // columns only where the data is wide: the initial row set and step 6.
+  // Every cover / star mask is four 32-bit words held in REGISTERS of warp 0, identical in all
+  // lanes, so the serial state machine (steps 3-5) spends its time on a handful of broadcast
+  // shared-memory loads per iteration instead of mask traffic.  The wide parts use the data
+  // layout that suits them: step 1 one thread per row, step 2 the clash-free-prefix trick of
+  // greedy_stars(), step 6 the whole CTA with one warp per row and lanes across columns
+  // (conflict-free, a few hundred cycles per round).  Z rows are kept in shared memory with an
+  // odd word stride; "rows that gained an uncovered zero when column sc was uncovered" is one
+  // conflict-free load + ballot per 32 rows, so no column-major copy of Z has to be maintained.
   // =============================================================================================
-  typedef unsigned long long u64;
+  // Four named words rather than an array: nothing can turn a bit update into a dynamically
+  // indexed (= local memory) access.
+  struct M4 {
+    uint32_t a, b, c, d;
+    __device__ __forceinline__ int first() const {
+      if (a) return __ffs(a) - 1;
+      if (b) return 32 + __ffs(b) - 1;
+      if (c) return 64 + __ffs(c) - 1;
+      if (d) return 96 + __ffs(d) - 1;
+      return -1;
+    }
+    __device__ __forceinline__ uint32_t word(int k) const { return k == 0 ? a : k == 1 ? b : k == 2 ? c : d; }
+    __device__ __forceinline__ bool test(int i) const { return (word(i >> 5) >> (i & 31)) & 1u; }
+    __device__ __forceinline__ void set(int i) {
+      const uint32_t bit = 1u << (i & 31);
+      const int k = i >> 5;
+      a |= (k == 0) ? bit : 0u;
+      b |= (k == 1) ? bit : 0u;
+      c |= (k == 2) ? bit : 0u;
+      d |= (k == 3) ? bit : 0u;
+    }
+    __device__ __forceinline__ void clear(int i) {
+      const uint32_t bit = 1u << (i & 31);
+      const int k = i >> 5;
+      a &= (k == 0) ? ~bit : ~0u;
+      b &= (k == 1) ? ~bit : ~0u;
+      c &= (k == 2) ? ~bit : ~0u;
+      d &= (k == 3) ? ~bit : ~0u;
+    }
+  };
 
-  __device__ __forceinline__ static u64 low_mask(int k) { return k >= 64 ? ~0ull : ((1ull << k) - 1ull); }
+  // first zero of row r outside `cov`, or -1 (lane-private row, or the same row in every lane)
+  __device__ __forceinline__ int first_zero_outside(int r, const M4 &cov) const {
+    const uint32_t *zr = g.Z + (size_t)r * zs;
+    M4 v = {0u, 0u, 0u, 0u};
+    v.a = zr[0] & ~cov.a;
+    if (mw > 1) v.b = zr[1] & ~cov.b;
+    if (mw > 2) v.c = zr[2] & ~cov.c;
+    if (mw > 3) v.d = zr[3] & ~cov.d;
+    return v.first();
+  }
 
-  __device__ int solve_small() {
-    u64 *Zr = reinterpret_cast<u64 *>(g.Z), *Zc = Zr + 64;
+  // uncovered rows (of the 32-row group `grp`, one per lane) for which `pred` holds, as a ballot
+  template <class PRED>
+  __device__ __forceinline__ uint32_t rows_where(int grp, uint32_t rowcov_word, PRED pred) const {
+    const int r = grp * 32 + lane_id();
+    const bool ok = (r < n) && !((rowcov_word >> lane_id()) & 1u) && pred(r);
+    return __ballot_sync(0xffffffffu, ok);
+  }
+
+  // Step 1 for one row straight from the registers of the warp that has just computed it: lane L
+  // holds the costs of columns L, L+32, L+64, L+96 (val[k] for k < mw; anything for columns >= m).
+  // Row minimum, subtract, store, zero bit words.  Lets the producer of the cost matrix skip the
+  // separate pass of step 1 (solve_block(true)).  All lanes of the warp call it.
+  __device__ __forceinline__ void store_reduced_row(int r, const float (&val)[4]) {
     const int lane = lane_id();
-    // ---- step 1 (CTA): row minimum, subtract, zero masks by row (one thread per row) ...
+    float mn = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (k < mw && k * 32 + lane < m) mn = fminf(mn, val[k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    float *row = g.C + (size_t)r * ldc;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < mw) {
+        const int c = k * 32 + lane;
+        bool z = false;
+        if (c < m) {
+          const float v = val[k] - mn;
+          row[c] = v;
+          z = (v == 0.0f);
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, z);
+        if (lane == 0) g.Z[(size_t)r * zs + k] = word;
+      }
+    }
+    if (lane == 0) { g.row_star[r] = -1; g.row_prime[r] = -1; }
+  }
+
+  // true when solve() will take the shared-memory path below (and store_reduced_row may be used)
+  __device__ __forceinline__ bool block_path() const { return rowwise && m <= 128; }
+
+  __device__ int solve_block(bool reduced = false) {
+    const int lane = lane_id(), warp = warp_id();
+    const int nwr = munkres_words(n);
+    // ---- step 1 (CTA, one thread per row): row minimum, subtract, zero bit words
     for (int c = threadIdx.x; c < m; c += BLOCK) g.col_star[c] = -1;
-    for (int r = threadIdx.x; r < n; r += BLOCK) {
+    for (int r = threadIdx.x; r < n && !reduced; r += BLOCK) {
       float *row = g.C + (size_t)r * ldc;
       float mn = row[0];
       for (int c = 1; c < m; c++) mn = fminf(mn, row[c]);
-      u64 zr = 0ull;
-      for (int c = 0; c < m; c++) {
-        const float v = row[c] - mn;
-        row[c] = v;
-        zr |= (v == 0.0f) ? (1ull << c) : 0ull;
+      for (int k = 0; k < mw; k++) {
+        uint32_t word = 0u;
+        const int c1 = min(32, m - k * 32);
+        for (int b = 0; b < c1; b++) {
+          const float v = row[k * 32 + b] - mn;
+          row[k * 32 + b] = v;
+          word |= (v == 0.0f) ? (1u << b) : 0u;
+        }
+        g.Z[(size_t)r * zs + k] = word;
       }
-      Zr[r] = zr;
       g.row_star[r] = -1;
       g.row_prime[r] = -1;
     }
     __syncthreads();
-    // ... and by column (one thread per column; consecutive threads read consecutive floats)
-    for (int c = threadIdx.x; c < m; c += BLOCK) {
-      u64 zc = 0ull;
-      for (int r = 0; r < n; r++) zc |= (g.C[(size_t)r * ldc + c] == 0.0f) ? (1ull << r) : 0ull;
-      Zc[c] = zc;
-    }
-    __syncthreads();
     tick(3);
-    if (warp_id() == 0) {
-      const u64 nmask = low_mask(n), mmask = low_mask(m);
-      // ---- step 2: greedy stars in row-major order.  Lane L keeps rows L and L+32 in registers;
-      // the serial loop gets row r by shuffle, so its only loop-carried chain is the cover word.
-      u64 starcols = 0ull;
-      int stars = 0;
-      {
-        const u64 z0 = (lane < n) ? Zr[lane] : 0ull, z1 = (lane + 32 < n) ? Zr[lane + 32] : 0ull;
-        int rs0 = -1, rs1 = -1;  // star column of rows lane, lane+32
-        int cs0 = -1, cs1 = -1;  // star row of columns lane, lane+32
-        for (int r = 0; r < n; r++) {
-          const u64 zr = __shfl_sync(0xffffffffu, (r < 32) ? z0 : z1, r & 31);
-          const u64 v = zr & ~starcols;
-          if (v) {
-            const int c = __ffsll((long long)v) - 1;
-            if (lane == (r & 31)) { if (r < 32) rs0 = c; else rs1 = c; }
-            if (lane == (c & 31)) { if (c < 32) cs0 = r; else cs1 = r; }
-            starcols |= 1ull << c;
-            stars++;
-          }
-        }
-        if (lane < n) g.row_star[lane] = rs0;
-        if (lane + 32 < n) g.row_star[lane + 32] = rs1;
-        if (lane < m) g.col_star[lane] = cs0;
-        if (lane + 32 < m) g.col_star[lane + 32] = cs1;
-      }
-      // Every lane executes the scalar state machine redundantly on identical values; lanes are
-      // re-aligned (and their shared-memory accesses ordered) wherever one lane could otherwise
-      // overwrite a word another lane has yet to read.
-      __syncwarp();
-      tick(4);
-      int act = 0;
-      int budget = 4 * n * n + 64 * (n + m) + 1024;
-      while (stars < n) {
-        // ---- step 3: cover the starred columns, uncover all rows
-        u64 rowcov = 0ull, colcov = starcols;
-        for (;;) {
-          // rows that own an uncovered zero, from scratch (entering step 4 / after a cost shift)
-          u64 rowhas;
-          {
-            const int r0 = lane, r1 = lane + 32;
-            const bool h0 = (r0 < n) && !((rowcov >> r0) & 1ull) && (Zr[r0] & ~colcov) != 0ull;
-            const bool h1 = (r1 < n) && !((rowcov >> r1) & 1ull) && (Zr[r1] & ~colcov) != 0ull;
-            const unsigned lo = __ballot_sync(0xffffffffu, h0), hi = __ballot_sync(0xffffffffu, h1);
-            rowhas = (u64)lo | ((u64)hi << 32);
-          }
-          bool augmented = false;
-          // ---- step 4: prime uncovered zeros in row-major order
-          while (rowhas) {
-            if (--budget < 0) { act = 9; break; }
-            const int fr = __ffsll((long long)rowhas) - 1;
-            const int sc = g.row_star[fr];
-            const int fc = __ffsll((long long)(Zr[fr] & ~colcov)) - 1;
-            if (sc < 0) {
-              // ---- step 5: flip stars along the alternating path from the primed zero (fr, fc)
-              int r = fr, c = fc;
-              __syncwarp();
-              for (int hops = 0;; hops++) {
-                const int rs = g.col_star[c];
-                __syncwarp();  // all lanes have read the old star before any lane replaces it
-                g.row_star[r] = c;
-                g.col_star[c] = r;
-                if (rs < 0) {
-                  starcols |= 1ull << c;
-                  break;
-                }
-                r = rs;
-                c = g.row_prime[r];
-                if (c < 0 || hops > n + m) { act = 9; break; }  // cannot happen in a valid state
+
+    M4 starcols = {0u, 0u, 0u, 0u}, colcov = {0u, 0u, 0u, 0u}, rowcov = {0u, 0u, 0u, 0u};
+    int stars = 0, act = 0;
+    int budget = 4 * n * n + 64 * (n + m) + 1024;
+    bool fresh = true;  // first entry: step 2 still to do
+    for (;;) {
+      if (warp == 0) {
+        const unsigned lt = (1u << lane) - 1u;
+        if (fresh) {
+          // ---- step 2: greedy stars in row-major order; the longest prefix of pending rows whose
+          // proposals are pairwise distinct is exactly what the sequential loop would star
+          for (int rb = 0; rb < n; rb += 32) {
+            const int r = rb + lane;
+            bool pending = r < n;
+            for (;;) {
+              int cand = -1;
+              if (pending) {
+                cand = first_zero_outside(r, starcols);
+                if (cand < 0) pending = false;  // every zero of the row is taken: no star
               }
-              __syncwarp();
+              if (!__ballot_sync(0xffffffffu, pending)) break;
+              const unsigned peers = __match_any_sync(0xffffffffu, pending ? cand : (-2 - lane));
+              const unsigned clash = __ballot_sync(0xffffffffu, pending && (peers & lt) != 0u);
+              const int first_clash = clash ? (__ffs(clash) - 1) : 32;
+              const bool commit = pending && lane < first_clash;
+              M4 add = {0u, 0u, 0u, 0u};
+              if (commit) {
+                g.row_star[r] = cand;
+                g.col_star[cand] = r;
+                add.set(cand);
+                pending = false;
+              }
+              starcols.a |= __reduce_or_sync(0xffffffffu, add.a);
+              if (mw > 1) starcols.b |= __reduce_or_sync(0xffffffffu, add.b);
+              if (mw > 2) starcols.c |= __reduce_or_sync(0xffffffffu, add.c);
+              if (mw > 3) starcols.d |= __reduce_or_sync(0xffffffffu, add.d);
+              stars += __popc(__ballot_sync(0xffffffffu, commit));
+            }
+          }
+          __syncwarp();
+          tick(4);
+          fresh = false;
+          colcov = starcols;
+        }
+        // (otherwise: back from a cost shift — covers, stars and primes are untouched, step 6 -> step 4)
+        // ---- steps 3-5
+        for (;;) {
+          if (stars >= n) { act = 0; break; }
+          // rows that own an uncovered zero, from scratch
+          M4 rowhas = {0u, 0u, 0u, 0u};
+          auto open_zero = [&](int r) { return first_zero_outside(r, colcov) >= 0; };
+          rowhas.a = rows_where(0, rowcov.a, open_zero);
+          if (nwr > 1) rowhas.b = rows_where(1, rowcov.b, open_zero);
+          if (nwr > 2) rowhas.c = rows_where(2, rowcov.c, open_zero);
+          if (nwr > 3) rowhas.d = rows_where(3, rowcov.d, open_zero);
+          bool augmented = false;
+          for (;;) {
+            // step 4: first uncovered zero in row-major order
+            if (--budget < 0) { act = 9; break; }
+            if (TIMERS && threadIdx.x == 0) ph[12]++;
+            const int fr = rowhas.first();
+            if (fr < 0) { act = 6; break; }
+            const int sc = g.row_star[fr];
+            const int fc = first_zero_outside(fr, colcov);
+            if (sc < 0) {
+              // step 5: flip stars along the alternating path that starts at the primed zero (fr, fc)
+              int endc = -1;
+              if (lane == 0) {
+                int r = fr, c = fc;
+                for (int hops = 0;; hops++) {
+                  const int rs = g.col_star[c];
+                  g.row_star[r] = c;
+                  g.col_star[c] = r;
+                  if (rs < 0) { endc = c; break; }
+                  r = rs;
+                  c = g.row_prime[r];
+                  if (c < 0 || hops > n + m) { endc = -2; break; }  // cannot happen in a valid state
+                }
+              }
+              endc = __shfl_sync(0xffffffffu, endc, 0);
+              if (endc < 0) { act = 9; break; }
+              starcols.set(endc);
               stars++;
               augmented = true;
               break;
             }
-            g.row_prime[fr] = fc;
-            rowcov |= 1ull << fr;
-            colcov &= ~(1ull << sc);
-            rowhas = (rowhas & ~(1ull << fr)) | (Zc[sc] & ~rowcov & nmask);
+            // the row has a star: prime the zero, cover the row, uncover the star's column
+            if (lane == 0) g.row_prime[fr] = fc;
+            rowcov.set(fr);
+            colcov.clear(sc);
+            rowhas.clear(fr);
+            // uncovered rows with a zero in the newly uncovered column now own an uncovered zero
+            const int kw = sc >> 5;
+            const uint32_t bit = 1u << (sc & 31);
+            auto zero_at_sc = [&](int r) { return (g.Z[(size_t)r * zs + kw] & bit) != 0u; };
+            rowhas.a |= rows_where(0, rowcov.a, zero_at_sc);
+            if (nwr > 1) rowhas.b |= rows_where(1, rowcov.b, zero_at_sc);
+            if (nwr > 2) rowhas.c |= rows_where(2, rowcov.c, zero_at_sc);
+            if (nwr > 3) rowhas.d |= rows_where(3, rowcov.d, zero_at_sc);
           }
-          if (augmented || act) break;
+          if (!augmented) break;  // act = 6 or 9
+          // step 3: cover the starred columns, uncover all rows (stale primes are never read)
           __syncwarp();
-          tick(5);
-          // ---- step 6: min over uncovered rows x uncovered columns; covered rows += min,
-          //      uncovered columns -= min (float32, in that order)
-          if (--budget < 0) { act = 9; break; }
-          const u64 ucols = ~colcov & mmask, urows = ~rowcov & nmask;
-          float mn = INFINITY;
-#pragma unroll
-          for (int half = 0; half < 2; half++) {
-            const int r = lane + 32 * half;
-            if ((urows >> r) & 1ull) {
-              const float *row = g.C + (size_t)r * ldc;
-              for (u64 rem = ucols; rem; rem &= rem - 1ull) mn = fminf(mn, row[__ffsll((long long)rem) - 1]);
-            }
-          }
-#pragma unroll
-          for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-          if (mn == INFINITY) { act = 9; break; }
-          for (u64 rem = rowcov & nmask; rem; rem &= rem - 1ull) {
-            const int r = __ffsll((long long)rem) - 1;
-            float *row = g.C + (size_t)r * ldc;
-            u64 zbits = 0ull;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-              const int c = lane + 32 * half;
-              bool z = false;
-              if (c < m) {
-                float v = row[c] + mn;
-                if ((ucols >> c) & 1ull) v = v - mn;
-                row[c] = v;
-                z = (v == 0.0f);
-                Zc[c] = (Zc[c] & ~(1ull << r)) | ((u64)z << r);
-              }
-              zbits |= (u64)__ballot_sync(0xffffffffu, z) << (32 * half);
-            }
-            Zr[r] = zbits;
-          }
-          __syncwarp();  // Zc words written by their owning lanes above are read by every lane below
-          {
-            const int r0 = lane, r1 = lane + 32;
-            const bool a0 = (urows >> r0) & 1ull, a1 = (urows >> r1) & 1ull;
-            float *row0 = g.C + (size_t)r0 * ldc, *row1 = g.C + (size_t)r1 * ldc;
-            u64 zr0 = a0 ? Zr[r0] : 0ull, zr1 = a1 ? Zr[r1] : 0ull;
-            for (u64 rem = ucols; rem; rem &= rem - 1ull) {
-              const int c = __ffsll((long long)rem) - 1;
-              bool f0 = false, f1 = false;
-              if (a0) {
-                const float v = row0[c] - mn;
-                row0[c] = v;
-                f0 = (v == 0.0f);
-                zr0 = (zr0 & ~(1ull << c)) | ((u64)f0 << c);
-              }
-              if (a1) {
-                const float v = row1[c] - mn;
-                row1[c] = v;
-                f1 = (v == 0.0f);
-                zr1 = (zr1 & ~(1ull << c)) | ((u64)f1 << c);
-              }
-              const u64 colbits = (u64)__ballot_sync(0xffffffffu, f0) | ((u64)__ballot_sync(0xffffffffu, f1) << 32);
-              Zc[c] = (Zc[c] & ~urows) | colbits;
-            }
-            if (a0) Zr[r0] = zr0;
-            if (a1) Zr[r1] = zr1;
-          }
-          __syncwarp();
-          tick(6);
+          colcov = starcols;
+          rowcov = M4{0u, 0u, 0u, 0u};
         }
-        if (act) break;
+        if (act == 6) {
+          // step 6 prologue: compact index lists, so that the CTA touches only the cells that change:
+          // uncovered columns -> g.ucols[0..nu), uncovered rows -> g.ucols[128..128+nur), covered
+          // rows -> g.crows[0..ncr)
+          const unsigned ltm = (1u << lane) - 1u;
+          int nu = 0, nur = 0, ncr = 0;
+          for (int k = 0; k < mw; k++) {
+            const int c = k * 32 + lane;
+            const bool open = (c < m) && !((colcov.word(k) >> lane) & 1u);
+            const unsigned b = __ballot_sync(0xffffffffu, open);
+            if (open) g.ucols[nu + __popc(b & ltm)] = c;
+            nu += __popc(b);
+          }
+          for (int k = 0; k < nwr; k++) {
+            const int r = k * 32 + lane;
+            const bool cov = (rowcov.word(k) >> lane) & 1u;
+            const unsigned bu = __ballot_sync(0xffffffffu, (r < n) && !cov);
+            const unsigned bc = __ballot_sync(0xffffffffu, (r < n) && cov);
+            if (r < n && !cov) g.ucols[128 + nur + __popc(bu & ltm)] = r;
+            if (r < n && cov) g.crows[ncr + __popc(bc & ltm)] = r;
+            nur += __popc(bu);
+            ncr += __popc(bc);
+          }
+          if (lane == 0) { s->ctl[1] = nu; s->ctl[2] = ncr; s->ctl[3] = nur; }
+        }
+        tick(5);
+        if (lane == 0) {
+          s->ctl[0] = act;
+          s->colcov[0] = colcov.a; s->colcov[1] = colcov.b; s->colcov[2] = colcov.c; s->colcov[3] = colcov.d;
+        }
       }
-      tick(5);
-      if (lane == 0) s->ctl[0] = act;
+      __syncthreads();
+      act = s->ctl[0];
+      if (act != 6) return act;
+      if (TIMERS && threadIdx.x == 0) ph[11]++;
+      // ---- step 6 (CTA): min over uncovered rows x uncovered columns; covered rows += min, then
+      // uncovered columns -= min (float32, in that order).  Only the cells that change are visited:
+      // (uncovered rows x uncovered columns) and (covered rows x all columns).
+      const int nu = s->ctl[1], ncr = s->ctl[2], nur = s->ctl[3];
+      const int *ucols = g.ucols, *urows = g.ucols + 128, *crows = g.crows;
+      // flat cell index i -> (uncovered row i / nu, uncovered column i % nu); four independent cells
+      // per thread and trip, so their shared-memory round trips overlap
+      const int ncell = nur * nu;
+      const unsigned inv_nu = nu > 0 ? (0xffffffffu / (unsigned)nu + 1u) : 0u;  // exact for i < 2^16
+      auto cell = [&](int i, int &r, int &c) {
+        const int q = (nu == 1) ? i : (int)__umulhi((unsigned)i, inv_nu);  // 2^32 / 1 does not fit
+        r = urows[q];
+        c = ucols[i - q * nu];
+      };
+      float mn = INFINITY;
+      for (int base = threadIdx.x; base < ncell; base += 4 * BLOCK) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int i = base + j * BLOCK;
+          v[j] = INFINITY;
+          if (i < ncell) {
+            int r, c;
+            cell(i, r, c);
+            v[j] = g.C[(size_t)r * ldc + c];
+          }
+        }
+        mn = fminf(fminf(mn, v[0]), fminf(fminf(v[1], v[2]), v[3]));
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if (lane == 0) s->red[warp] = mn;
+      __syncthreads();
+      mn = s->red[0];
+#pragma unroll
+      for (int i = 1; i < NW; i++) mn = fminf(mn, s->red[i]);
+      if (mn != INFINITY) {  // nothing uncovered: the reference leaves the matrix alone
+        // covered rows: every column gets +min, the uncovered ones then -min (two roundings)
+        const M4 cc = {s->colcov[0], s->colcov[1], s->colcov[2], s->colcov[3]};
+        for (int i = warp; i < ncr; i += NW) {
+          const int r = crows[i];
+          float *row = g.C + (size_t)r * ldc;
+          for (int k = 0; k < mw; k++) {
+            const int c = k * 32 + lane;
+            bool z = false;
+            if (c < m) {
+              float v = row[c] + mn;
+              if (!((cc.word(k) >> lane) & 1u)) v = v - mn;
+              row[c] = v;
+              z = (v == 0.0f);
+            }
+            const unsigned word = __ballot_sync(0xffffffffu, z);
+            if (lane == 0) g.Z[(size_t)r * zs + k] = word;
+          }
+        }
+        // uncovered rows: only the uncovered columns change (-min).  None of these cells was zero
+        // (step 4 ran out of uncovered zeros), so zero bits are only ever set here.
+        for (int base = threadIdx.x; base < ncell; base += 4 * BLOCK) {
+          float v[4];
+          int rr[4], cc4[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int i = base + j * BLOCK;
+            rr[j] = -1;
+            if (i < ncell) {
+              cell(i, rr[j], cc4[j]);
+              v[j] = g.C[(size_t)rr[j] * ldc + cc4[j]];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (rr[j] >= 0) {
+              const float w = v[j] - mn;
+              g.C[(size_t)rr[j] * ldc + cc4[j]] = w;
+              if (w == 0.0f) atomicOr(&g.Z[(size_t)rr[j] * zs + (cc4[j] >> 5)], 1u << (cc4[j] & 31));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      tick(6);
     }
-    __syncthreads();
-    return s->ctl[0];
   }
 
   // Whole solve.  Precondition: g.C holds the n x m costs (n <= m).  All threads call it.
   // Returns 0, or 9 if the iteration budget ran out (malformed input such as NaN costs).
-  __device__ int solve() {
-    if (rowwise && m <= 64) return solve_small();
+  __device__ int solve(bool reduced = false) {
+    if (block_path()) return solve_block(reduced);
     for (int i = threadIdx.x; i < n; i += BLOCK) { g.row_star[i] = -1; g.row_prime[i] = -1; }
     for (int i = threadIdx.x; i < m; i += BLOCK) g.col_star[i] = -1;
     reduce_rows();

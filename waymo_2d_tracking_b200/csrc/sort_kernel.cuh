@@ -48,6 +48,7 @@ constexpr int kSmemZ = 512;      // words : zero bit matrix
 constexpr int kSmemN = 128;      // rows
 constexpr int kSmemM = 256;      // columns
 constexpr int kSmemBox = 256;    // predicted tracker boxes staged per image
+constexpr int kSmemDet = 128;    // detections of the next image prefetched while this one is tracked
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   __shared__ int s_rstar[kSmemN], s_rprime[kSmemN], s_crows[kSmemN];
   __shared__ int s_cstar[kSmemM], s_ucols[kSmemM];
   __shared__ double s_box[5][kSmemBox];  // x1, y1, x2, y2, area (NaN when the box is inverted)
+  __shared__ __align__(16) float4 s_det[2][kSmemDet];  // double buffer: detections of this / the next image
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int q = P.order[blockIdx.x];
@@ -202,6 +204,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
 
   int T = 0, frame_count = 0, err = 0;
   bool started = false;
+
+  // Software pipeline over the images: the (exists, count, start) triple of image i+1 is loaded
+  // at the top of iteration i and its detections are copied to shared memory with cp.async in
+  // the middle of iteration i, so that no DRAM round trip sits on the serial path.
+  auto load_meta = [&](int img, int &exists, int &cnt, int &start) {
+    exists = (P.p.img_exists == nullptr) ? 1 : (int)P.p.img_exists[img];
+    cnt = P.p.det_count[img * NC + c];
+    start = P.p.det_start[img * NC + c];
+  };
+  auto prefetch_dets = [&](int buf, int exists, int cnt, int start) {
+    if (exists && cnt <= kSmemDet) {
+      for (int i = tid; i < cnt; i += BLOCK) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_det[buf][i]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(det_box + start + i) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int cur_exists = 0, cur_cnt = 0, cur_start = 0, buf = 0;
+  if (img0 < img1) {
+    load_meta(img0, cur_exists, cur_cnt, cur_start);
+    prefetch_dets(0, cur_exists, cur_cnt, cur_start);
+  }
   long long ph[TIMERS ? 16 : 1];
   if (TIMERS) {
 #pragma unroll
@@ -211,10 +236,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   }
 #define W2T_TICK(i) mk.tick(i)
 
-  for (int img = img0; img < img1; ++img) {
+  for (int img = img0; img < img1; ++img, buf ^= 1) {
     const int g = img * NC + c;
-    bool skip = (P.p.img_exists != nullptr) && (P.p.img_exists[img] == 0);
-    const int D = skip ? 0 : P.p.det_count[g];
+    const int this_exists = cur_exists, this_cnt = cur_cnt, this_start = cur_start;
+    bool next_issued = true;
+    if (img + 1 < img1) {
+      load_meta(img + 1, cur_exists, cur_cnt, cur_start);  // in flight while this image is tracked
+      next_issued = false;
+    }
+    // every path through this iteration ends up issuing the prefetch of the next image once
+    auto issue_next = [&]() {
+      if (!next_issued) {
+        prefetch_dets(buf ^ 1, cur_exists, cur_cnt, cur_start);
+        next_issued = true;
+      }
+    };
+    bool skip = (this_exists == 0);
+    const int D = skip ? 0 : this_cnt;
     if (!skip && !started) {
       if (D == 0) skip = true;  // no Sort object for this category yet (tracker_sort.py:32-33)
       else {
@@ -225,11 +263,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
     if (!skip && !err && (D > Dcap || D > kMunkresMaxDim || T > kMunkresMaxDim)) err = W2T_ERR_CAPACITY;
     if (skip || err) {
       if (tid == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
+      issue_next();
       continue;
     }
     frame_count++;
-    const int base = P.p.det_start[g];
-    const float4 *dets = det_box + base;
+    const int base = this_start;
+    // this image's detections: prefetched into shared memory unless there are too many
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const float4 *dets = (D <= kSmemDet) ? s_det[buf] : det_box + base;
 
     // ---- trackers whose predicted box is NaN are dropped before association (sort.py:261-265)
     if (s_nan) {
@@ -299,24 +341,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
         }
         return -iou_pair(d, t0, t1, t2, t3);
       };
+      const bool fused = mk.block_path();  // step 1 of the solver is applied to each row as it is produced
       for (int r = warp; r < n; r += NW) {
         float *row = mk.g.C + (size_t)r * mk.ldc;
+        float val[4] = {0.f, 0.f, 0.f, 0.f};
         if (!flipped) {
           const float4 d = dets[r];
-          for (int cc = lane; cc < m; cc += 32) {
-            double t0, t1, t2, t3, at;
-            tbox(cc, t0, t1, t2, t3, at);
-            row[cc] = neg_iou(d, t0, t1, t2, t3, at);
+          if (fused) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int cc = k * 32 + lane;
+              if (k < mk.mw && cc < m) {
+                double t0, t1, t2, t3, at;
+                tbox(cc, t0, t1, t2, t3, at);
+                val[k] = neg_iou(d, t0, t1, t2, t3, at);
+              }
+            }
+          } else {
+            for (int cc = lane; cc < m; cc += 32) {
+              double t0, t1, t2, t3, at;
+              tbox(cc, t0, t1, t2, t3, at);
+              row[cc] = neg_iou(d, t0, t1, t2, t3, at);
+            }
           }
         } else {
           double t0, t1, t2, t3, at;
           tbox(r, t0, t1, t2, t3, at);
-          for (int cc = lane; cc < m; cc += 32) row[cc] = neg_iou(dets[cc], t0, t1, t2, t3, at);
+          if (fused) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int cc = k * 32 + lane;
+              if (k < mk.mw && cc < m) val[k] = neg_iou(dets[cc], t0, t1, t2, t3, at);
+            }
+          } else {
+            for (int cc = lane; cc < m; cc += 32) row[cc] = neg_iou(dets[cc], t0, t1, t2, t3, at);
+          }
         }
+        if (fused) mk.store_reduced_row(r, val);
       }
       __syncthreads();
       W2T_TICK(2);
-      if (mk.solve() != 0) err = W2T_ERR_ARG;
+      if (TIMERS && tid == 0) ph[13]++;
+      if (mk.solve(fused) != 0) err = W2T_ERR_ARG;
       for (int d = tid; d < D; d += BLOCK) {
         const int t = flipped ? mk.g.col_star[d] : mk.g.row_star[d];
         int stt = 0;
@@ -334,6 +400,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
     }
     __syncthreads();
     W2T_TICK(7);
+    issue_next();  // by now the next image's (count, start) have arrived
     int n_un, n_rej;
     partition3<BLOCK>(
         D, [&](int i) { return i; }, [&](int i) { return dstat[i] == 0; }, [&](int i) { return dstat[i] == 2; },

@@ -39,9 +39,9 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) lap_kernel(const float *cost, int D, int T, int32_t *pairs, int32_t *n_pairs,
                                                    char *ws) {
   __shared__ MunkresShared ms;
-  __shared__ __align__(16) float s_C[64 * 65];
-  __shared__ __align__(16) uint32_t s_Z[256];
-  __shared__ int s_rstar[64], s_rprime[64], s_crows[64], s_cstar[64], s_ucols[64];
+  __shared__ __align__(16) float s_C[kSmemC];
+  __shared__ __align__(16) uint32_t s_Z[kSmemZ];
+  __shared__ int s_rstar[kSmemN], s_rprime[kSmemN], s_crows[kSmemN], s_cstar[kSmemM], s_ucols[kSmemM];
   const bool flipped = T < D;
   const int n = flipped ? T : D, m = flipped ? D : T;
   const LapLayout L = lap_layout(D, T);
@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(BLOCK) lap_kernel(const float *cost, int D, in
   mk.g.row_prime = reinterpret_cast<int *>(ws + L.rprime);
   mk.g.ucols = reinterpret_cast<int *>(ws + L.ucols);
   mk.g.crows = reinterpret_cast<int *>(ws + L.crows);
-  if (m <= 64) {  // same dispatch as the tracker kernel: small problems live in shared memory
+  // same dispatch as the tracker kernel: problems that fit live in shared memory
+  if ((n * mk.ldc <= kSmemC) && (n * mk.zs <= kSmemZ) && (n <= kSmemN) && (m <= kSmemM)) {
     mk.rowwise = true;
     mk.g.C = s_C; mk.g.Z = s_Z; mk.g.row_star = s_rstar; mk.g.col_star = s_cstar; mk.g.row_prime = s_rprime;
     mk.g.ucols = s_ucols; mk.g.crows = s_crows;

@@ -345,7 +345,7 @@ def assign_ids(n_streams, n_classes, h_offsets, h_start, h_out_count, h_created,
 
 
 def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank, id_base, rows_cap, image_base=0,
-                    rows=None):
+                    rows=None, id_base_device=None):
     """Device-side ids + dense rows (``w2t_sort_finalize``) on the tensors ``sort_track_device`` returned.
     ``rows``: preallocated output tensors (same keys) to write into instead of allocating."""
     device = trk["out_box"].device
@@ -358,7 +358,7 @@ def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank,
         "rows_id": torch.empty(cap, dtype=torch.int64, device=device),
         "rows_img": torch.empty(cap, dtype=torch.int32, device=device),
         "rows_cat": torch.empty(cap, dtype=torch.int32, device=device),
-        "totals": torch.zeros(2, dtype=torch.int64, device=device),
+        "totals": torch.zeros(3, dtype=torch.int64, device=device),
     }
     ws = torch.empty(int(lib().w2t_sort_finalize_workspace(int(n_streams), NC, n_groups)), dtype=torch.uint8,
                      device=device)
@@ -373,6 +373,7 @@ def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank,
     crows.image, crows.category, crows.totals = _ptr(rows["rows_img"]), _ptr(rows["rows_cat"]), _ptr(rows["totals"])
     crows.capacity = cap
     crows.image_base = int(image_base)
+    crows.id_base_device = _ptr(id_base_device)
     with _timed("finalize_kernels"):
         check(lib().w2t_sort_finalize(C.byref(prob), C.byref(res), _ptr(d_class_rank), int(id_base), n_groups,
                                       _ptr(ws), C.byref(crows), _stream()), "w2t_sort_finalize")
@@ -518,6 +519,17 @@ def _pinned_pool(tag, dtype, n, keep=0, quiesce=None):
 
 
 _STREAMS = {}
+TRACE = None   # debug aid: list receiving (label, host seconds, cuda event or None) from the pipelined path
+
+
+def _trace(label, stream=None):
+    if TRACE is not None:
+        import time
+        ev = None
+        if stream is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+        TRACE.append((label, time.perf_counter(), ev))
 
 
 def _side_streams(device):
@@ -525,6 +537,14 @@ def _side_streams(device):
     if key not in _STREAMS:
         _STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
     return _STREAMS[key]
+
+
+def _compute_streams(device, n=3):
+    """n compute streams + one for the finalize kernels."""
+    key = (device.index, "compute")
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device) for _ in range(n + 1)]
+    return list(_STREAMS[key])
 
 
 def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
@@ -597,6 +617,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     for t in (d_goff, d_rows):
         t.record_stream(s_in)
 
+    _trace("alloc done", main)
     # 1. all host->device copies are queued up front on the copy-in stream, chunk by chunk
     h2d_done = []
     with torch.cuda.stream(s_in):
@@ -609,75 +630,89 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
             ev = torch.cuda.Event()
             ev.record(s_in)
             h2d_done.append(ev)
+            _trace("h2d queued %d" % len(h2d_done), s_in)
 
-    # 2. kernels per chunk on the main stream; results of chunk k-1 go home while chunk k computes
-    pending = None            # (chunk index, dense rows, totals on host, event)
-    host = {}
-    n_rows_total, created_total, n_trk_rows = 0, 0, 0
-    keep_alive = []
-    d2h_bytes = 0
-
-    def drain(p):
-        nonlocal n_rows_total, created_total, d2h_bytes
-        rows_k, h_tot, ev = p
-        ev.synchronize()
-        created_k, n_k = int(h_tot[0]), int(h_tot[1])
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev)
-            for key in _ROW_KEYS[:-1]:
-                src = rows_k[key][:n_k]
-                width = src.shape[1] if src.dim() > 1 else 1
-                pool = _pinned_pool("pipe_" + key, src.dtype, (n_rows_total + n_k) * width, n_rows_total * width,
-                                    quiesce=s_out.synchronize)
-                dst = pool[n_rows_total * width:(n_rows_total + n_k) * width].view(src.shape)
-                dst.copy_(src, non_blocking=True)
-                src.record_stream(s_out)
-                d2h_bytes += src.numel() * src.element_size()
-        n_rows_total += n_k
-        created_total += created_k
-        return created_k
-
+    # 2. kernels: chunk k on compute stream k mod 3, so the latency-bound SORT kernels of
+    #    neighbouring chunks overlap; the finalize kernels of all chunks run in order on one stream
+    #    and hand the running id base from chunk to chunk on the device (w2t_rows_t.id_base_device)
+    comp = _compute_streams(device)
+    fin = comp[-1]
+    comp = comp[:-1]
+    for cs in comp + [fin]:
+        cs.wait_stream(main)
+    keep_alive, fin_done, rows_of, h_totals = [], [], [], _pinned_pool("pipe_totals", torch.int64, 3 * len(chunks))
+    prev_totals = None
     for k, (s0, s1) in enumerate(chunks):
         img0, img1 = int(h_offsets[s0]), int(h_offsets[s1])
         g0, g1 = img0 * NC, img1 * NC
         ns = s1 - s0
         loc_offsets = (h_offsets[s0:s1 + 1] - h_offsets[s0]).astype(np.int32)
         plan = make_plan(ns, NC, loc_offsets, sizes[g0:g1], exists_ub[img0:img1], max_age)
-        main.wait_event(h2d_done[k])
-        nms_k = {"ens_count": nms_out["ens_count"][g0:g1], "trk_count": nms_out["trk_count"][g0:g1],
-                 "trk_box": nms_out["trk_box"], "img_exists": nms_out["img_exists"][img0:img1],
-                 "status": nms_out["status"]}
-        softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score, NC,
-                              score_thr, out=nms_k)
-        trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"], "out_birth": trk_out["out_birth"],
-                 "out_count": trk_out["out_count"][g0:g1], "created": trk_out["created"][g0:g1],
-                 "first_img": trk_out["first_img"][s0 * NC:s1 * NC], "status": trk_out["status"]}
-        d_loc = _dev(loc_offsets, np.int32, device)
-        trk = sort_track_device(ns, NC, d_loc, d_goff[g0:g1], nms_k["trk_count"], nms_out["trk_box"],
-                                nms_k["img_exists"], d_cam[s0:s1], iou_thresholds, max_age, min_hits, plan, out=trk_k)
-        keep_alive.append(trk["_keepalive"])
-        if pending is not None:            # ids of this chunk continue after the previous chunk's
-            drain(pending)
-        rows_cap = int(go_np[g1] - go_np[g0])
-        rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk, None, id_base + created_total, rows_cap,
-                                 image_base=img0)
-        keep_alive.append(rows_k["_keepalive"])
-        h_tot = _pinned_pool("pipe_totals", torch.int64, 2 * len(chunks))[2 * k:2 * k + 2]
-        h_tot.copy_(rows_k["totals"], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        pending = (rows_k, h_tot, ev)
-    drain(pending)
+        _trace("plan %d" % k)
+        cs = comp[k % len(comp)]
+        with torch.cuda.stream(cs):
+            cs.wait_event(h2d_done[k])
+            nms_k = {"ens_count": nms_out["ens_count"][g0:g1], "trk_count": nms_out["trk_count"][g0:g1],
+                     "trk_box": nms_out["trk_box"], "img_exists": nms_out["img_exists"][img0:img1],
+                     "status": nms_out["status"]}
+            softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
+                                  NC, score_thr, out=nms_k)
+            trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"],
+                     "out_birth": trk_out["out_birth"], "out_count": trk_out["out_count"][g0:g1],
+                     "created": trk_out["created"][g0:g1], "first_img": trk_out["first_img"][s0 * NC:s1 * NC],
+                     "status": trk_out["status"]}
+            d_loc = _dev(loc_offsets, np.int32, device)
+            trk = sort_track_device(ns, NC, d_loc, d_goff[g0:g1], nms_k["trk_count"], nms_out["trk_box"],
+                                    nms_k["img_exists"], d_cam[s0:s1], iou_thresholds, max_age, min_hits, plan,
+                                    out=trk_k)
+            sorted_ev = torch.cuda.Event()
+            sorted_ev.record(cs)
+            _trace("sort queued %d" % k, cs)
+        with torch.cuda.stream(fin):
+            fin.wait_event(sorted_ev)
+            rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk, None, id_base if k == 0 else 0,
+                                     int(go_np[g1] - go_np[g0]), image_base=img0,
+                                     id_base_device=None if prev_totals is None else prev_totals[2:])
+            prev_totals = rows_k["totals"]
+            h_totals[3 * k:3 * k + 3].copy_(rows_k["totals"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(fin)
+            fin_done.append(ev)
+            _trace("finalize queued %d" % k, fin)
+        keep_alive += [trk["_keepalive"], rows_k["_keepalive"], d_loc, nms_k, trk_k]
+        rows_of.append(rows_k)
+
+    # 3. results go home chunk by chunk, each as soon as its finalize is done, while later chunks compute
+    n_rows_total, d2h_bytes = 0, 0
+    for k in range(len(chunks)):
+        _trace("drain wait %d" % k)
+        fin_done[k].synchronize()
+        n_k = int(h_totals[3 * k + 1])
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(fin_done[k])
+            for key in _ROW_KEYS[:-1]:
+                src = rows_of[k][key][:n_k]
+                width = src.shape[1] if src.dim() > 1 else 1
+                pool = _pinned_pool("pipe_" + key, src.dtype, (n_rows_total + n_k) * width, n_rows_total * width,
+                                    quiesce=s_out.synchronize)
+                pool[n_rows_total * width:(n_rows_total + n_k) * width].view(src.shape).copy_(src, non_blocking=True)
+                d2h_bytes += src.numel() * src.element_size()
+            _trace("d2h queued %d" % k, s_out)
+        n_rows_total += n_k
+    created_total = int(h_totals[3 * (len(chunks) - 1) + 2]) - int(id_base)
+    for cs in comp + [fin, s_in]:
+        main.wait_stream(cs)
     h_status = _host(torch.stack([nms_out["status"][0], trk_out["status"][0]]), "pipe_status")
     main.wait_stream(s_out)
     main.synchronize()
+    _trace("all done")
     if int(h_status[1]) == _abi.W2T_ERR_CAPACITY:
         return ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, NC, iou_thresh, soft_nms_cut,
                                   min_score, score_thr, iou_thresholds, max_age, min_hits, max_group, False, id_base,
                                   raw=False)
     check_device_status(int(h_status[0]), "soft-NMS")
     check_device_status(int(h_status[1]), "SORT")
-    res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 16 * len(chunks) + 8,
+    res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 24 * len(chunks) + 8,
            "launches": 6 * len(chunks), "n_chunks": len(chunks)}
     for key in _ROW_KEYS[:-1]:
         pool = _PINNED[("pipe_" + key, {"rows_box": f64, "rows_score": f64, "rows_id": torch.int64,
