@@ -208,7 +208,11 @@ def sort_track(packed, iou_thresholds, max_age, min_hits, final_cap=0):
 def softnms_groups(group_offsets, rows, iou_thresh, soft_nms_cut, min_score, n_classes=0, score_thr=None,
                    box_format=0, top_k=0, conf_thresh=0.0, hard=False):
     group_offsets = _c(group_offsets, np.int32)
-    rows = _c(rows, np.float64).reshape(-1, 5)
+    if isinstance(rows, np.ndarray) and rows.dtype.names is not None:   # packing.compact_rows
+        rows = np.ascontiguousarray(rows)
+        box_format = _abi.W2T_BOX_LTWH_I16
+    else:
+        rows = _c(rows, np.float64).reshape(-1, 5)
     G, N = len(group_offsets) - 1, len(rows)
     prob = _abi.NmsProblem()
     prob.n_groups = G

@@ -713,13 +713,22 @@ static int nms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r, int hard)
     const int n = p->group_offsets[g + 1] - base;
     const double *rows = p->rows + 5 * (size_t)base;
     for (int i = 0; i < n; i++) {
+      double unpacked[5];
       const double *rw = rows + 5 * i;
+      if (p->box_format == W2T_BOX_LTWH_I16) { /* 16-byte compact rows: double score + 4 x int16 */
+        const unsigned char *q = (const unsigned char *)p->rows + 16 * ((size_t)base + i);
+        short b[4];
+        memcpy(&unpacked[0], q, 8);
+        memcpy(b, q + 8, 8);
+        for (int k = 0; k < 4; k++) unpacked[1 + k] = (double)b[k];
+        rw = unpacked;
+      }
       if (p->box_format == W2T_BOX_XYXY) {
         for (int k = 0; k < 4; k++) pf[4 * i + k] = rw[1 + k];
       } else {
         /* ensemble.py:19-22 (rows of convert_submission only) then box_utils.py:32-35 */
         double cx = rw[1], cy = rw[2];
-        if (p->box_format == W2T_BOX_LTWH) { cx = cx + rw[3] / 2; cy = cy + rw[4] / 2; }
+        if (p->box_format == W2T_BOX_LTWH || p->box_format == W2T_BOX_LTWH_I16) { cx = cx + rw[3] / 2; cy = cy + rw[4] / 2; }
         double hw = rw[3] * 0.5, hh = rw[4] * 0.5;
         pf[4 * i + 0] = cx - hw;
         pf[4 * i + 1] = cy - hh;

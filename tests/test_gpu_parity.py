@@ -319,3 +319,24 @@ def test_pipelined_chunks_equal_the_single_pass():
         assert got["n_rows"] == want["n_rows"] and got["id_next"] == want["id_next"]
         for k in ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat"):
             np.testing.assert_array_equal(got[k], want[k])
+
+
+def test_compact_input_rows_equal_float64_rows():
+    cfg = synth.SynthConfig(n_segments=2, cameras=("FRONT", "SIDE_LEFT"), n_frames=20, n_submissions=3,
+                            objects_per_frame=40.0, seed=45)
+    scene = synth.make_scene(cfg)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    compact = packing.compact_rows(groups.rows)
+    a = compare_nms(groups, 0.5, 0.9, 0.01)
+    b = runtime.softnms_groups(groups.group_offsets, compact, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR,
+                               max_group=groups.max_group)
+    for k in ("merged", "src_index", "ens_count", "trk_count", "img_exists"):
+        np.testing.assert_array_equal(a[k], b[k])
+    args = (scene.stream_img_offsets, scene.cam_wh(), 4, 0.5, 0.9, 0.01, helpers.SCORE_THR, helpers.IOU_THR, 2, 0)
+    want = runtime.ensemble_and_track(groups.group_offsets, groups.rows, *args, max_group=groups.max_group,
+                                      want_ensemble=False, raw=False)
+    want = {k: np.array(want[k]) for k in ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat")}
+    got = runtime.ensemble_and_track_pipelined(groups.group_offsets, compact, *args, max_group=groups.max_group,
+                                               n_chunks=3)
+    for k, v in want.items():
+        np.testing.assert_array_equal(got[k], v)

@@ -294,3 +294,17 @@ def test_c_oracle_nms_api_matches_reference_golden():
             sc = g[p + "scores"][keep]
         assert keep == g[p + "keep"].tolist(), i
         np.testing.assert_array_equal(sc, g[p + "out_scores"])
+
+
+def test_compact_rows_give_the_same_ensemble():
+    g = golden_io.load("ensemble_c2_small")
+    scene = helpers.golden_scene(g)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    compact = packing.compact_rows(groups.rows)
+    assert compact is not None and compact.dtype.itemsize == 16
+    a = c_oracle.softnms_groups(groups.group_offsets, groups.rows, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR)
+    b = c_oracle.softnms_groups(groups.group_offsets, compact, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR)
+    for k in ("merged", "src_index", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box"):
+        np.testing.assert_array_equal(a[k], b[k])
+    assert packing.compact_rows(np.array([[0.5, 1.5, 2, 3, 4]])) is None          # non-integer box
+    assert packing.compact_rows(np.array([[0.5, 1, 2, 40000, 4]])) is None        # beyond int16

@@ -94,7 +94,7 @@ class NmsProblem(C.Structure):
     ]
 
 
-W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY = 0, 1, 2
+W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY, W2T_BOX_LTWH_I16 = 0, 1, 2, 3
 
 
 class NmsResult(C.Structure):

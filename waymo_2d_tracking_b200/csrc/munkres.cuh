@@ -432,8 +432,15 @@ struct Munkres {
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if (k < mw && k * 32 + lane < m) mn = fminf(mn, val[k]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    {
+      // warp minimum in one REDUX on an order-preserving integer image of the float (NaN sorts last,
+      // like fminf ignores it) instead of five dependent shuffle steps
+      unsigned u = __float_as_uint(mn);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      u = __reduce_min_sync(0xffffffffu, u);
+      u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+      mn = __uint_as_float(u);
+    }
     float *row = g.C + (size_t)r * ldc;
 #pragma unroll
     for (int k = 0; k < 4; k++) {

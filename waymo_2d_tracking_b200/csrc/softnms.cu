@@ -25,8 +25,9 @@ using namespace w2t;
 
 namespace {
 
-constexpr int kBytesPerBox = 8 /*raw score*/ + 6 * 8 /*x1 y1 x2 y2 area score*/ + 4 /*source index*/;
+constexpr int kBytesPerBox = 8 /*raw score*/ + 6 * 8 /*x1 y1 x2 y2 area score*/ + 4 /*source index*/ + 4 /*strip mask*/;
 constexpr int kMaxSmem = 227 * 1024;
+constexpr int kMaskPad = 32;  // the mask array is read 32 entries at a time
 
 struct NmsParams {
   w2t_nms_problem_t p;
@@ -40,6 +41,21 @@ struct NmsParams {
 // HARD = false: the soft branch (box_utils.py:335-391).  HARD = true: the hard branch
 // (box_utils.py:329-333), i.e. torchvision.ops.nms on the ascending-sorted boxes: greedy
 // suppression of every lower ranked box with IoU > overlap, scores untouched.
+// Coarse occupancy mask of a box: bits 0-15 = the 128-unit column strips its x extent touches,
+// bits 16-31 = the 128-unit row strips of its y extent (indices clamped to 0..15, so anything
+// outside [0, 2048) lands in the edge strips).  The strip index is a monotone function of the
+// coordinate: two boxes whose masks share no x strip (or no y strip) are strictly separated in
+// x (or y), their intersection is exactly +0, and the pair needs no FP64 arithmetic at all.
+// Irregular boxes (NaN, non-positive extent) get all ones = "always compute".
+__device__ __forceinline__ uint32_t strip_mask(double x1, double y1, double x2, double y2) {
+  if (!(x2 > x1 && y2 > y1)) return 0xffffffffu;
+  const int a = min(max(__double2int_rd(x1 * (1.0 / 128.0)), 0), 15), b = min(max(__double2int_rd(x2 * (1.0 / 128.0)), 0), 15);
+  const int c = min(max(__double2int_rd(y1 * (1.0 / 128.0)), 0), 15), d = min(max(__double2int_rd(y2 * (1.0 / 128.0)), 0), 15);
+  const uint32_t mx = ((2u << b) - 1u) & ~((1u << a) - 1u);
+  const uint32_t my = ((2u << d) - 1u) & ~((1u << c) - 1u);
+  return (mx & 0xffffu) | (my << 16);
+}
+
 template <int BLOCK, bool HARD>
 __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -49,6 +65,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   double *sx1 = raw + cap, *sy1 = sx1 + cap, *sx2 = sy1 + cap, *sy2 = sx2 + cap;
   double *sar = sy2 + cap, *ssc = sar + cap;
   int *src = reinterpret_cast<int *>(ssc + cap);
+  uint32_t *smk = reinterpret_cast<uint32_t *>(src + cap);  // coarse occupancy masks, see strip_mask()
 
   const int tid = threadIdx.x;
   const int g = blockIdx.x;
@@ -63,7 +80,22 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     }
     return;
   }
-  const double *rows = P.p.rows + 5 * (size_t)base;
+  const int fmt = P.p.box_format;
+  // row i of the group: score and the four box columns, from 40-byte double rows or 16-byte compact rows
+  const unsigned char *bytes = reinterpret_cast<const unsigned char *>(P.p.rows);
+  auto row_score = [&](int i) -> double {
+    return (fmt == W2T_BOX_LTWH_I16) ? *reinterpret_cast<const double *>(bytes + 16 * ((size_t)base + i))
+                                     : P.p.rows[5 * ((size_t)base + i)];
+  };
+  auto row_box = [&](int i, double &b0, double &b1, double &b2, double &b3) {
+    if (fmt == W2T_BOX_LTWH_I16) {
+      const short4 q = *reinterpret_cast<const short4 *>(bytes + 16 * ((size_t)base + i) + 8);
+      b0 = (double)q.x; b1 = (double)q.y; b2 = (double)q.z; b3 = (double)q.w;
+    } else {
+      const double *rw = P.p.rows + 5 * ((size_t)base + i);
+      b0 = rw[1]; b1 = rw[2]; b2 = rw[3]; b3 = rw[4];
+    }
+  };
 
   // 1. scores to shared memory
   const double conf = P.p.conf_thresh;
@@ -71,7 +103,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   const bool sequential = HARD || conf > 0.;
   bool bad = false;
   for (int i = tid; i < n; i += BLOCK) {
-    const double sc = rows[5 * i];
+    const double sc = row_score(i);
     raw[i] = sc;
     // without removals the reference keeps every box only if no score ever fails `ge(conf_thresh)`
     if (!HARD && !sequential && !(sc >= (conf < 0. ? conf : 0.))) bad = true;
@@ -82,7 +114,6 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   // 2. rank by counting, scatter the point-form box into rank order; with top_k only the best
   //    top_k boxes take part (box_utils.py:325-327)
   const int m = (P.p.top_k > 0 && P.p.top_k < n) ? P.p.top_k : n;
-  const int fmt = P.p.box_format;
   for (int i = tid; i < n; i += BLOCK) {
     const double si = raw[i];
     // G boxes score higher; of the equal ones L come earlier and H later in the input.
@@ -104,14 +135,15 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
       const int sel = E < m - G ? E : m - G;
       rank = G + L - (E - sel);
     }
-    const double *rw = rows + 5 * i;
+    double b0, b1, b2, b3;
+    row_box(i, b0, b1, b2, b3);
     double x1, y1, x2, y2;
     if (fmt == W2T_BOX_XYXY) {
-      x1 = rw[1]; y1 = rw[2]; x2 = rw[3]; y2 = rw[4];
+      x1 = b0; y1 = b1; x2 = b2; y2 = b3;
     } else {
-      const double w = rw[3], h = rw[4];
-      double cx = rw[1], cy = rw[2];
-      if (fmt == W2T_BOX_LTWH) { cx = cx + w / 2; cy = cy + h / 2; }  // lxly2cxcy, ensemble.py:19-22
+      const double w = b2, h = b3;
+      double cx = b0, cy = b1;
+      if (fmt == W2T_BOX_LTWH || fmt == W2T_BOX_LTWH_I16) { cx = cx + w / 2; cy = cy + h / 2; }  // lxly2cxcy, ensemble.py:19-22
       const double hw = w * 0.5, hh = h * 0.5;                         // point_form, box_utils.py:32-35
       x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
     }
@@ -121,6 +153,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     sar[rank] = area;
     ssc[rank] = si;
     src[rank] = i;
+    smk[rank] = strip_mask(x1, y1, x2, y2);
   }
   if (bad && P.status) atomicMax(P.status, W2T_ERR_ARG);
   __syncthreads();
@@ -135,6 +168,9 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   // weight box i (kept, higher ranked) applies to box j; box_utils.py:349-370
   auto pair_weight = [&](int i, double x1, double y1, double x2, double y2, double area, bool &one) -> double {
     const double ix1 = sx1[i], iy1 = sy1[i], ix2 = sx2[i], iy2 = sy2[i];
+    // strictly separated boxes: the clamped width or height below is 0, so inter = +0 (sufficient,
+    // not necessary: touching or degenerate cases fall through to the full computation)
+    if (skip_disjoint && (x2 <= ix1 || ix2 <= x1 || y2 <= iy1 || iy2 <= y1)) { one = true; return 1.0; }
     const double xx1 = x1 > ix1 ? x1 : ix1;
     const double yy1 = y1 > iy1 ? y1 : iy1;
     const double xx2 = x2 < ix2 ? x2 : ix2;
@@ -153,16 +189,42 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     if (wt > 1.) wt = 1.;
     return wt;
   };
+  // separated pairs leave box j untouched: weight exactly 1.0 (soft) / overlap 0 <= threshold (hard)
+  const bool mask_skip = HARD ? (P.p.iou_thresh >= 0.) : skip_disjoint;
   int *alive = reinterpret_cast<int *>(raw);  // the input-order scores are no longer needed
   if (!sequential) {
     // fixed-order triangular product: thread j multiplies the weights of every i ranked above it
     for (int j = tid; j < m; j += BLOCK) {
       const double x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j], area = sar[j];
       double live = ssc[j];
-      for (int i = 0; i < j; i++) {
-        bool one;
-        const double wt = pair_weight(i, x1, y1, x2, y2, area, one);
-        if (!one) live = live * wt;
+      const uint32_t mj = smk[j];
+      // 32 higher ranked boxes at a time: a divergence-free integer loop collects the candidates whose
+      // strip masks meet this box's in x and in y (a few percent of the pairs); only those go through
+      // the FP64 arithmetic, in rank order, so the product is multiplied in the reference's order.
+      for (int i0 = 0; i0 < j; i0 += 32) {
+        uint32_t cand = 0xffffffffu;
+        if (mask_skip) {
+          cand = 0u;
+          const uint4 *mk4 = reinterpret_cast<const uint4 *>(smk + i0);  // broadcast loads; padded past m
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const uint4 v = mk4[q];
+            const uint32_t t0 = mj & v.x, t1 = mj & v.y, t2 = mj & v.z, t3 = mj & v.w;
+            cand |= (uint32_t)((t0 & 0xffffu) != 0u && (t0 >> 16) != 0u) << (4 * q + 0);
+            cand |= (uint32_t)((t1 & 0xffffu) != 0u && (t1 >> 16) != 0u) << (4 * q + 1);
+            cand |= (uint32_t)((t2 & 0xffffu) != 0u && (t2 >> 16) != 0u) << (4 * q + 2);
+            cand |= (uint32_t)((t3 & 0xffffu) != 0u && (t3 >> 16) != 0u) << (4 * q + 3);
+          }
+        }
+        const int lim = j - i0;
+        if (lim < 32) cand &= (1u << lim) - 1u;
+        while (cand) {
+          const int i = i0 + __ffs(cand) - 1;
+          cand &= cand - 1u;
+          bool one;
+          const double wt = pair_weight(i, x1, y1, x2, y2, area, one);
+          if (!one) live = live * wt;
+        }
       }
       ssc[j] = live;
     }
@@ -174,8 +236,16 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     __syncthreads();
     for (int k = 0; k + 1 < m; k++) {
       if (!alive[k]) continue;  // uniform: shared memory, barrier-ordered
+      const uint32_t mk = smk[k];
       for (int j = k + 1 + tid; j < m; j += BLOCK) {
         if (!alive[j]) continue;
+        const uint32_t both = mk & smk[j];
+        const bool apart = mask_skip && ((both & 0xffffu) == 0u || (both >> 16) == 0u);
+        if (apart) {
+          // soft branch: the score is unchanged but still has to pass `ge(conf_thresh)` (box_utils.py:379)
+          if (!HARD && !(ssc[j] >= conf)) alive[j] = 0;
+          continue;
+        }
         if (HARD) {
           // torchvision nms_kernel_impl: ovr = inter / (iarea + areas[j] - inter); suppress if > thr
           const double kx1 = sx1[k], ky1 = sy1[k], kx2 = sx2[k], ky2 = sy2[k];
@@ -284,7 +354,7 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
   }
   if (problem->n_groups == 0) return W2T_OK;
   if (!problem->group_offsets || !problem->rows || !result->ens_count || (result->ens_box && !result->ens_score) ||
-      problem->box_format < W2T_BOX_LTWH || problem->box_format > W2T_BOX_XYXY || problem->top_k < 0) {
+      problem->box_format < W2T_BOX_LTWH || problem->box_format > W2T_BOX_LTWH_I16 || problem->top_k < 0) {
     set_last_error("%s: null buffer or bad box_format / top_k", who);
     return W2T_ERR_ARG;
   }
@@ -304,9 +374,9 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
   for (int i = 0; i < W2T_MAX_CLASSES; i++)
     P.score_thr[i] = (P.has_thr && i < problem->n_classes) ? problem->score_thr[i] : 0.0;
   P.p.score_thr = nullptr;
-  P.cap = (std::max(max_group_size, 1) + 1) & ~1;  // even: keeps the int array 8-byte aligned
+  P.cap = (std::max(max_group_size, 1) + 3) & ~3;  // multiple of 4: keeps the int arrays 16-byte aligned
   P.status = status;
-  const size_t smem = (size_t)P.cap * kBytesPerBox;
+  const size_t smem = (size_t)P.cap * kBytesPerBox + 4 * kMaskPad;
   if (max_group_size <= 96) return launch<64, HARD>(P, problem->n_groups, smem, stream);
   if (max_group_size <= 768) return launch<128, HARD>(P, problem->n_groups, smem, stream);
   return launch<256, HARD>(P, problem->n_groups, smem, stream);
@@ -314,7 +384,7 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
 
 }  // namespace
 
-extern "C" int w2t_softnms_max_group(void) { return (kMaxSmem - 1024) / kBytesPerBox; }
+extern "C" int w2t_softnms_max_group(void) { return (kMaxSmem - 1024 - 4 * kMaskPad) / kBytesPerBox; }
 
 extern "C" int w2t_softnms_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int max_group_size,
                                   int32_t *status, w2t_stream_t stream) {

@@ -110,6 +110,18 @@ __device__ __forceinline__ float iou_pair(const float4 d, const double t0, const
   return (float)(wh / den);
 }
 
+// Coarse occupancy mask of a box: bits 0-15 = the 120-pixel column strips its x extent touches,
+// bits 16-31 = the 80-pixel row strips of its y extent (indices clamped to 0..15).  The strip index
+// is a monotone function of the coordinate, so two boxes whose masks do not intersect in x (or
+// in y) are strictly disjoint in x (or y): their IoU is exactly +0 and needs no FP64 arithmetic.
+__device__ __forceinline__ uint32_t strip_mask(double x1, double y1, double x2, double y2) {
+  const int a = min(max(__double2int_rd(x1 * (1.0 / 120.0)), 0), 15), b = min(max(__double2int_rd(x2 * (1.0 / 120.0)), 0), 15);
+  const int c = min(max(__double2int_rd(y1 * (1.0 / 80.0)), 0), 15), d = min(max(__double2int_rd(y2 * (1.0 / 80.0)), 0), 15);
+  const uint32_t mx = ((2u << b) - 1u) & ~((1u << a) - 1u);
+  const uint32_t my = ((2u << d) - 1u) & ~((1u << c) - 1u);
+  return (mx & 0xffffu) | (my << 16);
+}
+
 __device__ __forceinline__ double clipd(double v, double lo, double hi) {
   // numpy.clip: minimum(maximum(v, lo), hi), NaN propagates
   if (v < lo) v = lo;
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   __shared__ int s_cstar[kSmemM], s_ucols[kSmemM];
   __shared__ double s_box[5][kSmemBox];  // x1, y1, x2, y2, area (NaN when the box is inverted)
   __shared__ __align__(16) float4 s_det[2][kSmemDet];  // double buffer: detections of this / the next image
+  __shared__ uint32_t s_tmask[kSmemBox], s_dmask[kSmemDet];  // strip masks (all ones = "always test exactly")
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int q = P.order[blockIdx.x];
@@ -316,10 +329,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
           double b[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) { b[k] = st[(kBoxAt + k) * Tcap + sl]; s_box[k][t] = b[k]; }
-          s_box[4][t] = (b[2] > b[0] && b[3] > b[1]) ? (b[2] - b[0]) * (b[3] - b[1]) : NAN;
+          const double area = (b[2] > b[0] && b[3] > b[1]) ? (b[2] - b[0]) * (b[3] - b[1]) : NAN;
+          s_box[4][t] = area;
+          s_tmask[t] = (area > 0.) ? strip_mask(b[0], b[1], b[2], b[3]) : 0xffffffffu;
         }
-        __syncthreads();
       }
+      const bool masked = boxes_staged && D <= kSmemDet;
+      if (masked) {
+        for (int d = tid; d < D; d += BLOCK) {
+          const float4 b = dets[d];
+          // regular detection: positive extent (its float32 area is then >= +0, sort.py:40-46)
+          s_dmask[d] = (b.z > b.x && b.w > b.y) ? strip_mask((double)b.x, (double)b.y, (double)b.z, (double)b.w)
+                                                : 0xffffffffu;
+        }
+      }
+      if (boxes_staged) __syncthreads();
       auto tbox = [&](int t, double &t0, double &t1, double &t2, double &t3, double &at) {
         if (boxes_staged) {
           t0 = s_box[0][t]; t1 = s_box[1][t]; t2 = s_box[2][t]; t3 = s_box[3][t]; at = s_box[4][t];
@@ -345,7 +369,26 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
       for (int r = warp; r < n; r += NW) {
         float *row = mk.g.C + (size_t)r * mk.ldc;
         float val[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!flipped) {
+        if (fused && masked) {
+          // strip masks settle almost every pair with one AND; the rest take the exact test
+          const uint32_t rm = flipped ? s_tmask[r] : s_dmask[r];
+          const uint32_t *cmask = flipped ? s_dmask : s_tmask;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int cc = k * 32 + lane;
+            if (k < mk.mw && cc < m) {
+              const uint32_t both = rm & cmask[cc];
+              float v = -0.0f;
+              if ((both & 0xffffu) != 0u && (both >> 16) != 0u) {
+                const int di = flipped ? cc : r, ti = flipped ? r : cc;
+                double t0, t1, t2, t3, at;
+                tbox(ti, t0, t1, t2, t3, at);
+                v = neg_iou(dets[di], t0, t1, t2, t3, at);
+              }
+              val[k] = v;
+            }
+          }
+        } else if (!flipped) {
           const float4 d = dets[r];
           if (fused) {
 #pragma unroll

@@ -264,3 +264,20 @@ def rows_to_dicts(packed, res):
     cat = np.asarray(res["rows_cat"]).tolist()
     return [{'image_id': ids[i], 'bbox': b, 'score': s, 'category_id': c, 'object_id': '%i' % o}
             for i, b, s, c, o in zip(img, box, score, cat, oid)]
+
+
+COMPACT_ROW = np.dtype([('score', np.float64), ('box', np.int16, 4)])   # 16 bytes, W2T_BOX_LTWH_I16
+
+
+def compact_rows(rows):
+    """[N,5] float64 rows (score*weight, left, top, width, height) -> 16-byte compact rows
+    (``W2T_BOX_LTWH_I16``) when every box coordinate is an integer in int16 range (how detectors
+    write them, detnet/data/coco.py:250), else None.  Same values, 2.5x fewer bytes to ship."""
+    rows = np.asarray(rows, np.float64).reshape(-1, 5)
+    box = rows[:, 1:]
+    if len(rows) and not (np.all(box == np.rint(box)) and box.min() >= -32768 and box.max() <= 32767):
+        return None
+    out = np.empty(len(rows), COMPACT_ROW)
+    out['score'] = rows[:, 0]
+    out['box'] = box.astype(np.int16)
+    return out

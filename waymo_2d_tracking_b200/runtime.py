@@ -70,6 +70,18 @@ def _dev(a, dtype, device):
     return a.to(device, non_blocking=True).contiguous()
 
 
+def _host_rows(rows):
+    """Ensemble input rows as a host tensor + their W2T_BOX_* layout: float64 [N,5] rows, or the
+    16-byte compact rows of ``packing.compact_rows`` (structured array / uint8 [N,16] tensor)."""
+    if isinstance(rows, np.ndarray) and rows.dtype.names is not None:
+        rows = torch.from_numpy(np.ascontiguousarray(rows).view(np.uint8).reshape(-1, 16))
+    if torch.is_tensor(rows) and rows.dtype == torch.uint8:
+        return rows.reshape(-1, 16), _abi.W2T_BOX_LTWH_I16
+    if isinstance(rows, np.ndarray):
+        rows = torch.from_numpy(np.ascontiguousarray(rows, np.float64))
+    return rows.reshape(-1, 5), _abi.W2T_BOX_LTWH
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -179,7 +191,10 @@ def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_sc
             offs_np = torch.as_tensor(group_offsets).cpu().numpy()
         max_group = int(np.diff(offs_np).max()) if n_groups > 0 else 0
     d_offsets = _dev(group_offsets, np.int32, device)
-    d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
+    t_rows, fmt = _host_rows(rows)
+    if fmt == _abi.W2T_BOX_LTWH_I16:
+        box_format = fmt
+    d_rows = t_rows.to(device, non_blocking=True).contiguous()
     out = softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
                                 n_classes, score_thr, want_merged, box_format, top_k, conf_thresh, want_ensemble,
                                 hard)
@@ -456,9 +471,10 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
         go = group_offsets if isinstance(group_offsets, np.ndarray) else torch.as_tensor(group_offsets).cpu().numpy()
         max_group = int(np.diff(go).max()) if n_groups else 0
     d_goff = _dev(group_offsets, np.int32, device)
-    d_rows = _dev(rows, np.float64, device).reshape(-1, 5)
+    t_rows, fmt = _host_rows(rows)
+    d_rows = t_rows.to(device, non_blocking=True).contiguous()
     nms = softnms_groups_device(d_goff, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, NC,
-                                score_thr, want_merged=False, want_ensemble=want_ensemble)
+                                score_thr, want_merged=False, want_ensemble=want_ensemble, box_format=fmt)
     d_offsets = _dev(h_offsets, np.int32, device)
     d_start = d_goff[:-1]
     if host_group_offsets is not None and not to_host and n_groups:
@@ -580,8 +596,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     h_offsets = np.ascontiguousarray(stream_img_offsets, np.int32)
     S = len(h_offsets) - 1
     t_goff = group_offsets if torch.is_tensor(group_offsets) else torch.from_numpy(np.ascontiguousarray(group_offsets, np.int32))
-    t_rows = rows if torch.is_tensor(rows) else torch.from_numpy(np.ascontiguousarray(rows, np.float64))
-    t_rows = t_rows.reshape(-1, 5)
+    t_rows, fmt = _host_rows(rows)
     go_np = t_goff.numpy()
     G = int(go_np.shape[0]) - 1
     N = int(t_rows.shape[0])
@@ -603,7 +618,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     i32, f64 = torch.int32, torch.float64
     n_img = int(h_offsets[-1])
     d_goff = torch.empty(G + 1, dtype=i32, device=device)
-    d_rows = torch.empty((N, 5), dtype=f64, device=device)
+    d_rows = torch.empty(t_rows.shape, dtype=t_rows.dtype, device=device)
     nms_out = {"ens_count": torch.empty(G, dtype=i32, device=device),
                "trk_count": torch.empty(G, dtype=i32, device=device),
                "trk_box": torch.empty((N, 4), dtype=torch.float32, device=device),
@@ -656,7 +671,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                      "trk_box": nms_out["trk_box"], "img_exists": nms_out["img_exists"][img0:img1],
                      "status": nms_out["status"]}
             softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
-                                  NC, score_thr, out=nms_k)
+                                  NC, score_thr, out=nms_k, box_format=fmt)
             trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"],
                      "out_birth": trk_out["out_birth"], "out_count": trk_out["out_count"][g0:g1],
                      "created": trk_out["created"][g0:g1], "first_img": trk_out["first_img"][s0 * NC:s1 * NC],
