@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-frames", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=6, help="pipeline depth of the end-to-end leg")
+    ap.add_argument("--skip-e2e", action="store_true",
+                    help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
     ap.add_argument("--wide-rows", action="store_true", help="ship 40-byte float64 input rows instead of 16-byte compact ones")
     return ap.parse_args()
 
@@ -245,9 +247,12 @@ def main():
     ms_dev, out = timed(step_device, args.steps)
     kernel_ms = runtime.collect_profile()
     runtime.PROFILE = None
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    ms_e2e, out_e2e = timed(step_e2e, args.steps)
+    if args.skip_e2e:
+        ms_e2e, out_e2e = float("nan"), {"n_rows": int(out["rows"]["totals"][1].item()), "d2h_bytes": 0}
+    else:
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        ms_e2e, out_e2e = timed(step_e2e, args.steps)
     clocks = sampler.summary()
 
     # ---- bookkeeping -------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; e
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err; cat $out/${tag}_bench_ref.json
 # launch list of the same command (shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-e2e > $out/${tag}_bench_under_ncu.log 2>&1
 # full captures (smaller batch: ncu replays each launch ~40 times)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sort_track_kernel -s 1 -c 1 -f -o $out/${tag}_prof_sort \
     python bench.py --segments 30 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_sort.log 2>&1
