@@ -33,6 +33,11 @@ const char *w2t_last_error(void);
 /* SM count and compute capability of the current device */
 int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Stream-ordered wait: work queued on `stream` after this call starts only once
+ * *addr >= value (device int32, e.g. a w2t_sort_plan_t.chunk_done counter).  Uses the driver's
+ * cuStreamWaitValue32; returns W2T_ERR_CUDA if the device does not support it. */
+int w2t_stream_wait_value32(w2t_stream_t stream, const int32_t *addr, int32_t value);
+
 /* ---- soft-NMS ensemble ------------------------------------------------- */
 
 /* Replaces the per-image loop of detnet/ensemble.py:145-157, i.e. ensemble()

@@ -47,6 +47,12 @@ typedef struct w2t_sort_plan_t {
   int32_t *det_cap;      /* max detections of that category in any one image of the stream   */
   int64_t *ws_offset;    /* byte offset of the sub-stream's slab in the workspace            */
   int64_t  ws_bytes;     /* total workspace size                                             */
+  /* optional completion tracking (both NULL = off): sub-stream q belongs to chunk chunk_of[q];  */
+  /* when its CTA has written everything it adds 1 to chunk_done[chunk_of[q]] (device int32,     */
+  /* zeroed by the caller).  Another stream can wait for a whole chunk with                      */
+  /* w2t_stream_wait_value32 and post-process it while the rest of the launch is still running.  */
+  const int32_t *chunk_of;
+  int32_t *chunk_done;
 } w2t_sort_plan_t;
 
 /* Inputs of the SORT stage (tracking/utils.py:25-60 for every stream at once).
@@ -105,6 +111,9 @@ typedef struct w2t_rows_t {
   int64_t  capacity;
   int32_t  image_base; /* added to every image index written: lets a caller finalize a shard   */
                        /*   (chunk of streams with shard-local image indices) of a larger job   */
+  int64_t  birth_group_base; /* subtracted from out_birth's group index: set it to the first    */
+                       /*   group of the shard when w2t_sort_track ran over the whole job but   */
+                       /*   w2t_sort_finalize is called per shard with shard-local arrays       */
 } w2t_rows_t;
 
 /* layout of the four box columns of w2t_nms_problem_t.rows */

@@ -33,7 +33,7 @@ def test_version_and_struct_sizes():
     lib = _lib.lib()
     assert b"sm_100a" in lib.w2t_version()
     assert ctypes.sizeof(_abi.SortProblem) == 8 + 6 * 8 + 8 * 8 + 8
-    assert ctypes.sizeof(_abi.SortPlan) == 5 * 8
+    assert ctypes.sizeof(_abi.SortPlan) == 7 * 8
 
 
 def test_sort_plan_bounds_and_order():

@@ -31,6 +31,8 @@ class SortPlan(C.Structure):
         ("det_cap", _p),
         ("ws_offset", _p),
         ("ws_bytes", C.c_int64),
+        ("chunk_of", _p),
+        ("chunk_done", _p),
     ]
 
 
@@ -75,6 +77,7 @@ class Rows(C.Structure):
         ("id_base_device", _p),
         ("capacity", C.c_int64),
         ("image_base", C.c_int32),
+        ("birth_group_base", C.c_int64),
     ]
 
 
@@ -116,6 +119,7 @@ EXPORTS = {
     "w2t_version": (C.c_char_p, []),
     "w2t_last_error": (C.c_char_p, []),
     "w2t_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "w2t_stream_wait_value32": (C.c_int, [_p, _p, C.c_int32]),
     "w2t_softnms_groups": (C.c_int, [C.POINTER(NmsProblem), C.POINTER(NmsResult), C.c_int, _p, _p]),
     "w2t_hardnms_groups": (C.c_int, [C.POINTER(NmsProblem), C.POINTER(NmsResult), C.c_int, _p, _p]),
     "w2t_softnms_max_group": (C.c_int, []),

@@ -31,6 +31,7 @@ struct FinParams {
   int32_t *rows_img, *rows_cat;
   int64_t rows_cap;
   int32_t image_base;
+  int64_t birth_base;
 };
 
 // One block per stream.
@@ -109,7 +110,7 @@ __global__ void rows_kernel(const FinParams P) {
       const double4 b = reinterpret_cast<const double4 *>(P.out_box)[src];
       reinterpret_cast<double4 *>(P.rows_box)[dst] = b;
       P.rows_score[dst] = P.out_score[src];
-      const int bg = P.out_birth[2 * src], bk = P.out_birth[2 * src + 1];
+      const int bg = (int)(P.out_birth[2 * src] - P.birth_base), bk = P.out_birth[2 * src + 1];
       P.rows_id[dst] = id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
       P.rows_img[dst] = img + P.image_base;
       P.rows_cat[dst] = c + 1;
@@ -177,6 +178,7 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
   P.rows_cat = rows->category;
   P.rows_cap = rows->capacity;
   P.image_base = rows->image_base;
+  P.birth_base = rows->birth_group_base;
   order_kernel<<<P.n_streams, 256, 0, st>>>(P);
   scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_created, P.scan_created, n_groups, P.totals);
   scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_count, P.scan_count, n_groups, P.totals + 1);

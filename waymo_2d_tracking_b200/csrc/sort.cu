@@ -76,14 +76,24 @@ extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_
   P.det_cap = plan->det_cap;
   P.ws_offset = plan->ws_offset;
   P.ws = static_cast<char *>(workspace);
+  P.chunk_of = plan->chunk_of;
+  P.chunk_done = (plan->chunk_of != nullptr) ? plan->chunk_done : nullptr;
   P.status = status;
   // debug aid: W2T_SORT_TIMERS=<device pointer as decimal> receives [n_substreams,16] phase cycle
   // counters from an instrumented instantiation of the same kernel (scripts/phase_timers.py)
   P.timers = getenv("W2T_SORT_TIMERS") ? reinterpret_cast<long long *>(strtoull(getenv("W2T_SORT_TIMERS"), nullptr, 10))
                                         : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  // occupancy experiment (debug aid): W2T_SORT_VARIANT selects a launch shape
+  const int variant = getenv("W2T_SORT_VARIANT") ? atoi(getenv("W2T_SORT_VARIANT")) : 0;
   if (P.timers != nullptr)
     sort_track_kernel<kSortBlock, kSortMinBlocks, true><<<nq, kSortBlock, 0, st>>>(P);
+  else if (variant == 1)
+    sort_track_kernel<64, 6, false, 4096><<<nq, 64, 0, st>>>(P);
+  else if (variant == 2)
+    sort_track_kernel<64, 7, false, 3072><<<nq, 64, 0, st>>>(P);
+  else if (variant == 3)
+    sort_track_kernel<96, 5, false, 4608><<<nq, 96, 0, st>>>(P);
   else
     sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq, kSortBlock, 0, st>>>(P);
   W2T_CUDA_TRY(cudaGetLastError());

@@ -47,7 +47,7 @@ constexpr int kSmemC = 6144;     // floats: cost matrix incl. pitch (e.g. 76 x 8
 constexpr int kSmemZ = 512;      // words : zero bit matrix
 constexpr int kSmemN = 128;      // rows
 constexpr int kSmemM = 256;      // columns
-constexpr int kSmemBox = 256;    // predicted tracker boxes staged per image
+constexpr int kSmemBox = 128;    // predicted tracker boxes staged per image
 constexpr int kSmemDet = 128;    // detections of the next image prefetched while this one is tracked
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -88,6 +88,8 @@ struct SortParams {
   char *ws;
   int32_t *status;
   long long *timers;  // optional [n_substreams,16] phase cycle counters (debug aid, may be NULL)
+  const int32_t *chunk_of;  // optional completion tracking, see w2t_sort_plan_t
+  int32_t *chunk_done;
 };
 
 // iou() of sort.py:33-47 as numba compiles it for (float32[:], float64[:]): the detection's
@@ -153,13 +155,16 @@ __device__ void partition3(int n, VAL val, FA fa, FB fb, int *dst, int *tmp, int
   nb = cb;
 }
 
-template <int BLOCK, int MINB, bool TIMERS>
+// SMEMC: floats of the shared-memory cost matrix (larger matrices live in the slab, everything else
+// of the solver stays in shared memory); with BLOCK and MINB (CTAs per SM the register budget is
+// capped for) it sets how many sub-streams an SM holds at a time.
+template <int BLOCK, int MINB, bool TIMERS, int SMEMC = kSmemC>
 __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParams P) {
   constexpr int NW = BLOCK / 32;
   __shared__ MunkresShared ms;
   __shared__ int s_scan[2 * NW];
   __shared__ int s_nan;
-  __shared__ __align__(16) float s_C[kSmemC];
+  __shared__ __align__(16) float s_C[SMEMC];
   __shared__ __align__(16) uint32_t s_Z[kSmemZ];
   __shared__ int s_rstar[kSmemN], s_rprime[kSmemN], s_crows[kSmemN];
   __shared__ int s_cstar[kSmemM], s_ucols[kSmemM];
@@ -318,8 +323,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
       mk.mw = munkres_words(m);
       mk.zs = munkres_zstride(m);
       mk.ldc = munkres_pitch(m);
-      const bool fits = (n * mk.ldc <= kSmemC) && (n * mk.zs <= kSmemZ) && (n <= kSmemN) && (m <= kSmemM);
+      // masks, stars and index lists of the solver live in shared memory whenever the problem is at
+      // most 128 x 128; the cost matrix itself joins them if it is small enough, else it stays in the
+      // slab (L1/L2) and the same solver runs on it
+      const bool fits = (n * mk.zs <= kSmemZ) && (n <= kSmemN) && (m <= 128);
       mk.g = fits ? g_smem : g_glob;
+      if (fits && n * mk.ldc > SMEMC) mk.g.C = g_glob.C;
       mk.rowwise = fits;
       // predicted boxes of the live trackers, by list position
       const bool boxes_staged = T <= kSmemBox;
@@ -578,6 +587,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
         kfb_to_dense(pb, Pd);
         for (int k = 0; k < 49; k++) dst[7 + k] = Pd[k];
       }
+    }
+  }
+
+  // completion tracking: everything this CTA wrote is visible before its chunk's counter moves
+  if (P.chunk_done != nullptr) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&P.chunk_done[P.chunk_of[q]], 1);
     }
   }
 }

@@ -332,6 +332,9 @@ def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, 
     for k in ("order", "track_cap", "det_cap", "ws_offset"):
         setattr(cplan, k, _ptr(d_plan[k]))
     cplan.ws_bytes = plan["ws_bytes"]
+    if plan.get("chunk_of") is not None:      # completion counters per chunk of sub-streams
+        d_plan["chunk_of"] = _dev(plan["chunk_of"], np.int32, device)
+        cplan.chunk_of, cplan.chunk_done = _ptr(d_plan["chunk_of"]), _ptr(plan["chunk_done"])
     res = _abi.SortResult()
     for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img", "final_count", "final_state"):
         setattr(res, k, _ptr(out.get(k)))
@@ -360,7 +363,7 @@ def assign_ids(n_streams, n_classes, h_offsets, h_start, h_out_count, h_created,
 
 
 def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank, id_base, rows_cap, image_base=0,
-                    rows=None, id_base_device=None):
+                    rows=None, id_base_device=None, birth_group_base=0):
     """Device-side ids + dense rows (``w2t_sort_finalize``) on the tensors ``sort_track_device`` returned.
     ``rows``: preallocated output tensors (same keys) to write into instead of allocating."""
     device = trk["out_box"].device
@@ -389,6 +392,7 @@ def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank,
     crows.capacity = cap
     crows.image_base = int(image_base)
     crows.id_base_device = _ptr(id_base_device)
+    crows.birth_group_base = int(birth_group_base)
     with _timed("finalize_kernels"):
         check(lib().w2t_sort_finalize(C.byref(prob), C.byref(res), _ptr(d_class_rank), int(id_base), n_groups,
                                       _ptr(ws), C.byref(crows), _stream()), "w2t_sort_finalize")
@@ -559,7 +563,9 @@ def _compute_streams(device, n=3):
     """n compute streams + one for the finalize kernels."""
     key = (device.index, "compute")
     if key not in _STREAMS:
-        _STREAMS[key] = [torch.cuda.Stream(device) for _ in range(n + 1)]
+        # the last one (finalize + hand-over kernels) gets the highest priority: its small CTAs must
+        # slip in between the CTAs of a SORT launch that fills the machine
+        _STREAMS[key] = [torch.cuda.Stream(device) for _ in range(n)] + [torch.cuda.Stream(device, priority=-1)]
     return list(_STREAMS[key])
 
 
@@ -582,9 +588,12 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                                  soft_nms_cut, min_score, score_thr, iou_thresholds, max_age, min_hits,
                                  max_group=None, id_base=0, n_chunks=6):
     """Host buffers in, dense host rows out (``rows_box/score/id/img/cat``), the same result as
-    :func:`ensemble_and_track` — with the streams cut into chunks so that the host->device copy of
-    chunk k+1, the kernels of chunk k and the device->host copy of chunk k-1 run concurrently
-    (three CUDA streams; PCIe is full duplex).
+    :func:`ensemble_and_track` — with the streams cut into chunks so that copies and kernels overlap
+    (PCIe is full duplex): the host->device copies of all chunks are queued on a copy stream; the
+    soft-NMS of a chunk starts when its rows have landed; the SORT stage is one launch over all
+    sub-streams whose CTAs are ordered chunk by chunk and count themselves into per-chunk completion
+    counters; ids, dense rows and the device->host copy of chunk k start as soon as chunk k is tracked
+    (stream wait on the counter), while the later chunks are still being tracked.
 
     No mid-pipeline round trip: the launch plan of the SORT stage (slab capacities) is computed on
     the host from the INPUT group sizes, an upper bound of what survives the ensemble.  (An image
@@ -647,23 +656,35 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
             h2d_done.append(ev)
             _trace("h2d queued %d" % len(h2d_done), s_in)
 
-    # 2. kernels: chunk k on compute stream k mod 3, so the latency-bound SORT kernels of
-    #    neighbouring chunks overlap; the finalize kernels of all chunks run in order on one stream
-    #    and hand the running id base from chunk to chunk on the device (w2t_rows_t.id_base_device)
+    # 2. kernels.  soft-NMS runs chunk by chunk behind the copies.  The SORT stage is ONE launch over
+    #    all sub-streams (it is latency-bound: a launch costs a full chain of images however few streams
+    #    it holds), ordered chunk by chunk, heaviest sub-stream first inside a chunk; every CTA counts
+    #    itself into its chunk's completion counter.  The finalize kernels of chunk k wait for that
+    #    counter on their own high-priority stream (w2t_stream_wait_value32), so ids, dense rows and the
+    #    copy home of chunk k overlap with the tracking of the later chunks.  The id base is handed
+    #    from chunk to chunk on the device (w2t_rows_t.id_base_device).
     comp = _compute_streams(device)
     fin = comp[-1]
     comp = comp[:-1]
     for cs in comp + [fin]:
         cs.wait_stream(main)
-    keep_alive, fin_done, rows_of, h_totals = [], [], [], _pinned_pool("pipe_totals", torch.int64, 3 * len(chunks))
-    prev_totals = None
+    nq = S * NC
+    plan_all = {"order": np.zeros(nq, np.int32), "track_cap": np.zeros(nq, np.int32), "det_cap": np.zeros(nq, np.int32),
+                "ws_offset": np.zeros(nq, np.int64), "chunk_of": np.zeros(nq, np.int32), "ws_bytes": 0}
+    pos = 0
     for k, (s0, s1) in enumerate(chunks):
         img0, img1 = int(h_offsets[s0]), int(h_offsets[s1])
         g0, g1 = img0 * NC, img1 * NC
-        ns = s1 - s0
         loc_offsets = (h_offsets[s0:s1 + 1] - h_offsets[s0]).astype(np.int32)
-        plan = make_plan(ns, NC, loc_offsets, sizes[g0:g1], exists_ub[img0:img1], max_age)
-        _trace("plan %d" % k)
+        plan = make_plan(s1 - s0, NC, loc_offsets, sizes[g0:g1], exists_ub[img0:img1], max_age)
+        q0, q1 = s0 * NC, s1 * NC
+        plan_all["order"][pos:pos + (q1 - q0)] = plan["order"] + q0
+        pos += q1 - q0
+        plan_all["track_cap"][q0:q1] = plan["track_cap"]
+        plan_all["det_cap"][q0:q1] = plan["det_cap"]
+        plan_all["ws_offset"][q0:q1] = plan["ws_offset"] + plan_all["ws_bytes"]
+        plan_all["ws_bytes"] += plan["ws_bytes"]
+        plan_all["chunk_of"][q0:q1] = k
         cs = comp[k % len(comp)]
         with torch.cuda.stream(cs):
             cs.wait_event(h2d_done[k])
@@ -672,30 +693,42 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                      "status": nms_out["status"]}
             softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
                                   NC, score_thr, out=nms_k, box_format=fmt)
-            trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"],
-                     "out_birth": trk_out["out_birth"], "out_count": trk_out["out_count"][g0:g1],
-                     "created": trk_out["created"][g0:g1], "first_img": trk_out["first_img"][s0 * NC:s1 * NC],
-                     "status": trk_out["status"]}
-            d_loc = _dev(loc_offsets, np.int32, device)
-            trk = sort_track_device(ns, NC, d_loc, d_goff[g0:g1], nms_k["trk_count"], nms_out["trk_box"],
-                                    nms_k["img_exists"], d_cam[s0:s1], iou_thresholds, max_age, min_hits, plan,
-                                    out=trk_k)
-            sorted_ev = torch.cuda.Event()
-            sorted_ev.record(cs)
-            _trace("sort queued %d" % k, cs)
-        with torch.cuda.stream(fin):
-            fin.wait_event(sorted_ev)
-            rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk, None, id_base if k == 0 else 0,
-                                     int(go_np[g1] - go_np[g0]), image_base=img0,
+    _trace("plans + nms queued")
+    for cs in comp + [s_in]:
+        main.wait_stream(cs)
+    done = torch.zeros(len(chunks), dtype=i32, device=device)
+    plan_all["chunk_done"] = done
+    d_offsets = _dev(h_offsets, np.int32, device)
+    counters_zeroed = torch.cuda.Event()     # recorded BEFORE the launch: the finalize stream must not wait for the kernel
+    counters_zeroed.record(main)
+    trk = sort_track_device(S, NC, d_offsets, d_goff[:-1], nms_out["trk_count"], nms_out["trk_box"],
+                            nms_out["img_exists"], d_cam, iou_thresholds, max_age, min_hits, plan_all, out=trk_out)
+    _trace("sort queued", main)
+    keep_alive, fin_done, rows_of, h_totals = [trk["_keepalive"]], [], [], _pinned_pool("pipe_totals", torch.int64, 3 * len(chunks))
+    prev_totals = None
+    with torch.cuda.stream(fin):
+        fin.wait_event(counters_zeroed)
+        for k, (s0, s1) in enumerate(chunks):
+            img0, img1 = int(h_offsets[s0]), int(h_offsets[s1])
+            g0, g1 = img0 * NC, img1 * NC
+            ns = s1 - s0
+            d_loc = _dev((h_offsets[s0:s1 + 1] - h_offsets[s0]).astype(np.int32), np.int32, device)
+            check(lib().w2t_stream_wait_value32(C.c_void_p(fin.cuda_stream), _ptr(done[k:]), ns * NC),
+                  "w2t_stream_wait_value32")
+            trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"], "out_birth": trk_out["out_birth"],
+                     "out_count": trk_out["out_count"][g0:g1], "created": trk_out["created"][g0:g1],
+                     "first_img": trk_out["first_img"][s0 * NC:s1 * NC]}
+            rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk_k, None, id_base if k == 0 else 0,
+                                     int(go_np[g1] - go_np[g0]), image_base=img0, birth_group_base=g0,
                                      id_base_device=None if prev_totals is None else prev_totals[2:])
             prev_totals = rows_k["totals"]
             h_totals[3 * k:3 * k + 3].copy_(rows_k["totals"], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(fin)
             fin_done.append(ev)
+            keep_alive += [rows_k["_keepalive"], d_loc]
+            rows_of.append(rows_k)
             _trace("finalize queued %d" % k, fin)
-        keep_alive += [trk["_keepalive"], rows_k["_keepalive"], d_loc, nms_k, trk_k]
-        rows_of.append(rows_k)
 
     # 3. results go home chunk by chunk, each as soon as its finalize is done, while later chunks compute
     n_rows_total, d2h_bytes = 0, 0
@@ -728,7 +761,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     check_device_status(int(h_status[0]), "soft-NMS")
     check_device_status(int(h_status[1]), "SORT")
     res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 24 * len(chunks) + 8,
-           "launches": 6 * len(chunks), "n_chunks": len(chunks)}
+           "launches": 5 * len(chunks) + 1, "n_chunks": len(chunks)}
     for key in _ROW_KEYS[:-1]:
         pool = _PINNED[("pipe_" + key, {"rows_box": f64, "rows_score": f64, "rows_id": torch.int64,
                                          "rows_img": i32, "rows_cat": i32}[key])]
