@@ -266,8 +266,22 @@ def main():
         if int(out[stage]["status"].item()) != 0:
             raise SystemExit("bench.py: %s kernel reported status %d" % (stage, int(out[stage]["status"].item())))
     n_trk = int(out["nms"]["trk_count"].sum().item())
-    if int(out["rows"]["totals"][1].item()) != int(out_e2e["n_rows"]):
+    n_dev_rows = int(out["rows"]["totals"][1].item())
+    if n_dev_rows != int(out_e2e["n_rows"]):
         raise SystemExit("bench.py: device-resident and end-to-end legs disagree on the number of rows")
+    parity = None
+    if not args.skip_e2e:
+        # full-size consistency of the two legs (single launch vs chunked pipeline): every row's track id,
+        # image, category and box must be identical, bit for bit
+        dev_rows = out["rows"]
+        same = True
+        for key, host_arr in (("rows_id", out_e2e["rows_id"]), ("rows_img", out_e2e["rows_img"]),
+                              ("rows_cat", out_e2e["rows_cat"]), ("rows_box", out_e2e["rows_box"]),
+                              ("rows_score", out_e2e["rows_score"])):
+            same = same and bool(torch.equal(dev_rows[key][:n_dev_rows].cpu(), torch.from_numpy(np.asarray(host_arr))))
+        if not same:
+            raise SystemExit("bench.py: the chunked end-to-end leg and the single-launch leg produced different rows")
+        parity = "all %d rows of the e2e leg (6 chunks) bit-identical to the single-launch leg" % n_dev_rows
     n_out = int(out_e2e["n_rows"])
     h2d = int(h_rows.numel() * h_rows.element_size() + h_offs.numel() * 4)
     d2h = int(out_e2e["d2h_bytes"])
@@ -301,7 +315,7 @@ def main():
                    "input_rows": "16 B compact (f64 score + 4 x int16 box)" if compact is not None else "40 B (5 x f64)",
                    "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (h2d / 1e9),
                    "parallelism": "streams sharded by segment, %d rank(s), no collective" % world,
-                   "generate_s": round(gen_s, 1)},
+                   "generate_s": round(gen_s, 1), "full_size_check": parity},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(out["launches"]) * K,

@@ -133,6 +133,34 @@ int w2t_assign_ids(int32_t n_streams, int32_t n_classes, const int32_t *stream_i
                    const int32_t *first_img, const int32_t *class_rank, const int32_t *out_birth,
                    int64_t id_base, int64_t *out_id, int64_t *id_next);
 
+/* ---- JSON in / out (host code) ----------------------- */
+
+/* Replaces json.load + the per-dict loops of detnet/ensemble.py:79 (load_input_submissions) and
+ * tracking/utils.py:65-67 (read_data_file): parses a submission / annotation file — a list of
+ * {"image_id", "category_id", "bbox": [x,y,w,h], "score"} objects, or {"annotations": [...]};
+ * "score" is optional (ground truth), other keys are skipped — straight into flat arrays.
+ * Image ids are interned in first-appearance order.  All functions here are HOST functions. */
+typedef struct w2t_json_dets w2t_json_dets_t;
+int w2t_json_load(const char *path, w2t_json_dets_t **out);
+int64_t w2t_json_count(const w2t_json_dets_t *dets);     /* rows                    */
+int64_t w2t_json_n_images(const w2t_json_dets_t *dets);  /* distinct image ids      */
+/* any pointer may be NULL; bbox is [count,4]; has_score[i] = 0 where the row had no "score" (score 1.0) */
+int w2t_json_copy(const w2t_json_dets_t *dets, int32_t *image_index, int32_t *category, double *bbox,
+                  double *score, uint8_t *has_score);
+/* the distinct image ids, each followed by '\n', in first-appearance order; valid until w2t_json_free */
+const char *w2t_json_image_ids(w2t_json_dets_t *dets, int64_t *bytes);
+void w2t_json_free(w2t_json_dets_t *dets);
+
+/* Replace json.dump of tracking/track.py:50 (rows of tracking/utils.py:52-58) and of
+ * detnet/ensemble.py:159-160 (rows of :61-62).  Byte-identical to the reference's files: default
+ * separators, ensure_ascii, floats as Python's float.__repr__.  image_ids[k] = NUL-terminated
+ * id of image k; image[i] indexes it. */
+int w2t_json_write_tracks(const char *path, int64_t n, const char *const *image_ids, const int32_t *image,
+                          const double *bbox, const double *score, const int32_t *category,
+                          const int64_t *object_id);
+int w2t_json_write_detections(const char *path, int64_t n, const char *const *image_ids, const int32_t *image,
+                              const int32_t *category, const int32_t *bbox, const double *score);
+
 /* ---- building blocks (unit-parity entry points) ------------------------- */
 
 /* iou() of sort.py:33-47 for every (detection, tracker) pair, as filled into

@@ -1,0 +1,130 @@
+"""CPU tests of the native JSON reader / writer (csrc/json_io.cpp) and of the array packers that sit
+behind both CLIs: same arrays as Python's json + the reference-shaped dict loops, and files that are
+byte-identical to json.dump of the reference's row dicts."""
+import json
+
+import numpy as np
+import pytest
+
+import helpers
+from waymo_2d_tracking_b200 import native_json, packing, synth
+from waymo_2d_tracking_b200._lib import W2TError
+from waymo_2d_tracking_b200.detnet import ensemble as ens
+from waymo_2d_tracking_b200.tracking import utils as trk_utils
+
+
+def scene_and_lists(seed=9):
+    cfg = synth.SynthConfig(n_segments=3, cameras=("SIDE_LEFT", "FRONT", "FRONT_RIGHT"), n_frames=12,
+                            n_submissions=3, objects_per_frame=25.0, seed=seed)
+    scene = synth.make_scene(cfg)
+    return scene, [synth.to_json_list(scene, s) for s in scene.submissions]
+
+
+def test_reader_matches_python_json(tmp_path):
+    _, subs = scene_and_lists()
+    dets = subs[0]
+    dets[3]['extra'] = {"a": [1, 2, {"b": None}], "c": "x\"y\\z", "d": [True, False, 1.5e-3]}
+    dets[5]['score'] = 1                              # an int where a float is usual
+    dets[7]['image_id'] = 'se\u00e9g/12/FRONT'         # non-ASCII id (json.dump escapes it)
+    del dets[9]['score']                              # ground-truth style row
+    dets[11]['bbox'] = [1.5, -2.25, 3e2, 4.0]
+    path = tmp_path / "s.json"
+    path.write_text(json.dumps(dets, indent=1))       # whitespace everywhere
+    got = native_json.load(path)
+    ref = json.loads(path.read_text())
+    assert [got.image_ids[i] for i in got.image_index] == [r['image_id'] for r in ref]
+    assert got.image_ids == list(dict.fromkeys(r['image_id'] for r in ref))       # first-appearance order
+    assert got.category.tolist() == [r['category_id'] for r in ref]
+    assert got.bbox.tolist() == [[float(v) for v in r['bbox']] for r in ref]
+    assert got.score.tolist() == [float(r.get('score', 1.0)) for r in ref]
+    assert got.has_score.tolist() == [int('score' in r) for r in ref]
+    path.write_text(json.dumps({'images': [{'id': 1}], 'annotations': dets[:10]}))
+    assert len(native_json.load(path)) == 10
+    path.write_text("[]")
+    empty = native_json.load(path)
+    assert len(empty) == 0 and empty.image_ids == []
+
+
+@pytest.mark.parametrize("text", ['[{"image_id": "a/1/FRONT", "category_id": 1}]', '[{"image_id": "a", "bbox": [1,2,3]',
+                                  '{"images": []}', '[1, 2]', '[] trailing'])
+def test_reader_refuses_malformed_input(tmp_path, text):
+    path = tmp_path / "bad.json"
+    path.write_text(text)
+    with pytest.raises(W2TError):
+        native_json.load(path)
+    with pytest.raises(W2TError):
+        native_json.load(tmp_path / "missing.json")
+
+
+def test_writers_are_byte_identical_to_json_dump(tmp_path):
+    rng = np.random.default_rng(0)
+    ids = ['seg_%d/%d/FRONT' % (i // 7, 1000 + i) for i in range(40)] + ['s\u00e9g "q"\\/1/SIDE_LEFT']
+    n = 3000
+    box = np.c_[rng.uniform(0, 1920, (n, 2)), rng.uniform(1, 300, (n, 2))]
+    box[0] = [0.0, 1e-7, 123456789.0, 1e16]                          # repr switches to exponents at 1e16 ...
+    box[1] = [5e-324, 1.7976931348623157e308, 0.1 + 0.2, 100.0]
+    box[2] = [1e-5, 0.0001, 1e15, 123456.789e3]                       # ... and below 1e-4
+    box[3] = [-0.0, -1.5, 2.0 ** 53, 1 / 3]
+    score = np.clip(rng.uniform(0, 1.2, n), 0.2, 1.0)
+    img, cat, oid = rng.integers(0, len(ids), n), rng.integers(1, 5, n), rng.integers(1, 10 ** 9, n)
+    rows = [{'image_id': ids[i], 'bbox': [np.float64(v) for v in b], 'score': np.float64(s), 'category_id': int(c),
+             'object_id': '%i' % o} for i, b, s, c, o in zip(img, box, score, cat, oid)]
+    a, b = tmp_path / "py.json", tmp_path / "native.json"
+    a.write_text(json.dumps(rows))
+    native_json.write_tracks(b, ids, img, box, score, cat, oid)
+    assert a.read_bytes() == b.read_bytes()
+    ibox = rng.integers(-5, 2000, (n, 4))
+    s5 = np.round(rng.uniform(0, 1, n), 5)
+    rows = [{'image_id': ids[i], 'category_id': int(c), 'bbox': [int(v) for v in bb], 'score': np.float64(s)}
+            for i, c, bb, s in zip(img, cat, ibox, s5)]
+    a.write_text(json.dumps(rows))
+    native_json.write_detections(b, ids, img, cat, ibox, s5)
+    assert a.read_bytes() == b.read_bytes()
+    native_json.write_tracks(b, [], [], np.zeros((0, 4)), [], [], [])
+    assert b.read_text() == "[]"
+
+
+def test_array_packers_equal_the_dict_packers(tmp_path):
+    scene, subs = scene_and_lists()
+    rng = np.random.default_rng(1)
+    d = subs[0]
+    rng.shuffle(d)                                   # streams, frames and categories first appear in any order
+    d = [r for r in d if not (r['image_id'].endswith('FRONT') and r['image_id'].split('/')[1].endswith('500000'))]
+    d[5]['bbox'][2] = 0                              # invalid box: the frame still exists
+    d[6]['score'] = 0.0
+    path = tmp_path / "a.json"
+    path.write_text(json.dumps(d))
+    pred = trk_utils.read_data_file(str(path), helpers.SCORE_THR)
+    want = packing.pack_predictions(pred, 4)
+    got = packing.pack_detections(native_json.load(path), helpers.SCORE_THR, 4)
+    assert got.streams == want.streams
+    for k in ("frame_ids", "stream_img_offsets", "det_start", "det_count", "det_box", "cam_wh", "class_rank"):
+        np.testing.assert_array_equal(getattr(got, k), getattr(want, k), err_msg=k)
+    seg = want.streams[2][0]
+    one = packing.pack_detections(native_json.load(path), helpers.SCORE_THR, 4, segment_id=seg)
+    w1 = packing.pack_predictions({seg: pred[seg]}, 4)
+    assert one.streams == w1.streams
+    np.testing.assert_array_equal(one.det_box, w1.det_box)
+    np.testing.assert_array_equal(one.class_rank, w1.class_rank)
+    # errors of the dict path, raised by the array path too
+    d.append({'image_id': d[0]['image_id'], 'category_id': 9, 'bbox': [0, 0, 5, 5], 'score': 1.0})
+    path.write_text(json.dumps(d))
+    with pytest.raises(IndexError):
+        packing.pack_detections(native_json.load(path), helpers.SCORE_THR, 4)
+    path.write_text(json.dumps([{'image_id': 'no-slashes', 'category_id': 1, 'bbox': [0, 0, 5, 5], 'score': 1.0}]))
+    with pytest.raises(ValueError):
+        packing.pack_detections(native_json.load(path), helpers.SCORE_THR, 4)
+    path.write_text(json.dumps([{'image_id': 'a/1/TOP', 'category_id': 1, 'bbox': [0, 0, 5, 5], 'score': 1.0}]))
+    with pytest.raises(KeyError):
+        packing.pack_detections(native_json.load(path), helpers.SCORE_THR, 4)
+    # ensemble side
+    files = []
+    for k, s in enumerate(subs):
+        pk = tmp_path / ("s%d.json" % k)
+        pk.write_text(json.dumps(s))
+        files.append(native_json.load(pk))
+    a = packing.pack_detection_files(files, [1.0, 0.5, 0.25], 0.05)
+    b = ens.pack_submission_lists(subs, [1.0, 0.5, 0.25], 0.05)
+    assert a.image_ids == b.image_ids and a.category_ids == b.category_ids and a.max_group == b.max_group
+    for k in ("group_offsets", "rows", "sub_counts"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)

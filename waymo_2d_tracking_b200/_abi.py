@@ -138,6 +138,14 @@ EXPORTS = {
     "w2t_kf_init": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
     "w2t_kf_predict": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
     "w2t_kf_update": (C.c_int, [_p, _p, _p, _p, C.c_int32, _p]),
+    "w2t_json_load": (C.c_int, [C.c_char_p, C.POINTER(_p)]),
+    "w2t_json_count": (C.c_int64, [_p]),
+    "w2t_json_n_images": (C.c_int64, [_p]),
+    "w2t_json_copy": (C.c_int, [_p, _p, _p, _p, _p, _p]),
+    "w2t_json_image_ids": (_p, [_p, C.POINTER(C.c_int64)]),
+    "w2t_json_free": (None, [_p]),
+    "w2t_json_write_tracks": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p, _p]),
+    "w2t_json_write_detections": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p]),
     "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, _p]),
     "w2t_x_to_bbox": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
 }

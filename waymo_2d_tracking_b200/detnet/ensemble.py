@@ -32,12 +32,12 @@ from pathlib import Path
 import numpy as np
 
 try:
-    from .. import _abi, packing, runtime, sharding
+    from .. import _abi, native_json, packing, runtime, sharding
 except ImportError:                     # imported as top-level `detnet` (PYTHONPATH=.../waymo_2d_tracking_b200)
     import os as _os
     import sys as _sys
     _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
-    from waymo_2d_tracking_b200 import _abi, packing, runtime, sharding
+    from waymo_2d_tracking_b200 import _abi, native_json, packing, runtime, sharding
 from .nn.tta import merge_detections, nms_detections
 from .trainer.utils import get_num_workers
 
@@ -259,9 +259,9 @@ def main(argv=None):
     elif args.method == 'soft_nms':
         merge_func = partial(nms_detections, iou_thresh=args.iou_thresh, soft=True, soft_nms_cut=args.soft_nms_cut)
 
-    submissions = [json.load(Path(f).open()) for f in input_files]
     import os
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        submissions = [json.load(Path(f).open()) for f in input_files]
         # launched by torchrun: images sharded over the ranks / GPUs, rank 0 gathers and writes
         sharding.init_from_env()
         output_json = sharding.ensemble_sharded(submissions, list(input_weights), args.method, args.iou_thresh,
@@ -270,17 +270,20 @@ def main(argv=None):
             with output_file.open('wt') as fp:
                 json.dump(output_json, fp)
         return output_json
-    groups = pack_submission_lists(submissions, input_weights, args.min_score)
+    # native reader / writer: files <-> flat arrays, no per-detection Python objects
+    groups = packing.pack_detection_files([native_json.load(f) for f in input_files], input_weights, args.min_score)
     print('No. Images:', len(groups.image_ids))
     print('No. categories:', len(groups.category_ids))
-    output_json = []
-    if len(groups.image_ids):
-        res = merge_groups(groups, args.method, args.iou_thresh, args.soft_nms_cut, args.min_score)
-        output_json = rows_to_json(groups, res)
-
-    with output_file.open('wt') as fp:
-        json.dump(output_json, fp)
-    return output_json
+    if not len(groups.image_ids):
+        native_json.write_detections(output_file, [], [], [], np.zeros((0, 4), np.int32), [])
+        return 0
+    res = merge_groups(groups, args.method, args.iou_thresh, args.soft_nms_cut, args.min_score)
+    ncat = len(groups.category_ids)
+    rows, grp = packing.valid_row_index(np.asarray(groups.group_offsets, np.int64)[:-1], res["ens_count"])
+    native_json.write_detections(output_file, groups.image_ids, grp // ncat,
+                                 np.asarray(groups.category_ids, np.int32)[grp % ncat], res["ens_box"][rows],
+                                 res["ens_score"][rows])
+    return len(rows)
 
 
 if __name__ == '__main__':

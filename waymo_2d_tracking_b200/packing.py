@@ -281,3 +281,120 @@ def compact_rows(rows):
     out['score'] = rows[:, 0]
     out['box'] = box.astype(np.int16)
     return out
+
+
+# ---------------------------------------------------------------------------
+# array paths (native JSON reader -> packed arrays, no per-detection Python objects)
+# ---------------------------------------------------------------------------
+
+def pack_detections(dets, score_threshold, n_classes, segment_id=None):
+    """``read_data_file`` (tracking/utils.py:63-96) + :func:`pack_predictions` on the flat arrays of
+    ``native_json.load``: same streams (segments, then cameras, in first-appearance order of the
+    file), same frames (every frame that occurs in the file, filtered or not), same surviving rows
+    in the same order, same category first-appearance ranks.  ``segment_id`` keeps one segment only
+    (``track.py --segment-id``)."""
+    NC = int(n_classes)
+    thr = np.asarray(score_threshold, np.float64)
+    # image id -> (segment, frame, camera); ValueError for anything but two slashes, like utils.py:70
+    seg_of, cam_of, frame_of = [], [], np.zeros(len(dets.image_ids), np.int64)
+    seg_index, cam_names = {}, {}
+    for i, image_id in enumerate(dets.image_ids):
+        seg, frame, cam = image_id.split('/')
+        seg_of.append(seg_index.setdefault(seg, len(seg_index)))
+        cam_of.append(cam_names.setdefault(cam, len(cam_names)))
+        frame_of[i] = int(frame)
+    seg_of, cam_of = np.asarray(seg_of, np.int64), np.asarray(cam_of, np.int64)
+    segments, cameras = list(seg_index), list(cam_names)
+    n_cam = max(len(cameras), 1)
+    # streams in first-appearance order: segment dict order, camera dict order inside the segment.
+    # image ids are interned in first-appearance order, so the first image of a (segment, camera)
+    # pair has the smallest image index of that pair.
+    pair = seg_of * n_cam + cam_of
+    upair, first_img = np.unique(pair, return_index=True)
+    seg_first = np.full(len(segments), np.iinfo(np.int64).max)
+    np.minimum.at(seg_first, upair // n_cam, first_img)
+    order = np.lexsort((first_img, seg_first[upair // n_cam]))
+    stream_pairs = upair[order]
+    if segment_id is not None:
+        mask = np.asarray([segments[int(p) // n_cam] == segment_id for p in stream_pairs], bool)
+        stream_pairs = stream_pairs[mask] if len(stream_pairs) else stream_pairs
+    stream_of_pair = {int(p): s for s, p in enumerate(stream_pairs)}
+    streams = [(segments[int(p) // n_cam], cameras[int(p) % n_cam]) for p in stream_pairs]
+    for _, cam in streams:
+        camera_size(cam)                                  # KeyError for an unknown camera (utils.py:21)
+    S = len(streams)
+    # images of each stream sorted by frame id
+    img_stream = np.asarray([stream_of_pair.get(int(p), -1) for p in pair], np.int64)
+    used = np.nonzero(img_stream >= 0)[0]
+    img_order = used[np.lexsort((frame_of[used], img_stream[used]))]
+    new_img = np.full(len(dets.image_ids), -1, np.int64)
+    new_img[img_order] = np.arange(len(img_order))
+    offsets = np.zeros(S + 1, np.int64)
+    np.cumsum(np.bincount(img_stream[used], minlength=S), out=offsets[1:])
+    # filters of read_data_file, in its order: box validity first, then the category's threshold
+    box = dets.bbox
+    valid = ~((box[:, 2] < 1) | (box[:, 3] < 1)) & (new_img[dets.image_index] >= 0)
+    cat = dets.category.astype(np.int64)
+    bad_cat = valid & ((cat < 1) | (cat > min(NC, len(thr))))
+    if bad_cat.any():
+        raise IndexError("list index out of range: category_id %d with %d thresholds"
+                         % (int(cat[np.nonzero(bad_cat)[0][0]]), min(NC, len(thr))))
+    keep = valid.copy()
+    keep[valid] = ~(dets.score[valid] < thr[cat[valid] - 1])
+    rows = np.nonzero(keep)[0]
+    img = new_img[dets.image_index[rows]]
+    key = img * NC + (cat[rows] - 1)
+    order = np.argsort(key, kind='stable')               # file order inside a group
+    b = box[rows][order]
+    det_box = np.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2], b[:, 1] + b[:, 3]], 1).astype(np.float32)
+    n_img = int(offsets[-1])
+    counts = np.bincount(key, minlength=n_img * NC).astype(np.int32)
+    start = (np.cumsum(counts, dtype=np.int64) - counts).astype(np.int32)
+    # position of each category in the stream's tracker dict: first surviving row in (frame, file) order
+    pos_first = np.full(S * NC, np.iinfo(np.int64).max, np.int64)
+    stream_of_row = np.searchsorted(offsets, img, side='right') - 1
+    np.minimum.at(pos_first, stream_of_row * NC + (cat[rows] - 1), img * (len(dets) + 1) + rows)
+    rank = np.argsort(np.argsort(pos_first.reshape(S, NC), axis=1, kind='stable'), axis=1, kind='stable')
+    cam_wh = np.asarray([camera_size(c) for _, c in streams], np.float64).reshape(-1, 2)
+    return PackedTracks(
+        n_streams=S, n_classes=NC, streams=streams, frame_ids=frame_of[img_order],
+        stream_img_offsets=offsets.astype(np.int32), det_start=start, det_count=counts,
+        det_box=np.ascontiguousarray(det_box), cam_wh=cam_wh, img_exists=None,
+        class_rank=rank.astype(np.int32).reshape(-1), n_rows=int(det_box.shape[0]))
+
+
+def pack_detection_files(files, weights, min_score):
+    """``load_input_submissions`` (detnet/ensemble.py:78-84) + grouping on the flat arrays of
+    ``native_json.load``: one ``Detections`` per input file -> :class:`PackedGroups` with images in
+    sorted order and categories ascending, rows of a group in (file, JSON) order."""
+    category_ids = sorted(set(int(c) for d in files for c in np.unique(d.category)))
+    cat_index = np.full((max(category_ids) + 1) if category_ids else 1, -1, np.int64)
+    for i, c in enumerate(category_ids):
+        cat_index[c] = i
+    kept = []
+    for d, w in zip(files, weights):
+        score = d.score * np.float64(w)
+        keep = (d.bbox[:, 2] > 0) & (d.bbox[:, 3] > 0) & (score >= min_score)
+        kept.append((keep, score))
+    image_ids = sorted(set(d.image_ids[i] for d, (keep, _) in zip(files, kept) for i in np.unique(d.image_index[keep])))
+    img_index = {s: i for i, s in enumerate(image_ids)}
+    ncat = max(len(category_ids), 1)
+    G = len(image_ids) * ncat
+    per_file_keys, per_file_rows = [], []
+    for d, (keep, score) in zip(files, kept):
+        local_to_global = np.asarray([img_index.get(s, -1) for s in d.image_ids], np.int64)
+        idx = np.nonzero(keep)[0]
+        per_file_keys.append(local_to_global[d.image_index[idx]] * ncat + cat_index[d.category[idx]])
+        per_file_rows.append(np.concatenate([score[idx, None], d.bbox[idx]], axis=1))
+    keys = np.concatenate(per_file_keys) if per_file_keys else np.zeros(0, np.int64)
+    rows = np.concatenate(per_file_rows) if per_file_rows else np.zeros((0, 5))
+    order = np.argsort(keys, kind='stable')
+    counts = np.bincount(keys, minlength=G) if G else np.zeros(0, np.int64)
+    offsets = np.zeros(G + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    if G:
+        sub_counts = np.stack([np.bincount(k, minlength=G) for k in per_file_keys], axis=1).astype(np.int32)
+    else:
+        sub_counts = np.zeros((0, max(len(files), 1)), np.int32)
+    return PackedGroups(image_ids, category_ids, offsets.astype(np.int32), np.ascontiguousarray(rows[order]),
+                        int(counts.max()) if G else 0, sub_counts)

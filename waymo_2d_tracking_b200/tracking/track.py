@@ -18,9 +18,9 @@ import warnings
 from os.path import dirname, join
 
 try:
-    from .utils import read_data_file, track_all, sharding
+    from .utils import native_json, packing, read_data_file, sharding, track_packed
 except ImportError:                     # run as a script from inside tracking/, like the reference
-    from utils import read_data_file, track_all, sharding
+    from utils import native_json, packing, read_data_file, sharding, track_packed
 
 warnings.simplefilter(action='ignore', category=FutureWarning)
 
@@ -50,32 +50,43 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     print(args)
 
-    predictions = read_data_file(args.input, args.score_threshold)
+    # native reader: the file goes straight into flat arrays (no per-detection dicts); the grouping,
+    # filters and ordering of read_data_file (utils.py:63-96) are applied by packing.pack_detections
+    dets = native_json.load(args.input)
     image_id2path = {}
     ground_truth_dir = dirname(args.ground_truth)
     with open(args.ground_truth) as fp:
         for image in json.load(fp):
             image_id2path[image['id']] = join(ground_truth_dir, image['file_name'])
 
-    if args.segment_id:
-        predictions = {k: v for k, v in predictions.items() if k == args.segment_id}
-
-    start_time = time.time()
-    for segment_id in predictions.keys():
-        print(segment_id)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         # launched by torchrun: one rank per GPU, segments sharded, rank 0 gathers and writes
+        predictions = read_data_file(args.input, args.score_threshold)
+        if args.segment_id:
+            predictions = {k: v for k, v in predictions.items() if k == args.segment_id}
+        start_time = time.time()
+        for segment_id in predictions.keys():
+            print(segment_id)
         sharding.init_from_env()
         tracked_predictions, _ = sharding.track_all_sharded(predictions, args.iou_threshold, args.max_age,
                                                             args.min_hits)
         if tracked_predictions is None:
             return None
-    else:
-        tracked_predictions = track_all(predictions, args.iou_threshold, args.max_age, args.min_hits)
+        print("duration: %.2fs" % (time.time() - start_time))
+        with open(args.output, 'wt') as fp:
+            json.dump(tracked_predictions, fp)
+        return len(tracked_predictions)
+
+    n_classes = len(args.iou_threshold)
+    packed = packing.pack_detections(dets, args.score_threshold, n_classes, segment_id=args.segment_id or None)
+    start_time = time.time()
+    for segment_id in dict.fromkeys(seg for seg, _ in packed.streams):
+        print(segment_id)
+    res = track_packed(packed, args.iou_threshold, args.max_age, args.min_hits)
     print("duration: %.2fs" % (time.time() - start_time))
-    with open(args.output, 'wt') as fp:
-        json.dump(tracked_predictions, fp)
-    return tracked_predictions
+    native_json.write_tracks(args.output, packing.image_id_strings(packed), res["rows_img"], res["rows_box"],
+                             res["rows_score"], res["rows_cat"], res["rows_id"])
+    return int(res["n_rows"])
 
 
 if __name__ == '__main__':

@@ -12,13 +12,13 @@ import warnings
 import numpy as np
 
 try:                                    # package import (python -m waymo_2d_tracking_b200.tracking.track)
-    from .. import packing, runtime, sharding
+    from .. import native_json, packing, runtime, sharding
     from .sort import sort as _sort
 except ImportError:                     # `python track.py` inside tracking/, or top-level `tracking` package
     import os as _os
     import sys as _sys
     _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
-    from waymo_2d_tracking_b200 import packing, runtime, sharding
+    from waymo_2d_tracking_b200 import native_json, packing, runtime, sharding
     from waymo_2d_tracking_b200.tracking.sort import sort as _sort
 
 warnings.simplefilter(action='ignore', category=FutureWarning)
@@ -88,6 +88,17 @@ def track_streams(predictions, streams, iou_thresholds, max_age, min_hits):
                              id_base=_sort.KalmanBoxTracker.count, raw=False)
     _sort.KalmanBoxTracker.count = res["id_next"]
     return packing.rows_to_dicts(packed, res)
+
+
+def track_packed(packed, iou_thresholds, max_age, min_hits):
+    """Track already packed streams (``packing.pack_detections`` / ``pack_predictions``); returns the
+    dense result arrays (``rows_box/score/id/img/cat``) and advances the global id counter."""
+    if packed.n_classes > runtime._abi.W2T_MAX_CLASSES:
+        raise ValueError("at most %d categories are supported" % runtime._abi.W2T_MAX_CLASSES)
+    res = runtime.sort_track(packed, list(iou_thresholds)[:packed.n_classes], max_age, min_hits,
+                             id_base=_sort.KalmanBoxTracker.count, raw=False)
+    _sort.KalmanBoxTracker.count = res["id_next"]
+    return res
 
 
 def track_sort(predictions, segment_id, camera_id, iou_thresholds, max_age, min_hits):
