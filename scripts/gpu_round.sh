@@ -14,9 +14,10 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_
 # launch list of the same command (shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-e2e > $out/${tag}_bench_under_ncu.log 2>&1
-# full captures (smaller batch: ncu replays each launch ~40 times)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sort_track_kernel -s 1 -c 1 -f -o $out/${tag}_prof_sort \
-    python bench.py --segments 30 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_sort.log 2>&1
+# full captures of one launch of each kernel at the bench's own size (ncu replays the launch ~40 times)
+SEG=${2:-150}
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sort_track_kernel -s 1 -c 1 -f -o $out/${tag}_prof_sort \
+    python bench.py --segments $SEG --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e > $out/${tag}_ncu_sort.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:softnms_kernel -s 1 -c 1 -f -o $out/${tag}_prof_nms \
-    python bench.py --segments 30 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_nms.log 2>&1
+    python bench.py --segments $SEG --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e > $out/${tag}_ncu_nms.log 2>&1
 ls -la $out

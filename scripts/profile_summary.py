@@ -27,8 +27,22 @@ for k, name in (("sort", "sort_track_kernel"), ("nms", "softnms_kernel")):
     r = list(csv.reader(raw.splitlines()))
     h, u, v = r[0], r[1], r[2]
     with open(os.path.join(pr, "%s_ncu_%s_metrics.txt" % (tag, k)), "w") as f:
-        f.write("# ncu --set full --clock-control none, one launch of %s, bench.py --segments 30 (%s)\n" % (name, tag))
+        f.write("# ncu --set full --clock-control none, one launch of %s, bench.py at its default size (%s)\n" % (name, tag))
         for i, n in enumerate(h):
             if any(w in n for w in keys) and 'peak_sustained.' not in n and 'not_issued' not in n:
                 f.write("%s | %s | %s\n" % (n, u[i], v[i]))
-print("ok")
+# DRAM traffic per launch of each kernel -> profiles/traffic.json (bench.py's roofline.traffic)
+import json
+traffic = {}
+for k, name in (("sort", "sort_track_kernel"), ("nms", "softnms_kernel")):
+    vals = {}
+    for line in open(os.path.join(pr, "%s_ncu_%s_metrics.txt" % (tag, k))):
+        parts = [x.strip() for x in line.split("|")]
+        if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
+            vals[parts[0]] = float(parts[2]) * scale
+    if len(vals) == 2:
+        traffic[name] = sum(vals.values())
+traffic["source"] = "ncu --set full, one launch, %s (dram__bytes_read.sum + dram__bytes_write.sum)" % tag
+json.dump(traffic, open(os.path.join(pr, "traffic.json"), "w"), indent=1)
+print("ok", traffic)

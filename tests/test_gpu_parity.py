@@ -71,7 +71,9 @@ def test_iou_matrix_bit_exact():
 
 def test_linear_assignment_bit_exact_including_ties():
     rng = np.random.default_rng(2)
-    shapes = [(1, 1), (1, 9), (9, 1), (5, 5), (17, 40), (40, 17), (33, 33), (64, 65), (70, 200), (150, 90)]
+    # (100, 128), (128, 128), (90, 120): the shared-memory solver with its cost matrix left in global memory
+    shapes = [(1, 1), (1, 9), (9, 1), (5, 5), (17, 40), (40, 17), (33, 33), (64, 65), (70, 200), (150, 90),
+              (100, 128), (128, 128), (120, 90), (65, 96), (128, 129)]
     for trial, (D, T) in enumerate(shapes * 4):
         kind = trial % 5
         if kind == 0:
@@ -177,6 +179,19 @@ def test_sort_ragged_and_empty_streams():
                                  np.zeros(0, np.int32), 0)
     out = runtime.sort_track(empty, helpers.IOU_THR, 2, 0)
     assert out["id_next"] == 0 and len(out["ids"]) == 0
+
+
+def test_sort_medium_density_matches_oracle():
+    # 80-128 detections / trackers per category: assignment problems that use the shared-memory solver
+    # with the cost matrix in the global slab (n * pitch > 6144 floats, m <= 128)
+    cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT", "SIDE_RIGHT"), n_frames=14, n_submissions=1,
+                            objects_per_frame=340.0, class_mix=(0.5, 0.45, 0.0, 0.05), size_range=(12.0, 90.0),
+                            mean_life=25.0, seed=19)
+    scene = synth.make_scene(cfg)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    per_class = packed.det_count.reshape(-1, 4)
+    assert 80 <= per_class[:, 0].max() <= 128 and per_class[:, 0].mean() > 90
+    compare_sort(packed, helpers.IOU_THR, 2, 0)
 
 
 def test_sort_crowded_matches_oracle():

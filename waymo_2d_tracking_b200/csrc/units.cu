@@ -58,11 +58,14 @@ __global__ void __launch_bounds__(BLOCK) lap_kernel(const float *cost, int D, in
   mk.g.row_prime = reinterpret_cast<int *>(ws + L.rprime);
   mk.g.ucols = reinterpret_cast<int *>(ws + L.ucols);
   mk.g.crows = reinterpret_cast<int *>(ws + L.crows);
-  // same dispatch as the tracker kernel: problems that fit live in shared memory
-  if ((n * mk.ldc <= kSmemC) && (n * mk.zs <= kSmemZ) && (n <= kSmemN) && (m <= kSmemM)) {
+  // same dispatch as the tracker kernel: up to 128 x 128 the solver's masks, stars and index lists
+  // live in shared memory, and so does the cost matrix if it is small enough (else it stays in the
+  // global workspace and the same solver runs on it); anything larger takes the global path
+  if ((n * mk.zs <= kSmemZ) && (n <= kSmemN) && (m <= 128)) {
     mk.rowwise = true;
-    mk.g.C = s_C; mk.g.Z = s_Z; mk.g.row_star = s_rstar; mk.g.col_star = s_cstar; mk.g.row_prime = s_rprime;
+    mk.g.Z = s_Z; mk.g.row_star = s_rstar; mk.g.col_star = s_cstar; mk.g.row_prime = s_rprime;
     mk.g.ucols = s_ucols; mk.g.crows = s_crows;
+    if (n * mk.ldc <= kSmemC) mk.g.C = s_C;
   }
   for (size_t i = threadIdx.x; i < (size_t)n * m; i += BLOCK) {
     const int r = (int)(i / m), c = (int)(i % m);
