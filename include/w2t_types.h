@@ -53,7 +53,12 @@ typedef struct w2t_sort_plan_t {
   /* w2t_stream_wait_value32 and post-process it while the rest of the launch is still running.  */
   const int32_t *chunk_of;
   int32_t *chunk_done;
+  /* the first n_wide entries of `order` are sub-streams with more than W2T_WIDE_DETS detections in */
+  /* some image (crowded scenes): they are tracked by 512-thread CTAs, the rest by 128-thread ones */
+  int32_t  n_wide;
 } w2t_sort_plan_t;
+
+#define W2T_WIDE_DETS 320
 
 /* Inputs of the SORT stage (tracking/utils.py:25-60 for every stream at once).
  * Pointers are device pointers for the CUDA library and host pointers for the oracle. */

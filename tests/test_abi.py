@@ -33,7 +33,7 @@ def test_version_and_struct_sizes():
     lib = _lib.lib()
     assert b"sm_100a" in lib.w2t_version()
     assert ctypes.sizeof(_abi.SortProblem) == 8 + 6 * 8 + 8 * 8 + 8
-    assert ctypes.sizeof(_abi.SortPlan) == 7 * 8
+    assert ctypes.sizeof(_abi.SortPlan) == 8 * 8
 
 
 def test_sort_plan_bounds_and_order():
@@ -47,6 +47,13 @@ def test_sort_plan_bounds_and_order():
     assert plan["det_cap"].tolist() == [7, 1, 1, 9]
     assert plan["order"].tolist()[:2] == [0, 3]
     assert plan["ws_offset"][0] == 0 and np.all(np.diff(plan["ws_offset"]) > 0) and plan["ws_bytes"] > 0
+    assert plan["n_wide"] == 0
+    # crowded sub-streams (more than W2T_WIDE_DETS detections in some image) lead the launch order
+    cnt[5, 1] = 400
+    cnt[1, 0] = 321
+    cnt[2, 0] = 5000 // 100          # heavy by total work, but not crowded
+    plan = runtime.make_plan(2, 2, offs, cnt.reshape(-1), None, max_age=1)
+    assert plan["n_wide"] == 2 and sorted(plan["order"].tolist()[:2]) == [0, 3]
 
 
 def test_assign_ids_c_matches_numpy_statement():

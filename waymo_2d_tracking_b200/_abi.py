@@ -33,6 +33,7 @@ class SortPlan(C.Structure):
         ("ws_bytes", C.c_int64),
         ("chunk_of", _p),
         ("chunk_done", _p),
+        ("n_wide", C.c_int32),
     ]
 
 

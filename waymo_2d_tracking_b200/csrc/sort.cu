@@ -43,8 +43,15 @@ extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t
       work[q] = w;
     }
   }
+  // crowded sub-streams first (they get wide CTAs), each part heaviest first
   std::iota(plan->order, plan->order + nq, 0);
-  std::stable_sort(plan->order, plan->order + nq, [&](int a, int b) { return work[a] > work[b]; });
+  auto wide = [&](int q) { return plan->det_cap[q] > W2T_WIDE_DETS; };
+  std::stable_sort(plan->order, plan->order + nq, [&](int a, int b) {
+    if (wide(a) != wide(b)) return wide(a);
+    return work[a] > work[b];
+  });
+  plan->n_wide = 0;
+  for (int q = 0; q < nq; q++) plan->n_wide += wide(q) ? 1 : 0;
   int64_t off = 0;
   for (int q = 0; q < nq; q++) {
     plan->ws_offset[q] = off;
@@ -94,8 +101,16 @@ extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_
     sort_track_kernel<64, 7, false, 3072><<<nq, 64, 0, st>>>(P);
   else if (variant == 3)
     sort_track_kernel<96, 5, false, 4608><<<nq, 96, 0, st>>>(P);
-  else
-    sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq, kSortBlock, 0, st>>>(P);
+  else {
+    // crowded sub-streams (the first n_wide of the launch order): 512 threads walk the big cost
+    // matrices of the global-memory solver; everything else: 128 threads, 4 CTAs per SM
+    const int n_wide = std::min(std::max(plan->n_wide, 0), nq);
+    if (n_wide > 0) sort_track_kernel<512, 1, false><<<n_wide, 512, 0, st>>>(P);
+    if (nq > n_wide) {
+      P.order = plan->order + n_wide;
+      sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq - n_wide, kSortBlock, 0, st>>>(P);
+    }
+  }
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
 }

@@ -291,6 +291,7 @@ def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age):
                               None if h_exists is None else h_exists.ctypes.data_as(C.c_void_p),
                               int(max_age), C.byref(plan)), "w2t_sort_plan")
     arrays["ws_bytes"] = int(plan.ws_bytes)
+    arrays["n_wide"] = int(plan.n_wide)
     return arrays
 
 
@@ -332,6 +333,7 @@ def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, 
     for k in ("order", "track_cap", "det_cap", "ws_offset"):
         setattr(cplan, k, _ptr(d_plan[k]))
     cplan.ws_bytes = plan["ws_bytes"]
+    cplan.n_wide = int(plan.get("n_wide", 0))
     if plan.get("chunk_of") is not None:      # completion counters per chunk of sub-streams
         d_plan["chunk_of"] = _dev(plan["chunk_of"], np.int32, device)
         cplan.chunk_of, cplan.chunk_done = _ptr(d_plan["chunk_of"]), _ptr(plan["chunk_done"])
