@@ -91,16 +91,8 @@ extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_
   P.timers = getenv("W2T_SORT_TIMERS") ? reinterpret_cast<long long *>(strtoull(getenv("W2T_SORT_TIMERS"), nullptr, 10))
                                         : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  // occupancy experiment (debug aid): W2T_SORT_VARIANT selects a launch shape
-  const int variant = getenv("W2T_SORT_VARIANT") ? atoi(getenv("W2T_SORT_VARIANT")) : 0;
   if (P.timers != nullptr)
     sort_track_kernel<kSortBlock, kSortMinBlocks, true><<<nq, kSortBlock, 0, st>>>(P);
-  else if (variant == 1)
-    sort_track_kernel<64, 6, false, 4096><<<nq, 64, 0, st>>>(P);
-  else if (variant == 2)
-    sort_track_kernel<64, 7, false, 3072><<<nq, 64, 0, st>>>(P);
-  else if (variant == 3)
-    sort_track_kernel<96, 5, false, 4608><<<nq, 96, 0, st>>>(P);
   else {
     // crowded sub-streams (the first n_wide of the launch order): 512 threads walk the big cost
     // matrices of the global-memory solver; everything else: 128 threads, 4 CTAs per SM
