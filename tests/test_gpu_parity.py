@@ -156,6 +156,26 @@ def test_sort_seeded_vs_oracle(seed, max_age, min_hits):
     compare_sort(packed, helpers.IOU_THR, max_age, min_hits, final_cap=160)
 
 
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_sort_random_configurations_vs_oracle(seed):
+    # thresholds, lifecycle parameters, densities and class mixes drawn at random: IoU thresholds of 0
+    # (zero-IoU matches are kept, Munkres tie-breaking decides), 1 (nothing ever matches), long max_age
+    # (trackers outnumber detections), short lives and many misses (detections outnumber trackers)
+    rng = np.random.default_rng(seed)
+    mix = rng.dirichlet([1.0, 1.0, 0.3, 0.6])
+    cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT", "SIDE_LEFT"), n_frames=int(rng.integers(20, 45)),
+                            n_submissions=1, objects_per_frame=float(rng.uniform(5, 130)),
+                            class_mix=tuple(float(v) for v in mix), mean_life=float(rng.uniform(3, 50)),
+                            p_miss=float(rng.uniform(0.0, 0.5)), jitter=float(rng.uniform(0.5, 6.0)),
+                            fp_per_frame=float(rng.uniform(0, 15)), confident=float(rng.uniform(0.5, 0.98)),
+                            size_range=(float(rng.uniform(8, 30)), float(rng.uniform(60, 250))), seed=seed)
+    scene = synth.make_scene(cfg)
+    score_thr = [float(rng.choice([0.0, 0.3, 0.6, 0.9, 0.95])) for _ in range(4)]
+    iou_thr = [float(rng.choice([0.0, 0.01, 0.3, 0.5, 1.0])) for _ in range(4)]
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], score_thr)
+    compare_sort(packed, iou_thr, int(rng.integers(0, 5)), int(rng.integers(0, 4)), final_cap=128)
+
+
 def test_sort_ragged_and_empty_streams():
     # empty stream, a stream whose detections are all filtered, missing images, a late-starting category
     cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT", "SIDE_LEFT", "SIDE_RIGHT"), n_frames=25,
