@@ -308,3 +308,39 @@ def test_compact_rows_give_the_same_ensemble():
         np.testing.assert_array_equal(a[k], b[k])
     assert packing.compact_rows(np.array([[0.5, 1.5, 2, 3, 4]])) is None          # non-integer box
     assert packing.compact_rows(np.array([[0.5, 1, 2, 40000, 4]])) is None        # beyond int16
+
+
+def _random_tracking_case(seed, n_frames=14):
+    rng = np.random.default_rng(seed)
+    mix = rng.dirichlet([1.0, 1.0, 0.3, 0.6])
+    cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT", "SIDE_RIGHT"), n_frames=n_frames, n_submissions=1,
+                            objects_per_frame=float(rng.uniform(5, 70)), class_mix=tuple(float(v) for v in mix),
+                            mean_life=float(rng.uniform(3, 50)), p_miss=float(rng.uniform(0.0, 0.5)),
+                            jitter=float(rng.uniform(0.5, 6.0)), seed=seed)
+    scene = synth.make_scene(cfg)
+    score_thr = [float(rng.choice([0.0, 0.3, 0.6, 0.9, 0.95])) for _ in range(4)]
+    iou_thr = [float(rng.choice([0.0, 0.01, 0.3, 0.5, 1.0])) for _ in range(4)]
+    return scene, score_thr, iou_thr, int(rng.integers(0, 5)), int(rng.integers(0, 4))
+
+
+@pytest.mark.parametrize("seed", range(300, 310))
+def test_c_oracle_equals_numpy_port_on_random_configurations(seed):
+    scene, score_thr, iou_thr, max_age, min_hits = _random_tracking_case(seed)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], score_thr)
+    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits)
+    got = helpers.track_rows_as_arrays(packed, res, scene.image_ids())
+    pred = sort_port.group_entries(synth.to_json_list(scene, scene.submissions[0]), score_thr)
+    want = golden_io.tracks_to_arrays(sort_port.track_all(pred, iou_thr, max_age, min_hits), scene.image_ids())
+    helpers.assert_tracks_equal(got, want, score_rtol=1e-12, box_exact=False)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+@pytest.mark.parametrize("seed", [400, 401, 402])
+def test_reference_itself_equals_c_oracle_on_random_configurations(seed):
+    scene, score_thr, iou_thr, max_age, min_hits = _random_tracking_case(seed, n_frames=10)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], score_thr)
+    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits)
+    got = helpers.track_rows_as_arrays(packed, res, scene.image_ids())
+    pred = sort_port.group_entries(synth.to_json_list(scene, scene.submissions[0]), score_thr)
+    want = golden_io.tracks_to_arrays(ref_shim.ref_track_all(pred, iou_thr, max_age, min_hits), scene.image_ids())
+    helpers.assert_tracks_equal(got, want, score_rtol=1e-12, box_exact=False)
