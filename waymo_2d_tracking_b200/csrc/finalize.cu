@@ -8,9 +8,11 @@
 // over per-(image, category) counts taken in that processing order:
 //   1. order kernel : per stream, rank the categories and permute the `created` and
 //                     `out_count` arrays into processing order;
-//   2. two scans    : id base per group, dense row offset per group;
+//   2. two scans    : id base per group, dense row offset per group (three small kernels for both);
 //   3. rows kernel  : one warp per group copies its rows to their dense position (reversed)
 //                     and resolves object_id = base[birth group] + k + 1 (sort.py:288).
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace w2t;
@@ -63,30 +65,85 @@ __global__ void order_kernel(const FinParams P) {
   }
 }
 
-// Exclusive scan of n int32 by ONE block: contiguous chunk per thread, block scan of chunk sums.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) scan_kernel(const int32_t *in, int32_t *out, int64_t n, int64_t *total) {
-  __shared__ int64_t s_sum[BLOCK];
-  const int64_t chunk = (n + BLOCK - 1) / BLOCK;
-  const int64_t lo = min((int64_t)threadIdx.x * chunk, n), hi = min(lo + chunk, n);
-  int64_t sum = 0;
-  for (int64_t i = lo; i < hi; i++) sum += in[i];
-  s_sum[threadIdx.x] = sum;
+// Exclusive scans of the two permuted count arrays (ids created, rows emitted) over all groups,
+// in three small kernels: per-block sums of contiguous chunks, a one-block scan of those sums, and
+// the per-block scan of each chunk from its offset.  kScanBlocks chunks keep every SM busy.
+constexpr int kScanBlocks = 592;
+constexpr int kScanThreads = 256;
+
+__device__ __forceinline__ int64_t block_sum(int64_t v, int64_t *s_red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
-  // Hillis-Steele inclusive scan over the chunk sums
-  for (int o = 1; o < BLOCK; o <<= 1) {
-    const int64_t v = (threadIdx.x >= o) ? s_sum[threadIdx.x - o] : 0;
+  int64_t t = 0;
+  for (int i = 0; i < kScanThreads / 32; i++) t += s_red[i];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(const int32_t *a, const int32_t *b, int64_t n,
+                                                                 int64_t *sums) {
+  __shared__ int64_t s_red[kScanThreads / 32];
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = min((int64_t)blockIdx.x * chunk, n), hi = min(lo + chunk, n);
+  int64_t sa = 0, sb = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += kScanThreads) { sa += a[i]; sb += b[i]; }
+  sa = block_sum(sa, s_red);
+  sb = block_sum(sb, s_red);
+  if (threadIdx.x == 0) { sums[2 * blockIdx.x] = sa; sums[2 * blockIdx.x + 1] = sb; }
+}
+
+// one block: exclusive scan of the per-chunk sums in place; totals[0] = all of a, totals[1] = all of b
+__global__ void scan_offsets_kernel(int64_t *sums, int nb, int64_t *totals) {
+  if (threadIdx.x == 0) {
+    int64_t ra = 0, rb = 0;
+    for (int i = 0; i < nb; i++) {
+      const int64_t va = sums[2 * i], vb = sums[2 * i + 1];
+      sums[2 * i] = ra;
+      sums[2 * i + 1] = rb;
+      ra += va;
+      rb += vb;
+    }
+    totals[0] = ra;
+    totals[1] = rb;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t *a, const int32_t *b, int64_t n,
+                                                                  const int64_t *sums, int32_t *out_a, int32_t *out_b) {
+  __shared__ int64_t s_red[kScanThreads / 32];
+  __shared__ int s_wa[kScanThreads / 32], s_wb[kScanThreads / 32];
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = min((int64_t)blockIdx.x * chunk, n), hi = min(lo + chunk, n);
+  int64_t run_a = sums[2 * blockIdx.x], run_b = sums[2 * blockIdx.x + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i0 = lo; i0 < hi; i0 += kScanThreads) {
+    const int64_t i = i0 + threadIdx.x;
+    const int va = (i < hi) ? a[i] : 0, vb = (i < hi) ? b[i] : 0;
+    int ia = va, ib = vb;  // inclusive warp scans
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
     __syncthreads();
-    s_sum[threadIdx.x] += v;
+    int pa = 0, pb = 0, ta = 0, tb = 0;
+    for (int w = 0; w < kScanThreads / 32; w++) {
+      if (w < warp) { pa += s_wa[w]; pb += s_wb[w]; }
+      ta += s_wa[w];
+      tb += s_wb[w];
+    }
+    if (i < hi) {
+      out_a[i] = (int32_t)(run_a + pa + ia - va);
+      out_b[i] = (int32_t)(run_b + pb + ib - vb);
+    }
+    run_a += ta;
+    run_b += tb;
     __syncthreads();
   }
-  int64_t run = s_sum[threadIdx.x] - sum;
-  for (int64_t i = lo; i < hi; i++) {
-    const int32_t v = in[i];
-    out[i] = (int32_t)run;
-    run += v;
-  }
-  if (threadIdx.x == BLOCK - 1 && total) *total = s_sum[BLOCK - 1];
+  (void)s_red;
 }
 
 // One block per stream, one warp per (image, category) group at a time.
@@ -121,7 +178,8 @@ __global__ void rows_kernel(const FinParams P) {
 }  // namespace
 
 extern "C" size_t w2t_sort_finalize_workspace(int32_t n_streams, int32_t n_classes, int64_t n_groups) {
-  return (size_t)(4 * n_groups + (int64_t)n_streams * n_classes) * sizeof(int32_t) + 256;
+  return (size_t)(4 * n_groups + (int64_t)n_streams * n_classes) * sizeof(int32_t) + 256 +
+         2 * kScanBlocks * sizeof(int64_t);
 }
 
 extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_sort_result_t *result,
@@ -180,8 +238,13 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
   P.image_base = rows->image_base;
   P.birth_base = rows->birth_group_base;
   order_kernel<<<P.n_streams, 256, 0, st>>>(P);
-  scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_created, P.scan_created, n_groups, P.totals);
-  scan_kernel<1024><<<1, 1024, 0, st>>>(P.perm_count, P.scan_count, n_groups, P.totals + 1);
+  // 8-byte aligned scratch for the per-chunk sums, behind the int32 arrays
+  const size_t ints = (size_t)(4 * n_groups + (int64_t)P.n_streams * P.n_classes);
+  int64_t *sums = reinterpret_cast<int64_t *>(static_cast<char *>(workspace) + ((ints * sizeof(int32_t) + 7) / 8) * 8);
+  const int nb = (int)std::min<int64_t>(kScanBlocks, (n_groups + kScanThreads - 1) / kScanThreads);
+  scan_sums_kernel<<<nb, kScanThreads, 0, st>>>(P.perm_created, P.perm_count, n_groups, sums);
+  scan_offsets_kernel<<<1, 32, 0, st>>>(sums, nb, P.totals);
+  scan_apply_kernel<<<nb, kScanThreads, 0, st>>>(P.perm_created, P.perm_count, n_groups, sums, P.scan_created, P.scan_count);
   rows_kernel<<<P.n_streams, 256, 0, st>>>(P);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
