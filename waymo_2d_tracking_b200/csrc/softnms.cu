@@ -116,13 +116,21 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   const int m = (P.p.top_k > 0 && P.p.top_k < n) ? P.p.top_k : n;
   for (int i = tid; i < n; i += BLOCK) {
     const double si = raw[i];
-    // G boxes score higher; of the equal ones L come earlier and H later in the input.
-    int G = 0, L = 0, H = 0;
+    // G boxes score higher; of the equal ones L come earlier and H later in the input.  Ties are
+    // rare, so the main loop only counts "greater" and "greater or equal" (two compares per box)
+    // and the positions of the equal ones are looked at only when there are any.
+    int G = 0, GE = 0, L = 0, H = 0;
     for (int k = 0; k < n; k++) {
       const double sk = raw[k];
       G += (sk > si) ? 1 : 0;
-      L += (sk == si && k < i) ? 1 : 0;
-      H += (sk == si && k > i) ? 1 : 0;
+      GE += (sk >= si) ? 1 : 0;
+    }
+    if (GE - G > 1) {
+      for (int k = 0; k < n; k++) {
+        const double sk = raw[k];
+        L += (sk == si && k < i) ? 1 : 0;
+        H += (sk == si && k > i) ? 1 : 0;
+      }
     }
     // The reference sorts ascending (stable, canonical rule) and consumes from the end, so among
     // equal scores the later box ranks higher; top_k cuts that order (box_utils.py:324-327).
