@@ -11,10 +11,12 @@ h_rows = torch.from_numpy(compact.view(np.uint8).reshape(-1, 16)).pin_memory()
 h_offs = torch.from_numpy(groups.group_offsets).pin_memory()
 kw = dict(stream_img_offsets=scene.stream_img_offsets, cam_wh=scene.cam_wh(), n_classes=4, score_thr=bench.SCORE_THR,
           iou_thresholds=bench.IOU_THR, max_age=2, min_hits=0, max_group=groups.max_group, **bench.NMS)
-for chunks in [int(c) for c in sys.argv[1:]] or [1, 2, 3, 4, 6, 8]:
+def parse(a):
+    return [float(x) for x in a.split(",")] if "," in a else int(a)
+for chunks in [parse(c) for c in sys.argv[1:]] or [1, 2, 3, 4, 6, 8]:
     ts = []
     for it in range(4):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         res = runtime.ensemble_and_track_pipelined(h_offs, h_rows, n_chunks=chunks, **kw)
         torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - t0))
-    print("chunks %d: %s ms  (rows %d)" % (chunks, " ".join("%.1f" % t for t in ts), res["n_rows"]))
+    print("chunks %s: %s ms  (rows %d)" % (chunks, " ".join("%.1f" % t for t in ts), res["n_rows"]))

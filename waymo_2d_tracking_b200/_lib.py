@@ -9,7 +9,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libw2t.so")
+# W2T_LIB: an experimental build of the same library (debug aid for A/B timing, csrc/Makefile)
+LIB_PATH = os.environ.get("W2T_LIB") or os.path.join(_HERE, "libw2t.so")
 _lib = None
 
 

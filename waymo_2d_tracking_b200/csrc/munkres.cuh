@@ -39,6 +39,10 @@
 
 #include "common.cuh"
 
+#ifndef W2T_SOLVE_BLOCK_INLINE
+#define W2T_SOLVE_BLOCK_INLINE __forceinline__
+#endif
+
 namespace w2t {
 
 constexpr int kMunkresMaxWords = 64;                      // mask words kept in shared memory
@@ -404,8 +408,8 @@ struct Munkres {
   };
 
   // first zero of row r outside `cov`, or -1 (lane-private row, or the same row in every lane)
-  __device__ __forceinline__ int first_zero_outside(int r, const M4 &cov) const {
-    const uint32_t *zr = g.Z + (size_t)r * zs;
+  static __device__ __forceinline__ int first_zero_outside_at(const uint32_t *Z, int zs, int mw, int r, const M4 &cov) {
+    const uint32_t *zr = Z + (size_t)r * zs;
     M4 v = {0u, 0u, 0u, 0u};
     v.a = zr[0] & ~cov.a;
     if (mw > 1) v.b = zr[1] & ~cov.b;
@@ -416,10 +420,20 @@ struct Munkres {
 
   // uncovered rows (of the 32-row group `grp`, one per lane) for which `pred` holds, as a ballot
   template <class PRED>
-  __device__ __forceinline__ uint32_t rows_where(int grp, uint32_t rowcov_word, PRED pred) const {
+  static __device__ __forceinline__ uint32_t rows_where_n(int n, int grp, uint32_t rowcov_word, PRED pred) {
     const int r = grp * 32 + lane_id();
     const bool ok = (r < n) && !((rowcov_word >> lane_id()) & 1u) && pred(r);
     return __ballot_sync(0xffffffffu, ok);
+  }
+
+  // order-preserving integer image of a float: a < b  <=>  ordered(a) < ordered(b), -0.0f < +0.0f,
+  // NaN (positive payload) sorts last
+  static __device__ __forceinline__ uint32_t ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+  static __device__ __forceinline__ float unordered(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
   }
 
   // Step 1 for one row straight from the registers of the warp that has just computed it: lane L
@@ -462,7 +476,139 @@ struct Munkres {
   // true when solve() will take the shared-memory path below (and store_reduced_row may be used)
   __device__ __forceinline__ bool block_path() const { return rowwise && m <= 128; }
 
-  __device__ int solve_block(bool reduced = false) {
+  // ---- warp 0 of the block solver: step 2 on first entry, then steps 3-5 until all rows are starred
+  // (returns 0), the costs must shift (6: step 6, after which the caller comes back with the covers,
+  // stars and primes untouched) or the iteration budget ran out (9).
+  struct Drive {
+    M4 starcols, colcov, rowcov;
+    int stars, budget;
+    bool fresh;  // first entry: step 2 still to do
+    __device__ __forceinline__ void init(int n, int m) {
+      starcols = M4{0u, 0u, 0u, 0u};
+      colcov = starcols;
+      rowcov = starcols;
+      stars = 0;
+      budget = 4 * n * n + 64 * (n + m) + 1024;
+      fresh = true;
+    }
+  };
+
+  __device__ __forceinline__ int drive_block(Drive &d, const int n, const int m, const int mw, const int zs,
+                                             const MunkresGlobal &g) {
+    auto first_zero_outside = [&](int r, const M4 &cov) { return first_zero_outside_at(g.Z, zs, mw, r, cov); };
+    auto rows_where = [&](int grp, uint32_t rowcov_word, auto pred) { return rows_where_n(n, grp, rowcov_word, pred); };
+    const int lane = lane_id();
+    const int nwr = munkres_words(n);
+    int act = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    if (d.fresh) {
+      // ---- step 2: greedy d.stars in row-major order; the longest prefix of pending rows whose
+      // proposals are pairwise distinct is exactly what the sequential loop would star
+      for (int rb = 0; rb < n; rb += 32) {
+        const int r = rb + lane;
+        bool pending = r < n;
+        for (;;) {
+          int cand = -1;
+          if (pending) {
+            cand = first_zero_outside(r, d.starcols);
+            if (cand < 0) pending = false;  // every zero of the row is taken: no star
+          }
+          if (!__ballot_sync(0xffffffffu, pending)) break;
+          const unsigned peers = __match_any_sync(0xffffffffu, pending ? cand : (-2 - lane));
+          const unsigned clash = __ballot_sync(0xffffffffu, pending && (peers & lt) != 0u);
+          const int first_clash = clash ? (__ffs(clash) - 1) : 32;
+          const bool commit = pending && lane < first_clash;
+          M4 add = {0u, 0u, 0u, 0u};
+          if (commit) {
+            g.row_star[r] = cand;
+            g.col_star[cand] = r;
+            add.set(cand);
+            pending = false;
+          }
+          d.starcols.a |= __reduce_or_sync(0xffffffffu, add.a);
+          if (mw > 1) d.starcols.b |= __reduce_or_sync(0xffffffffu, add.b);
+          if (mw > 2) d.starcols.c |= __reduce_or_sync(0xffffffffu, add.c);
+          if (mw > 3) d.starcols.d |= __reduce_or_sync(0xffffffffu, add.d);
+          d.stars += __popc(__ballot_sync(0xffffffffu, commit));
+        }
+      }
+      __syncwarp();
+      tick(4);
+      d.fresh = false;
+      d.colcov = d.starcols;
+    }
+    // (otherwise: back from a cost shift — covers, d.stars and primes are untouched, step 6 -> step 4)
+    // ---- steps 3-5
+    for (;;) {
+      if (d.stars >= n) { act = 0; break; }
+      // rows that own an uncovered zero, from scratch
+      M4 rowhas = {0u, 0u, 0u, 0u};
+      auto open_zero = [&](int r) { return first_zero_outside(r, d.colcov) >= 0; };
+      rowhas.a = rows_where(0, d.rowcov.a, open_zero);
+      if (nwr > 1) rowhas.b = rows_where(1, d.rowcov.b, open_zero);
+      if (nwr > 2) rowhas.c = rows_where(2, d.rowcov.c, open_zero);
+      if (nwr > 3) rowhas.d = rows_where(3, d.rowcov.d, open_zero);
+      bool augmented = false;
+      for (;;) {
+        // step 4: first uncovered zero in row-major order
+        if (--d.budget < 0) { act = 9; break; }
+        if (TIMERS && threadIdx.x == 0) ph[12]++;
+        const int fr = rowhas.first();
+        if (fr < 0) { act = 6; break; }
+        const int sc = g.row_star[fr];
+        const int fc = first_zero_outside(fr, d.colcov);
+        if (sc < 0) {
+          // step 5: flip d.stars along the alternating path that starts at the primed zero (fr, fc)
+          int endc = -1;
+          if (lane == 0) {
+            int r = fr, c = fc;
+            for (int hops = 0;; hops++) {
+              const int rs = g.col_star[c];
+              g.row_star[r] = c;
+              g.col_star[c] = r;
+              if (rs < 0) { endc = c; break; }
+              r = rs;
+              c = g.row_prime[r];
+              if (c < 0 || hops > n + m) { endc = -2; break; }  // cannot happen in a valid state
+            }
+          }
+          endc = __shfl_sync(0xffffffffu, endc, 0);
+          if (endc < 0) { act = 9; break; }
+          d.starcols.set(endc);
+          d.stars++;
+          augmented = true;
+          break;
+        }
+        // the row has a star: prime the zero, cover the row, uncover the star's column
+        if (lane == 0) g.row_prime[fr] = fc;
+        d.rowcov.set(fr);
+        d.colcov.clear(sc);
+        rowhas.clear(fr);
+        // uncovered rows with a zero in the newly uncovered column now own an uncovered zero
+        const int kw = sc >> 5;
+        const uint32_t bit = 1u << (sc & 31);
+        auto zero_at_sc = [&](int r) { return (g.Z[(size_t)r * zs + kw] & bit) != 0u; };
+        rowhas.a |= rows_where(0, d.rowcov.a, zero_at_sc);
+        if (nwr > 1) rowhas.b |= rows_where(1, d.rowcov.b, zero_at_sc);
+        if (nwr > 2) rowhas.c |= rows_where(2, d.rowcov.c, zero_at_sc);
+        if (nwr > 3) rowhas.d |= rows_where(3, d.rowcov.d, zero_at_sc);
+      }
+      if (!augmented) break;  // act = 6 or 9
+      // step 3: cover the starred columns, uncover all rows (stale primes are never read)
+      __syncwarp();
+      d.colcov = d.starcols;
+      d.rowcov = M4{0u, 0u, 0u, 0u};
+    }
+    return act;
+  }
+
+  // Memory-resident matrix (g.C in shared memory, or in the slab when it is too big for it).
+  // Inlined: measured 1.7 ms per C3 step faster than a real call (which turns every access to the
+  // shared-memory arrays into a generic load and keeps the solver object in local memory).
+  __device__ W2T_SOLVE_BLOCK_INLINE int solve_block(bool reduced = false) {
+    const int n = this->n, m = this->m, mw = this->mw, zs = this->zs, ldc = this->ldc;
+    const MunkresGlobal g = this->g;
+    MunkresShared *const s = this->s;
     const int lane = lane_id(), warp = warp_id();
     const int nwr = munkres_words(n);
     // ---- step 1 (CTA, one thread per row): row minimum, subtract, zero bit words
@@ -487,111 +633,13 @@ struct Munkres {
     __syncthreads();
     tick(3);
 
-    M4 starcols = {0u, 0u, 0u, 0u}, colcov = {0u, 0u, 0u, 0u}, rowcov = {0u, 0u, 0u, 0u};
-    int stars = 0, act = 0;
-    int budget = 4 * n * n + 64 * (n + m) + 1024;
-    bool fresh = true;  // first entry: step 2 still to do
+    Drive d;
+    d.init(n, m);
+    int act = 0;
     for (;;) {
       if (warp == 0) {
-        const unsigned lt = (1u << lane) - 1u;
-        if (fresh) {
-          // ---- step 2: greedy stars in row-major order; the longest prefix of pending rows whose
-          // proposals are pairwise distinct is exactly what the sequential loop would star
-          for (int rb = 0; rb < n; rb += 32) {
-            const int r = rb + lane;
-            bool pending = r < n;
-            for (;;) {
-              int cand = -1;
-              if (pending) {
-                cand = first_zero_outside(r, starcols);
-                if (cand < 0) pending = false;  // every zero of the row is taken: no star
-              }
-              if (!__ballot_sync(0xffffffffu, pending)) break;
-              const unsigned peers = __match_any_sync(0xffffffffu, pending ? cand : (-2 - lane));
-              const unsigned clash = __ballot_sync(0xffffffffu, pending && (peers & lt) != 0u);
-              const int first_clash = clash ? (__ffs(clash) - 1) : 32;
-              const bool commit = pending && lane < first_clash;
-              M4 add = {0u, 0u, 0u, 0u};
-              if (commit) {
-                g.row_star[r] = cand;
-                g.col_star[cand] = r;
-                add.set(cand);
-                pending = false;
-              }
-              starcols.a |= __reduce_or_sync(0xffffffffu, add.a);
-              if (mw > 1) starcols.b |= __reduce_or_sync(0xffffffffu, add.b);
-              if (mw > 2) starcols.c |= __reduce_or_sync(0xffffffffu, add.c);
-              if (mw > 3) starcols.d |= __reduce_or_sync(0xffffffffu, add.d);
-              stars += __popc(__ballot_sync(0xffffffffu, commit));
-            }
-          }
-          __syncwarp();
-          tick(4);
-          fresh = false;
-          colcov = starcols;
-        }
-        // (otherwise: back from a cost shift — covers, stars and primes are untouched, step 6 -> step 4)
-        // ---- steps 3-5
-        for (;;) {
-          if (stars >= n) { act = 0; break; }
-          // rows that own an uncovered zero, from scratch
-          M4 rowhas = {0u, 0u, 0u, 0u};
-          auto open_zero = [&](int r) { return first_zero_outside(r, colcov) >= 0; };
-          rowhas.a = rows_where(0, rowcov.a, open_zero);
-          if (nwr > 1) rowhas.b = rows_where(1, rowcov.b, open_zero);
-          if (nwr > 2) rowhas.c = rows_where(2, rowcov.c, open_zero);
-          if (nwr > 3) rowhas.d = rows_where(3, rowcov.d, open_zero);
-          bool augmented = false;
-          for (;;) {
-            // step 4: first uncovered zero in row-major order
-            if (--budget < 0) { act = 9; break; }
-            if (TIMERS && threadIdx.x == 0) ph[12]++;
-            const int fr = rowhas.first();
-            if (fr < 0) { act = 6; break; }
-            const int sc = g.row_star[fr];
-            const int fc = first_zero_outside(fr, colcov);
-            if (sc < 0) {
-              // step 5: flip stars along the alternating path that starts at the primed zero (fr, fc)
-              int endc = -1;
-              if (lane == 0) {
-                int r = fr, c = fc;
-                for (int hops = 0;; hops++) {
-                  const int rs = g.col_star[c];
-                  g.row_star[r] = c;
-                  g.col_star[c] = r;
-                  if (rs < 0) { endc = c; break; }
-                  r = rs;
-                  c = g.row_prime[r];
-                  if (c < 0 || hops > n + m) { endc = -2; break; }  // cannot happen in a valid state
-                }
-              }
-              endc = __shfl_sync(0xffffffffu, endc, 0);
-              if (endc < 0) { act = 9; break; }
-              starcols.set(endc);
-              stars++;
-              augmented = true;
-              break;
-            }
-            // the row has a star: prime the zero, cover the row, uncover the star's column
-            if (lane == 0) g.row_prime[fr] = fc;
-            rowcov.set(fr);
-            colcov.clear(sc);
-            rowhas.clear(fr);
-            // uncovered rows with a zero in the newly uncovered column now own an uncovered zero
-            const int kw = sc >> 5;
-            const uint32_t bit = 1u << (sc & 31);
-            auto zero_at_sc = [&](int r) { return (g.Z[(size_t)r * zs + kw] & bit) != 0u; };
-            rowhas.a |= rows_where(0, rowcov.a, zero_at_sc);
-            if (nwr > 1) rowhas.b |= rows_where(1, rowcov.b, zero_at_sc);
-            if (nwr > 2) rowhas.c |= rows_where(2, rowcov.c, zero_at_sc);
-            if (nwr > 3) rowhas.d |= rows_where(3, rowcov.d, zero_at_sc);
-          }
-          if (!augmented) break;  // act = 6 or 9
-          // step 3: cover the starred columns, uncover all rows (stale primes are never read)
-          __syncwarp();
-          colcov = starcols;
-          rowcov = M4{0u, 0u, 0u, 0u};
-        }
+        act = drive_block(d, n, m, mw, zs, g);
+        const M4 &colcov = d.colcov, &rowcov = d.rowcov;
         if (act == 6) {
           // step 6 prologue: compact index lists, so that the CTA touches only the cells that change:
           // uncovered columns -> g.ucols[0..nu), uncovered rows -> g.ucols[128..128+nur), covered

@@ -33,7 +33,10 @@
 namespace w2t {
 
 constexpr int kSortBlock = 128;
-constexpr int kSortMinBlocks = 4;   // CTAs per SM the register budget is capped for
+#ifndef W2T_MINB
+#define W2T_MINB 4
+#endif
+constexpr int kSortMinBlocks = W2T_MINB;   // CTAs per SM the register budget is capped for
 constexpr int kStateDoubles = 24;  // x[7], block-form P[13] (kalman.cuh), predicted box[4]
 constexpr int kBoxAt = 20;         // first of the 4 box components
 
@@ -171,6 +174,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   __shared__ double s_box[5][kSmemBox];  // x1, y1, x2, y2, area (NaN when the box is inverted)
   __shared__ __align__(16) float4 s_det[2][kSmemDet];  // double buffer: detections of this / the next image
   __shared__ uint32_t s_tmask[kSmemBox], s_dmask[kSmemDet];  // strip masks (all ones = "always test exactly")
+  __shared__ __align__(16) uint32_t s_strip[32][4];   // per strip (0-15 x, 16-31 y): the columns whose box touches it
+  __shared__ __align__(16) uint32_t s_cand[kSmemN][4];  // per row: columns that need the exact IoU
+  __shared__ float s_rowmin[kSmemN];
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int q = P.order[blockIdx.x];
@@ -374,62 +380,105 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
         }
         return -iou_pair(d, t0, t1, t2, t3);
       };
-      const bool fused = mk.block_path();  // step 1 of the solver is applied to each row as it is produced
-      for (int r = warp; r < n; r += NW) {
-        float *row = mk.g.C + (size_t)r * mk.ldc;
-        float val[4] = {0.f, 0.f, 0.f, 0.f};
-        if (fused && masked) {
-          // strip masks settle almost every pair with one AND; the rest take the exact test
-          const uint32_t rm = flipped ? s_tmask[r] : s_dmask[r];
-          const uint32_t *cmask = flipped ? s_dmask : s_tmask;
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int cc = k * 32 + lane;
-            if (k < mk.mw && cc < m) {
-              const uint32_t both = rm & cmask[cc];
-              float v = -0.0f;
-              if ((both & 0xffffu) != 0u && (both >> 16) != 0u) {
-                const int di = flipped ? cc : r, ti = flipped ? r : cc;
-                double t0, t1, t2, t3, at;
-                tbox(ti, t0, t1, t2, t3, at);
-                v = neg_iou(dets[di], t0, t1, t2, t3, at);
-              }
-              val[k] = v;
+      const bool fused = mk.block_path() && masked;  // step 1 of the solver is folded into the construction of the matrix
+      if (fused) {
+        // Block path (everything but crowded scenes; boxes and detections are staged, n, m <= 128).
+        // Almost every pair is strictly disjoint and costs -0.0f, so the matrix is built from the few
+        // pairs that are not:
+        //   1. every column enters the bit sets of the strips its box touches (s_strip);
+        //   2. one thread per row: candidate columns = (union of the sets of the row's x strips) AND
+        //      (union over its y strips) - the same predicate as "the strip masks meet in x and in y";
+        //      exact cost of each candidate, row minimum (step 1 of the solver, munkres.cuh);
+        //   3. one thread per (row, 32 columns): reduced costs and the zero bit word.
+        const uint32_t *rmask = flipped ? s_tmask : s_dmask, *cmask = flipped ? s_dmask : s_tmask;
+        for (int i = tid; i < 32 * 4; i += BLOCK) (&s_strip[0][0])[i] = 0u;
+        __syncthreads();
+        for (int cc = tid; cc < m; cc += BLOCK) {
+          uint32_t w = cmask[cc];
+          const uint32_t bit = 1u << (cc & 31);
+          while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1u;
+            atomicOr(&s_strip[b][cc >> 5], bit);
+          }
+        }
+        __syncthreads();
+        for (int r = tid; r < n; r += BLOCK) {
+          uint4 cx = make_uint4(0u, 0u, 0u, 0u), cy = cx;
+          const uint32_t rm = rmask[r];
+          for (uint32_t w = rm & 0xffffu; w; w &= w - 1u) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s_strip[__ffs(w) - 1]);
+            cx.x |= v.x; cx.y |= v.y; cx.z |= v.z; cx.w |= v.w;
+          }
+          for (uint32_t w = rm >> 16; w; w &= w - 1u) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s_strip[16 + __ffs(w) - 1]);
+            cy.x |= v.x; cy.y |= v.y; cy.z |= v.z; cy.w |= v.w;
+          }
+          const uint4 cand = make_uint4(cx.x & cy.x, cx.y & cy.y, cx.z & cy.z, cx.w & cy.w);
+          *reinterpret_cast<uint4 *>(s_cand[r]) = cand;
+          float *row = mk.g.C + (size_t)r * mk.ldc;
+          // minimum on the order-preserving integer image of the float (NaN sorts last, like fminf
+          // ignores it); every column that is not a candidate contributes -0.0f
+          const int ncand = __popc(cand.x) + __popc(cand.y) + __popc(cand.z) + __popc(cand.w);
+          uint32_t mn_u = (ncand < m) ? Munkres<BLOCK, TIMERS>::ordered(-0.0f) : 0xffffffffu;
+          int k = 0;
+          uint32_t w = cand.x;
+          for (;;) {
+            while (w == 0u && ++k < 4) w = (k == 1) ? cand.y : (k == 2) ? cand.z : cand.w;
+            if (w == 0u) break;
+            const int cc = k * 32 + __ffs(w) - 1;
+            w &= w - 1u;
+            const int di = flipped ? cc : r, ti = flipped ? r : cc;
+            double t0, t1, t2, t3, at;
+            tbox(ti, t0, t1, t2, t3, at);
+            const float v = neg_iou(dets[di], t0, t1, t2, t3, at);
+            row[cc] = v;
+            mn_u = min(mn_u, Munkres<BLOCK, TIMERS>::ordered(v));
+          }
+          s_rowmin[r] = Munkres<BLOCK, TIMERS>::unordered(mn_u);
+          mk.g.row_star[r] = -1;
+          mk.g.row_prime[r] = -1;
+        }
+        __syncthreads();
+        const int mw = mk.mw;
+        for (int it = tid; it < n * mw; it += BLOCK) {
+          const int r = it / mw, k = it - r * mw;
+          const uint32_t cw = s_cand[r][k];
+          const float mn = s_rowmin[r];
+          const int nb = min(32, m - k * 32);
+          float *row = mk.g.C + (size_t)r * mk.ldc + k * 32;
+          uint32_t z = 0u;
+          if (cw == 0u) {
+            const float bg = -0.0f - mn;
+            for (int b = 0; b < nb; b++) row[b] = bg;
+            if (bg == 0.0f) z = (nb == 32) ? 0xffffffffu : ((1u << nb) - 1u);
+          } else {
+#pragma unroll 4
+            for (int b = 0; b < nb; b++) {
+              const float raw = ((cw >> b) & 1u) ? row[b] : -0.0f;
+              const float v = raw - mn;
+              row[b] = v;
+              z |= (v == 0.0f) ? (1u << b) : 0u;
             }
           }
-        } else if (!flipped) {
-          const float4 d = dets[r];
-          if (fused) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int cc = k * 32 + lane;
-              if (k < mk.mw && cc < m) {
-                double t0, t1, t2, t3, at;
-                tbox(cc, t0, t1, t2, t3, at);
-                val[k] = neg_iou(d, t0, t1, t2, t3, at);
-              }
-            }
-          } else {
+          mk.g.Z[(size_t)r * mk.zs + k] = z;
+        }
+      } else {
+        for (int r = warp; r < n; r += NW) {
+          float *row = mk.g.C + (size_t)r * mk.ldc;
+          if (!flipped) {
+            const float4 d = dets[r];
             for (int cc = lane; cc < m; cc += 32) {
               double t0, t1, t2, t3, at;
               tbox(cc, t0, t1, t2, t3, at);
               row[cc] = neg_iou(d, t0, t1, t2, t3, at);
             }
-          }
-        } else {
-          double t0, t1, t2, t3, at;
-          tbox(r, t0, t1, t2, t3, at);
-          if (fused) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int cc = k * 32 + lane;
-              if (k < mk.mw && cc < m) val[k] = neg_iou(dets[cc], t0, t1, t2, t3, at);
-            }
           } else {
+            double t0, t1, t2, t3, at;
+            tbox(r, t0, t1, t2, t3, at);
             for (int cc = lane; cc < m; cc += 32) row[cc] = neg_iou(dets[cc], t0, t1, t2, t3, at);
           }
         }
-        if (fused) mk.store_reduced_row(r, val);
       }
       __syncthreads();
       W2T_TICK(2);

@@ -572,14 +572,21 @@ def _compute_streams(device, n=3):
 
 
 def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
-    """Split the streams into at most ``n_chunks`` contiguous blocks with about equal input rows."""
+    """Split the streams into at most ``n_chunks`` contiguous blocks with about equal input rows;
+    ``n_chunks`` may also be a sequence of fractions of the input rows (one per block)."""
     S = len(h_offsets) - 1
     rows_at_stream = group_offsets_np[np.asarray(h_offsets, np.int64) * NC].astype(np.int64)
     total = int(rows_at_stream[-1])
-    n_chunks = max(1, min(int(n_chunks), S))
+    if isinstance(n_chunks, (list, tuple)):
+        fr = np.cumsum(np.asarray(n_chunks, np.float64))
+        fr = (fr / fr[-1])[:max(1, min(len(fr), S))]
+        n_chunks = len(fr)
+    else:
+        n_chunks = max(1, min(int(n_chunks), S))
+        fr = np.arange(1, n_chunks + 1) / n_chunks
     cuts = [0]
     for k in range(1, n_chunks):
-        s = int(np.searchsorted(rows_at_stream, total * k / n_chunks, side="left"))
+        s = int(np.searchsorted(rows_at_stream, total * fr[k - 1], side="left"))
         s = min(max(s, cuts[-1] + 1), S - (n_chunks - k))
         cuts.append(s)
     cuts.append(S)
