@@ -52,7 +52,8 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=6, help="pipeline depth of the end-to-end leg")
     ap.add_argument("--skip-e2e", action="store_true",
                     help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
-    ap.add_argument("--wide-rows", action="store_true", help="ship 40-byte float64 input rows instead of 16-byte compact ones")
+    ap.add_argument("--wide-rows", action="store_true", help="ship 40-byte float64 input rows instead of the packed ones")
+    ap.add_argument("--compact-rows", action="store_true", help="ship 16-byte rows (f64 score + 4 x int16) instead of 8-byte packed ones")
     return ap.parse_args()
 
 
@@ -203,11 +204,16 @@ def main():
     # the synthetic submissions carry integer pixel boxes like real detector output (detnet/data/coco.py:250),
     # so the packer emits 16-byte compact rows (double score + 4 x int16) instead of 5 doubles
     from waymo_2d_tracking_b200 import packing
-    compact = None if args.wide_rows else packing.compact_rows(groups.rows)
-    if compact is None:
-        h_rows = torch.from_numpy(groups.rows).pin_memory()
-    else:
+    # ... and 5-decimal scores (coco.py:249), so 8-byte packed rows hold them exactly (packing.packed_rows
+    # verifies that bit for bit and returns None otherwise)
+    packed = None if (args.wide_rows or args.compact_rows) else packing.packed_rows(groups.rows)
+    compact = None if (args.wide_rows or packed is not None) else packing.compact_rows(groups.rows)
+    if packed is not None:
+        h_rows = torch.from_numpy(packed.view(np.uint8).reshape(-1, 8)).pin_memory()
+    elif compact is not None:
         h_rows = torch.from_numpy(compact.view(np.uint8).reshape(-1, 16)).pin_memory()
+    else:
+        h_rows = torch.from_numpy(groups.rows).pin_memory()
     h_offs = torch.from_numpy(groups.group_offsets).pin_memory()
     d_rows, d_offs = h_rows.cuda(), h_offs.cuda()
     cam_wh = scene.cam_wh()
@@ -312,7 +318,8 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.segments), "frames_per_gpu": n_frames,
                    "boxes_in_per_gpu": n_in, "tracked_dets_per_gpu": n_trk, "track_rows_per_gpu": n_out,
-                   "input_rows": "16 B compact (f64 score + 4 x int16 box)" if compact is not None else "40 B (5 x f64)",
+                   "input_rows": ("8 B packed (17-bit score*1e5 + 13/12/11/11-bit box, verified lossless by the packer)" if packed is not None else
+                                  "16 B compact (f64 score + 4 x int16 box)" if compact is not None else "40 B (5 x f64)"),
                    "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (h2d / 1e9),
                    "parallelism": "streams sharded by segment, %d rank(s), no collective" % world,
                    "generate_s": round(gen_s, 1), "full_size_check": parity},

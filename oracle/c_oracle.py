@@ -211,6 +211,9 @@ def softnms_groups(group_offsets, rows, iou_thresh, soft_nms_cut, min_score, n_c
     if isinstance(rows, np.ndarray) and rows.dtype.names is not None:   # packing.compact_rows
         rows = np.ascontiguousarray(rows)
         box_format = _abi.W2T_BOX_LTWH_I16
+    elif isinstance(rows, np.ndarray) and rows.dtype == np.uint64:      # packing.packed_rows
+        rows = np.ascontiguousarray(rows)
+        box_format = _abi.W2T_BOX_LTWH_P64
     else:
         rows = _c(rows, np.float64).reshape(-1, 5)
     G, N = len(group_offsets) - 1, len(rows)

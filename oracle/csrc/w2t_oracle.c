@@ -723,12 +723,22 @@ static int nms_groups(const w2t_nms_problem_t *p, w2t_nms_result_t *r, int hard)
         for (int k = 0; k < 4; k++) unpacked[1 + k] = (double)b[k];
         rw = unpacked;
       }
+      if (p->box_format == W2T_BOX_LTWH_P64) { /* 8-byte packed rows, layout in include/w2t_types.h */
+        unsigned long long q;
+        memcpy(&q, (const unsigned char *)p->rows + 8 * ((size_t)base + i), 8);
+        unpacked[0] = (double)(q & 0x1ffffu) / 100000.0;
+        unpacked[1] = (double)((int)((q >> 17) & 0x1fffu) - 3072);
+        unpacked[2] = (double)((int)((q >> 30) & 0xfffu) - 1536);
+        unpacked[3] = (double)((q >> 42) & 0x7ffu);
+        unpacked[4] = (double)(q >> 53);
+        rw = unpacked;
+      }
       if (p->box_format == W2T_BOX_XYXY) {
         for (int k = 0; k < 4; k++) pf[4 * i + k] = rw[1 + k];
       } else {
         /* ensemble.py:19-22 (rows of convert_submission only) then box_utils.py:32-35 */
         double cx = rw[1], cy = rw[2];
-        if (p->box_format == W2T_BOX_LTWH || p->box_format == W2T_BOX_LTWH_I16) { cx = cx + rw[3] / 2; cy = cy + rw[4] / 2; }
+        if (p->box_format != W2T_BOX_CXCYWH) { cx = cx + rw[3] / 2; cy = cy + rw[4] / 2; }
         double hw = rw[3] * 0.5, hh = rw[4] * 0.5;
         pf[4 * i + 0] = cx - hw;
         pf[4 * i + 1] = cy - hh;

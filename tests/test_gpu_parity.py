@@ -375,3 +375,27 @@ def test_compact_input_rows_equal_float64_rows():
                                                n_chunks=3)
     for k, v in want.items():
         np.testing.assert_array_equal(got[k], v)
+
+
+def test_packed_input_rows_equal_float64_rows():
+    """8-byte packed rows (W2T_BOX_LTWH_P64) through soft-NMS, the fused ensemble -> SORT path and the
+    pipelined host path: bit-identical to the float64 rows and to the oracle."""
+    cfg = synth.SynthConfig(n_segments=2, cameras=("FRONT", "SIDE_LEFT"), n_frames=20, n_submissions=3,
+                            objects_per_frame=40.0, seed=46)
+    scene = synth.make_scene(cfg)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    packed = packing.packed_rows(groups.rows)
+    assert packed is not None and packed.dtype == np.uint64
+    a = compare_nms(groups, 0.5, 0.9, 0.01)        # float64 rows, checked against the oracle
+    b = runtime.softnms_groups(groups.group_offsets, packed, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR,
+                               max_group=groups.max_group)
+    for k in ("merged", "src_index", "ens_count", "trk_count", "img_exists"):
+        np.testing.assert_array_equal(a[k], b[k])
+    args = (scene.stream_img_offsets, scene.cam_wh(), 4, 0.5, 0.9, 0.01, helpers.SCORE_THR, helpers.IOU_THR, 2, 0)
+    want = runtime.ensemble_and_track(groups.group_offsets, groups.rows, *args, max_group=groups.max_group,
+                                      want_ensemble=False, raw=False)
+    want = {k: np.array(want[k]) for k in ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat")}
+    got = runtime.ensemble_and_track_pipelined(groups.group_offsets, packed, *args, max_group=groups.max_group,
+                                               n_chunks=3)
+    for k, v in want.items():
+        np.testing.assert_array_equal(got[k], v)

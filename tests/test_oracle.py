@@ -310,6 +310,40 @@ def test_compact_rows_give_the_same_ensemble():
     assert packing.compact_rows(np.array([[0.5, 1, 2, 40000, 4]])) is None        # beyond int16
 
 
+def test_packed_rows_give_the_same_ensemble():
+    g = golden_io.load("ensemble_c2_small")
+    scene = helpers.golden_scene(g)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    packed = packing.packed_rows(groups.rows)
+    assert packed is not None and packed.dtype == np.uint64 and len(packed) == len(groups.rows)
+    # lossless by construction: score and box decode to the very same doubles
+    np.testing.assert_array_equal((packed & np.uint64(0x1ffff)).astype(np.float64) / 1e5, groups.rows[:, 0])
+    for j, (shift, mask, bias) in enumerate(((17, 0x1fff, 3072), (30, 0xfff, 1536), (42, 0x7ff, 0), (53, 0x7ff, 0))):
+        np.testing.assert_array_equal(((packed >> np.uint64(shift)) & np.uint64(mask)).astype(np.float64) - bias,
+                                      groups.rows[:, 1 + j])
+    a = c_oracle.softnms_groups(groups.group_offsets, groups.rows, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR)
+    b = c_oracle.softnms_groups(groups.group_offsets, packed, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR)
+    for k in ("merged", "src_index", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box"):
+        np.testing.assert_array_equal(a[k], b[k])
+    # anything the 8 bytes cannot hold exactly is refused
+    assert packing.packed_rows(np.array([[0.5, 1.5, 2, 3, 4]])) is None           # non-integer box
+    assert packing.packed_rows(np.array([[0.5, 1, 2, 2048, 4]])) is None          # beyond 11 bits
+    assert packing.packed_rows(np.array([[0.5, -1, 2, 3, 4]])) is not None        # negative left is fine ...
+    assert packing.packed_rows(np.array([[0.5, 1, 2, -3, 4]])) is None            # ... a negative width is not
+    assert packing.packed_rows(np.array([[0.5, -3073, 2, 3, 4]])) is None
+    assert packing.packed_rows(np.array([[0.5, 1, 2560, 3, 4]])) is None
+    assert packing.packed_rows(np.array([[0.123456, 1, 2, 3, 4]])) is None        # not a 5-decimal score
+    assert packing.packed_rows(np.array([[0.12345 * 0.7, 1, 2, 3, 4]])) is None   # weighted score
+    assert packing.packed_rows(np.array([[1.5, 1, 2, 3, 4]])) is None             # k >= 2**17
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 100001, 20000)
+    exact = np.array([float("%.5f" % (v / 1e5)) for v in k])       # how Python parses the 5-decimal literal
+    rows = np.column_stack([exact, rng.integers(-3072, 5120, 20000), rng.integers(-1536, 2560, 20000), rng.integers(0, 2048, (20000, 2))]).astype(np.float64)
+    p = packing.packed_rows(rows)
+    assert p is not None
+    np.testing.assert_array_equal((p & np.uint64(0x1ffff)).astype(np.int64), k)
+
+
 def _random_tracking_case(seed, n_frames=14):
     rng = np.random.default_rng(seed)
     mix = rng.dirichlet([1.0, 1.0, 0.3, 0.6])

@@ -84,11 +84,19 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   // row i of the group: score and the four box columns, from 40-byte double rows or 16-byte compact rows
   const unsigned char *bytes = reinterpret_cast<const unsigned char *>(P.p.rows);
   auto row_score = [&](int i) -> double {
+    if (fmt == W2T_BOX_LTWH_P64) {
+      const unsigned long long q = *reinterpret_cast<const unsigned long long *>(bytes + 8 * ((size_t)base + i));
+      return (double)(unsigned)(q & 0x1ffffu) / 100000.0;  // correctly rounded: the double Python parses "0.ddddd" to
+    }
     return (fmt == W2T_BOX_LTWH_I16) ? *reinterpret_cast<const double *>(bytes + 16 * ((size_t)base + i))
                                      : P.p.rows[5 * ((size_t)base + i)];
   };
   auto row_box = [&](int i, double &b0, double &b1, double &b2, double &b3) {
-    if (fmt == W2T_BOX_LTWH_I16) {
+    if (fmt == W2T_BOX_LTWH_P64) {
+      const unsigned long long q = *reinterpret_cast<const unsigned long long *>(bytes + 8 * ((size_t)base + i));
+      b0 = (double)((int)((q >> 17) & 0x1fffu) - 3072); b1 = (double)((int)((q >> 30) & 0xfffu) - 1536);
+      b2 = (double)(unsigned)((q >> 42) & 0x7ffu); b3 = (double)(unsigned)(q >> 53);
+    } else if (fmt == W2T_BOX_LTWH_I16) {
       const short4 q = *reinterpret_cast<const short4 *>(bytes + 16 * ((size_t)base + i) + 8);
       b0 = (double)q.x; b1 = (double)q.y; b2 = (double)q.z; b3 = (double)q.w;
     } else {
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     } else {
       const double w = b2, h = b3;
       double cx = b0, cy = b1;
-      if (fmt == W2T_BOX_LTWH || fmt == W2T_BOX_LTWH_I16) { cx = cx + w / 2; cy = cy + h / 2; }  // lxly2cxcy, ensemble.py:19-22
+      if (fmt != W2T_BOX_CXCYWH) { cx = cx + w / 2; cy = cy + h / 2; }  // lxly2cxcy, ensemble.py:19-22
       const double hw = w * 0.5, hh = h * 0.5;                         // point_form, box_utils.py:32-35
       x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
     }
@@ -362,7 +370,7 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
   }
   if (problem->n_groups == 0) return W2T_OK;
   if (!problem->group_offsets || !problem->rows || !result->ens_count || (result->ens_box && !result->ens_score) ||
-      problem->box_format < W2T_BOX_LTWH || problem->box_format > W2T_BOX_LTWH_I16 || problem->top_k < 0) {
+      problem->box_format < W2T_BOX_LTWH || problem->box_format > W2T_BOX_LTWH_P64 || problem->top_k < 0) {
     set_last_error("%s: null buffer or bad box_format / top_k", who);
     return W2T_ERR_ARG;
   }

@@ -283,6 +283,33 @@ def compact_rows(rows):
     return out
 
 
+def packed_rows(rows):
+    """[N,5] float64 rows -> 8-byte packed rows (``W2T_BOX_LTWH_P64``, one uint64 each: 17 bits of
+    ``score*weight * 1e5``, 13 bits of left (biased by 3072), 12 bits of top (biased by 1536),
+    11 + 11 bits of width / height) when that loses nothing: every ``score*weight`` is bit for bit
+    ``k / 1e5`` for an integer ``k < 2**17`` (5-decimal detector scores with unit weights,
+    detnet/data/coco.py:249), left is an integer in [-3072, 5119], top in [-1536, 2559], width and
+    height in [0, 2047].
+    Else None (use :func:`compact_rows` or the float64 rows).  5x fewer bytes to ship."""
+    rows = np.asarray(rows, np.float64).reshape(-1, 5)
+    box = rows[:, 1:]
+    if len(rows) == 0:
+        return np.zeros(0, np.uint64)
+    if not (np.all(box == np.rint(box)) and box[:, 0].min() >= -3072 and box[:, 0].max() <= 5119
+            and box[:, 1].min() >= -1536 and box[:, 1].max() <= 2559
+            and box[:, 2:].min() >= 0 and box[:, 2:].max() <= 2047):
+        return None
+    k = np.rint(rows[:, 0] * 1e5)
+    if not (k.min() >= 0 and k.max() < 2 ** 17 and np.array_equal(k / 1e5, rows[:, 0])):
+        return None
+    out = k.astype(np.uint64)
+    out |= (box[:, 0] + 3072).astype(np.uint64) << np.uint64(17)
+    out |= (box[:, 1] + 1536).astype(np.uint64) << np.uint64(30)
+    out |= box[:, 2].astype(np.uint64) << np.uint64(42)
+    out |= box[:, 3].astype(np.uint64) << np.uint64(53)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # array paths (native JSON reader -> packed arrays, no per-detection Python objects)
 # ---------------------------------------------------------------------------

@@ -73,9 +73,13 @@ def _dev(a, dtype, device):
 def _host_rows(rows):
     """Ensemble input rows as a host tensor + their W2T_BOX_* layout: float64 [N,5] rows, or the
     16-byte compact rows of ``packing.compact_rows`` (structured array / uint8 [N,16] tensor)."""
+    if isinstance(rows, np.ndarray) and rows.dtype == np.uint64:      # packing.packed_rows
+        rows = torch.from_numpy(np.ascontiguousarray(rows).view(np.uint8).reshape(-1, 8))
     if isinstance(rows, np.ndarray) and rows.dtype.names is not None:
         rows = torch.from_numpy(np.ascontiguousarray(rows).view(np.uint8).reshape(-1, 16))
     if torch.is_tensor(rows) and rows.dtype == torch.uint8:
+        if rows.dim() == 2 and rows.shape[1] == 8:
+            return rows, _abi.W2T_BOX_LTWH_P64
         return rows.reshape(-1, 16), _abi.W2T_BOX_LTWH_I16
     if isinstance(rows, np.ndarray):
         rows = torch.from_numpy(np.ascontiguousarray(rows, np.float64))
@@ -192,7 +196,7 @@ def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_sc
         max_group = int(np.diff(offs_np).max()) if n_groups > 0 else 0
     d_offsets = _dev(group_offsets, np.int32, device)
     t_rows, fmt = _host_rows(rows)
-    if fmt == _abi.W2T_BOX_LTWH_I16:
+    if fmt in (_abi.W2T_BOX_LTWH_I16, _abi.W2T_BOX_LTWH_P64):
         box_format = fmt
     d_rows = t_rows.to(device, non_blocking=True).contiguous()
     out = softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
