@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--cpu-sample-frames", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=6, help="pipeline depth of the end-to-end leg")
+    ap.add_argument("--chunks", type=int, default=12, help="pipeline depth of the end-to-end leg")
     ap.add_argument("--skip-e2e", action="store_true",
                     help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
     ap.add_argument("--wide-rows", action="store_true", help="ship 40-byte float64 input rows instead of the packed ones")
@@ -287,7 +287,7 @@ def main():
             same = same and bool(torch.equal(dev_rows[key][:n_dev_rows].cpu(), torch.from_numpy(np.asarray(host_arr))))
         if not same:
             raise SystemExit("bench.py: the chunked end-to-end leg and the single-launch leg produced different rows")
-        parity = "all %d rows of the e2e leg (6 chunks) bit-identical to the single-launch leg" % n_dev_rows
+        parity = "all %d rows of the e2e leg (%d chunks) bit-identical to the single-launch leg" % (n_dev_rows, args.chunks)
     n_out = int(out_e2e["n_rows"])
     h2d = int(h_rows.numel() * h_rows.element_size() + h_offs.numel() * 4)
     d2h = int(out_e2e["d2h_bytes"])

@@ -599,12 +599,14 @@ def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
 
 def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh,
                                  soft_nms_cut, min_score, score_thr, iou_thresholds, max_age, min_hits,
-                                 max_group=None, id_base=0, n_chunks=6):
+                                 max_group=None, id_base=0, n_chunks=12, hoist=1.0):
     """Host buffers in, dense host rows out (``rows_box/score/id/img/cat``), the same result as
     :func:`ensemble_and_track` — with the streams cut into chunks so that copies and kernels overlap
     (PCIe is full duplex): the host->device copies of all chunks are queued on a copy stream; the
     soft-NMS of a chunk starts when its rows have landed; the SORT stage is one launch over all
-    sub-streams whose CTAs are ordered chunk by chunk and count themselves into per-chunk completion
+    sub-streams whose CTAs are ordered chunk by chunk — after the long chains (``hoist``: of that
+    fraction of trailing chunks; 1.0 = of all chunks, measured best), which start first so that none
+    of them is left running alone at the end — and count themselves into per-chunk completion
     counters; ids, dense rows and the device->host copy of chunk k start as soon as chunk k is tracked
     (stream wait on the counter), while the later chunks are still being tracked.
 
@@ -706,6 +708,19 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                      "status": nms_out["status"]}
             softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
                                   NC, score_thr, out=nms_k, box_format=fmt)
+    # Launch order of the single SORT launch: chunk by chunk, so that the early chunks finish early and
+    # go home while the rest is tracked — except that the LONG chains (the crowded category) of the
+    # trailing chunks are hoisted to the front: started last, a 200-image chain of that category would
+    # run on alone after everything else is done (longest-processing-time-first for the tail).
+    if hoist and len(chunks) > 1 and np.all(np.diff(h_offsets) > 0):
+        cnt = sizes.reshape(-1, NC).astype(np.int64)
+        work = np.add.reduceat(cnt * cnt + cnt, h_offsets[:-1].astype(np.int64), axis=0).reshape(-1)
+        order = plan_all["order"]
+        late = plan_all["chunk_of"][order] >= len(chunks) - max(1, int(round(hoist * len(chunks))))
+        front = late & (work[order] > 0.4 * np.percentile(work, 95))
+        first = order[front]
+        first = first[np.argsort(-work[first], kind="stable")]
+        plan_all["order"] = np.ascontiguousarray(np.concatenate([first, order[~front]]), np.int32)
     _trace("plans + nms queued")
     for cs in comp + [s_in]:
         main.wait_stream(cs)
