@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--cpu-sample-frames", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=12, help="pipeline depth of the end-to-end leg")
+    ap.add_argument("--chunks", type=int, default=8, help="pipeline depth of the end-to-end leg")
     ap.add_argument("--skip-e2e", action="store_true",
                     help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
     ap.add_argument("--wide-rows", action="store_true", help="ship 40-byte float64 input rows instead of the packed ones")

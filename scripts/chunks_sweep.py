@@ -19,6 +19,6 @@ for chunks in [parse(c) for c in sys.argv[1:]] or [1, 2, 3, 4, 6, 8]:
     ts = []
     for it in range(4):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        res = runtime.ensemble_and_track_pipelined(h_offs, h_rows, n_chunks=chunks, hoist=hoist, **kw)
+        res = runtime.ensemble_and_track_pipelined(h_offs, h_rows, n_chunks=chunks, hoist=abs(hoist), hoist_by_work=hoist < 0, **kw)
         torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - t0))
     print("chunks %s hoist %.2f: %s ms  (rows %d)" % (chunks, hoist, " ".join("%.1f" % t for t in ts), res["n_rows"]), flush=True)

@@ -599,7 +599,7 @@ def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
 
 def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh,
                                  soft_nms_cut, min_score, score_thr, iou_thresholds, max_age, min_hits,
-                                 max_group=None, id_base=0, n_chunks=12, hoist=1.0):
+                                 max_group=None, id_base=0, n_chunks=8, hoist=1.0, hoist_by_work=False):
     """Host buffers in, dense host rows out (``rows_box/score/id/img/cat``), the same result as
     :func:`ensemble_and_track` — with the streams cut into chunks so that copies and kernels overlap
     (PCIe is full duplex): the host->device copies of all chunks are queued on a copy stream; the
@@ -630,13 +630,16 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
         return ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, NC, iou_thresh, soft_nms_cut,
                                   min_score, score_thr, iou_thresholds, max_age, min_hits, max_group, False, id_base,
                                   raw=False)
-    sizes = np.diff(go_np).astype(np.int32)
+    # host work is ordered so that the copies and the soft-NMS launches are queued first; everything
+    # only the SORT launch needs (group sizes, plans) is computed while they run
+    sizes = None
     if max_group is None:
+        sizes = np.diff(go_np).astype(np.int32)
         max_group = int(sizes.max())
-    exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
     chunks = _chunk_bounds(h_offsets, go_np, NC, n_chunks)
     cam = np.ascontiguousarray(cam_wh, np.float64).reshape(S, 2)
 
+    _trace("host prep done")
     main = torch.cuda.current_stream()
     s_in, s_out = _side_streams(device)
     i32, f64 = torch.int32, torch.float64
@@ -684,6 +687,21 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     for cs in comp + [fin]:
         cs.wait_stream(main)
     nq = S * NC
+    for k, (s0, s1) in enumerate(chunks):
+        img0, img1 = int(h_offsets[s0]), int(h_offsets[s1])
+        g0, g1 = img0 * NC, img1 * NC
+        cs = comp[k % len(comp)]
+        with torch.cuda.stream(cs):
+            cs.wait_event(h2d_done[k])
+            nms_k = {"ens_count": nms_out["ens_count"][g0:g1], "trk_count": nms_out["trk_count"][g0:g1],
+                     "trk_box": nms_out["trk_box"], "img_exists": nms_out["img_exists"][img0:img1],
+                     "status": nms_out["status"]}
+            softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
+                                  NC, score_thr, out=nms_k, box_format=fmt)
+    _trace("nms queued")
+    if sizes is None:
+        sizes = np.diff(go_np).astype(np.int32)
+    exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
     plan_all = {"order": np.zeros(nq, np.int32), "track_cap": np.zeros(nq, np.int32), "det_cap": np.zeros(nq, np.int32),
                 "ws_offset": np.zeros(nq, np.int64), "chunk_of": np.zeros(nq, np.int32), "ws_bytes": 0}
     pos = 0
@@ -700,26 +718,18 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
         plan_all["ws_offset"][q0:q1] = plan["ws_offset"] + plan_all["ws_bytes"]
         plan_all["ws_bytes"] += plan["ws_bytes"]
         plan_all["chunk_of"][q0:q1] = k
-        cs = comp[k % len(comp)]
-        with torch.cuda.stream(cs):
-            cs.wait_event(h2d_done[k])
-            nms_k = {"ens_count": nms_out["ens_count"][g0:g1], "trk_count": nms_out["trk_count"][g0:g1],
-                     "trk_box": nms_out["trk_box"], "img_exists": nms_out["img_exists"][img0:img1],
-                     "status": nms_out["status"]}
-            softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
-                                  NC, score_thr, out=nms_k, box_format=fmt)
     # Launch order of the single SORT launch: chunk by chunk, so that the early chunks finish early and
     # go home while the rest is tracked — except that the LONG chains (the crowded category) of the
     # trailing chunks are hoisted to the front: started last, a 200-image chain of that category would
     # run on alone after everything else is done (longest-processing-time-first for the tail).
-    if hoist and len(chunks) > 1 and np.all(np.diff(h_offsets) > 0):
-        cnt = sizes.reshape(-1, NC).astype(np.int64)
-        work = np.add.reduceat(cnt * cnt + cnt, h_offsets[:-1].astype(np.int64), axis=0).reshape(-1)
+    if hoist and len(chunks) > 1:
+        work = plan_all["det_cap"].astype(np.int64) * plan_all["track_cap"]   # size of the largest assignment problem
         order = plan_all["order"]
         late = plan_all["chunk_of"][order] >= len(chunks) - max(1, int(round(hoist * len(chunks))))
         front = late & (work[order] > 0.4 * np.percentile(work, 95))
-        first = order[front]
-        first = first[np.argsort(-work[first], kind="stable")]
+        first = order[front]          # chunk by chunk as well: the last wave of long chains then belongs to the last chunks
+        if hoist_by_work:
+            first = first[np.argsort(-work[first], kind="stable")]
         plan_all["order"] = np.ascontiguousarray(np.concatenate([first, order[~front]]), np.int32)
     _trace("plans + nms queued")
     for cs in comp + [s_in]:
