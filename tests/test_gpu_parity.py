@@ -356,6 +356,25 @@ def test_pipelined_chunks_equal_the_single_pass():
             np.testing.assert_array_equal(got[k], want[k])
 
 
+def test_pipelined_crowded_streams_and_launch_orders():
+    """Crowded sub-streams (more than W2T_WIDE_DETS detections in an image: wide CTAs, assignment problems in
+    global memory) through the pipelined path, with every launch-order policy: same rows as the single pass."""
+    cfg = synth.preset("c4", n_segments=3, cameras=("FRONT", "SIDE_LEFT"), n_frames=5, n_submissions=2, seed=9)
+    scene = synth.make_scene(cfg)
+    groups = synth.groups_from_scene(scene, None, 0.01)
+    assert int(np.diff(groups.group_offsets).max()) > 2 * 320
+    args = (groups.group_offsets, groups.rows, scene.stream_img_offsets, scene.cam_wh(), 4, 0.5, 0.9, 0.01,
+            helpers.SCORE_THR, helpers.IOU_THR, 2, 0)
+    want = runtime.ensemble_and_track(*args, max_group=groups.max_group, want_ensemble=False, raw=False)
+    want = {k: np.array(want[k]) for k in ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat")}
+    assert len(want["rows_id"]) > 0
+    for n_chunks, hoist, by_work in ((3, 1.0, False), (3, 0.5, True), (2, 0.0, False), ([0.2, 0.8], 1.0, True)):
+        got = runtime.ensemble_and_track_pipelined(*args, max_group=groups.max_group, n_chunks=n_chunks, hoist=hoist,
+                                                   hoist_by_work=by_work)
+        for k, v in want.items():
+            np.testing.assert_array_equal(got[k], v)
+
+
 def test_compact_input_rows_equal_float64_rows():
     cfg = synth.SynthConfig(n_segments=2, cameras=("FRONT", "SIDE_LEFT"), n_frames=20, n_submissions=3,
                             objects_per_frame=40.0, seed=45)

@@ -98,6 +98,7 @@ class NmsProblem(C.Structure):
     ]
 
 
+W2T_WIDE_DETS = 320          # include/w2t_types.h
 W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY, W2T_BOX_LTWH_I16, W2T_BOX_LTWH_P64 = 0, 1, 2, 3, 4
 
 

@@ -731,6 +731,11 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
         if hoist_by_work:
             first = first[np.argsort(-work[first], kind="stable")]
         plan_all["order"] = np.ascontiguousarray(np.concatenate([first, order[~front]]), np.int32)
+    # crowded sub-streams get the wide CTAs of w2t_sort_track: they lead the launch order (w2t_sort_plan_t.n_wide)
+    wide = plan_all["det_cap"][plan_all["order"]] > _abi.W2T_WIDE_DETS
+    if wide.any():
+        plan_all["order"] = np.ascontiguousarray(np.concatenate([plan_all["order"][wide], plan_all["order"][~wide]]), np.int32)
+    plan_all["n_wide"] = int(wide.sum())
     _trace("plans + nms queued")
     for cs in comp + [s_in]:
         main.wait_stream(cs)
