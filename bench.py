@@ -144,17 +144,37 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
 
+    def _nvml(self):
+        """In-process NVML handle (nvidia_ml_py); querying it does not spawn a process or take the
+        driver locks `nvidia-smi` takes at start-up, which can stall kernel launches for milliseconds."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
+        self.source = "nvml (same counters as nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*)" if nv is not None else "nvidia-smi"
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    bits = (0x8, 0x40, 0x20, 0x4)   # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+                    self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 6:
+                        self.samples.append(parts)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if nv is not None else 0.1)
 
     def summary(self):
         self.stop_flag = True
@@ -164,7 +184,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": getattr(self, "source", "nvidia-smi")}
 
 
 # ---------------------------------------------------------------------------------------------

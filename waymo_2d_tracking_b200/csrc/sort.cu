@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "sort_kernel.cuh"
@@ -21,27 +22,46 @@ extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t
   const int nq = n_streams * NC;
   const int window = max_age + 2;  // images whose detections can still own a live tracker
   std::vector<int64_t> work(nq, 0);
-  std::vector<int> ring(window);
-  for (int s = 0; s < n_streams; s++) {
-    for (int c = 0; c < NC; c++) {
-      const int q = s * NC + c;
+  // one pass over the images of a stream for all categories at once (det_count is image-major);
+  // streams are independent, so the pass is split over a few host threads when the job is large
+  auto plan_streams = [&](int s_begin, int s_end) {
+    std::vector<int> ring((size_t)window * NC);
+    for (int s = s_begin; s < s_end; s++) {
       std::fill(ring.begin(), ring.end(), 0);
-      int64_t sum = 0, best = 0, w = 0;
-      int dmax = 0, pos = 0;
+      int64_t sum[W2T_MAX_CLASSES] = {0}, best[W2T_MAX_CLASSES] = {0}, w[W2T_MAX_CLASSES] = {0};
+      int dmax[W2T_MAX_CLASSES] = {0};
+      int pos = 0;
       for (int img = stream_img_offsets[s]; img < stream_img_offsets[s + 1]; img++) {
         if (img_exists && !img_exists[img]) continue;
-        const int d = det_count[(size_t)img * NC + c];
-        sum += d - ring[pos];
-        ring[pos] = d;
-        pos = (pos + 1) % window;
-        best = std::max(best, sum);
-        dmax = std::max(dmax, d);
-        w += (int64_t)d * d + d;
+        const int32_t *cnt = det_count + (size_t)img * NC;
+        int *slot = ring.data() + (size_t)pos * NC;
+        for (int c = 0; c < NC; c++) {
+          const int d = cnt[c];
+          sum[c] += d - slot[c];
+          slot[c] = d;
+          if (sum[c] > best[c]) best[c] = sum[c];
+          if (d > dmax[c]) dmax[c] = d;
+          w[c] += (int64_t)d * d + d;
+        }
+        if (++pos == window) pos = 0;
       }
-      plan->track_cap[q] = (int32_t)std::max<int64_t>(best, 1);
-      plan->det_cap[q] = std::max(dmax, 1);
-      work[q] = w;
+      for (int c = 0; c < NC; c++) {
+        const int q = s * NC + c;
+        plan->track_cap[q] = (int32_t)std::max<int64_t>(best[c], 1);
+        plan->det_cap[q] = std::max(dmax[c], 1);
+        work[q] = w[c];
+      }
     }
+  };
+  const int n_img_total = n_streams > 0 ? stream_img_offsets[n_streams] : 0;
+  const int n_threads = (n_img_total >= 40000 && n_streams >= 8) ? 4 : 1;
+  if (n_threads == 1) {
+    plan_streams(0, n_streams);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++)
+      pool.emplace_back(plan_streams, (int)((int64_t)n_streams * t / n_threads), (int)((int64_t)n_streams * (t + 1) / n_threads));
+    for (auto &th : pool) th.join();
   }
   // crowded sub-streams first (they get wide CTAs), each part heaviest first
   std::iota(plan->order, plan->order + nq, 0);

@@ -698,26 +698,19 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                      "status": nms_out["status"]}
             softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
                                   NC, score_thr, out=nms_k, box_format=fmt)
-    _trace("nms queued")
     if sizes is None:
         sizes = np.diff(go_np).astype(np.int32)
-    exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
-    plan_all = {"order": np.zeros(nq, np.int32), "track_cap": np.zeros(nq, np.int32), "det_cap": np.zeros(nq, np.int32),
-                "ws_offset": np.zeros(nq, np.int64), "chunk_of": np.zeros(nq, np.int32), "ws_bytes": 0}
-    pos = 0
+    exists_ub = (np.diff(go_np[::NC]) > 0).astype(np.uint8)      # an image exists if any of its groups has a row
+    # one plan for all streams (slab capacities and offsets, heaviest-first order); the launch order is then
+    # regrouped chunk by chunk, heaviest first inside a chunk
+    plan_all = make_plan(S, NC, h_offsets, sizes, exists_ub, max_age)
+    chunk_of_stream = np.zeros(S, np.int32)
     for k, (s0, s1) in enumerate(chunks):
-        img0, img1 = int(h_offsets[s0]), int(h_offsets[s1])
-        g0, g1 = img0 * NC, img1 * NC
-        loc_offsets = (h_offsets[s0:s1 + 1] - h_offsets[s0]).astype(np.int32)
-        plan = make_plan(s1 - s0, NC, loc_offsets, sizes[g0:g1], exists_ub[img0:img1], max_age)
-        q0, q1 = s0 * NC, s1 * NC
-        plan_all["order"][pos:pos + (q1 - q0)] = plan["order"] + q0
-        pos += q1 - q0
-        plan_all["track_cap"][q0:q1] = plan["track_cap"]
-        plan_all["det_cap"][q0:q1] = plan["det_cap"]
-        plan_all["ws_offset"][q0:q1] = plan["ws_offset"] + plan_all["ws_bytes"]
-        plan_all["ws_bytes"] += plan["ws_bytes"]
-        plan_all["chunk_of"][q0:q1] = k
+        chunk_of_stream[s0:s1] = k
+    plan_all["chunk_of"] = np.repeat(chunk_of_stream, NC)
+    plan_all["order"] = np.ascontiguousarray(
+        plan_all["order"][np.argsort(plan_all["chunk_of"][plan_all["order"]], kind="stable")], np.int32)
+    _trace("nms queued")
     # Launch order of the single SORT launch: chunk by chunk, so that the early chunks finish early and
     # go home while the rest is tracked — except that the LONG chains (the crowded category) of the
     # trailing chunks are hoisted to the front: started last, a 200-image chain of that category would
