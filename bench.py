@@ -42,7 +42,7 @@ UNIT = "frames/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20; 3 for --impl reference, whose steps take seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--segments", type=int, default=150, help="segments per GPU (150 = configuration C3)")
@@ -54,7 +54,10 @@ def parse_args():
                     help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
     ap.add_argument("--wide-rows", action="store_true", help="ship 40-byte float64 input rows instead of the packed ones")
     ap.add_argument("--compact-rows", action="store_true", help="ship 16-byte rows (f64 score + 4 x int16) instead of 8-byte packed ones")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 3 if args.impl == "reference" else 20
+    return args
 
 
 def workload_name(segments):
