@@ -270,6 +270,7 @@ struct Munkres {
         const int sc = g.row_star[fr];
         if (sc < 0) {
           // step 5: augment along the alternating path that starts at the primed zero (fr, fc)
+          __syncwarp();  // every lane has read row_star[fr] before lane 0 rewrites the stars
           if (lane == 0) {
             int r = fr, c = fc;
             for (int hops = 0;; hops++) {
@@ -560,6 +561,7 @@ struct Munkres {
         if (sc < 0) {
           // step 5: flip d.stars along the alternating path that starts at the primed zero (fr, fc)
           int endc = -1;
+          __syncwarp();  // every lane has read row_star[fr] before lane 0 rewrites the stars
           if (lane == 0) {
             int r = fr, c = fc;
             for (int hops = 0;; hops++) {
