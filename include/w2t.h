@@ -110,6 +110,26 @@ int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t *stream_im
 int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
                    w2t_sort_result_t *result, void *workspace, int32_t *status, w2t_stream_t stream);
 
+/* Frame-by-frame tracking with device-resident state: the stateful API of the reference —
+ * Sort.update (tracking/sort/sort.py:244-296) called once per image and category by
+ * MultiClassTrackerSort.track (tracking/sort/tracker_sort.py:41-49).  The same kernel as
+ * w2t_sort_track over a problem that holds ONE new image per stream (or a few); between calls the
+ * trackers stay in the workspace slabs and `sub_state` (DEVICE int32 [n_streams*n_classes, 4],
+ * zeroed by the caller before the first call) carries each sub-stream's live-tracker count,
+ * frame_count, "Sort object exists" and flags.  The plan is the caller's: fixed capacities
+ * track_cap / det_cap per sub-stream, slabs of w2t_sort_slab_bytes(track_cap, det_cap) bytes
+ * at ws_offset (no window bound exists for an open-ended stream); exceeding a capacity reports
+ * W2T_ERR_CAPACITY in *status.  Rows are those Sort.update returns (sort.py:280-289): out_box =
+ * [x1, y1, x2, y2] and out_score = exp(-0.1 * error), both unclipped, in tracker-list order (the
+ * reference returns the reversed list); clipping, the size filter and the confidence clip of
+ * tracking/utils.py:37-58 are left to the caller.  out_birth = (group_base + group of the image
+ * the tracker was created in, k): the caller, who knows KalmanBoxTracker.count at every
+ * Sort.update call, turns it into the object id.  result->first_img is not used. */
+int w2t_sort_step(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
+                  w2t_sort_result_t *result, void *workspace, int32_t *sub_state, int32_t group_base,
+                  int32_t *status, w2t_stream_t stream);
+size_t w2t_sort_slab_bytes(int32_t track_cap, int32_t det_cap);
+
 /* Device-side id assignment + dense output list (finalize.cu): object ids by an exclusive
  * scan of `created` in the reference's processing order (KalmanBoxTracker.count,
  * sort.py:86,140-141), rows gathered into the order tracking/utils.py:37-58 appends them.

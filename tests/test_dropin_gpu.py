@@ -18,7 +18,7 @@ from waymo_2d_tracking_b200.detnet.utils import box_utils
 from waymo_2d_tracking_b200.tracking import track as track_cli
 from waymo_2d_tracking_b200.tracking import utils as trk_utils
 from waymo_2d_tracking_b200.tracking.sort import sort as sort_mod
-from waymo_2d_tracking_b200.tracking.sort.tracker_sort import MultiClassTrackerSort
+from waymo_2d_tracking_b200.tracking.sort.tracker_sort import DeviceMultiClassTrackerSort, MultiClassTrackerSort
 
 pytestmark = pytest.mark.gpu
 
@@ -212,6 +212,45 @@ def test_stateful_sort_api_matches_port_frame_by_frame():
             assert a[k].shape == b[k].shape
             np.testing.assert_array_equal(a[k][:, :5], b[k][:, :5])           # boxes and ids
             np.testing.assert_allclose(a[k][:, 5], b[k][:, 5], rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("max_age,min_hits,seed", [(2, 0, 17), (1, 2, 18), (3, 1, 19)])
+def test_device_resident_stateful_api_matches_port_frame_by_frame(max_age, min_hits, seed):
+    """w2t_sort_step: one launch per frame, filters / lists / counters resident on the device between
+    calls; frame by frame the same dict (key order), rows, ids and confidences as the reference's
+    MultiClassTrackerSort (oracle port), including frames without detections of a category, an empty
+    frame and a category that appears late."""
+    cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT",), n_frames=16, n_submissions=1, objects_per_frame=30.0,
+                            seed=seed)
+    scene = synth.make_scene(cfg)
+    pred = sort_port.group_entries(synth.to_json_list(scene, scene.submissions[0]), helpers.SCORE_THR)
+    frames = pred[scene.segments[0]]['FRONT']
+    sort_mod.KalmanBoxTracker.count = 5
+    sort_port.BoxTracker.count = 5
+    ours = DeviceMultiClassTrackerSort(max_age=max_age, min_hits=min_hits, track_cap=128, det_cap=64)
+    ref = sort_port.MultiClassTracker(max_age=max_age, min_hits=min_hits)
+    n_rows = 0
+    for i, fid in enumerate(sorted(frames)):
+        rows = [[e['bbox'][0], e['bbox'][1], e['bbox'][0] + e['bbox'][2], e['bbox'][1] + e['bbox'][3], e['score'],
+                 e['category_id']] for e in frames[fid]]
+        if i < 3:
+            rows = [r for r in rows if r[5] != 1]     # vehicles appear late: their Sort object is created last
+        if i == 7:
+            rows = []                                  # an image without any detection still steps every tracker
+        if i in (9, 10):
+            rows = [r for r in rows if r[5] != 2]     # a category without detections is stepped with an empty array
+        a, b = ours.track(rows, helpers.IOU_THR), ref.track(rows, helpers.IOU_THR)
+        assert list(a.keys()) == list(b.keys()) == ours.trackers
+        for k in a:
+            assert a[k].shape == b[k].shape, (i, k)
+            np.testing.assert_array_equal(a[k][:, 4], b[k][:, 4])                      # ids
+            np.testing.assert_allclose(a[k][:, :4], b[k][:, :4], rtol=1e-9, atol=0)    # boxes
+            np.testing.assert_allclose(a[k][:, 5], b[k][:, 5], rtol=1e-9, atol=0)      # confidence
+            n_rows += len(a[k])
+        assert sort_mod.KalmanBoxTracker.count == sort_port.BoxTracker.count
+    assert n_rows > 100
+    with pytest.raises(runtime.W2TError):
+        DeviceMultiClassTrackerSort(track_cap=8, det_cap=4).track([[0, 0, 10, 10, 1.0, 1]] * 5, helpers.IOU_THR)
 
 
 def test_sort_building_blocks_python_surface():

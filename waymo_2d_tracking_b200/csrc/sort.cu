@@ -81,21 +81,25 @@ extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t
   return W2T_OK;
 }
 
-extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
-                              w2t_sort_result_t *result, void *workspace, int32_t *status, w2t_stream_t stream) {
+static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
+                       w2t_sort_result_t *result, void *workspace, int32_t *sub_state, int32_t group_base,
+                       int32_t *status, w2t_stream_t stream) {
+  const bool step = sub_state != nullptr;
   if (!problem || !plan || !result || !status || problem->n_classes < 1 ||
       problem->n_classes > W2T_MAX_CLASSES || problem->n_streams < 0) {
-    set_last_error("w2t_sort_track: bad argument");
+    set_last_error("%s: bad argument", who);
     return W2T_ERR_ARG;
   }
   const int nq = problem->n_streams * problem->n_classes;
   if (nq == 0) return W2T_OK;
   if (!workspace || !result->out_box || !result->out_score || !result->out_birth || !result->out_count ||
-      !result->created || !result->first_img) {
-    set_last_error("w2t_sort_track: null buffer");
+      !result->created || (!step && !result->first_img)) {
+    set_last_error("%s: null buffer", who);
     return W2T_ERR_ARG;
   }
   SortParams P;
+  P.sub_state = sub_state;
+  P.group_base = group_base;
   P.p = *problem;
   P.r = *result;
   P.order = plan->order;
@@ -111,7 +115,14 @@ extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_
   P.timers = getenv("W2T_SORT_TIMERS") ? reinterpret_cast<long long *>(strtoull(getenv("W2T_SORT_TIMERS"), nullptr, 10))
                                         : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  if (P.timers != nullptr)
+  if (step) {
+    const int n_wide = std::min(std::max(plan->n_wide, 0), nq);
+    if (n_wide > 0) sort_track_kernel<512, 1, false, kSmemC, true><<<n_wide, 512, 0, st>>>(P);
+    if (nq > n_wide) {
+      P.order = plan->order + n_wide;
+      sort_track_kernel<kSortBlock, kSortMinBlocks, false, kSmemC, true><<<nq - n_wide, kSortBlock, 0, st>>>(P);
+    }
+  } else if (P.timers != nullptr)
     sort_track_kernel<kSortBlock, kSortMinBlocks, true><<<nq, kSortBlock, 0, st>>>(P);
   else {
     // crowded sub-streams (the first n_wide of the launch order): 512 threads walk the big cost
@@ -125,6 +136,25 @@ extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_
   }
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
+}
+
+extern "C" int w2t_sort_track(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
+                              w2t_sort_result_t *result, void *workspace, int32_t *status, w2t_stream_t stream) {
+  return launch_sort("w2t_sort_track", problem, plan, result, workspace, nullptr, 0, status, stream);
+}
+
+extern "C" int w2t_sort_step(const w2t_sort_problem_t *problem, const w2t_sort_plan_t *plan,
+                             w2t_sort_result_t *result, void *workspace, int32_t *sub_state, int32_t group_base,
+                             int32_t *status, w2t_stream_t stream) {
+  if (!sub_state) {
+    set_last_error("w2t_sort_step: sub_state is required");
+    return W2T_ERR_ARG;
+  }
+  return launch_sort("w2t_sort_step", problem, plan, result, workspace, sub_state, group_base, status, stream);
+}
+
+extern "C" size_t w2t_sort_slab_bytes(int32_t track_cap, int32_t det_cap) {
+  return slab_layout(std::max(track_cap, 1), std::max(det_cap, 1)).total;
 }
 
 extern "C" int w2t_assign_ids(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,

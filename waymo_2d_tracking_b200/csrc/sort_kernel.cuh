@@ -93,6 +93,12 @@ struct SortParams {
   long long *timers;  // optional [n_substreams,16] phase cycle counters (debug aid, may be NULL)
   const int32_t *chunk_of;  // optional completion tracking, see w2t_sort_plan_t
   int32_t *chunk_done;
+  // frame-by-frame mode (w2t_sort_step, STEP instantiation only): [n_substreams,4] ints that carry a
+  // sub-stream from one call to the next — live trackers, frame_count, "Sort object exists", flags
+  // (bit 0: a predicted box is NaN, bit 1: slab initialised) — and the number the groups of this
+  // call are offset by in the birth records (groups of different calls must not collide)
+  int32_t *sub_state;
+  int32_t group_base;
 };
 
 // iou() of sort.py:33-47 as numba compiles it for (float32[:], float64[:]): the detection's
@@ -161,7 +167,10 @@ __device__ void partition3(int n, VAL val, FA fa, FB fb, int *dst, int *tmp, int
 // SMEMC: floats of the shared-memory cost matrix (larger matrices live in the slab, everything else
 // of the solver stays in shared memory); with BLOCK and MINB (CTAs per SM the register budget is
 // capped for) it sets how many sub-streams an SM holds at a time.
-template <int BLOCK, int MINB, bool TIMERS, int SMEMC = kSmemC>
+// STEP: frame-by-frame instantiation behind w2t_sort_step — the tracker state survives the launch in
+// the slab and in P.sub_state, rows are emitted as Sort.update returns them (sort.py:280-289: corners
+// and confidence unclipped, no size filter; utils.py:37-58 is then the caller's business).
+template <int BLOCK, int MINB, bool TIMERS, int SMEMC = kSmemC, bool STEP = false>
 __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParams P) {
   constexpr int NW = BLOCK / 32;
   __shared__ MunkresShared ms;
@@ -222,12 +231,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   const int max_age = P.p.max_age, min_hits = P.p.min_hits;
   const float4 *det_box = reinterpret_cast<const float4 *>(P.p.det_box);
 
-  for (int i = tid; i < Tcap; i += BLOCK) list[i] = i;
-  if (tid == 0) { P.r.first_img[q] = -1; s_nan = 0; }
-  __syncthreads();
-
   int T = 0, frame_count = 0, err = 0;
   bool started = false;
+  if (STEP) {
+    const int4 sv = reinterpret_cast<const int4 *>(P.sub_state)[q];
+    if (!(sv.w & 2))
+      for (int i = tid; i < Tcap; i += BLOCK) list[i] = i;
+    else { T = sv.x; frame_count = sv.y; started = sv.z != 0; }
+    if (tid == 0) s_nan = sv.w & 1;
+  } else {
+    for (int i = tid; i < Tcap; i += BLOCK) list[i] = i;
+    if (tid == 0) { P.r.first_img[q] = -1; s_nan = 0; }
+  }
+  __syncthreads();
 
   // Software pipeline over the images: the (exists, count, start) triple of image i+1 is loaded
   // at the top of iteration i and its detections are copied to shared memory with cp.async in
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
       if (D == 0) skip = true;  // no Sort object for this category yet (tracker_sort.py:32-33)
       else {
         started = true;
-        if (tid == 0) P.r.first_img[q] = img - img0;
+        if (!STEP && tid == 0) P.r.first_img[q] = img - img0;
       }
     }
     if (!skip && !err && (D > Dcap || D > kMunkresMaxDim || T > kMunkresMaxDim)) err = W2T_ERR_CAPACITY;
@@ -532,7 +548,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
           kfb_init(dd, x, Pm);
           tsu = 0;
           hs = 0;
-          obg = g;
+          obg = STEP ? g + P.group_base : g;
           obk = t - T;
           bgA[sl] = obg;
           bkA[sl] = obk;
@@ -560,13 +576,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
           x_to_bbox(x, b);
           const double e = ((Pm[0] + Pm[4]) + Pm[8]) / 3.0;  // mean(P00, P11, P22), sort.py:190
           const double conf = exp(-e * 0.1);
-          const double x1 = clipd(b[0], 0., camW), y1 = clipd(b[1], 0., camH);
-          const double x2 = clipd(b[2], 0., camW), y2 = clipd(b[3], 0., camH);
-          const double wd = x2 - x1, ht = y2 - y1;
-          if (!(wd < 1 || ht < 1)) {
+          if (STEP) {
             ok = true;
-            ob0 = x1; ob1 = y1; ob2 = wd; ob3 = ht;
-            oconf = clipd(conf, 0.2, 1.0);
+            ob0 = b[0]; ob1 = b[1]; ob2 = b[2]; ob3 = b[3];
+            oconf = conf;
+          } else {
+            const double x1 = clipd(b[0], 0., camW), y1 = clipd(b[1], 0., camH);
+            const double x2 = clipd(b[2], 0., camW), y2 = clipd(b[3], 0., camH);
+            const double wd = x2 - x1, ht = y2 - y1;
+            if (!(wd < 1 || ht < 1)) {
+              ok = true;
+              ob0 = x1; ob1 = y1; ob2 = wd; ob3 = ht;
+              oconf = clipd(conf, 0.2, 1.0);
+            }
           }
         }
         const bool surv = !(tsu > max_age);  // sort.py:292
@@ -621,6 +643,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
 #undef W2T_TICK
 
   if (err && tid == 0) atomicMax(P.status, err);
+  if (STEP) {
+    __syncthreads();
+    if (tid == 0) reinterpret_cast<int4 *>(P.sub_state)[q] = make_int4(T, frame_count, started ? 1 : 0, (s_nan ? 1 : 0) | 2);
+  }
 
   // optional: filter state of every live tracker, already predicted one step past the last image
   if (P.r.final_count != nullptr) {

@@ -599,7 +599,7 @@ def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
 
 def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh,
                                  soft_nms_cut, min_score, score_thr, iou_thresholds, max_age, min_hits,
-                                 max_group=None, id_base=0, n_chunks=8, hoist=1.0, hoist_by_work=False):
+                                 max_group=None, id_base=0, n_chunks=8, hoist=1.0, hoist_by_work=False, light_first=0):
     """Host buffers in, dense host rows out (``rows_box/score/id/img/cat``), the same result as
     :func:`ensemble_and_track` — with the streams cut into chunks so that copies and kernels overlap
     (PCIe is full duplex): the host->device copies of all chunks are queued on a copy stream; the
@@ -723,7 +723,14 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
         first = order[front]          # chunk by chunk as well: the last wave of long chains then belongs to the last chunks
         if hoist_by_work:
             first = first[np.argsort(-work[first], kind="stable")]
-        plan_all["order"] = np.ascontiguousarray(np.concatenate([first, order[~front]]), np.int32)
+        rest = order[~front]
+        if light_first > 0:
+            # the short chains of the first chunk(s) start together with the long ones, so that those chunks are
+            # complete — and on their way home — as soon as their own long chains are
+            early = plan_all["chunk_of"][rest] < light_first
+            first = np.concatenate([rest[early], first])
+            rest = rest[~early]
+        plan_all["order"] = np.ascontiguousarray(np.concatenate([first, rest]), np.int32)
     # crowded sub-streams get the wide CTAs of w2t_sort_track: they lead the launch order (w2t_sort_plan_t.n_wide)
     wide = plan_all["det_cap"][plan_all["order"]] > _abi.W2T_WIDE_DETS
     if wide.any():
@@ -804,6 +811,152 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
         width = 4 if key == "rows_box" else 1
         res[key] = pool[:n_rows_total * width].view((n_rows_total, 4) if width == 4 else (n_rows_total,)).numpy()
     return res
+
+
+# ---------------------------------------------------------------------------
+# frame-by-frame tracking with device-resident state (w2t_sort_step)
+# ---------------------------------------------------------------------------
+
+class SortStepper:
+    """Device-resident state of ``n_streams`` multi-category SORT trackers, advanced one image per
+    stream and call: what a ``MultiClassTrackerSort`` per stream holds in the reference
+    (tracking/sort/tracker_sort.py:10-51), except that filters, lists and counters never leave the
+    GPU between calls — a call is one small H2D copy, ONE launch of the tracker kernel
+    (``w2t_sort_step``) and one small D2H copy.
+
+    ``track_cap`` / ``det_cap``: most trackers alive / detections per image and category (fixed
+    slab capacities; exceeding them raises ``W2TError``).  Object ids follow
+    ``KalmanBoxTracker.count`` (sort.py:86,140-141) in the order the reference would create the
+    trackers: stream by stream within a call, category by category in each stream's
+    first-appearance order, unmatched detections in the order of sort.py:208-222.
+    """
+
+    def __init__(self, iou_thresholds, max_age=1, min_hits=0, n_streams=1, track_cap=256, det_cap=256, id_base=0):
+        self.device = require_cuda()
+        self.S, self.NC = int(n_streams), len(iou_thresholds)
+        if not 1 <= self.NC <= _abi.W2T_MAX_CLASSES:
+            raise IndexError("iou_thresholds must hold 1..%d categories" % _abi.W2T_MAX_CLASSES)
+        self.iou_thresholds = [float(t) for t in iou_thresholds]
+        self.max_age, self.min_hits = int(max_age), int(min_hits)
+        self.track_cap, self.det_cap = int(track_cap), int(det_cap)
+        nq = self.S * self.NC
+        slab = int(lib().w2t_sort_slab_bytes(self.track_cap, self.det_cap))
+        self._plan = {
+            "order": _dev(np.arange(nq, dtype=np.int32), np.int32, self.device),
+            "track_cap": _dev(np.full(nq, self.track_cap, np.int32), np.int32, self.device),
+            "det_cap": _dev(np.full(nq, self.det_cap, np.int32), np.int32, self.device),
+            "ws_offset": _dev(np.arange(nq, dtype=np.int64) * slab, np.int64, self.device),
+        }
+        self._n_wide = nq if self.det_cap > _abi.W2T_WIDE_DETS else 0
+        self._ws_bytes = nq * slab
+        self._workspace = torch.empty(max(self._ws_bytes, 256), dtype=torch.uint8, device=self.device)
+        self._sub_state = torch.zeros((nq, 4), dtype=torch.int32, device=self.device)
+        self._cam = torch.zeros((self.S, 2), dtype=torch.float64, device=self.device)   # unused by the raw rows
+        self.count = int(id_base)            # KalmanBoxTracker.count
+        self.calls = 0
+        self._bases = []                     # per call: [S, NC] id of the first tracker each group created
+        self.class_order = [[] for _ in range(self.S)]   # categories (0-based) in first-appearance order
+
+    def step(self, boxes, exists=None):
+        """``boxes[s][c]``: float [D,4] array (x1, y1, x2, y2; rounded to float32 like tracker_sort.py:45)
+        of stream ``s``, category index ``c`` (0-based) — or ``None`` / empty; ``boxes[s]`` may also be a
+        ``(rows[D,>=4], categories[D])`` pair in detection order, which also fixes the order in which
+        categories that appear for the first time get their trackers (tracker_sort.py:28-36).
+        ``exists[s]`` False = stream ``s`` has no image in this call (nothing is stepped, like a frame
+        absent from the input).  Returns ``out[s] = {c: ndarray[m,6] = x1, y1, x2, y2, id, confidence}``
+        for every category that has a ``Sort`` object, rows in the reference's (newest first) order."""
+        S, NC = self.S, self.NC
+        if len(boxes) != S:
+            raise ValueError("expected detections for %d streams" % S)
+        per = [[None] * NC for _ in range(S)]
+        for s in range(S):
+            b = boxes[s]
+            if isinstance(b, tuple):
+                cats = np.asarray(b[1], np.int64).reshape(-1)
+                rows = np.asarray(b[0], np.float64)
+                rows = rows.reshape(len(cats), rows.shape[-1] if rows.ndim > 1 and len(cats) else 4)
+                for c in cats.tolist():
+                    if not 0 <= c < NC:
+                        raise IndexError("category index %d outside the threshold list" % c)
+                    if c not in self.class_order[s] and (exists is None or exists[s]):
+                        self.class_order[s].append(c)
+                for c in range(NC):
+                    per[s][c] = rows[cats == c, :4]
+            else:
+                for c in range(NC):
+                    a = None if b is None or b[c] is None else np.asarray(b[c], np.float64).reshape(-1, np.shape(b[c])[-1] if np.ndim(b[c]) > 1 else 4)[:, :4]
+                    per[s][c] = a
+                    if a is not None and len(a) and c not in self.class_order[s] and (exists is None or exists[s]):
+                        self.class_order[s].append(c)
+        counts = np.array([[0 if per[s][c] is None else len(per[s][c]) for c in range(NC)] for s in range(S)], np.int32)
+        if counts.max(initial=0) > self.det_cap:
+            raise W2TError("%d detections of one category in an image exceed det_cap=%d" % (int(counts.max()), self.det_cap))
+        N = int(counts.sum())
+        start = np.concatenate([[0], np.cumsum(counts.reshape(-1))[:-1]]).astype(np.int32)
+        det = np.zeros((max(N, 1), 4), np.float32)
+        for s in range(S):
+            for c in range(NC):
+                if counts[s, c]:
+                    o = start[s * NC + c]
+                    det[o:o + counts[s, c]] = per[s][c].astype(np.float32)
+        ex = np.ones(S, np.uint8) if exists is None else np.asarray(exists, np.uint8)
+        dev = self.device
+        d_offsets = _dev(np.arange(S + 1, dtype=np.int32), np.int32, dev)
+        d_start, d_count = _dev(start, np.int32, dev), _dev(counts.reshape(-1), np.int32, dev)
+        d_box, d_ex = _dev(det, np.float32, dev), _dev(ex, np.uint8, dev)
+        G = S * NC
+        out = {"out_box": torch.zeros((max(N, 1), 4), dtype=torch.float64, device=dev),
+               "out_score": torch.zeros(max(N, 1), dtype=torch.float64, device=dev),
+               "out_birth": torch.zeros((max(N, 1), 2), dtype=torch.int32, device=dev),
+               "out_count": torch.zeros(G, dtype=torch.int32, device=dev),
+               "created": torch.zeros(G, dtype=torch.int32, device=dev),
+               "status": torch.zeros(1, dtype=torch.int32, device=dev)}
+        prob = _abi.SortProblem()
+        prob.n_streams, prob.n_classes = S, NC
+        prob.stream_img_offsets = _ptr(d_offsets)
+        prob.det_start, prob.det_count, prob.det_box = _ptr(d_start), _ptr(d_count), _ptr(d_box)
+        prob.img_exists, prob.cam_wh = _ptr(d_ex), _ptr(self._cam)
+        for i in range(NC):
+            prob.iou_thr[i] = self.iou_thresholds[i]
+        prob.max_age, prob.min_hits = self.max_age, self.min_hits
+        cplan = _abi.SortPlan()
+        for k in ("order", "track_cap", "det_cap", "ws_offset"):
+            setattr(cplan, k, _ptr(self._plan[k]))
+        cplan.ws_bytes, cplan.n_wide = self._ws_bytes, self._n_wide
+        res = _abi.SortResult()
+        for k in ("out_box", "out_score", "out_birth", "out_count", "created"):
+            setattr(res, k, _ptr(out[k]))
+        check(lib().w2t_sort_step(C.byref(prob), C.byref(cplan), C.byref(res), _ptr(self._workspace),
+                                  _ptr(self._sub_state), int(self.calls * G), _ptr(out["status"]), _stream()),
+              "w2t_sort_step")
+        h = {k: v.cpu().numpy() for k, v in out.items()}
+        check_device_status(int(h["status"][0]), "w2t_sort_step")
+        # ids: KalmanBoxTracker.count advances stream by stream, category by category (dict order)
+        created = h["created"].reshape(S, NC)
+        base = np.zeros((S, NC), np.int64)
+        for s in range(S):
+            for c in self.class_order[s]:
+                base[s, c] = self.count
+                self.count += int(created[s, c])
+        self._bases.append(base)
+        self.calls += 1
+        result = []
+        for s in range(S):
+            tracked = {}
+            for c in self.class_order[s]:
+                if not ex[s]:
+                    continue
+                g = s * NC + c
+                o, m = int(start[g]), int(h["out_count"][g])
+                birth = h["out_birth"][o:o + m]
+                call, sc = birth[:, 0] // G, birth[:, 0] % G
+                ids = np.array([self._bases[ci][si // NC, si % NC] for ci, si in zip(call.tolist(), sc.tolist())],
+                               np.int64).reshape(-1) + birth[:, 1] + 1
+                rows = np.concatenate([h["out_box"][o:o + m], ids[:, None].astype(np.float64),
+                                       h["out_score"][o:o + m, None]], axis=1)
+                tracked[c] = rows[::-1].copy() if m else np.empty((0, 6))
+            result.append(tracked)
+        return result
 
 
 # ---------------------------------------------------------------------------
