@@ -253,6 +253,43 @@ def test_device_resident_stateful_api_matches_port_frame_by_frame(max_age, min_h
         DeviceMultiClassTrackerSort(track_cap=8, det_cap=4).track([[0, 0, 10, 10, 1.0, 1]] * 5, helpers.IOU_THR)
 
 
+def test_sort_stepper_two_streams_in_lockstep():
+    """runtime.SortStepper over two streams advanced together (one launch per call for both); a stream may
+    sit a call out (`exists`), which steps nothing — like a frame absent from the input.  Ids follow the
+    global counter in call order: stream by stream, category by category."""
+    scenes = [synth.make_scene(synth.SynthConfig(n_segments=1, cameras=(cam,), n_frames=12, n_submissions=1,
+                                                 objects_per_frame=25.0, seed=sd)) for cam, sd in (("FRONT", 31), ("SIDE_LEFT", 32))]
+    frames = []
+    for sc in scenes:
+        pred = sort_port.group_entries(synth.to_json_list(sc, sc.submissions[0]), helpers.SCORE_THR)
+        f = pred[sc.segments[0]][sc.cameras[0]]
+        frames.append([f[k] for k in sorted(f)])
+    sort_port.BoxTracker.count = 0
+    refs = [sort_port.MultiClassTracker(max_age=2, min_hits=0) for _ in scenes]
+    stepper = runtime.SortStepper(helpers.IOU_THR, max_age=2, min_hits=0, n_streams=2, track_cap=128, det_cap=64)
+    total = 0
+    for i in range(12):
+        exists = [True, i not in (4, 5)]
+        batch, want = [], []
+        for s in range(2):
+            rows = [[e['bbox'][0], e['bbox'][1], e['bbox'][0] + e['bbox'][2], e['bbox'][1] + e['bbox'][3], e['score'],
+                     e['category_id']] for e in frames[s][i]]
+            batch.append((np.asarray([r[:5] for r in rows], np.float64).reshape(-1, 5),
+                          np.asarray([r[5] - 1 for r in rows], np.int64)))
+            want.append(refs[s].track(rows, helpers.IOU_THR) if exists[s] else {})
+        got = stepper.step(batch, exists)
+        for s in range(2):
+            assert [c + 1 for c in got[s]] == list(want[s].keys()), (i, s)
+            for c, v in got[s].items():
+                w = want[s][c + 1]
+                assert v.shape == w.shape
+                np.testing.assert_array_equal(v[:, 4], w[:, 4])
+                np.testing.assert_allclose(v[:, :4], w[:, :4], rtol=1e-9, atol=0)
+                np.testing.assert_allclose(v[:, 5], w[:, 5], rtol=1e-9, atol=0)
+                total += len(v)
+    assert stepper.count == sort_port.BoxTracker.count and total > 100
+
+
 def test_sort_building_blocks_python_surface():
     d = np.array([10, 20, 50, 80, 0.9], np.float32)
     t = np.array([12.5, 18.0, 55.0, 77.0])

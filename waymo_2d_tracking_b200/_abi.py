@@ -132,6 +132,9 @@ EXPORTS = {
     "w2t_sort_step": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortPlan), C.POINTER(SortResult), _p, _p, C.c_int32,
                                 _p, _p]),
     "w2t_sort_slab_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "w2t_pb_write_submission": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, _p, C.c_int32,
+                                          C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, _p, C.c_int64,
+                                          _p, _p, _p, _p, _p]),
     "w2t_sort_finalize_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
     "w2t_sort_finalize": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortResult), _p, C.c_int64, C.c_int64, _p,
                                     C.POINTER(Rows), _p]),
