@@ -183,9 +183,8 @@ int w2t_json_write_detections(const char *path, int64_t n, const char *const *im
 
 /* Replaces create_pb_submission / create_pd_objects / create_pd_object of coco_to_waymo.py:16-82, the
  * consumer of both output files (README.md:46,55 of the reference): writes the serialized
- * waymo_open_dataset Submission (or, with objects_only, just its metrics.Objects — what
- * generate_prediction_for_metrics.py produces for predictions) for rows in the layout of the JSON
- * writers above.  object_id NULL = detection rows (no Label.id).  Strings are NUL-terminated; a NULL
+ * waymo_open_dataset Submission (or, with objects_only, just its metrics.Objects message) for rows in
+ * the layout of the JSON writers above.  object_id NULL = detection rows (no Label.id).  Strings are NUL-terminated; a NULL
  * string is an unset field.  Schema: field numbers restated from the package's published protos
  * (csrc/waymo_pb.cpp; PARITY UNPINNED there — the package is not available to check against). */
 int w2t_pb_write_submission(const char *path, int32_t objects_only, int32_t task, const char *account_name,

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from waymo_2d_tracking_b200 import coco_to_waymo as c2w
+from waymo_2d_tracking_b200 import generate_prediction_for_metrics as gpm
 
 pb = pytest.importorskip("google.protobuf")
 from google.protobuf import descriptor_pb2, descriptor_pool, message_factory  # noqa: E402
@@ -31,7 +32,9 @@ def _schema():
 
     O, R = F.LABEL_OPTIONAL, F.LABEL_REPEATED
     label = msg(fd, "Label", [("box", 1, F.TYPE_MESSAGE, O, ".w2t.waymo.Label.Box"), ("type", 3, F.TYPE_INT32, O, None),
-                              ("id", 4, F.TYPE_STRING, O, None)])
+                              ("id", 4, F.TYPE_STRING, O, None), ("detection_difficulty_level", 5, F.TYPE_INT32, O, None),
+                              ("tracking_difficulty_level", 6, F.TYPE_INT32, O, None),
+                              ("num_lidar_points_in_box", 7, F.TYPE_INT32, O, None)])
     msg(label, "Box", [(n, i, F.TYPE_DOUBLE, O, None) for n, i in (("center_x", 1), ("center_y", 2), ("center_z", 3),
                                                                   ("width", 4), ("length", 5), ("height", 6), ("heading", 7))])
     msg(fd, "Object", [("object", 1, F.TYPE_MESSAGE, O, ".w2t.waymo.Label"), ("score", 2, F.TYPE_FLOAT, O, None),
@@ -155,3 +158,57 @@ def test_errors_of_the_reference(tmp_path):
         c2w._rows_to_arrays([dict(base, category_id=0)])                    # TYPE_UNKNOWN
     with pytest.raises(TypeError):                                          # --description omitted: protobuf rejects None
         c2w.create_pb_submission_file([base], tmp_path / "x.bin", "m", None, "a", False)
+
+
+def test_metrics_objects_file_equals_the_protobuf_runtime(tmp_path):
+    """generate_prediction_for_metrics.py:44-80 statement for statement on the restated schema, predictions
+    (tracker rows) and ground truth (annotation file with string ids and difficulty levels)."""
+    Submission, Objects, Object = _schema()
+
+    def reference(entries):
+        objects = Objects()
+        for e in entries:
+            segment_id, frame_id, camera_id = e['image_id'].split('/')
+            o = Object()
+            o.context_name = segment_id
+            o.frame_timestamp_micros = int(frame_id)
+            o.camera_name = gpm.CAMERA_NAMES[camera_id]
+            bbox = e['bbox']
+            o.object.box.center_x = bbox[0] + bbox[2] / 2
+            o.object.box.center_y = bbox[1] + bbox[3] / 2
+            o.object.box.center_z = 0
+            o.object.box.length = bbox[2]
+            o.object.box.width = bbox[3]
+            o.object.box.height = 0
+            o.object.box.heading = 0
+            o.object.type = e['category_id']
+            if 'score' in e:
+                o.score = e['score']
+            if 'object_id' in e:
+                o.object.id = e['object_id']
+            if 'tracking_difficulty_level' in e:
+                o.object.tracking_difficulty_level = e['tracking_difficulty_level']
+            if 'detection_difficulty_level' in e:
+                o.object.detection_difficulty_level = e['detection_difficulty_level']
+            o.object.num_lidar_points_in_box = 100
+            objects.objects.append(o)
+        return objects.SerializeToString(deterministic=True)
+
+    pred = _rows(120, True, seed=21)
+    src = tmp_path / "pred.json"
+    src.write_text(json.dumps(pred))
+    out = tmp_path / "pred.bin"
+    gpm.main(["--input", str(src), "--output", str(out)])
+    assert out.read_bytes() == reference(pred)
+
+    rng = np.random.default_rng(5)
+    gt = [{'image_id': r['image_id'], 'bbox': [int(v) for v in rng.integers(0, 1900, 4)], 'category_id': r['category_id'],
+           'object_id': "gt-%x_é" % int(rng.integers(1 << 40)), 'tracking_difficulty_level': int(rng.integers(1, 3)),
+           'detection_difficulty_level': int(rng.integers(1, 3)), 'id': i} for i, r in enumerate(_rows(80, False, seed=22))]
+    src = tmp_path / "annotations.json"
+    src.write_text(json.dumps({'annotations': gt, 'images': []}))
+    out = tmp_path / "gt.bin"
+    gpm.main(["--type", "ground-truth", "--input", str(src), "--output", str(out)])
+    assert out.read_bytes() == reference(gt)
+    with pytest.raises(KeyError):
+        gpm.encode_object(dict(pred[0], image_id="seg/1/REAR"))          # camera_names[camera_id]

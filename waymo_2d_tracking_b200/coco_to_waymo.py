@@ -69,7 +69,7 @@ def _rows_to_arrays(detections):
 def write_submission(path, image_ids, image, bbox, score, category, object_id=None, *, unique_method_name='',
                      description='', account_name='', tracking=False, objects_only=False):
     """Flat arrays (``image`` indexes ``image_ids``; the layout of ``native_json.write_*``) -> file.
-    ``objects_only``: just the ``metrics.Objects`` message (generate_prediction_for_metrics.py)."""
+    ``objects_only``: just the ``metrics.Objects`` message of the submission."""
     for name, v in (('unique_method_name', unique_method_name), ('description', description),
                     ('account_name', account_name)):
         if not objects_only and not isinstance(v, str):

@@ -1,8 +1,7 @@
 // waymo_pb.cpp — Waymo Open Dataset `Submission` / `Objects` protobuf writer (host code).
 //
-// Replaces create_pd_object / create_pd_objects / create_pb_submission of coco_to_waymo.py:16-82
-// (and the Objects file of generate_prediction_for_metrics.py for predictions): the consumer of
-// the path's output JSON (README.md:46,55 of the reference).  The reference builds the messages
+// Replaces create_pd_object / create_pd_objects / create_pb_submission of coco_to_waymo.py:16-82: the
+// consumer of the path's output JSON (README.md:46,55 of the reference).  The reference builds the messages
 // with the generated classes of the `waymo_open_dataset` package, which is neither under
 // /root/reference nor installable here; the wire format is written by hand from the package's
 // published .proto files (waymo-open-dataset v1.2, May 2020):
