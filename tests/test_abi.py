@@ -56,6 +56,59 @@ def test_sort_plan_bounds_and_order():
     assert plan["n_wide"] == 2 and sorted(plan["order"].tolist()[:2]) == [0, 3]
 
 
+def _plan_numpy(n_streams, NC, offs, cnt, exists, max_age):
+    """Plain restatement of w2t_sort_plan's capacities and work (one sub-stream at a time)."""
+    window = max_age + 2
+    cnt = cnt.reshape(-1, NC)
+    tcap, dcap, work = [], [], []
+    for s in range(n_streams):
+        imgs = [i for i in range(offs[s], offs[s + 1]) if exists is None or exists[i]]
+        for c in range(NC):
+            d = cnt[imgs, c].astype(np.int64) if imgs else np.zeros(0, np.int64)
+            best = max([int(d[max(0, j - window + 1):j + 1].sum()) for j in range(len(d))], default=0)
+            tcap.append(max(best, 1))
+            dcap.append(max(int(d.max(initial=0)), 1))
+            work.append(int((d * d + d).sum()))
+    return np.array(tcap), np.array(dcap), np.array(work)
+
+
+@pytest.mark.parametrize("n_streams,frames,max_age", [(12, 4000, 2), (3, 50, 0), (9, 37, 5)])
+def test_sort_plan_threaded_pass_matches_restatement(n_streams, frames, max_age):
+    """Large jobs (>= 40 000 images, >= 8 streams) are planned by four host threads, one pass per stream for
+    all categories; small ones by the calling thread: same capacities, same heaviest-first order either way."""
+    rng = np.random.default_rng(n_streams)
+    NC = 4
+    lens = rng.integers(frames // 2, frames + 1, n_streams)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n_img = int(offs[-1])
+    cnt = rng.poisson([55, 25, 5, 10], (n_img, NC)).astype(np.int32)
+    cnt[rng.random((n_img, NC)) < 0.05] = 0
+    exists = (rng.random(n_img) > 0.03).astype(np.uint8)
+    plan = runtime.make_plan(n_streams, NC, offs, cnt.reshape(-1), exists, max_age)
+    tcap, dcap, work = _plan_numpy(n_streams, NC, offs, cnt, exists, max_age)
+    np.testing.assert_array_equal(plan["track_cap"], tcap)
+    np.testing.assert_array_equal(plan["det_cap"], dcap)
+    order = plan["order"]
+    assert sorted(order.tolist()) == list(range(n_streams * NC)) and plan["n_wide"] == 0
+    assert np.all(np.diff(work[order]) <= 0)                       # heaviest first ...
+    ties = np.diff(work[order]) == 0
+    assert np.all(np.diff(order)[ties] > 0)                        # ... ties in sub-stream order (stable)
+    assert np.all(np.diff(plan["ws_offset"]) > 0) and plan["ws_bytes"] > plan["ws_offset"][-1]
+
+
+def test_chunk_bounds_counts_and_fractions():
+    offs = np.arange(0, 11, dtype=np.int32) * 3          # 10 streams x 3 images
+    NC = 2
+    sizes = np.tile([4, 1], 30)
+    go = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    for n in (1, 3, 4, 10, 25):
+        ch = runtime._chunk_bounds(offs, go, NC, n)
+        assert ch[0][0] == 0 and ch[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert len(ch) == min(n, 10) and all(b > a for a, b in ch)
+    ch = runtime._chunk_bounds(offs, go, NC, [0.2, 0.3, 0.5])
+    assert ch == [(0, 2), (2, 5), (5, 10)]
+
+
 def test_assign_ids_c_matches_numpy_statement():
     rng = np.random.default_rng(0)
     S, NC, F = 3, 4, 5
