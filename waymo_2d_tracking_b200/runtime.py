@@ -854,7 +854,7 @@ class SortStepper:
         self._cam = torch.zeros((self.S, 2), dtype=torch.float64, device=self.device)   # unused by the raw rows
         self.count = int(id_base)            # KalmanBoxTracker.count
         self.calls = 0
-        self._bases = []                     # per call: [S, NC] id of the first tracker each group created
+        self._bases = np.zeros((64, nq), np.int64)   # [call, group]: id of the first tracker the group created
         self.class_order = [[] for _ in range(self.S)]   # categories (0-based) in first-appearance order
 
     def step(self, boxes, exists=None):
@@ -938,7 +938,9 @@ class SortStepper:
             for c in self.class_order[s]:
                 base[s, c] = self.count
                 self.count += int(created[s, c])
-        self._bases.append(base)
+        if self.calls == len(self._bases):
+            self._bases = np.concatenate([self._bases, np.zeros_like(self._bases)])
+        self._bases[self.calls] = base.reshape(-1)
         self.calls += 1
         result = []
         for s in range(S):
@@ -949,9 +951,7 @@ class SortStepper:
                 g = s * NC + c
                 o, m = int(start[g]), int(h["out_count"][g])
                 birth = h["out_birth"][o:o + m]
-                call, sc = birth[:, 0] // G, birth[:, 0] % G
-                ids = np.array([self._bases[ci][si // NC, si % NC] for ci, si in zip(call.tolist(), sc.tolist())],
-                               np.int64).reshape(-1) + birth[:, 1] + 1
+                ids = self._bases[birth[:, 0] // G, birth[:, 0] % G] + birth[:, 1] + 1
                 rows = np.concatenate([h["out_box"][o:o + m], ids[:, None].astype(np.float64),
                                        h["out_score"][o:o + m, None]], axis=1)
                 tracked[c] = rows[::-1].copy() if m else np.empty((0, 6))
