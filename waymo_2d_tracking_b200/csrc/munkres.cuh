@@ -437,44 +437,8 @@ struct Munkres {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
   }
 
-  // Step 1 for one row straight from the registers of the warp that has just computed it: lane L
-  // holds the costs of columns L, L+32, L+64, L+96 (val[k] for k < mw; anything for columns >= m).
-  // Row minimum, subtract, store, zero bit words.  Lets the producer of the cost matrix skip the
-  // separate pass of step 1 (solve_block(true)).  All lanes of the warp call it.
-  __device__ __forceinline__ void store_reduced_row(int r, const float (&val)[4]) {
-    const int lane = lane_id();
-    float mn = INFINITY;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (k < mw && k * 32 + lane < m) mn = fminf(mn, val[k]);
-    {
-      // warp minimum in one REDUX on an order-preserving integer image of the float (NaN sorts last,
-      // like fminf ignores it) instead of five dependent shuffle steps
-      unsigned u = __float_as_uint(mn);
-      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-      u = __reduce_min_sync(0xffffffffu, u);
-      u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-      mn = __uint_as_float(u);
-    }
-    float *row = g.C + (size_t)r * ldc;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (k < mw) {
-        const int c = k * 32 + lane;
-        bool z = false;
-        if (c < m) {
-          const float v = val[k] - mn;
-          row[c] = v;
-          z = (v == 0.0f);
-        }
-        const unsigned word = __ballot_sync(0xffffffffu, z);
-        if (lane == 0) g.Z[(size_t)r * zs + k] = word;
-      }
-    }
-    if (lane == 0) { g.row_star[r] = -1; g.row_prime[r] = -1; }
-  }
-
-  // true when solve() will take the shared-memory path below (and store_reduced_row may be used)
+  // true when solve() will take the shared-memory path below (the producer of the cost matrix may then fold
+  // step 1 into its own pass, sort_kernel.cuh, and call solve(true))
   __device__ __forceinline__ bool block_path() const { return rowwise && m <= 128; }
 
   // ---- warp 0 of the block solver: step 2 on first entry, then steps 3-5 until all rows are starred
