@@ -53,12 +53,34 @@ typedef struct w2t_sort_plan_t {
   /* w2t_stream_wait_value32 and post-process it while the rest of the launch is still running.  */
   const int32_t *chunk_of;
   int32_t *chunk_done;
-  /* the first n_wide entries of `order` are sub-streams with more than W2T_WIDE_DETS detections in */
-  /* some image (crowded scenes): they are tracked by 512-thread CTAs, the rest by 128-thread ones */
+  /* Launch classes.  `order` is [wide | mid | narrow]:                                             */
+  /*   the first n_wide entries are sub-streams with more than W2T_WIDE_DETS detections in some     */
+  /*   image (crowded scenes): 512-thread CTAs; the next n_mid entries have more than              */
+  /*   W2T_NARROW_DETS: 128-thread CTAs; the rest are tracked by one WARP each (persistent warps    */
+  /*   that pull sub-streams from a queue in this order).  A narrow sub-stream whose live trackers  */
+  /*   outgrow W2T_NARROW_DETS is tracked again by a 128-thread CTA (flag in the aux area).         */
   int32_t  n_wide;
+  int32_t  n_mid;
+  /* byte offset, inside the workspace, of the auxiliary area of the warp kernel (w2t_sort_plan     */
+  /* sets it and includes its W2T_SORT_AUX_BYTES(n_substreams) in ws_bytes): work-queue counter +    */
+  /* one flag per sub-stream.  < 0 = no aux area: every sub-stream is tracked by CTAs.               */
+  int64_t  aux_offset;
+  /* most detections any NARROW sub-stream has in one image: picks how many warps (= sub-streams)   */
+  /* share an SM's shared memory, i.e. how large a cost matrix each can hold (0 = unknown)          */
+  int32_t  narrow_cap;
 } w2t_sort_plan_t;
 
 #define W2T_WIDE_DETS 320
+#define W2T_NARROW_DETS 128
+#define W2T_SORT_AUX_BYTES(n_substreams) (64 + 4 * (int64_t)(n_substreams))
+
+/* NumPy promotion regime the tracker reproduces (w2t_sort_problem_t.promotion):                     */
+/*   LEGACY  NumPy 1.x value-based casting — the reference's pinned environment (python 3.7,         */
+/*           environment.yml:7): in convert_bbox_to_z (sort.py:50-62) x, y and r are float64, only   */
+/*           s = w*h stays float32; `iou_matrix[..] < iou_threshold` (sort.py:220) compares in       */
+/*           float64.                                                                                */
+/*   NEP50   NumPy 2: all four components of z are float32, the threshold is compared in float32.    */
+enum { W2T_PROMOTION_LEGACY = 0, W2T_PROMOTION_NEP50 = 1 };
 
 /* Inputs of the SORT stage (tracking/utils.py:25-60 for every stream at once).
  * Pointers are device pointers for the CUDA library and host pointers for the oracle. */
@@ -77,6 +99,7 @@ typedef struct w2t_sort_problem_t {
   double  iou_thr[W2T_MAX_CLASSES];  /* --iou-threshold, track.py:25-26                       */
   int32_t max_age;                   /* track.py:21                                           */
   int32_t min_hits;                  /* track.py:22                                           */
+  int32_t promotion;                 /* W2T_PROMOTION_*                                       */
 } w2t_sort_problem_t;
 
 /* Outputs of the SORT stage.  Row k of group g is at det_start[g] + k, in tracker-list

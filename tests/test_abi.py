@@ -32,8 +32,8 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_struct_sizes():
     lib = _lib.lib()
     assert b"sm_100a" in lib.w2t_version()
-    assert ctypes.sizeof(_abi.SortProblem) == 8 + 6 * 8 + 8 * 8 + 8
-    assert ctypes.sizeof(_abi.SortPlan) == 8 * 8
+    assert ctypes.sizeof(_abi.SortProblem) == 8 + 6 * 8 + 8 * 8 + 16     # max_age, min_hits, promotion + padding
+    assert ctypes.sizeof(_abi.SortPlan) == 10 * 8     # ... n_wide + n_mid share a word, aux_offset, narrow_cap + padding
 
 
 def test_sort_plan_bounds_and_order():
@@ -53,7 +53,14 @@ def test_sort_plan_bounds_and_order():
     cnt[1, 0] = 321
     cnt[2, 0] = 5000 // 100          # heavy by total work, but not crowded
     plan = runtime.make_plan(2, 2, offs, cnt.reshape(-1), None, max_age=1)
-    assert plan["n_wide"] == 2 and sorted(plan["order"].tolist()[:2]) == [0, 3]
+    assert plan["n_wide"] == 2 and plan["n_mid"] == 0 and sorted(plan["order"].tolist()[:2]) == [0, 3]
+    # sub-streams above W2T_NARROW_DETS come next (CTAs), everything else is tracked by warps
+    cnt[7, 1] = 0
+    cnt[5, 1] = 200
+    plan = runtime.make_plan(2, 2, offs, cnt.reshape(-1), None, max_age=1)
+    assert plan["n_wide"] == 1 and plan["n_mid"] == 1 and plan["order"].tolist()[:2] == [0, 3]
+    # the auxiliary area of the warp kernel follows the slabs
+    assert plan["aux_offset"] > plan["ws_offset"][-1] and plan["ws_bytes"] >= plan["aux_offset"] + _abi.sort_aux_bytes(4)
 
 
 def _plan_numpy(n_streams, NC, offs, cnt, exists, max_age):

@@ -34,6 +34,9 @@ class SortPlan(C.Structure):
         ("chunk_of", _p),
         ("chunk_done", _p),
         ("n_wide", C.c_int32),
+        ("n_mid", C.c_int32),
+        ("aux_offset", C.c_int64),
+        ("narrow_cap", C.c_int32),
     ]
 
 
@@ -50,6 +53,7 @@ class SortProblem(C.Structure):
         ("iou_thr", C.c_double * W2T_MAX_CLASSES),
         ("max_age", C.c_int32),
         ("min_hits", C.c_int32),
+        ("promotion", C.c_int32),
     ]
 
 
@@ -99,6 +103,13 @@ class NmsProblem(C.Structure):
 
 
 W2T_WIDE_DETS = 320          # include/w2t_types.h
+W2T_NARROW_DETS = 128
+W2T_PROMOTION_LEGACY, W2T_PROMOTION_NEP50 = 0, 1
+
+
+def sort_aux_bytes(n_substreams):
+    """W2T_SORT_AUX_BYTES of include/w2t_types.h."""
+    return 64 + 4 * int(n_substreams)
 W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY, W2T_BOX_LTWH_I16, W2T_BOX_LTWH_P64 = 0, 1, 2, 3, 4
 
 

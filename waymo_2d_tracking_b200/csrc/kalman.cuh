@@ -30,6 +30,28 @@ __device__ __forceinline__ void bbox_to_z(const float (&d)[4], float (&z)[4]) {
   z[3] = w / h;
 }
 
+// convert_bbox_to_z (sort.py:50-62) of a float32 row under either NumPy promotion regime, widened to
+// the float64 the filter then works in (np.array([x, y, s, r]), sort.py:62 -> kf.update / kf.x[:4]):
+//   legacy (NumPy 1.x value-based casting, the reference's pinned environment: python 3.7,
+//     environment.yml:7): w, h, s = w*h are float32 scalars, but float32-scalar (op) python-float is
+//     float64, so x = bbox[0] + w/2. , y and r = w/float(h) are computed in float64;
+//   NEP 50 (NumPy 2): the python floats adopt float32, all four components are float32.
+__device__ __forceinline__ void bbox_to_z_d(const float d0, const float d1, const float d2, const float d3,
+                                            const bool nep50, double (&z)[4]) {
+  const float w = d2 - d0;
+  const float h = d3 - d1;
+  if (nep50) {
+    z[0] = (double)(d0 + w / 2.0f);
+    z[1] = (double)(d1 + h / 2.0f);
+    z[3] = (double)(w / h);
+  } else {
+    z[0] = (double)d0 + (double)w / 2.0;
+    z[1] = (double)d1 + (double)h / 2.0;
+    z[3] = (double)w / (double)h;
+  }
+  z[2] = (double)(w * h);
+}
+
 // convert_x_to_bbox, sort.py:65-75.
 __device__ __forceinline__ void x_to_bbox(const double (&x)[7], double (&b)[4]) {
   const double w = sqrt(x[2] * x[3]);
@@ -41,11 +63,11 @@ __device__ __forceinline__ void x_to_bbox(const double (&x)[7], double (&b)[4]) 
 }
 
 // sort.py:97-137
-__device__ __forceinline__ void kf_init(const float (&det)[4], double (&x)[7], double (&P)[49]) {
-  float z[4];
-  bbox_to_z(det, z);
+__device__ __forceinline__ void kf_init(const float (&det)[4], double (&x)[7], double (&P)[49], const bool nep50 = true) {
+  double z[4];
+  bbox_to_z_d(det[0], det[1], det[2], det[3], nep50, z);
 #pragma unroll
-  for (int i = 0; i < 4; i++) x[i] = (double)z[i];
+  for (int i = 0; i < 4; i++) x[i] = z[i];
   x[4] = x[5] = x[6] = 0.;
 #pragma unroll
   for (int i = 0; i < 49; i++) P[i] = 0.;
@@ -161,12 +183,12 @@ __device__ __forceinline__ void inv4_lapack(double (&a)[16], double (&b)[16]) {
 }
 
 // sort.py:164 -> filterpy update (Joseph form).
-__device__ __forceinline__ void kf_update(double (&x)[7], double (&P)[49], const float (&det)[4]) {
-  float zf[4];
-  bbox_to_z(det, zf);
+__device__ __forceinline__ void kf_update(double (&x)[7], double (&P)[49], const float (&det)[4], const bool nep50 = true) {
+  double zf[4];
+  bbox_to_z_d(det[0], det[1], det[2], det[3], nep50, zf);
   double y[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) y[i] = (double)zf[i] - x[i];
+  for (int i = 0; i < 4; i++) y[i] = zf[i] - x[i];
   // S = P[:4,:4] + R, column-major for the LAPACK-order inverse
   double S[16], SI[16];
 #pragma unroll
@@ -242,11 +264,9 @@ __device__ __forceinline__ void kf_update(double (&x)[7], double (&P)[49], const
 // p[4a+0] = P[a][a], p[4a+1] = P[a][a+4], p[4a+2] = P[a+4][a], p[4a+3] = P[a+4][a+4], p[12] = P[3][3].
 constexpr int kBlockP = 13;
 
-__device__ __forceinline__ void kfb_init(const float (&det)[4], double (&x)[7], double (&p)[kBlockP]) {
-  float z[4];
-  bbox_to_z(det, z);
+__device__ __forceinline__ void kfb_init_z(const double (&z)[4], double (&x)[7], double (&p)[kBlockP]) {
 #pragma unroll
-  for (int i = 0; i < 4; i++) x[i] = (double)z[i];
+  for (int i = 0; i < 4; i++) x[i] = z[i];
   x[4] = x[5] = x[6] = 0.;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
@@ -256,6 +276,12 @@ __device__ __forceinline__ void kfb_init(const float (&det)[4], double (&x)[7], 
     p[4 * a + 3] = 10000.;
   }
   p[12] = 10.;
+}
+
+__device__ __forceinline__ void kfb_init(const float (&det)[4], double (&x)[7], double (&p)[kBlockP], const bool nep50 = true) {
+  double z[4];
+  bbox_to_z_d(det[0], det[1], det[2], det[3], nep50, z);
+  kfb_init_z(z, x, p);
 }
 
 __device__ __forceinline__ void kfb_predict(double (&x)[7], double (&p)[kBlockP]) {
@@ -275,12 +301,10 @@ __device__ __forceinline__ void kfb_predict(double (&x)[7], double (&p)[kBlockP]
   p[12] = p[12] + q_diag(3);
 }
 
-__device__ __forceinline__ void kfb_update(double (&x)[7], double (&p)[kBlockP], const float (&det)[4]) {
-  float zf[4];
-  bbox_to_z(det, zf);
+__device__ __forceinline__ void kfb_update_z(double (&x)[7], double (&p)[kBlockP], const double (&zf)[4]) {
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    const double y = (double)zf[a] - x[a];
+    const double y = zf[a] - x[a];
     const double P00 = p[4 * a + 0], P01 = p[4 * a + 1], P10 = p[4 * a + 2], P11 = p[4 * a + 3];
     const double si = 1.0 * (1.0 / (P00 + r_diag(a)));
     const double k0 = P00 * si, k1 = P10 * si;
@@ -296,7 +320,7 @@ __device__ __forceinline__ void kfb_update(double (&x)[7], double (&p)[kBlockP],
     p[4 * a + 3] = ((m10 * a1) + m11) + (kr1 * k1);
   }
   {
-    const double y = (double)zf[3] - x[3];
+    const double y = zf[3] - x[3];
     const double P33 = p[12];
     const double si = 1.0 * (1.0 / (P33 + r_diag(3)));
     const double k = P33 * si;
@@ -305,6 +329,12 @@ __device__ __forceinline__ void kfb_update(double (&x)[7], double (&p)[kBlockP],
     const double m = a3 * P33;
     p[12] = (m * a3) + ((k * r_diag(3)) * k);
   }
+}
+
+__device__ __forceinline__ void kfb_update(double (&x)[7], double (&p)[kBlockP], const float (&det)[4], const bool nep50 = true) {
+  double z[4];
+  bbox_to_z_d(det[0], det[1], det[2], det[3], nep50, z);
+  kfb_update_z(x, p, z);
 }
 
 // scatter / gather between the block form and the dense 7x7 (unit entry points, debug dumps)

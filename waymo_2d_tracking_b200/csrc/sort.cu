@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "sort_kernel.cuh"
+#include "sort_warp.cuh"
 
 using namespace w2t;
 
@@ -63,21 +64,28 @@ extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t
       pool.emplace_back(plan_streams, (int)((int64_t)n_streams * t / n_threads), (int)((int64_t)n_streams * (t + 1) / n_threads));
     for (auto &th : pool) th.join();
   }
-  // crowded sub-streams first (they get wide CTAs), each part heaviest first
+  // launch classes [wide | mid | narrow] (w2t_sort_plan_t), each heaviest first
   std::iota(plan->order, plan->order + nq, 0);
-  auto wide = [&](int q) { return plan->det_cap[q] > W2T_WIDE_DETS; };
+  auto cls = [&](int q) { return plan->det_cap[q] > W2T_WIDE_DETS ? 0 : plan->det_cap[q] > W2T_NARROW_DETS ? 1 : 2; };
   std::stable_sort(plan->order, plan->order + nq, [&](int a, int b) {
-    if (wide(a) != wide(b)) return wide(a);
+    if (cls(a) != cls(b)) return cls(a) < cls(b);
     return work[a] > work[b];
   });
   plan->n_wide = 0;
-  for (int q = 0; q < nq; q++) plan->n_wide += wide(q) ? 1 : 0;
+  plan->n_mid = 0;
+  plan->narrow_cap = 0;
+  for (int q = 0; q < nq; q++) {
+    plan->n_wide += cls(q) == 0 ? 1 : 0;
+    plan->n_mid += cls(q) == 1 ? 1 : 0;
+    if (cls(q) == 2) plan->narrow_cap = std::max(plan->narrow_cap, plan->det_cap[q]);
+  }
   int64_t off = 0;
   for (int q = 0; q < nq; q++) {
     plan->ws_offset[q] = off;
     off += (int64_t)slab_layout(plan->track_cap[q], plan->det_cap[q]).total;
   }
-  plan->ws_bytes = off;
+  plan->aux_offset = off;
+  plan->ws_bytes = off + (int64_t)align_up((size_t)W2T_SORT_AUX_BYTES(nq), 256);
   return W2T_OK;
 }
 
@@ -114,24 +122,101 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
   // counters from an instrumented instantiation of the same kernel (scripts/phase_timers.py)
   P.timers = getenv("W2T_SORT_TIMERS") ? reinterpret_cast<long long *>(strtoull(getenv("W2T_SORT_TIMERS"), nullptr, 10))
                                         : nullptr;
+  P.nep50 = problem->promotion == W2T_PROMOTION_NEP50 ? 1 : 0;
+  P.queue = nullptr;
+  P.bail = nullptr;
+  P.n_items = 0;
+  P.bail_want = 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const int n_wide = std::min(std::max(plan->n_wide, 0), nq);
+  const int n_mid = std::min(std::max(plan->n_mid, 0), nq - n_wide);
   if (step) {
-    const int n_wide = std::min(std::max(plan->n_wide, 0), nq);
     if (n_wide > 0) sort_track_kernel<512, 1, false, kSmemC, true><<<n_wide, 512, 0, st>>>(P);
     if (nq > n_wide) {
       P.order = plan->order + n_wide;
       sort_track_kernel<kSortBlock, kSortMinBlocks, false, kSmemC, true><<<nq - n_wide, kSortBlock, 0, st>>>(P);
     }
-  } else if (P.timers != nullptr)
-    sort_track_kernel<kSortBlock, kSortMinBlocks, true><<<nq, kSortBlock, 0, st>>>(P);
-  else {
-    // crowded sub-streams (the first n_wide of the launch order): 512 threads walk the big cost
-    // matrices of the global-memory solver; everything else: 128 threads, 4 CTAs per SM
-    const int n_wide = std::min(std::max(plan->n_wide, 0), nq);
-    if (n_wide > 0) sort_track_kernel<512, 1, false><<<n_wide, 512, 0, st>>>(P);
-    if (nq > n_wide) {
-      P.order = plan->order + n_wide;
-      sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq - n_wide, kSortBlock, 0, st>>>(P);
+  } else {
+    // The plan's classes [wide | mid | narrow] say what a sub-stream MAY need (its counts can be upper
+    // bounds); sort_classify_kernel decides from the actual counts.  Crowded sub-streams: 512 threads walk the
+    // big cost matrices of the global-memory solver; the middle class: 128 threads, 4 CTAs per SM; both run
+    // on a side stream next to the warp kernel (sort_warp.cuh: one warp per sub-stream, persistent warps
+    // pulling from a queue), which tracks everything else; what outgrows it is tracked again by CTAs.
+    // Without an aux area (hand-made plans) or with W2T_SORT_CTA_ONLY (A/B timing) CTAs track everything.
+    const bool warp_path = plan->aux_offset >= 0 && getenv("W2T_SORT_CTA_ONLY") == nullptr;
+    const bool tm = P.timers != nullptr;
+    if (!warp_path) {
+      if (n_wide > 0) {
+        if (tm) sort_track_kernel<512, 1, true><<<n_wide, 512, 0, st>>>(P);
+        else sort_track_kernel<512, 1, false><<<n_wide, 512, 0, st>>>(P);
+      }
+      if (nq > n_wide) {
+        P.order = plan->order + n_wide;
+        if (tm) sort_track_kernel<kSortBlock, kSortMinBlocks, true><<<nq - n_wide, kSortBlock, 0, st>>>(P);
+        else sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq - n_wide, kSortBlock, 0, st>>>(P);
+      }
+    } else {
+      static int sm_count = 0;
+      static cudaStream_t side[16] = {nullptr};
+      static cudaEvent_t ev_fork[16] = {nullptr}, ev_join[16] = {nullptr};
+      int dev = 0;
+      W2T_CUDA_TRY(cudaGetDevice(&dev));
+      if (sm_count == 0) W2T_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+      char *aux = P.ws + plan->aux_offset;
+      W2T_CUDA_TRY(cudaMemsetAsync(aux, 0, (size_t)W2T_SORT_AUX_BYTES(nq), st));
+      P.queue = reinterpret_cast<int32_t *>(aux);
+      P.bail = reinterpret_cast<int32_t *>(aux + 64);
+      P.n_items = nq;
+      sort_classify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(P.p, P.bail);
+      const int n_big = n_wide + n_mid;  // leading entries of the order that may be too crowded for a warp
+      const bool fork = n_big > 0 && dev < 16;
+      cudaStream_t sb = st;
+      if (fork) {
+        if (side[dev] == nullptr) {
+          W2T_CUDA_TRY(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+          W2T_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+          W2T_CUDA_TRY(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+        }
+        sb = side[dev];
+        W2T_CUDA_TRY(cudaEventRecord(ev_fork[dev], st));
+        W2T_CUDA_TRY(cudaStreamWaitEvent(sb, ev_fork[dev], 0));
+      }
+      if (n_wide > 0) {
+        P.bail_want = kClsWide;
+        sort_track_kernel<512, 1, false><<<n_wide, 512, 0, sb>>>(P);
+      }
+      if (n_big > 0) {
+        P.bail_want = kClsMid;
+        sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<n_big, kSortBlock, 0, sb>>>(P);
+      }
+      if (fork) W2T_CUDA_TRY(cudaEventRecord(ev_join[dev], sb));
+      // warps per SM <-> floats of cost matrix per warp: a crowd of D detections meets about 1.3 D trackers
+      // (max_age 2), so ceil8(D) * 1.3 D floats should fit; W2T_SORT_WARPS overrides (timing experiments)
+      const int cap = std::min(plan->narrow_cap > 0 ? plan->narrow_cap : 64, W2T_NARROW_DETS);
+      auto fits = [&](int floats) { return ((cap + 7) / 8 * 8) * std::min(kWarpDim, cap + cap / 3 + 8) <= floats; };
+      int warps = fits(WarpShared<8>::kC) ? 8 : fits(WarpShared<6>::kC) ? 6 : fits(WarpShared<4>::kC) ? 4 : 3;
+      if (const char *e = getenv("W2T_SORT_WARPS")) warps = atoi(e);
+      int rc = W2T_OK;
+      auto launch = [&](auto kernel, int W, size_t smem) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(sort_warp_kernel)"); return; }
+        const int ctas = std::min(sm_count, nq);  // one CTA per SM; the first round is dealt across them
+        kernel<<<ctas, W * 32, smem, st>>>(P);
+      };
+#define W2T_LAUNCH_WARPS(W) \
+  (tm ? launch(sort_warp_kernel<W, true>, W, sizeof(WarpShared<W>) * W) : launch(sort_warp_kernel<W, false>, W, sizeof(WarpShared<W>) * W))
+      switch (warps) {
+        case 8: W2T_LAUNCH_WARPS(8); break;
+        case 6: W2T_LAUNCH_WARPS(6); break;
+        case 4: W2T_LAUNCH_WARPS(4); break;
+        default: W2T_LAUNCH_WARPS(3); break;
+      }
+#undef W2T_LAUNCH_WARPS
+      if (rc != W2T_OK) return rc;
+      // second pass: sub-streams that outgrew the warp kernel are tracked again by CTAs
+      P.bail_want = kClsBailed;
+      sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq, kSortBlock, 0, st>>>(P);
+      if (fork) W2T_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[dev], 0));
     }
   }
   W2T_CUDA_TRY(cudaGetLastError());

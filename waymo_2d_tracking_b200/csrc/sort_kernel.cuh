@@ -99,7 +99,21 @@ struct SortParams {
   // call are offset by in the birth records (groups of different calls must not collide)
   int32_t *sub_state;
   int32_t group_base;
+  // NumPy promotion regime of convert_bbox_to_z and of the IoU threshold test (w2t_sort_problem_t.promotion)
+  int32_t nep50;
+  // warp kernel (sort_warp.cuh): work queue counter, number of queue entries (P.order[0..n_items)), and the
+  // per-sub-stream class flags (kCls*): classify_kernel marks the sub-streams that are too crowded for a warp
+  // (kClsWide / kClsMid, by their ACTUAL detection counts - the plan may be built from upper bounds), the warp
+  // kernel tracks those marked kClsWarp and flags the ones that outgrow it (kClsBailed).  A launch of the CTA
+  // kernel with `bail` set serves one flag value: CTAs of every other sub-stream exit at once.
+  int32_t *queue;
+  int32_t n_items;
+  int32_t *bail;
+  int32_t bail_want;   // the flag value a CTA launch serves
 };
+
+// values of SortParams::bail[q] (aux area of the workspace): who tracks sub-stream q
+enum { kClsWarp = 0, kClsBailed = 1, kClsWide = 2, kClsMid = 3 };
 
 // iou() of sort.py:33-47 as numba compiles it for (float32[:], float64[:]): the detection's
 // own area is a float32 product, everything else float64; the result is stored as float32.
@@ -189,6 +203,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int q = P.order[blockIdx.x];
+  if (!STEP && P.bail != nullptr && P.bail[q] != P.bail_want) return;  // not this launch's class of sub-stream
   const int NC = P.p.n_classes;
   const int s = q / NC, c = q % NC;
   const int Tcap = P.track_cap[q], Dcap = P.det_cap[q];
@@ -227,7 +242,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
 
   const int img0 = P.p.stream_img_offsets[s], img1 = P.p.stream_img_offsets[s + 1];
   const double camW = P.p.cam_wh[2 * s], camH = P.p.cam_wh[2 * s + 1];
-  const float thr_f = (float)P.p.iou_thr[c];  // NEP 50: the python float adopts float32 (sort.py:220)
+  // sort.py:220 `iou_matrix[m[0], m[1]] < iou_threshold`: NumPy 1.x compares the float32 entry with the python
+  // float in float64, under NEP 50 the python float adopts float32
+  const double thr_d = P.p.iou_thr[c];
+  const float thr_f = (float)thr_d;
+  const bool nep50 = P.nep50 != 0;
   const int max_age = P.p.max_age, min_hits = P.p.min_hits;
   const float4 *det_box = reinterpret_cast<const float4 *>(P.p.det_box);
 
@@ -507,7 +526,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
           double t0, t1, t2, t3, at;
           tbox(t, t0, t1, t2, t3, at);
           const float o = iou_pair(dets[d], t0, t1, t2, t3);
-          if (o < thr_f) stt = 2;  // assigned but rejected: becomes a new tracker AFTER the unassigned ones
+          if (nep50 ? (o < thr_f) : ((double)o < thr_d)) stt = 2;  // assigned but rejected: becomes a new tracker AFTER the unassigned ones
           else { stt = 1; flag[t] = d; }
         }
         dstat[d] = stt;
@@ -545,7 +564,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
         if (t >= T) {  // sort.py:276-278
           const float4 d4 = dets[newdet[t - T]];
           const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-          kfb_init(dd, x, Pm);
+          kfb_init(dd, x, Pm, nep50);
           tsu = 0;
           hs = 0;
           obg = STEP ? g + P.group_base : g;
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
           if (md >= 0) {  // sort.py:270-273, :153-164
             const float4 d4 = dets[md];
             const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            kfb_update(x, Pm, dd);
+            kfb_update(x, Pm, dd, nep50);
             tsu = 0;
             hs += 1;
           }

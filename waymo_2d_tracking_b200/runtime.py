@@ -12,6 +12,7 @@ Inputs may be NumPy arrays, CPU tensors (pinned ones are copied asynchronously) 
 tensors.  There is no CPU fallback: without a CUDA device these functions raise.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -51,6 +52,22 @@ def collect_profile():
     for name, a, b in PROFILE or []:
         acc.setdefault(name, []).append(a.elapsed_time(b))
     return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
+# NumPy promotion regime the tracker reproduces (include/w2t_types.h, W2T_PROMOTION_*): "legacy" = NumPy 1.x
+# value-based casting, the reference's pinned environment (python 3.7, environment.yml:7); "nep50" = NumPy 2.
+# Module default, overridable per call (``promotion=``) and by the environment variable W2T_PROMOTION.
+PROMOTION = os.environ.get("W2T_PROMOTION", "nep50")
+
+
+def promotion_code(promotion=None):
+    name = PROMOTION if promotion is None else promotion
+    if name in (_abi.W2T_PROMOTION_LEGACY, _abi.W2T_PROMOTION_NEP50):
+        return int(name)
+    try:
+        return {"legacy": _abi.W2T_PROMOTION_LEGACY, "nep50": _abi.W2T_PROMOTION_NEP50}[str(name).lower()]
+    except KeyError:
+        raise ValueError("promotion must be 'legacy' or 'nep50', not %r" % (name,))
 
 
 def require_cuda():
@@ -296,11 +313,24 @@ def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age):
                               int(max_age), C.byref(plan)), "w2t_sort_plan")
     arrays["ws_bytes"] = int(plan.ws_bytes)
     arrays["n_wide"] = int(plan.n_wide)
+    arrays["n_mid"] = int(plan.n_mid)
+    arrays["aux_offset"] = int(plan.aux_offset)
+    arrays["narrow_cap"] = int(plan.narrow_cap)
     return arrays
 
 
+def launch_classes(plan, order):
+    """Reorder ``order`` into the launch classes of ``w2t_sort_plan_t`` — [wide | mid | narrow], each part
+    keeping its relative order — and return (order, n_wide, n_mid)."""
+    cap = plan["det_cap"][order]
+    wide, mid = cap > _abi.W2T_WIDE_DETS, (cap > _abi.W2T_NARROW_DETS) & (cap <= _abi.W2T_WIDE_DETS)
+    if wide.any() or mid.any():
+        order = np.concatenate([order[wide], order[mid], order[~(wide | mid)]])
+    return np.ascontiguousarray(order, np.int32), int(wide.sum()), int(mid.sum())
+
+
 def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, d_exists, d_cam,
-                      iou_thresholds, max_age, min_hits, plan, final_cap=0, out=None):
+                      iou_thresholds, max_age, min_hits, plan, final_cap=0, out=None, promotion=None):
     """Launch on device tensors; ``plan`` = host arrays from :func:`make_plan`.  No synchronisation.
     ``out``: preallocated result tensors (keys of ``w2t_sort_result_t`` + ``status``) to write into."""
     device = d_box.device
@@ -333,11 +363,15 @@ def sort_track_device(n_streams, n_classes, d_offsets, d_start, d_count, d_box, 
     for i in range(NC):
         prob.iou_thr[i] = float(iou_thresholds[i])
     prob.max_age, prob.min_hits = int(max_age), int(min_hits)
+    prob.promotion = promotion_code(promotion)
     cplan = _abi.SortPlan()
     for k in ("order", "track_cap", "det_cap", "ws_offset"):
         setattr(cplan, k, _ptr(d_plan[k]))
     cplan.ws_bytes = plan["ws_bytes"]
     cplan.n_wide = int(plan.get("n_wide", 0))
+    cplan.n_mid = int(plan.get("n_mid", 0))
+    cplan.aux_offset = int(plan.get("aux_offset", -1))
+    cplan.narrow_cap = int(plan.get("narrow_cap", 0))
     if plan.get("chunk_of") is not None:      # completion counters per chunk of sub-streams
         d_plan["chunk_of"] = _dev(plan["chunk_of"], np.int32, device)
         cplan.chunk_of, cplan.chunk_done = _ptr(d_plan["chunk_of"]), _ptr(plan["chunk_done"])
@@ -430,7 +464,7 @@ def _collect(trk, rows, raw, extra=None):
     return res
 
 
-def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0, raw=True):
+def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0, raw=True, promotion=None):
     """SORT over every stream of ``packed`` (``packing.PackedTracks``).
 
     Returns the dense output list (``rows_box/score/id/img/cat`` in the reference's order, ids
@@ -444,7 +478,8 @@ def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_ba
     trk = sort_track_device(
         S, NC, d_offsets, d_start, _dev(packed.det_count, np.int32, device),
         _dev(packed.det_box, np.float32, device).reshape(-1, 4), _dev(packed.img_exists, np.uint8, device),
-        _dev(packed.cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan, final_cap)
+        _dev(packed.cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan, final_cap,
+        promotion=promotion)
     rows = finalize_device(S, NC, d_offsets, d_start, trk, _dev(packed.class_rank, np.int32, device), id_base,
                            int(np.asarray(packed.det_count, np.int64).sum()))
     res = _collect(trk, rows, raw)
@@ -462,7 +497,8 @@ def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_ba
 
 def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh, soft_nms_cut,
                        min_score, score_thr, iou_thresholds, max_age, min_hits, max_group=None,
-                       want_ensemble=True, id_base=0, raw=True, to_host=True, host_group_offsets=None):
+                       want_ensemble=True, id_base=0, raw=True, to_host=True, host_group_offsets=None,
+                       promotion=None):
     """Groups must be laid out as g = img * n_classes + (category - 1) with the images of a
     stream contiguous and in frame order (``synth.groups_from_scene`` / ``packing``).
 
@@ -494,7 +530,8 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
         exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
         plan = make_plan(S, NC, h_offsets, sizes, exists_ub, max_age)
         trk = sort_track_device(S, NC, d_offsets, d_start, nms["trk_count"], nms["trk_box"], nms["img_exists"],
-                                _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan)
+                                _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan,
+                                promotion=promotion)
         out_rows = finalize_device(S, NC, d_offsets, d_start, trk, None, id_base, int(d_rows.shape[0]))
         return {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": None, "launches": 6}
     # the plan needs the surviving counts on the host: one small D2H between the stages
@@ -504,7 +541,8 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     check_device_status(int(h_nms_status[0]), "soft-NMS")
     plan = make_plan(S, NC, h_offsets, h_cnt.numpy(), h_exists.numpy(), max_age)
     trk = sort_track_device(S, NC, d_offsets, d_start, nms["trk_count"], nms["trk_box"], nms["img_exists"],
-                            _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan)
+                            _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan,
+                            promotion=promotion)
     out_rows = finalize_device(S, NC, d_offsets, d_start, trk, None, id_base, int(h_cnt.numpy().sum(dtype=np.int64)))
     n_trk = int(h_cnt.numpy().sum(dtype=np.int64))
     if not to_host:
@@ -599,7 +637,8 @@ def _chunk_bounds(h_offsets, group_offsets_np, NC, n_chunks):
 
 def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh, n_classes, iou_thresh,
                                  soft_nms_cut, min_score, score_thr, iou_thresholds, max_age, min_hits,
-                                 max_group=None, id_base=0, n_chunks=8, hoist=1.0, hoist_by_work=False, light_first=0):
+                                 max_group=None, id_base=0, n_chunks=8, hoist=1.0, hoist_by_work=False, light_first=0,
+                                 promotion=None):
     """Host buffers in, dense host rows out (``rows_box/score/id/img/cat``), the same result as
     :func:`ensemble_and_track` — with the streams cut into chunks so that copies and kernels overlap
     (PCIe is full duplex): the host->device copies of all chunks are queued on a copy stream; the
@@ -629,7 +668,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     if S == 0 or G == 0:
         return ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, NC, iou_thresh, soft_nms_cut,
                                   min_score, score_thr, iou_thresholds, max_age, min_hits, max_group, False, id_base,
-                                  raw=False)
+                                  raw=False, promotion=promotion)
     # host work is ordered so that the copies and the soft-NMS launches are queued first; everything
     # only the SORT launch needs (group sizes, plans) is computed while they run
     sizes = None
@@ -731,11 +770,8 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
             first = np.concatenate([rest[early], first])
             rest = rest[~early]
         plan_all["order"] = np.ascontiguousarray(np.concatenate([first, rest]), np.int32)
-    # crowded sub-streams get the wide CTAs of w2t_sort_track: they lead the launch order (w2t_sort_plan_t.n_wide)
-    wide = plan_all["det_cap"][plan_all["order"]] > _abi.W2T_WIDE_DETS
-    if wide.any():
-        plan_all["order"] = np.ascontiguousarray(np.concatenate([plan_all["order"][wide], plan_all["order"][~wide]]), np.int32)
-    plan_all["n_wide"] = int(wide.sum())
+    # launch classes of w2t_sort_track ([wide | mid | narrow], w2t_sort_plan_t)
+    plan_all["order"], plan_all["n_wide"], plan_all["n_mid"] = launch_classes(plan_all, plan_all["order"])
     _trace("plans + nms queued")
     for cs in comp + [s_in]:
         main.wait_stream(cs)
@@ -745,7 +781,8 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     counters_zeroed = torch.cuda.Event()     # recorded BEFORE the launch: the finalize stream must not wait for the kernel
     counters_zeroed.record(main)
     trk = sort_track_device(S, NC, d_offsets, d_goff[:-1], nms_out["trk_count"], nms_out["trk_box"],
-                            nms_out["img_exists"], d_cam, iou_thresholds, max_age, min_hits, plan_all, out=trk_out)
+                            nms_out["img_exists"], d_cam, iou_thresholds, max_age, min_hits, plan_all, out=trk_out,
+                            promotion=promotion)
     _trace("sort queued", main)
     keep_alive, fin_done, rows_of, h_totals = [trk["_keepalive"]], [], [], _pinned_pool("pipe_totals", torch.int64, 3 * len(chunks))
     prev_totals = None
@@ -800,7 +837,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     if int(h_status[1]) == _abi.W2T_ERR_CAPACITY:
         return ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, NC, iou_thresh, soft_nms_cut,
                                   min_score, score_thr, iou_thresholds, max_age, min_hits, max_group, False, id_base,
-                                  raw=False)
+                                  raw=False, promotion=promotion)
     check_device_status(int(h_status[0]), "soft-NMS")
     check_device_status(int(h_status[1]), "SORT")
     res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 24 * len(chunks) + 8,
@@ -831,8 +868,10 @@ class SortStepper:
     first-appearance order, unmatched detections in the order of sort.py:208-222.
     """
 
-    def __init__(self, iou_thresholds, max_age=1, min_hits=0, n_streams=1, track_cap=256, det_cap=256, id_base=0):
+    def __init__(self, iou_thresholds, max_age=1, min_hits=0, n_streams=1, track_cap=256, det_cap=256, id_base=0,
+                 promotion=None):
         self.device = require_cuda()
+        self.promotion = promotion_code(promotion)
         self.S, self.NC = int(n_streams), len(iou_thresholds)
         if not 1 <= self.NC <= _abi.W2T_MAX_CLASSES:
             raise IndexError("iou_thresholds must hold 1..%d categories" % _abi.W2T_MAX_CLASSES)
@@ -919,10 +958,12 @@ class SortStepper:
         for i in range(NC):
             prob.iou_thr[i] = self.iou_thresholds[i]
         prob.max_age, prob.min_hits = self.max_age, self.min_hits
+        prob.promotion = self.promotion
         cplan = _abi.SortPlan()
         for k in ("order", "track_cap", "det_cap", "ws_offset"):
             setattr(cplan, k, _ptr(self._plan[k]))
         cplan.ws_bytes, cplan.n_wide = self._ws_bytes, self._n_wide
+        cplan.n_mid, cplan.aux_offset, cplan.narrow_cap = 0, -1, 0
         res = _abi.SortResult()
         for k in ("out_box", "out_score", "out_birth", "out_count", "created"):
             setattr(res, k, _ptr(out[k]))
