@@ -62,8 +62,8 @@ typedef struct w2t_sort_plan_t {
   int32_t  n_wide;
   int32_t  n_mid;
   /* byte offset, inside the workspace, of the auxiliary area of the warp kernel (w2t_sort_plan     */
-  /* sets it and includes its W2T_SORT_AUX_BYTES(n_substreams) in ws_bytes): work-queue counter +    */
-  /* one flag per sub-stream.  < 0 = no aux area: every sub-stream is tracked by CTAs.               */
+  /* sets it and includes its W2T_SORT_AUX_BYTES(n_substreams) in ws_bytes): work-queue counters,    */
+  /* one class flag per sub-stream and the two queues.  < 0 = no aux area: CTAs track everything.    */
   int64_t  aux_offset;
   /* most detections any NARROW sub-stream has in one image: picks how many warps (= sub-streams)   */
   /* share an SM's shared memory, i.e. how large a cost matrix each can hold (0 = unknown)          */
@@ -72,7 +72,7 @@ typedef struct w2t_sort_plan_t {
 
 #define W2T_WIDE_DETS 320
 #define W2T_NARROW_DETS 128
-#define W2T_SORT_AUX_BYTES(n_substreams) (64 + 4 * (int64_t)(n_substreams))
+#define W2T_SORT_AUX_BYTES(n_substreams) (64 + 12 * (int64_t)(n_substreams))
 
 /* NumPy promotion regime the tracker reproduces (w2t_sort_problem_t.promotion):                     */
 /*   LEGACY  NumPy 1.x value-based casting — the reference's pinned environment (python 3.7,         */

@@ -109,7 +109,7 @@ W2T_PROMOTION_LEGACY, W2T_PROMOTION_NEP50 = 0, 1
 
 def sort_aux_bytes(n_substreams):
     """W2T_SORT_AUX_BYTES of include/w2t_types.h."""
-    return 64 + 4 * int(n_substreams)
+    return 64 + 12 * int(n_substreams)
 W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY, W2T_BOX_LTWH_I16, W2T_BOX_LTWH_P64 = 0, 1, 2, 3, 4
 
 

@@ -164,10 +164,11 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
       if (sm_count == 0) W2T_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
       char *aux = P.ws + plan->aux_offset;
       W2T_CUDA_TRY(cudaMemsetAsync(aux, 0, (size_t)W2T_SORT_AUX_BYTES(nq), st));
-      P.queue = reinterpret_cast<int32_t *>(aux);
-      P.bail = reinterpret_cast<int32_t *>(aux + 64);
+      const WarpQueues Q = warp_queues(aux, nq);
+      P.queue = Q.hdr;
+      P.bail = Q.cls;
       P.n_items = nq;
-      sort_classify_kernel<<<(nq + 127) / 128, 128, 0, st>>>(P.p, P.bail);
+      sort_classify_kernel<<<1, 1024, 0, st>>>(P.p, plan->order, Q);
       const int n_big = n_wide + n_mid;  // leading entries of the order that may be too crowded for a warp
       const bool fork = n_big > 0 && dev < 16;
       cudaStream_t sb = st;
@@ -190,29 +191,18 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
         sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<n_big, kSortBlock, 0, sb>>>(P);
       }
       if (fork) W2T_CUDA_TRY(cudaEventRecord(ev_join[dev], sb));
-      // warps per SM <-> floats of cost matrix per warp: a crowd of D detections meets about 1.3 D trackers
-      // (max_age 2), so ceil8(D) * 1.3 D floats should fit; W2T_SORT_WARPS overrides (timing experiments)
-      const int cap = std::min(plan->narrow_cap > 0 ? plan->narrow_cap : 64, W2T_NARROW_DETS);
-      auto fits = [&](int floats) { return ((cap + 7) / 8 * 8) * std::min(kWarpDim, cap + cap / 3 + 8) <= floats; };
-      int warps = fits(WarpShared<8>::kC) ? 8 : fits(WarpShared<6>::kC) ? 6 : fits(WarpShared<4>::kC) ? 4 : 3;
-      if (const char *e = getenv("W2T_SORT_WARPS")) warps = atoi(e);
-      int rc = W2T_OK;
-      auto launch = [&](auto kernel, int W, size_t smem) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute(sort_warp_kernel)"); return; }
+      {
+        static bool attr_set[16] = {false};
+        const size_t smem = sizeof(WarpShared) * kWarpsPerCta;
+        if (dev >= 16 || !attr_set[dev]) {
+          W2T_CUDA_TRY(cudaFuncSetAttribute(sort_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          W2T_CUDA_TRY(cudaFuncSetAttribute(sort_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          if (dev < 16) attr_set[dev] = true;
+        }
         const int ctas = std::min(sm_count, nq);  // one CTA per SM; the first round is dealt across them
-        kernel<<<ctas, W * 32, smem, st>>>(P);
-      };
-#define W2T_LAUNCH_WARPS(W) \
-  (tm ? launch(sort_warp_kernel<W, true>, W, sizeof(WarpShared<W>) * W) : launch(sort_warp_kernel<W, false>, W, sizeof(WarpShared<W>) * W))
-      switch (warps) {
-        case 8: W2T_LAUNCH_WARPS(8); break;
-        case 6: W2T_LAUNCH_WARPS(6); break;
-        case 4: W2T_LAUNCH_WARPS(4); break;
-        default: W2T_LAUNCH_WARPS(3); break;
+        if (tm) sort_warp_kernel<true><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
+        else sort_warp_kernel<false><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
       }
-#undef W2T_LAUNCH_WARPS
-      if (rc != W2T_OK) return rc;
       // second pass: sub-streams that outgrew the warp kernel are tracked again by CTAs
       P.bail_want = kClsBailed;
       sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq, kSortBlock, 0, st>>>(P);

@@ -35,11 +35,17 @@ constexpr int kWarpDim = 128;       // most detections / live trackers per image
 constexpr int kWarpZS = 5;          // words per row of the zero bit matrix (4 + 1: odd stride)
 constexpr int kWarpSmemBytes = 232448;  // 227 KB: the most dynamic shared memory a CTA can have
 
-// Per-warp shared memory.  WARPS (warps = sub-streams per SM) trades occupancy against the size of the
-// cost matrix a warp can hold: 8 warps -> 4608 floats (e.g. 64 x 72), 6 -> 7040 (80 x 88), 4 -> 11904
-// (104 x 114), 3 -> 16768 (any 128 x 128 problem).  sort.cu picks WARPS from the plan's detection counts;
-// a problem that does not fit sends its sub-stream to the CTA kernel (P.bail).
-struct WarpSharedRest {
+// The cost matrix of a warp's current image lives in TENSOR MEMORY (256 KB per SM, 128 lanes x 512 columns x
+// 32 bit, reached with tcgen05.ld / tcgen05.st; SASS: LDTM / STTM).  A warp can only touch the 32 TMEM lanes of
+// its quarter (warp index % 4), which is exactly the shape this solver wants: TMEM lane = matrix column mod 32,
+// and one TMEM column holds one "cell word" (32 consecutive matrix columns of one row), so a single
+// 32x32b.x8 access moves the same 32 matrix columns of eight rows between TMEM and eight registers per lane —
+// one instruction and ~12 cycles where shared memory needs eight instructions and ~30, and the 18-40 KB per
+// warp the matrix would take in shared memory are free for more warps.  Cell word (row r, word k) of an
+// n x m problem sits in column k * ceil8(n) + r of the warp's share.  The 512 columns of a quarter are split
+// between the two warps that can reach it: 384 for a "big" warp (e.g. a 96 x 128 problem) and 128 for a
+// "small" one (e.g. 40 x 64); a problem that does not fit sends its sub-stream to the CTA kernel.
+struct __align__(128) WarpShared {
   float4 det[kWarpDim];                 // this image's detections
   double box[4][kWarpDim];              // predicted boxes of the live trackers, by list position
   uint32_t Z[kWarpDim * kWarpZS];       // zero bit matrix (while the matrix is built: candidate columns per row)
@@ -49,14 +55,28 @@ struct WarpSharedRest {
   int8_t match[kWarpDim];               // per tracker: matched detection or -1
   int8_t dstat[kWarpDim];               // per detection: 0 unassigned, 1 matched, 2 assigned but rejected
   int8_t newdet[kWarpDim];              // detections that become trackers, in the reference's order
+  float raw[32 * kWarpDim];             // exact costs of the candidate pairs of the 32 rows being built
 };
-template <int WARPS>
-struct __align__(128) WarpShared : WarpSharedRest {
-  static constexpr int kC = ((kWarpSmemBytes / WARPS - (int)sizeof(WarpSharedRest)) / 128) * 32;  // floats
-  float C[kC];                          // cost matrix, row pitch m; rows are padded to a multiple of 8
-};
-static_assert(sizeof(WarpShared<8>) * 8 <= kWarpSmemBytes && sizeof(WarpShared<3>) * 3 <= kWarpSmemBytes, "227 KB");
-static_assert(WarpShared<3>::kC >= kWarpDim * kWarpDim, "three warps per SM must hold any problem the warp kernel takes");
+static_assert(sizeof(WarpShared) * 8 <= kWarpSmemBytes, "shared memory of the warp kernel exceeds 227 KB");
+
+// eight TMEM columns <-> eight registers per lane (lane l talks to TMEM lane l of the warp's quarter)
+__device__ __forceinline__ void tm_ld8(const uint32_t taddr, float (&v)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = __uint_as_float(u[j]);
+}
+__device__ __forceinline__ void tm_st8(const uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // sqrt / divide of convert_x_to_bbox (sort.py:70-71), out of line: called twice per tracker and image
 __device__ __noinline__ void box_wh(const double s, const double r, double &w, double &h) {
@@ -75,16 +95,16 @@ __device__ __forceinline__ uint32_t strip_mask_checked(const double x1, const do
   return regular ? strip_mask(x1, y1, x2, y2) : 0xffffffffu;
 }
 
-// ---- scikit-learn 0.22.2 linear_assignment on the n x m (n <= m <= kWarpDim) matrix C, row pitch m, whose row
-// minima are already subtracted and whose zeros are mirrored in S.Z (step 1 is folded into the construction of
-// the matrix).  Same step machine, same decisions as munkres.cuh (see there for why each shortcut is exact).
+// ---- scikit-learn 0.22.2 linear_assignment on the n x m (n <= m <= kWarpDim) matrix in tensor memory at `tm`
+// (cell word (r, k) in column k * NP + r, NP = ceil8(n)), whose row minima are already subtracted and whose zeros
+// are mirrored in S.Z (step 1 is folded into the construction of the matrix).  Same step machine, same decisions as munkres.cuh (see there for why each shortcut is exact).
 // Lane k holds word k of every mask.  Returns 0, or 9 when the iteration budget ran out (NaN costs).
 template <bool TIMERS>
-__device__ __forceinline__ int warp_munkres(WarpSharedRest &S, float *C, const int n, const int m, long long *ph) {
+__device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, const int n, const int m, long long *ph) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
-  const int mw = (m + 31) >> 5, nwr = (n + 31) >> 5;
+  const int mw = (m + 31) >> 5, nwr = (n + 31) >> 5, NP = (n + 7) & ~7;
   uint32_t starcols = 0u, colcov = 0u, rowcov = 0u, rowhas = 0u;
   int stars = 0;
   int budget = 4 * n * n + 64 * (n + m) + 1024;
@@ -214,14 +234,16 @@ __device__ __forceinline__ int warp_munkres(WarpSharedRest &S, float *C, const i
     }
     if (TIMERS) { if (lane == 0) { const long long now = clock64(); ph[5] += now - ph[15]; ph[15] = now; ph[11]++; } }
     // ---- step 6: min over uncovered rows x uncovered columns; covered rows += min, then uncovered columns -= min
-    // (float32, in that order).  Lanes own columns (bit k of `uc`: column 32k + lane is uncovered); rows go
-    // eight at a time so that eight independent shared-memory round trips are in flight (the matrix holds
-    // ceil8(n) rows: the padding rows are computed on and never read).
-    uint32_t uc = 0u;
+    // (float32, in that order).  Lanes own columns (bit k of `uc`: column 32k + lane is uncovered, bit k of
+    // `ucw`: word k has an uncovered column at all); rows go eight at a time, one TMEM access per eight cell
+    // words (the matrix holds ceil8(n) rows: the padding rows are computed on and never read).
+    uint32_t uc = 0u, ucw = 0u;
 #pragma unroll 1
     for (int k = 0; k < mw; k++) {
       const uint32_t cw = __shfl_sync(FULL, colcov, k);
       if (k * 32 + lane < m && !((cw >> lane) & 1u)) uc |= 1u << k;
+      const uint32_t valid = (m - k * 32 >= 32) ? 0xffffffffu : ((1u << (m - k * 32)) - 1u);
+      if (~cw & valid) ucw |= 1u << k;
     }
     // costs are >= +0 here (or NaN), so their bit patterns order like the values and NaN sorts above +inf
     uint32_t mn_u = 0x7f800000u;
@@ -230,14 +252,16 @@ __device__ __forceinline__ int warp_munkres(WarpSharedRest &S, float *C, const i
       uint32_t ur = ~(__shfl_sync(FULL, rowcov, r0 >> 5) >> (r0 & 31));  // bit j: row r0 + j is uncovered
       if (n - r0 < 8) ur &= (1u << (n - r0)) - 1u;
       if ((ur & 0xffu) == 0u) continue;
-      const float *p = C + r0 * m + lane;
 #pragma unroll 1
-      for (uint32_t w = uc; w; w &= w - 1u) {
-        const float *pk = p + (__ffs(w) - 1) * 32;
-        uint32_t v[8];
+      for (uint32_t w = ucw; w; w &= w - 1u) {
+        const int k = __ffs(w) - 1;
+        float v[8];
+        tm_ld8(tm + k * NP + r0, v);
+        if ((uc >> k) & 1u) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = ((ur >> j) & 1u) ? __float_as_uint(pk[j * m]) : 0x7f800000u;
-        mn_u = min(min(min(v[0], v[1]), min(v[2], v[3])), min(min(min(v[4], v[5]), min(v[6], v[7])), mn_u));
+          for (int j = 0; j < 8; j++)
+            if ((ur >> j) & 1u) mn_u = min(mn_u, __float_as_uint(v[j]));
+        }
       }
     }
     mn_u = __reduce_min_sync(FULL, mn_u);
@@ -245,62 +269,113 @@ __device__ __forceinline__ int warp_munkres(WarpSharedRest &S, float *C, const i
       const float mn = __uint_as_float(mn_u);
 #pragma unroll 1
       for (int r0 = 0; r0 < n; r0 += 8) {
-        const uint32_t cr = __shfl_sync(FULL, rowcov, r0 >> 5) >> (r0 & 31);  // bit j: row r0 + j is covered
-        float *p = C + r0 * m + lane;
+        const uint32_t cr = (__shfl_sync(FULL, rowcov, r0 >> 5) >> (r0 & 31)) & 0xffu;  // bit j: row r0 + j is covered
         uint32_t *zp = S.Z + r0 * kWarpZS;
 #pragma unroll 1
         for (int k = 0; k < mw; k++) {
+          if (cr == 0u && !((ucw >> k) & 1u)) continue;  // uncovered rows x covered columns: nothing changes
           const bool colv = k * 32 + lane < m;
           const bool u = (uc >> k) & 1u;
-          float *pk = p + k * 32;
           float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) v[j] = colv ? pk[j * m] : 1.0f;
+          tm_ld8(tm + k * NP + r0, v);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            const bool cov = (cr >> j) & 1u;
-            if (cov) v[j] = v[j] + mn;
+            if ((cr >> j) & 1u) v[j] = v[j] + mn;
             if (u) v[j] = v[j] - mn;
-            if (colv && (cov || u)) pk[j * m] = v[j];
-            const uint32_t word = __ballot_sync(FULL, v[j] == 0.0f);
+            const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
             if (lane == 0) zp[j * kWarpZS + k] = word;
           }
+          tm_st8(tm + k * NP + r0, v);
         }
       }
+      tm_wait_st();
     }
     __syncwarp();
     if (TIMERS) { if (lane == 0) { const long long now = clock64(); ph[6] += now - ph[15]; ph[15] = now; } }
   }
 }
 
-template <int WARPS, bool TIMERS>
-__global__ void __launch_bounds__(WARPS * 32, 1) sort_warp_kernel(const SortParams P) {
+constexpr int kWarpsPerCta = 8;
+constexpr int kBigCols = 384, kSmallCols = 128;  // TMEM columns (= cell words of the cost matrix) of a big / small warp
+
+// aux area of the workspace (W2T_SORT_AUX_BYTES): 16 ints of header, then three arrays of n_substreams ints
+struct WarpQueues {
+  int32_t *hdr;         // [0] big items taken  [1] small items taken  [2] big items  [3] small items
+  int32_t *cls;         // per sub-stream: kCls*
+  int32_t *big, *small; // sub-streams for the warp kernel in launch order: those that need a big share of
+                        // tensor memory, and the rest
+};
+__host__ __device__ inline WarpQueues warp_queues(char *aux, int nq) {
+  WarpQueues Q;
+  Q.hdr = reinterpret_cast<int32_t *>(aux);
+  Q.cls = Q.hdr + 16;
+  Q.big = Q.cls + nq;
+  Q.small = Q.big + nq;
+  return Q;
+}
+
+// One CTA per SM, eight persistent warps.  Warps 0-3 own kBigCols columns of their tensor-memory quarter and
+// serve the queue of crowded sub-streams (then help with the other one); warps 4-7 own kSmallCols columns and
+// serve the queue of light sub-streams.
+template <bool TIMERS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const SortParams P) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char w2t_warp_smem[];
-  WarpShared<WARPS> &S = reinterpret_cast<WarpShared<WARPS> *>(w2t_warp_smem)[threadIdx.x >> 5];
+  __shared__ uint32_t s_tmem_base;
+  WarpShared &S = reinterpret_cast<WarpShared *>(w2t_warp_smem)[threadIdx.x >> 5];
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
+  // all of the SM's tensor memory: one CTA per SM (227 KB of shared memory see to that)
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        (uint32_t)__cvta_generic_to_shared(&s_tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  // this warp's share: the 32 lanes of its quarter; big warps take the low columns, small warps the rest
+  const bool bigw = (threadIdx.x >> 7) == 0;
+  const int wq = (threadIdx.x >> 5) & 3;
+  const int kCols = bigw ? kBigCols : kSmallCols;
+  const uint32_t tm = s_tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(bigw ? 0 : kBigCols);
   const int NC = P.p.n_classes;
   const float4 *det_box = reinterpret_cast<const float4 *>(P.p.det_box);
   const int max_age = P.p.max_age, min_hits = P.p.min_hits;
   const bool nep50 = P.nep50 != 0;
+  const WarpQueues Q = warp_queues(reinterpret_cast<char *>(P.queue), P.p.n_streams * NC);
+  const int n_big = Q.hdr[2], n_small = Q.hdr[3];
 
   // The first round of sub-streams is dealt out like cards — the k-th heaviest goes to SM k mod gridDim — so
-  // that every SM starts with the same mix of long and short chains; after that warps pull from the queue.
+  // that every SM starts with the same mix of long and short chains; after that warps pull from the queues.
   bool first = true;
 #pragma unroll 1
   for (;;) {
-    int item = 0;
-    if (first) {
-      item = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
+    int q = -1;
+    {
+      const int dealt = wq * (int)gridDim.x + (int)blockIdx.x, skip = 4 * (int)gridDim.x;
+      int i = dealt;
+      if (bigw) {
+        if (!first) {
+          if (lane == 0) i = atomicAdd(&Q.hdr[0], 1) + skip;
+          i = __shfl_sync(FULL, i, 0);
+        }
+        if (i < n_big) q = Q.big[i];
+        else {  // no crowded sub-stream left: take a light one
+          if (lane == 0) i = atomicAdd(&Q.hdr[1], 1) + skip;
+          i = __shfl_sync(FULL, i, 0);
+          if (i < n_small) q = Q.small[i];
+        }
+      } else {
+        if (!first) {
+          if (lane == 0) i = atomicAdd(&Q.hdr[1], 1) + skip;
+          i = __shfl_sync(FULL, i, 0);
+        }
+        if (i < n_small) q = Q.small[i];
+      }
       first = false;
-    } else {
-      if (lane == 0) item = atomicAdd(P.queue, 1) + WARPS * (int)gridDim.x;
-      item = __shfl_sync(FULL, item, 0);
     }
-    if (item >= P.n_items) break;
-    const int q = P.order[item];
-    if (P.bail[q] != kClsWarp) continue;  // too crowded for a warp (classify_kernel): CTAs track it
+    if (q < 0) break;
     const int s = q / NC, c = q - s * NC;
     const int Tcap = P.track_cap[q];
     char *slab = P.ws + P.ws_offset[q];
@@ -377,9 +452,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sort_warp_kernel(const SortPara
       if (T > 0 && D > 0) {
         const bool flipped = D > T;  // the solver transposes when there are more rows than columns
         const int n = flipped ? T : D, m = flipped ? D : T;
-        const int mw = (m + 31) >> 5;
-        if (((n + 7) & ~7) * m > WarpShared<WARPS>::kC) { bail = true; break; }  // the matrix does not fit this warp's share
-        float *C = S.C;
+        const int mw = (m + 31) >> 5, NP = (n + 7) & ~7;
+        if (mw * NP > kCols) { bail = true; break; }  // the matrix does not fit this warp's share of tensor memory
         auto mask_of = [&](const bool is_det, const int i) -> uint32_t {
           if (is_det) {
             const float4 b = S.det[i];
@@ -404,79 +478,84 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sort_warp_kernel(const SortPara
           S.strip[lane][k] = mine;
         }
         __syncwarp();
-        // 2. one lane per row: candidate columns = (union of the sets of the row's x strips) AND (union over
-        //    its y strips); exact cost of each candidate; row minimum (step 1 of the solver).  Every other
-        //    pair is strictly disjoint and costs -0.0f.
-#pragma unroll 1
-        for (int r = lane; r < n; r += 32) {
-          const uint32_t rm = mask_of(!flipped, r);
-          uint4 cx = make_uint4(0u, 0u, 0u, 0u), cy = cx;
-#pragma unroll 1
-          for (uint32_t w = rm & 0xffffu; w; w &= w - 1u) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[__ffs(w) - 1]);
-            cx.x |= v.x; cx.y |= v.y; cx.z |= v.z; cx.w |= v.w;
-          }
-#pragma unroll 1
-          for (uint32_t w = rm >> 16; w; w &= w - 1u) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[16 + __ffs(w) - 1]);
-            cy.x |= v.x; cy.y |= v.y; cy.z |= v.z; cy.w |= v.w;
-          }
-          uint32_t *zr = S.Z + r * kWarpZS;
-          zr[0] = cx.x & cy.x; zr[1] = cx.y & cy.y; zr[2] = cx.z & cy.z; zr[3] = cx.w & cy.w;
-          const int ncand = __popc(zr[0]) + __popc(zr[1]) + __popc(zr[2]) + __popc(zr[3]);
-          // minimum on the order-preserving integer image of the float (NaN sorts last, like fminf ignores it)
-          uint32_t mn_u = (ncand < m) ? Munkres<32>::ordered(-0.0f) : 0xffffffffu;
-          float *row = C + r * m;
-#pragma unroll 1
-          for (int k = 0; k < mw; k++) {
-#pragma unroll 1
-            for (uint32_t w = zr[k]; w; w &= w - 1u) {
-              const int cc = k * 32 + __ffs(w) - 1;
-              const int di = flipped ? cc : r, ti = flipped ? r : cc;
-              const float v = -iou_pair_call(S.det[di], S.box[0][ti], S.box[1][ti], S.box[2][ti], S.box[3][ti]);
-              row[cc] = v;
-              mn_u = min(mn_u, Munkres<32>::ordered(v));
-            }
-          }
-          S.rowmin[r] = Munkres<32>::unordered(mn_u);
-          S.row_star[r] = -1;
-          S.row_prime[r] = -1;
-        }
-#pragma unroll 1
+        // 2. + 3., 32 rows at a time.
+        //    One lane per row: candidate columns = (union of the sets of the row's x strips) AND (union over
+        //    its y strips); exact cost of each candidate (parked in S.raw); row minimum (step 1 of the solver).
+        //    Every other pair is strictly disjoint and costs -0.0f.
+        //    Then lanes own columns: reduced costs -> tensor memory, zero bit words -> S.Z, eight rows at a time.
         for (int cc = lane; cc < m; cc += 32) S.col_star[cc] = -1;
-        __syncwarp();
-        // 3. lanes own columns: reduced costs and the zero bit words, eight rows at a time
 #pragma unroll 1
-        for (int r0 = 0; r0 < n; r0 += 8) {
-          float mn[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) mn[j] = S.rowmin[r0 + j];
-          float *p = C + r0 * m + lane;
-          uint32_t *zp = S.Z + r0 * kWarpZS;
+        for (int rb = 0; rb < n; rb += 32) {
+          const int r = rb + lane;
+          if (r < n) {
+            const uint32_t rm = mask_of(!flipped, r);
+            uint4 cx = make_uint4(0u, 0u, 0u, 0u), cy = cx;
 #pragma unroll 1
-          for (int k = 0; k < mw; k++) {
-            const bool colv = k * 32 + lane < m;
-            float *pk = p + k * 32;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const uint32_t cw = zp[j * kWarpZS + k];
-              v[j] = -0.0f;
-              if ((cw >> lane) & 1u) v[j] = pk[j * m];
+            for (uint32_t w = rm & 0xffffu; w; w &= w - 1u) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[__ffs(w) - 1]);
+              cx.x |= v.x; cx.y |= v.y; cx.z |= v.z; cx.w |= v.w;
             }
+#pragma unroll 1
+            for (uint32_t w = rm >> 16; w; w &= w - 1u) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[16 + __ffs(w) - 1]);
+              cy.x |= v.x; cy.y |= v.y; cy.z |= v.z; cy.w |= v.w;
+            }
+            uint32_t *zr = S.Z + r * kWarpZS;
+            zr[0] = cx.x & cy.x; zr[1] = cx.y & cy.y; zr[2] = cx.z & cy.z; zr[3] = cx.w & cy.w;
+            const int ncand = __popc(zr[0]) + __popc(zr[1]) + __popc(zr[2]) + __popc(zr[3]);
+            // minimum on the order-preserving integer image of the float (NaN sorts last, like fminf ignores it)
+            uint32_t mn_u = (ncand < m) ? Munkres<32>::ordered(-0.0f) : 0xffffffffu;
+            float *row = S.raw + lane * m;
+#pragma unroll 1
+            for (int k = 0; k < mw; k++) {
+#pragma unroll 1
+              for (uint32_t w = zr[k]; w; w &= w - 1u) {
+                const int cc = k * 32 + __ffs(w) - 1;
+                const int di = flipped ? cc : r, ti = flipped ? r : cc;
+                const float v = -iou_pair_call(S.det[di], S.box[0][ti], S.box[1][ti], S.box[2][ti], S.box[3][ti]);
+                row[cc] = v;
+                mn_u = min(mn_u, Munkres<32>::ordered(v));
+              }
+            }
+            S.rowmin[r] = Munkres<32>::unordered(mn_u);
+            S.row_star[r] = -1;
+            S.row_prime[r] = -1;
+          }
+          __syncwarp();
+          const int r_end = min(rb + 32, NP);
+#pragma unroll 1
+          for (int r0 = rb; r0 < r_end; r0 += 8) {
+            float mn[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              v[j] = v[j] - mn[j];
-              if (colv) pk[j * m] = v[j];
-              const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
-              if (lane == 0) zp[j * kWarpZS + k] = word;
+            for (int j = 0; j < 8; j++) mn[j] = S.rowmin[r0 + j];
+            const float *p = S.raw + (r0 - rb) * m + lane;
+            uint32_t *zp = S.Z + r0 * kWarpZS;
+#pragma unroll 1
+            for (int k = 0; k < mw; k++) {
+              const bool colv = k * 32 + lane < m;
+              const float *pk = p + k * 32;
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const uint32_t cw = zp[j * kWarpZS + k];
+                v[j] = -0.0f;
+                if ((cw >> lane) & 1u) v[j] = pk[j * m];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                v[j] = v[j] - mn[j];
+                const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
+                if (lane == 0) zp[j * kWarpZS + k] = word;
+              }
+              tm_st8(tm + k * NP + r0, v);
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
+        tm_wait_st();
         W2T_WTICK(2);
         if (TIMERS && lane == 0) ph[13]++;
-        if (warp_munkres<TIMERS>(S, C, n, m, ph) != 0) err = W2T_ERR_ARG;
+        if (warp_munkres<TIMERS>(S, tm, n, m, ph) != 0) err = W2T_ERR_ARG;
         __syncwarp();
         W2T_WTICK(5);
         // matched / rejected detections (sort.py:217-222)
@@ -625,7 +704,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sort_warp_kernel(const SortPara
     }
 #undef W2T_WTICK
     if (bail) {  // tracked again from its first image by the CTA kernel
-      if (lane == 0) P.bail[q] = kClsBailed;
+      if (lane == 0) Q.cls[q] = kClsBailed;
       continue;
     }
     if (err && lane == 0) atomicMax(P.status, err);
@@ -655,19 +734,56 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sort_warp_kernel(const SortPara
       }
     }
   }
+  // every warp of the CTA is done with its share before the tensor memory goes back
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_tmem_base));
 }
 
-// Actual crowding of every sub-stream (the launch plan may have been computed from upper bounds, e.g. the
-// group sizes BEFORE the ensemble): most detections in one image -> class flag for the kernels above.
-__global__ void sort_classify_kernel(const w2t_sort_problem_t p, int32_t *cls) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  const int NC = p.n_classes;
-  if (q >= p.n_streams * NC) return;
-  const int s = q / NC, c = q - s * NC;
-  int dmax = 0;
-  for (int img = p.stream_img_offsets[s]; img < p.stream_img_offsets[s + 1]; img++)
-    if (p.img_exists == nullptr || p.img_exists[img]) dmax = max(dmax, p.det_count[img * NC + c]);
-  cls[q] = dmax > W2T_WIDE_DETS ? kClsWide : dmax > W2T_NARROW_DETS ? kClsMid : kClsWarp;
+// Actual crowding of every sub-stream (the launch plan may have been computed from upper bounds, e.g. the group
+// sizes BEFORE the ensemble): most detections in one image -> class flag (kCls*) for the kernels above, and the two
+// queues of the warp kernel, both in the plan's launch order (heaviest first).  One block.
+__global__ void __launch_bounds__(1024) sort_classify_kernel(const w2t_sort_problem_t p, const int32_t *order, WarpQueues Q) {
+  __shared__ int s_tot[2][32];
+  __shared__ int s_base[2];
+  const int NC = p.n_classes, nq = p.n_streams * NC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 2) s_base[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nq; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    bool big = false, small = false;
+    int q = 0;
+    if (i < nq) {
+      q = order[i];
+      const int s = q / NC, c = q - s * NC;
+      int dmax = 0;
+      for (int img = p.stream_img_offsets[s]; img < p.stream_img_offsets[s + 1]; img++)
+        if (p.img_exists == nullptr || p.img_exists[img]) dmax = max(dmax, p.det_count[img * NC + c]);
+      const int cls = dmax > W2T_WIDE_DETS ? kClsWide : dmax > W2T_NARROW_DETS ? kClsMid : kClsWarp;
+      Q.cls[q] = cls;
+      // a crowd of D detections meets about 1.3 D trackers (max_age 2): ceil8(D) rows x ceil32(1.3 D + 8) / 32 words
+      const int words = (min(kWarpDim, dmax + dmax / 3 + 8) + 31) >> 5;
+      big = cls == kClsWarp && ((dmax + 7) & ~7) * words > kSmallCols;
+      small = cls == kClsWarp && !big;
+    }
+    const unsigned bb = __ballot_sync(0xffffffffu, big), bs = __ballot_sync(0xffffffffu, small);
+    if (lane == 0) { s_tot[0][warp] = __popc(bb); s_tot[1][warp] = __popc(bs); }
+    __syncthreads();
+    int pb = s_base[0], ps = s_base[1], tb = 0, ts = 0;
+    for (int w = 0; w < 32; w++) {
+      if (w < warp) { pb += s_tot[0][w]; ps += s_tot[1][w]; }
+      tb += s_tot[0][w];
+      ts += s_tot[1][w];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (big) Q.big[pb + __popc(bb & lt)] = q;
+    if (small) Q.small[ps + __popc(bs & lt)] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) { s_base[0] += tb; s_base[1] += ts; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { Q.hdr[2] = s_base[0]; Q.hdr[3] = s_base[1]; }
 }
 
 }  // namespace w2t
