@@ -193,7 +193,7 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
       if (fork) W2T_CUDA_TRY(cudaEventRecord(ev_join[dev], sb));
       {
         static bool attr_set[16] = {false};
-        const size_t smem = sizeof(WarpShared) * kWarpsPerCta;
+        const size_t smem = sizeof(WarpShared) * kTeamsPerCta;
         if (dev >= 16 || !attr_set[dev]) {
           W2T_CUDA_TRY(cudaFuncSetAttribute(sort_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           W2T_CUDA_TRY(cudaFuncSetAttribute(sort_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,4 +1,4 @@
-// sort_warp.cuh — the SORT tracker with one WARP per (stream, category) sub-stream.
+// sort_warp.cuh — the SORT tracker with one WARP (or a pair of warps) per (stream, category) sub-stream.
 //
 // Replaces, like sort_kernel.cuh, the loop of tracking/track.py:42-47 (track_sort, tracking/utils.py:25-60 ->
 // MultiClassTrackerSort.track, tracking/sort/tracker_sort.py:22-51 -> Sort.update, tracking/sort/sort.py:244-296
@@ -6,25 +6,29 @@
 // scikit-learn 0.22.2 behind sort.py:206) — for every sub-stream whose images hold at most kWarpDim
 // detections and live trackers, which is everything but crowded scenes.
 //
-// Why a warp.  A sub-stream is a serial recurrence over its images, and inside an image the solver is a serial
+// Why warps.  A sub-stream is a serial recurrence over its images, and inside an image the solver is a serial
 // state machine; the CTA-per-sub-stream kernel (sort_kernel.cuh) spent its time at CTA barriers (three of four
 // warps waiting for the one that drives the solver) and, above all, on instruction fetch: its per-image path
 // is ~50 KB of SASS against a 32 KB instruction cache per SM, shared by CTAs in different phases
-// (profiles/r01h_*: i-cache hit rate 73 %, GPC instruction requests at 96 % of peak, issue slots 25 %).
-// Here one warp owns a sub-stream:
-//   * no CTA barrier anywhere — phases are separated by __syncwarp();
+// (profiles/r01h_*: i-cache hit rate 73 %, GPC instruction requests at 96 % of peak, issue slots 25 %).  Here:
+//   * no CTA barrier on the path — phases are separated by __syncwarp(), or by a 64-thread named barrier
+//     where two warps share a sub-stream;
 //   * every cover / star mask of the solver is ONE register per lane (lane k holds bits 32k..32k+31), so a
 //     mask operation is a predicated instruction, "first set bit" a ballot + shuffle, and the code has no
-//     per-word unrolling: the whole per-image path is a fraction of the old one and fits the instruction
-//     cache together with every other warp's;
+//     per-word unrolling: the whole per-image path fits the instruction cache (r02: hit rate 94-98 %);
+//   * the cost matrix lives in TENSOR MEMORY (below), eight rows per access;
 //   * trackers are kept in LIST ORDER (the reference's list, sort.py:238): the pass that updates / predicts
 //     them writes each survivor back at its new position, so removal (sort.py:292-293) costs nothing and the
 //     accesses are coalesced; the predicted boxes go straight to shared memory for the next image;
-//   * warps are persistent and pull sub-streams from a queue in the plan's order (heaviest first), eight
-//     warps per SM (shared memory: 28 KB per warp), no two warps ever wait for each other.
-// A sub-stream that outgrows kWarpDim (more detections in an image, or more live trackers) raises its flag
-// in P.bail and is tracked again from its first image by the CTA kernel (sort.cu launches it behind this
-// one; CTAs of sub-streams that did not bail exit at once).
+//   * warps are persistent and pull sub-streams from two queues in the plan's order (heaviest first).
+// Twelve warps per SM.  The job is bounded by its longest chains (the most crowded streams: 200 images one
+// after the other), so those get two warps: warps 0-3 ("leaders") serve the queue of crowded sub-streams,
+// each with a helper (warps 4-7) that takes every other block of rows in the wide phases — construction
+// of the cost matrix, the cost shifts of the solver (step 6), the Kalman pass — while the leader alone
+// drives the solver's serial steps; warps 8-11 serve the queue of light sub-streams on their own.
+// A sub-stream that outgrows the kernel (more than kWarpDim detections or live trackers, or a cost matrix
+// beyond its share of tensor memory) raises its flag and is tracked again from its first image by the CTA
+// kernel (sort.cu launches it behind this one; CTAs of all other sub-streams exit at once).
 #pragma once
 
 #include "sort_kernel.cuh"
@@ -34,17 +38,20 @@ namespace w2t {
 constexpr int kWarpDim = 128;       // most detections / live trackers per image
 constexpr int kWarpZS = 5;          // words per row of the zero bit matrix (4 + 1: odd stride)
 constexpr int kWarpSmemBytes = 232448;  // 227 KB: the most dynamic shared memory a CTA can have
+constexpr int kTeamsPerCta = 8;     // sub-streams in flight per SM: 4 pairs + 4 single warps
+constexpr int kWarpsPerCta = 12;
+constexpr int kBigCols = 384, kSmallCols = 128;  // TMEM columns (= cell words of the cost matrix) of a pair / a single warp
 
-// The cost matrix of a warp's current image lives in TENSOR MEMORY (256 KB per SM, 128 lanes x 512 columns x
+// The cost matrix of a team's current image lives in TENSOR MEMORY (256 KB per SM, 128 lanes x 512 columns x
 // 32 bit, reached with tcgen05.ld / tcgen05.st; SASS: LDTM / STTM).  A warp can only touch the 32 TMEM lanes of
 // its quarter (warp index % 4), which is exactly the shape this solver wants: TMEM lane = matrix column mod 32,
 // and one TMEM column holds one "cell word" (32 consecutive matrix columns of one row), so a single
 // 32x32b.x8 access moves the same 32 matrix columns of eight rows between TMEM and eight registers per lane —
 // one instruction and ~12 cycles where shared memory needs eight instructions and ~30, and the 18-40 KB per
-// warp the matrix would take in shared memory are free for more warps.  Cell word (row r, word k) of an
-// n x m problem sits in column k * ceil8(n) + r of the warp's share.  The 512 columns of a quarter are split
-// between the two warps that can reach it: 384 for a "big" warp (e.g. a 96 x 128 problem) and 128 for a
-// "small" one (e.g. 40 x 64); a problem that does not fit sends its sub-stream to the CTA kernel.
+// sub-stream the matrix would take in shared memory are free for more sub-streams.  Cell word (row r, word k)
+// of an n x m problem sits in column k * ceil8(n) + r of the team's share.  The 512 columns of a quarter are
+// split between the teams whose warps can reach it: 384 for the pair (e.g. a 96 x 128 problem), 128 for the
+// single warp (e.g. 40 x 64).
 struct __align__(128) WarpShared {
   float4 det[kWarpDim];                 // this image's detections
   double box[4][kWarpDim];              // predicted boxes of the live trackers, by list position
@@ -56,8 +63,15 @@ struct __align__(128) WarpShared {
   int8_t dstat[kWarpDim];               // per detection: 0 unassigned, 1 matched, 2 assigned but rejected
   int8_t newdet[kWarpDim];              // detections that become trackers, in the reference's order
   float raw[32 * kWarpDim];             // exact costs of the candidate pairs of the 32 rows being built
+  // mailbox of a pair (leader -> helper, and partial results)
+  uint32_t cov[2][4];                   // cost shift: row cover / column cover words
+  uint32_t part[2];                     // cost shift: minimum found by each warp
+  int32_t cmd;                          // inside the solver: 1 = shift the costs, 0 = solved, 9 = gave up
+  int32_t cur_q;                        // sub-stream the team works on, -1 = none left
+  int32_t n_new;                        // trackers created at this image
+  int32_t cnt[2][2][2];                 // Kalman pass: [trip parity][warp of the pair][survivors, rows emitted]
 };
-static_assert(sizeof(WarpShared) * 8 <= kWarpSmemBytes, "shared memory of the warp kernel exceeds 227 KB");
+static_assert(sizeof(WarpShared) * kTeamsPerCta <= kWarpSmemBytes, "shared memory of the warp kernel exceeds 227 KB");
 
 // eight TMEM columns <-> eight registers per lane (lane l talks to TMEM lane l of the warp's quarter)
 __device__ __forceinline__ void tm_ld8(const uint32_t taddr, float (&v)[8]) {
@@ -78,6 +92,20 @@ __device__ __forceinline__ void tm_st8(const uint32_t taddr, const float (&v)[8]
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// A team: one warp, or a pair (leader = half 0, helper = half 1) that meets at a 64-thread named barrier.
+struct Team {
+  int half, nh, bar;
+  __device__ __forceinline__ void sync() const {
+    if (nh == 2) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else {
+      __syncwarp();
+    }
+  }
+};
+
 // sqrt / divide of convert_x_to_bbox (sort.py:70-71), out of line: called twice per tracker and image
 __device__ __noinline__ void box_wh(const double s, const double r, double &w, double &h) {
   w = sqrt(s * r);
@@ -95,18 +123,91 @@ __device__ __forceinline__ uint32_t strip_mask_checked(const double x1, const do
   return regular ? strip_mask(x1, y1, x2, y2) : 0xffffffffu;
 }
 
+// ---- step 6 of the solver, by the whole team: min over uncovered rows x uncovered columns; covered rows += min,
+// then uncovered columns -= min (float32, in that order).  The covers come from S.cov.  Lanes own columns (bit k
+// of `uc`: column 32k + lane is uncovered, bit k of `ucw`: word k has an uncovered column at all); rows go eight
+// at a time, one TMEM access per eight cell words, the blocks of eight dealt out between the warps of the team
+// (the matrix holds ceil8(n) rows: the padding rows are computed on and never read).
+__device__ __forceinline__ void cost_shift(WarpShared &S, const uint32_t tm, const int n, const int m, const Team &team) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = lane_id();
+  const int mw = (m + 31) >> 5, NP = (n + 7) & ~7;
+  uint32_t uc = 0u, ucw = 0u;
+#pragma unroll 1
+  for (int k = 0; k < mw; k++) {
+    const uint32_t cw = S.cov[1][k];
+    if (k * 32 + lane < m && !((cw >> lane) & 1u)) uc |= 1u << k;
+    const uint32_t valid = (m - k * 32 >= 32) ? 0xffffffffu : ((1u << (m - k * 32)) - 1u);
+    if (~cw & valid) ucw |= 1u << k;
+  }
+  // costs are >= +0 here (or NaN), so their bit patterns order like the values and NaN sorts above +inf
+  uint32_t mn_u = 0x7f800000u;
+#pragma unroll 1
+  for (int r0 = team.half * 8; r0 < n; r0 += 8 * team.nh) {
+    uint32_t ur = ~(S.cov[0][r0 >> 5] >> (r0 & 31));  // bit j: row r0 + j is uncovered
+    if (n - r0 < 8) ur &= (1u << (n - r0)) - 1u;
+    if ((ur & 0xffu) == 0u) continue;
+#pragma unroll 1
+    for (uint32_t w = ucw; w; w &= w - 1u) {
+      const int k = __ffs(w) - 1;
+      float v[8];
+      tm_ld8(tm + k * NP + r0, v);
+      if ((uc >> k) & 1u) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if ((ur >> j) & 1u) mn_u = min(mn_u, __float_as_uint(v[j]));
+      }
+    }
+  }
+  mn_u = __reduce_min_sync(FULL, mn_u);
+  if (team.nh == 2) {
+    if (lane == 0) S.part[team.half] = mn_u;
+    team.sync();
+    mn_u = min(S.part[0], S.part[1]);
+  }
+  if (mn_u != 0x7f800000u) {  // nothing uncovered: the reference leaves the matrix alone
+    const float mn = __uint_as_float(mn_u);
+#pragma unroll 1
+    for (int r0 = team.half * 8; r0 < n; r0 += 8 * team.nh) {
+      const uint32_t cr = (S.cov[0][r0 >> 5] >> (r0 & 31)) & 0xffu;  // bit j: row r0 + j is covered
+      uint32_t *zp = S.Z + r0 * kWarpZS;
+#pragma unroll 1
+      for (int k = 0; k < mw; k++) {
+        if (cr == 0u && !((ucw >> k) & 1u)) continue;  // uncovered rows x covered columns: nothing changes
+        const bool colv = k * 32 + lane < m;
+        const bool u = (uc >> k) & 1u;
+        float v[8];
+        tm_ld8(tm + k * NP + r0, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if ((cr >> j) & 1u) v[j] = v[j] + mn;
+          if (u) v[j] = v[j] - mn;
+          const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
+          if (lane == 0) zp[j * kWarpZS + k] = word;
+        }
+        tm_st8(tm + k * NP + r0, v);
+      }
+    }
+    tm_wait_st();
+  }
+  team.sync();
+}
+
 // ---- scikit-learn 0.22.2 linear_assignment on the n x m (n <= m <= kWarpDim) matrix in tensor memory at `tm`
 // (cell word (r, k) in column k * NP + r, NP = ceil8(n)), whose row minima are already subtracted and whose zeros
-// are mirrored in S.Z (step 1 is folded into the construction of the matrix).  Same step machine, same decisions as munkres.cuh (see there for why each shortcut is exact).
-// Lane k holds word k of every mask.  Returns 0, or 9 when the iteration budget ran out (NaN costs).
+// are mirrored in S.Z (step 1 is folded into the construction of the matrix).  Same step machine, same decisions
+// as munkres.cuh (see there for why each shortcut is exact).  Runs in the team's leading warp; lane k holds
+// word k of every mask.  A helper warp follows in solver_helper().  Returns 0, or 9 when the iteration budget
+// ran out (NaN costs).
 template <bool TIMERS>
-__device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, const int n, const int m, long long *ph) {
+__device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, const int n, const int m, const Team &team,
+                                            long long *ph) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
-  const int mw = (m + 31) >> 5, nwr = (n + 31) >> 5, NP = (n + 7) & ~7;
+  const int mw = (m + 31) >> 5, nwr = (n + 31) >> 5;
   uint32_t starcols = 0u, colcov = 0u, rowcov = 0u, rowhas = 0u;
-  int stars = 0;
+  int stars = 0, act = 0;
   int budget = 4 * n * n + 64 * (n + m) + 1024;
 
   // ---- step 2: greedy stars in row-major order; the longest prefix of pending rows whose proposals are
@@ -150,7 +251,7 @@ __device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, co
 
 #pragma unroll 1
   for (;;) {
-    if (stars >= n) return 0;
+    if (stars >= n) break;
     // rows that own an uncovered zero, from scratch (after step 3 or after a cost shift)
     rowhas = 0u;
 #pragma unroll 1
@@ -170,7 +271,7 @@ __device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, co
 #pragma unroll 1
     for (;;) {
       // step 4: first uncovered zero in row-major order
-      if (--budget < 0) return 9;
+      if (--budget < 0) { act = 9; break; }
       if (TIMERS && lane == 0) ph[12]++;
       const unsigned hb = __ballot_sync(FULL, rowhas != 0u);
       if (!hb) break;  // none left: step 6
@@ -201,7 +302,7 @@ __device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, co
           }
         }
         endc = __shfl_sync(FULL, endc, 0);
-        if (endc < 0) return 9;
+        if (endc < 0) { act = 9; break; }
         if (lane == (endc >> 5)) starcols |= 1u << (endc & 31);
         stars++;
         augmented = true;
@@ -227,76 +328,37 @@ __device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, co
         if (lane == grp) rowhas |= b & ~rc;
       }
     }
+    if (act != 0) break;
     if (augmented) {  // step 3: cover the starred columns, uncover all rows (stale primes are never read)
       colcov = starcols;
       rowcov = 0u;
       continue;
     }
     if (TIMERS) { if (lane == 0) { const long long now = clock64(); ph[5] += now - ph[15]; ph[15] = now; ph[11]++; } }
-    // ---- step 6: min over uncovered rows x uncovered columns; covered rows += min, then uncovered columns -= min
-    // (float32, in that order).  Lanes own columns (bit k of `uc`: column 32k + lane is uncovered, bit k of
-    // `ucw`: word k has an uncovered column at all); rows go eight at a time, one TMEM access per eight cell
-    // words (the matrix holds ceil8(n) rows: the padding rows are computed on and never read).
-    uint32_t uc = 0u, ucw = 0u;
-#pragma unroll 1
-    for (int k = 0; k < mw; k++) {
-      const uint32_t cw = __shfl_sync(FULL, colcov, k);
-      if (k * 32 + lane < m && !((cw >> lane) & 1u)) uc |= 1u << k;
-      const uint32_t valid = (m - k * 32 >= 32) ? 0xffffffffu : ((1u << (m - k * 32)) - 1u);
-      if (~cw & valid) ucw |= 1u << k;
-    }
-    // costs are >= +0 here (or NaN), so their bit patterns order like the values and NaN sorts above +inf
-    uint32_t mn_u = 0x7f800000u;
-#pragma unroll 1
-    for (int r0 = 0; r0 < n; r0 += 8) {
-      uint32_t ur = ~(__shfl_sync(FULL, rowcov, r0 >> 5) >> (r0 & 31));  // bit j: row r0 + j is uncovered
-      if (n - r0 < 8) ur &= (1u << (n - r0)) - 1u;
-      if ((ur & 0xffu) == 0u) continue;
-#pragma unroll 1
-      for (uint32_t w = ucw; w; w &= w - 1u) {
-        const int k = __ffs(w) - 1;
-        float v[8];
-        tm_ld8(tm + k * NP + r0, v);
-        if ((uc >> k) & 1u) {
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            if ((ur >> j) & 1u) mn_u = min(mn_u, __float_as_uint(v[j]));
-        }
-      }
-    }
-    mn_u = __reduce_min_sync(FULL, mn_u);
-    if (mn_u != 0x7f800000u) {  // nothing uncovered: the reference leaves the matrix alone
-      const float mn = __uint_as_float(mn_u);
-#pragma unroll 1
-      for (int r0 = 0; r0 < n; r0 += 8) {
-        const uint32_t cr = (__shfl_sync(FULL, rowcov, r0 >> 5) >> (r0 & 31)) & 0xffu;  // bit j: row r0 + j is covered
-        uint32_t *zp = S.Z + r0 * kWarpZS;
-#pragma unroll 1
-        for (int k = 0; k < mw; k++) {
-          if (cr == 0u && !((ucw >> k) & 1u)) continue;  // uncovered rows x covered columns: nothing changes
-          const bool colv = k * 32 + lane < m;
-          const bool u = (uc >> k) & 1u;
-          float v[8];
-          tm_ld8(tm + k * NP + r0, v);
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            if ((cr >> j) & 1u) v[j] = v[j] + mn;
-            if (u) v[j] = v[j] - mn;
-            const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
-            if (lane == 0) zp[j * kWarpZS + k] = word;
-          }
-          tm_st8(tm + k * NP + r0, v);
-        }
-      }
-      tm_wait_st();
-    }
-    __syncwarp();
+    // step 6, with the helper if there is one
+    if (lane < 4) { S.cov[0][lane] = rowcov; S.cov[1][lane] = colcov; }
+    if (lane == 0) S.cmd = 1;
+    team.sync();
+    cost_shift(S, tm, n, m, team);
     if (TIMERS) { if (lane == 0) { const long long now = clock64(); ph[6] += now - ph[15]; ph[15] = now; } }
   }
+  if (team.nh == 2) {
+    if (lane == 0) S.cmd = act;
+    team.sync();
+  }
+  return act;
 }
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kBigCols = 384, kSmallCols = 128;  // TMEM columns (= cell words of the cost matrix) of a big / small warp
+// the helper's side of warp_munkres: cost shifts until the leader reports the outcome
+__device__ __forceinline__ int solver_helper(WarpShared &S, const uint32_t tm, const int n, const int m, const Team &team) {
+#pragma unroll 1
+  for (;;) {
+    team.sync();
+    const int cmd = S.cmd;
+    if (cmd != 1) return cmd;
+    cost_shift(S, tm, n, m, team);
+  }
+}
 
 // aux area of the workspace (W2T_SORT_AUX_BYTES): 16 ints of header, then three arrays of n_substreams ints
 struct WarpQueues {
@@ -314,16 +376,24 @@ __host__ __device__ inline WarpQueues warp_queues(char *aux, int nq) {
   return Q;
 }
 
-// One CTA per SM, eight persistent warps.  Warps 0-3 own kBigCols columns of their tensor-memory quarter and
-// serve the queue of crowded sub-streams (then help with the other one); warps 4-7 own kSmallCols columns and
-// serve the queue of light sub-streams.
+// One CTA per SM, twelve persistent warps: leaders 0-3 and their helpers 4-7 share kBigCols columns of their
+// tensor-memory quarter and serve the queue of crowded sub-streams (then help with the other one); warps 8-11
+// own kSmallCols columns and serve the queue of light sub-streams.
 template <bool TIMERS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const SortParams P) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char w2t_warp_smem[];
   __shared__ uint32_t s_tmem_base;
-  WarpShared &S = reinterpret_cast<WarpShared *>(w2t_warp_smem)[threadIdx.x >> 5];
   const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int wq = warp & 3;                  // quarter of tensor memory this warp can reach
+  const bool bigw = warp < 8;
+  Team team;
+  team.half = (warp >> 2) == 1 ? 1 : 0;
+  team.nh = bigw ? 2 : 1;
+  team.bar = 1 + wq;
+  const bool lead = team.half == 0;
+  WarpShared &S = reinterpret_cast<WarpShared *>(w2t_warp_smem)[bigw ? wq : 4 + wq];
   const unsigned lt = (1u << lane) - 1u;
   // all of the SM's tensor memory: one CTA per SM (227 KB of shared memory see to that)
   if (threadIdx.x < 32) {
@@ -334,9 +404,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  // this warp's share: the 32 lanes of its quarter; big warps take the low columns, small warps the rest
-  const bool bigw = (threadIdx.x >> 7) == 0;
-  const int wq = (threadIdx.x >> 5) & 3;
+  // this team's share: the 32 lanes of its quarter; pairs take the low columns, single warps the rest
   const int kCols = bigw ? kBigCols : kSmallCols;
   const uint32_t tm = s_tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(bigw ? 0 : kBigCols);
   const int NC = P.p.n_classes;
@@ -347,12 +415,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
   const int n_big = Q.hdr[2], n_small = Q.hdr[3];
 
   // The first round of sub-streams is dealt out like cards — the k-th heaviest goes to SM k mod gridDim — so
-  // that every SM starts with the same mix of long and short chains; after that warps pull from the queues.
+  // that every SM starts with the same mix of long and short chains; after that teams pull from the queues.
   bool first = true;
 #pragma unroll 1
   for (;;) {
     int q = -1;
-    {
+    if (lead) {
       const int dealt = wq * (int)gridDim.x + (int)blockIdx.x, skip = 4 * (int)gridDim.x;
       int i = dealt;
       if (bigw) {
@@ -375,6 +443,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
       }
       first = false;
     }
+    if (team.nh == 2) {
+      if (lead && lane == 0) S.cur_q = q;
+      team.sync();
+      q = S.cur_q;
+      team.sync();  // the helper has read it before the leader can post the next one
+    }
     if (q < 0) break;
     const int s = q / NC, c = q - s * NC;
     const int Tcap = P.track_cap[q];
@@ -392,7 +466,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
 
     int T = 0, frame_count = 0, err = 0;
     bool started = false, bail = false;
-    if (lane == 0) P.r.first_img[q] = -1;
+    if (lead && lane == 0) P.r.first_img[q] = -1;
     long long ph[TIMERS ? 16 : 1];
     if (TIMERS) {
 #pragma unroll
@@ -427,24 +501,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
         if (D == 0) skip = true;  // no Sort object for this category yet (tracker_sort.py:32-33)
         else {
           started = true;
-          if (lane == 0) P.r.first_img[q] = img - img0;
+          if (lead && lane == 0) P.r.first_img[q] = img - img0;
         }
       }
       if (skip || err) {
-        if (lane == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
+        if (lead && lane == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
         continue;
       }
       if (D > kWarpDim || T > kWarpDim) { bail = true; break; }
       frame_count++;
 #pragma unroll 1
-      for (int d = lane; d < D; d += 32) {
+      for (int d = team.half * 32 + lane; d < D; d += 32 * team.nh) {
         S.det[d] = __ldg(det_box + base + d);
         S.dstat[d] = 0;
       }
 #pragma unroll 1
-      for (int t = lane; t < T; t += 32) S.match[t] = -1;
-      __syncwarp();
-      if (img + 1 < img1 && cur_exists && lane * 8 < cur_cnt)
+      for (int t = team.half * 32 + lane; t < T; t += 32 * team.nh) S.match[t] = -1;
+      team.sync();
+      if (lead && img + 1 < img1 && cur_exists && lane * 8 < cur_cnt)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(det_box + cur_start + lane * 8));
       W2T_WTICK(1);
 
@@ -453,7 +527,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
         const bool flipped = D > T;  // the solver transposes when there are more rows than columns
         const int n = flipped ? T : D, m = flipped ? D : T;
         const int mw = (m + 31) >> 5, NP = (n + 7) & ~7;
-        if (mw * NP > kCols) { bail = true; break; }  // the matrix does not fit this warp's share of tensor memory
+        if (mw * NP > kCols) { bail = true; break; }  // the matrix does not fit this team's share of tensor memory
         auto mask_of = [&](const bool is_det, const int i) -> uint32_t {
           if (is_det) {
             const float4 b = S.det[i];
@@ -461,33 +535,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
           }
           return strip_mask_checked(S.box[0][i], S.box[1][i], S.box[2][i], S.box[3][i]);
         };
-        // 1. every column enters the bit sets of the strips its box touches: a 32 x 32 bit transpose per
-        //    column word (lane b collects bit b of every lane's mask)
-        *reinterpret_cast<uint4 *>(S.strip[lane]) = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
+        if (lead) {
+          // 1. every column enters the bit sets of the strips its box touches: a 32 x 32 bit transpose per
+          //    column word (lane b collects bit b of every lane's mask)
+          *reinterpret_cast<uint4 *>(S.strip[lane]) = make_uint4(0u, 0u, 0u, 0u);
+          __syncwarp();
 #pragma unroll 1
-        for (int k = 0; k < mw; k++) {
-          const int cc = k * 32 + lane;
-          const uint32_t cm = (cc < m) ? mask_of(flipped, cc) : 0u;
-          uint32_t mine = 0u;
+          for (int k = 0; k < mw; k++) {
+            const int cc = k * 32 + lane;
+            const uint32_t cm = (cc < m) ? mask_of(flipped, cc) : 0u;
+            uint32_t mine = 0u;
 #pragma unroll 4
-          for (int b = 0; b < 32; b++) {
-            const uint32_t w = __ballot_sync(FULL, (cm >> b) & 1u);
-            if (lane == b) mine = w;
+            for (int b = 0; b < 32; b++) {
+              const uint32_t w = __ballot_sync(FULL, (cm >> b) & 1u);
+              if (lane == b) mine = w;
+            }
+            S.strip[lane][k] = mine;
           }
-          S.strip[lane][k] = mine;
+#pragma unroll 1
+          for (int cc = lane; cc < m; cc += 32) S.col_star[cc] = -1;
+          __syncwarp();
         }
-        __syncwarp();
         // 2. + 3., 32 rows at a time.
-        //    One lane per row: candidate columns = (union of the sets of the row's x strips) AND (union over
-        //    its y strips); exact cost of each candidate (parked in S.raw); row minimum (step 1 of the solver).
-        //    Every other pair is strictly disjoint and costs -0.0f.
-        //    Then lanes own columns: reduced costs -> tensor memory, zero bit words -> S.Z, eight rows at a time.
-        for (int cc = lane; cc < m; cc += 32) S.col_star[cc] = -1;
+        //    The leader, one lane per row: candidate columns = (union of the sets of the row's x strips) AND
+        //    (union over its y strips); exact cost of each candidate (parked in S.raw); row minimum (step 1 of
+        //    the solver).  Every other pair is strictly disjoint and costs -0.0f.
+        //    Then the team, lanes own columns: reduced costs -> tensor memory, zero bit words -> S.Z, eight rows
+        //    at a time.
 #pragma unroll 1
         for (int rb = 0; rb < n; rb += 32) {
           const int r = rb + lane;
-          if (r < n) {
+          if (lead && r < n) {
             const uint32_t rm = mask_of(!flipped, r);
             uint4 cx = make_uint4(0u, 0u, 0u, 0u), cy = cx;
 #pragma unroll 1
@@ -521,10 +599,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
             S.row_star[r] = -1;
             S.row_prime[r] = -1;
           }
-          __syncwarp();
+          team.sync();
           const int r_end = min(rb + 32, NP);
 #pragma unroll 1
-          for (int r0 = rb; r0 < r_end; r0 += 8) {
+          for (int r0 = rb + team.half * 8; r0 < r_end; r0 += 8 * team.nh) {
             float mn[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) mn[j] = S.rowmin[r0 + j];
@@ -550,57 +628,64 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
               tm_st8(tm + k * NP + r0, v);
             }
           }
-          __syncwarp();
+          tm_wait_st();
+          team.sync();
         }
-        tm_wait_st();
         W2T_WTICK(2);
         if (TIMERS && lane == 0) ph[13]++;
-        if (warp_munkres<TIMERS>(S, tm, n, m, ph) != 0) err = W2T_ERR_ARG;
-        __syncwarp();
+        const int act = lead ? warp_munkres<TIMERS>(S, tm, n, m, team, ph) : solver_helper(S, tm, n, m, team);
+        if (act != 0) err = W2T_ERR_ARG;
         W2T_WTICK(5);
-        // matched / rejected detections (sort.py:217-222)
+        if (lead) {
+          __syncwarp();
+          // matched / rejected detections (sort.py:217-222)
 #pragma unroll 1
-        for (int d = lane; d < D; d += 32) {
-          const int t = flipped ? S.col_star[d] : S.row_star[d];
-          if (t >= 0) {
-            const float o = iou_pair_call(S.det[d], S.box[0][t], S.box[1][t], S.box[2][t], S.box[3][t]);
-            // NumPy 1.x compares the float32 entry with the python float in float64, NEP 50 in float32
-            const bool rejected = nep50 ? (o < thr_f) : ((double)o < thr);
-            if (rejected) S.dstat[d] = 2;  // becomes a new tracker AFTER the unassigned ones
-            else { S.dstat[d] = 1; S.match[t] = (int8_t)d; }
+          for (int d = lane; d < D; d += 32) {
+            const int t = flipped ? S.col_star[d] : S.row_star[d];
+            if (t >= 0) {
+              const float o = iou_pair_call(S.det[d], S.box[0][t], S.box[1][t], S.box[2][t], S.box[3][t]);
+              // NumPy 1.x compares the float32 entry with the python float in float64, NEP 50 in float32
+              const bool rejected = nep50 ? (o < thr_f) : ((double)o < thr);
+              if (rejected) S.dstat[d] = 2;  // becomes a new tracker AFTER the unassigned ones
+              else { S.dstat[d] = 1; S.match[t] = (int8_t)d; }
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       W2T_WTICK(7);
       // new trackers: unassigned detections first, then the rejected ones (sort.py:208-222, :276-278)
       int n_new = 0;
+      if (lead) {
 #pragma unroll 1
-      for (int pass = 0; pass < 2; pass++) {
+        for (int pass = 0; pass < 2; pass++) {
 #pragma unroll 1
-        for (int d0 = 0; d0 < D; d0 += 32) {
-          const int d = d0 + lane;
-          const bool a = d < D && S.dstat[d] == (pass ? 2 : 0);
-          const unsigned b = __ballot_sync(FULL, a);
-          if (a) S.newdet[n_new + __popc(b & lt)] = (int8_t)d;
-          n_new += __popc(b);
+          for (int d0 = 0; d0 < D; d0 += 32) {
+            const int d = d0 + lane;
+            const bool a = d < D && S.dstat[d] == (pass ? 2 : 0);
+            const unsigned b = __ballot_sync(FULL, a);
+            if (a) S.newdet[n_new + __popc(b & lt)] = (int8_t)d;
+            n_new += __popc(b);
+          }
         }
+        if (team.nh == 2 && lane == 0) S.n_new = n_new;
       }
-      __syncwarp();
+      team.sync();
+      if (team.nh == 2) n_new = S.n_new;
       const int Ttot = T + n_new;
       if (Ttot > Tcap) err = W2T_ERR_CAPACITY;
       if (err) {
-        if (lane == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
+        if (lead && lane == 0) { P.r.out_count[g] = 0; P.r.created[g] = 0; }
         continue;
       }
       W2T_WTICK(8);
 
       // ---- B. one pass over the tracker list: update or create, emit, age test, predict of the NEXT image;
-      // survivors are written back at their new list position ----------------------------------------
+      // survivors are written back at their new list position.  32 trackers per warp and trip. -----------
       int n_live = 0, emitted = 0;
 #pragma unroll 1
-      for (int t0 = 0; t0 < Ttot; t0 += 32) {
-        const int t = t0 + lane;
+      for (int tp = 0, par = 0; tp < Ttot; tp += 32 * team.nh, par ^= 1) {
+        const int t = tp + team.half * 32 + lane;
         bool ok = false, surv = false;
         double x[7], Pm[kBlockP], ob0 = 0., ob1 = 0., ob2 = 0., ob3 = 0., oconf = 0., nb[4];
         int tsu = 0, hs = 0, obg = 0, obk = 0;
@@ -661,10 +746,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
             else if (isinf(nb[0]) || isinf(nb[1]) || isinf(nb[2]) || isinf(nb[3])) atomicMax(P.status, W2T_ERR_NONFINITE);
           }
         }
-        __syncwarp();  // every lane has read its old position before any lane overwrites it
-        const unsigned bs = __ballot_sync(FULL, surv);
+        const unsigned bs = __ballot_sync(FULL, surv), be = __ballot_sync(FULL, ok);
+        int live0 = n_live, emit0 = emitted;  // where this warp's survivors / rows start
+        if (team.nh == 2) {
+          if (lane == 0) { S.cnt[par][team.half][0] = __popc(bs); S.cnt[par][team.half][1] = __popc(be); }
+          team.sync();  // also: every lane of the team has read its old position before any overwrites one
+          const int l0 = S.cnt[par][0][0], e0 = S.cnt[par][0][1], l1 = S.cnt[par][1][0], e1 = S.cnt[par][1][1];
+          if (team.half) { live0 += l0; emit0 += e0; }
+          n_live += l0 + l1;
+          emitted += e0 + e1;
+        } else {
+          __syncwarp();  // every lane has read its old position before any lane overwrites it
+          n_live += __popc(bs);
+          emitted += __popc(be);
+        }
         if (surv) {
-          const int pos = n_live + __popc(bs & lt);
+          const int pos = live0 + __popc(bs & lt);
 #pragma unroll
           for (int k = 0; k < 7; k++) st[k * Tcap + pos] = x[k];
 #pragma unroll
@@ -678,24 +775,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
             for (int k = 0; k < 4; k++) S.box[k][pos] = nb[k];
           }
         }
-        n_live += __popc(bs);
-        const unsigned be = __ballot_sync(FULL, ok);
         if (ok) {
-          const size_t o = (size_t)base + emitted + __popc(be & lt);
+          const size_t o = (size_t)base + emit0 + __popc(be & lt);
           double *ob = P.r.out_box + 4 * o;
           ob[0] = ob0; ob[1] = ob1; ob[2] = ob2; ob[3] = ob3;
           P.r.out_score[o] = oconf;
           P.r.out_birth[2 * o + 0] = obg;
           P.r.out_birth[2 * o + 1] = obk;
         }
-        emitted += __popc(be);
       }
-      if (lane == 0) { P.r.out_count[g] = emitted; P.r.created[g] = n_new; }
+      if (lead && lane == 0) { P.r.out_count[g] = emitted; P.r.created[g] = n_new; }
       T = n_live;
-      __syncwarp();
+      team.sync();
       W2T_WTICK(9);
     }
-    if (TIMERS && P.timers != nullptr && lane == 0) {
+    if (TIMERS && P.timers != nullptr && lead && lane == 0) {
       ph[0] = frame_count;
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
@@ -704,9 +798,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
     }
 #undef W2T_WTICK
     if (bail) {  // tracked again from its first image by the CTA kernel
-      if (lane == 0) Q.cls[q] = kClsBailed;
+      if (lead && lane == 0) Q.cls[q] = kClsBailed;
       continue;
     }
+    if (!lead) continue;
     if (err && lane == 0) atomicMax(P.status, err);
 
     // optional: filter state of every live tracker, already predicted one step past the last image
@@ -725,7 +820,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
         }
       }
     }
-    // completion tracking: everything this warp wrote is visible before its chunk's counter moves
+    // completion tracking: everything this team wrote is visible before its chunk's counter moves (the
+    // helper's writes reached the leader through the team barrier at the end of the last image)
     if (P.chunk_done != nullptr) {
       __syncwarp();
       if (lane == 0) {
