@@ -210,14 +210,17 @@ int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, int32_t *pair
 
 /* KalmanBoxTracker.__init__/predict/update (sort.py:88-178) on n independent
  * filters: x[n,7], P[n,49] row-major, dets[n,4] float32 x1,y1,x2,y2;
- * boxes[n,4] (may be NULL) receives convert_x_to_bbox(x) (sort.py:65-75). */
-int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, w2t_stream_t stream);
+ * boxes[n,4] (may be NULL) receives convert_x_to_bbox(x) (sort.py:65-75).
+ * promotion: W2T_PROMOTION_* — how convert_bbox_to_z (sort.py:50-62) treats the float32 row. */
+int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, int32_t promotion, w2t_stream_t stream);
 int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2t_stream_t stream);
-int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n, w2t_stream_t stream);
+int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n, int32_t promotion,
+                  w2t_stream_t stream);
 
-/* convert_bbox_to_z (sort.py:50-62) of n float32 rows x1,y1,x2,y2 -> z[n,4] = x, y, s, r, every
- * component float32 (NumPy 2 / NEP 50 semantics). */
-int w2t_bbox_to_z(const float *dets, float *z, int32_t n, w2t_stream_t stream);
+/* convert_bbox_to_z (sort.py:50-62) of n float32 rows x1,y1,x2,y2 -> z[n,4] = x, y, s, r as the float64 values
+ * the filter receives: under W2T_PROMOTION_NEP50 every component is a float32 value, under W2T_PROMOTION_LEGACY
+ * x, y and r are float64 computations and only s = w*h is a float32 product (w2t_types.h). */
+int w2t_bbox_to_z(const float *dets, double *z, int32_t n, int32_t promotion, w2t_stream_t stream);
 
 /* convert_x_to_bbox (sort.py:65-75) of n states: row i is x[i*ldx .. i*ldx+3] = x, y, s, r (ldx >= 4);
  * boxes[n,4] = x1, y1, x2, y2. */

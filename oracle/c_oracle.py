@@ -20,13 +20,14 @@ _p = C.c_void_p
 _EXPORTS = {
     "w2t_oracle_bbox_to_z": (None, [_p, _p]),
     "w2t_oracle_x_to_bbox": (None, [_p, _p]),
-    "w2t_oracle_kf_init": (None, [_p, _p, _p]),
+    "w2t_oracle_bbox_to_z_d": (None, [_p, C.c_int, _p]),
+    "w2t_oracle_kf_init": (None, [_p, _p, _p, C.c_int]),
     "w2t_oracle_kf_predict": (None, [_p, _p]),
-    "w2t_oracle_kf_update": (None, [_p, _p, _p]),
+    "w2t_oracle_kf_update": (None, [_p, _p, _p, C.c_int]),
     "w2t_oracle_inv4": (None, [_p, _p]),
     "w2t_oracle_iou_matrix": (None, [_p, C.c_int, _p, C.c_int, _p]),
     "w2t_oracle_linear_assignment": (C.c_int, [_p, C.c_int, C.c_int, _p]),
-    "w2t_oracle_associate": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_double, _p, _p]),
+    "w2t_oracle_associate": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_double, C.c_int, _p, _p]),
     "w2t_oracle_sort_track": (C.c_int, [C.POINTER(_abi.SortProblem), C.POINTER(_abi.SortResult)]),
     "w2t_oracle_softnms_groups": (C.c_int, [C.POINTER(_abi.NmsProblem), C.POINTER(_abi.NmsResult)]),
     "w2t_oracle_merge_detections": (C.c_int, [_p, _p, C.c_int, C.c_double, _p]),
@@ -63,10 +64,18 @@ def _c(a, dtype):
 
 # ---- building blocks ------------------------------------------------------
 
-def kf_init(det):
+def bbox_to_z(det, promotion=None):
+    """convert_bbox_to_z (sort.py:50-62) of one float32 row as the float64 values the filter receives."""
+    det = _c(det, np.float32)
+    z = np.zeros(4)
+    lib().w2t_oracle_bbox_to_z_d(_ptr(det), _abi.promotion_code(promotion), _ptr(z))
+    return z
+
+
+def kf_init(det, promotion=None):
     det = _c(det, np.float32)
     x, P = np.zeros(7), np.zeros(49)
-    lib().w2t_oracle_kf_init(_ptr(det), _ptr(x), _ptr(P))
+    lib().w2t_oracle_kf_init(_ptr(det), _ptr(x), _ptr(P), _abi.promotion_code(promotion))
     return x, P.reshape(7, 7)
 
 
@@ -76,10 +85,10 @@ def kf_predict(x, P):
     return x, P.reshape(7, 7)
 
 
-def kf_update(x, P, det):
+def kf_update(x, P, det, promotion=None):
     x, P = _c(x, np.float64).copy().reshape(7), _c(P, np.float64).copy().reshape(49)
     det = _c(det, np.float32)
-    lib().w2t_oracle_kf_update(_ptr(x), _ptr(P), _ptr(det))
+    lib().w2t_oracle_kf_update(_ptr(x), _ptr(P), _ptr(det), _abi.promotion_code(promotion))
     return x, P.reshape(7, 7)
 
 
@@ -170,7 +179,7 @@ def fusion_groups(group_offsets, rows, sub_counts, iou_thresh, min_score, n_clas
 
 # ---- packed stages ----------------------------------------------------------
 
-def sort_track(packed, iou_thresholds, max_age, min_hits, final_cap=0):
+def sort_track(packed, iou_thresholds, max_age, min_hits, final_cap=0, promotion=None):
     """``packed``: waymo_2d_tracking_b200.packing.PackedTracks (host arrays)."""
     S, NC = packed.n_streams, packed.n_classes
     n_img = int(packed.stream_img_offsets[-1])
@@ -191,6 +200,7 @@ def sort_track(packed, iou_thresholds, max_age, min_hits, final_cap=0):
     for i in range(NC):
         prob.iou_thr[i] = float(iou_thresholds[i])
     prob.max_age, prob.min_hits = int(max_age), int(min_hits)
+    prob.promotion = _abi.promotion_code(promotion)
     out = dict(
         out_box=np.zeros((N, 4)), out_score=np.zeros(N), out_birth=np.zeros((N, 2), np.int32),
         out_count=np.zeros(n_img * NC, np.int32), created=np.zeros(n_img * NC, np.int32),

@@ -33,6 +33,24 @@ void w2t_oracle_bbox_to_z(const float d[4], float z[4]) {
   z[3] = w / h;
 }
 
+/* sort.py:50-62 under either promotion regime (w2t_types.h, W2T_PROMOTION_*), widened to the float64 the
+ * filter works in.  Legacy (NumPy 1.x): w, h and s = w*h are float32 scalars, but float32-scalar (op)
+ * python-float is float64, so x = bbox[0] + w/2., y and r = w/float(h) are float64 computations. */
+void w2t_oracle_bbox_to_z_d(const float d[4], int promotion, double z[4]) {
+  float w = d[2] - d[0];
+  float h = d[3] - d[1];
+  if (promotion == W2T_PROMOTION_NEP50) {
+    z[0] = (double)(float)(d[0] + w / 2.0f);
+    z[1] = (double)(float)(d[1] + h / 2.0f);
+    z[3] = (double)(float)(w / h);
+  } else {
+    z[0] = (double)d[0] + (double)w / 2.0;
+    z[1] = (double)d[1] + (double)h / 2.0;
+    z[3] = (double)w / (double)h;
+  }
+  z[2] = (double)(float)(w * h);
+}
+
 void w2t_oracle_x_to_bbox(const double x[7], double b[4]) {
   double w = sqrt(x[2] * x[3]);
   double h = x[2] / w;
@@ -42,10 +60,10 @@ void w2t_oracle_x_to_bbox(const double x[7], double b[4]) {
   b[3] = x[1] + h / 2.;
 }
 
-void w2t_oracle_kf_init(const float det[4], double x[7], double P[49]) {
-  float z[4];
-  w2t_oracle_bbox_to_z(det, z);
-  for (int i = 0; i < 4; i++) x[i] = (double)z[i];
+void w2t_oracle_kf_init(const float det[4], double x[7], double P[49], int promotion) {
+  double z[4];
+  w2t_oracle_bbox_to_z_d(det, promotion, z);
+  for (int i = 0; i < 4; i++) x[i] = z[i];
   x[4] = x[5] = x[6] = 0.;
   memset(P, 0, 49 * sizeof(double));
   for (int i = 0; i < 4; i++) P[i * 7 + i] = 10.;
@@ -133,12 +151,12 @@ void w2t_oracle_inv4(const double S[16], double out[16]) {
 #undef B_
 }
 
-void w2t_oracle_kf_update(double x[7], double P[49], const float det[4]) {
-  float zf[4];
+void w2t_oracle_kf_update(double x[7], double P[49], const float det[4], int promotion) {
+  double zf[4];
   double y[4], S[16], SI[16], K[28], A[28], M[49], N[49];
-  w2t_oracle_bbox_to_z(det, zf);
+  w2t_oracle_bbox_to_z_d(det, promotion, zf);
   /* y = z - Hx */
-  for (int i = 0; i < 4; i++) y[i] = (double)zf[i] - x[i];
+  for (int i = 0; i < 4; i++) y[i] = zf[i] - x[i];
   /* S = H P H' + R  (H selects the leading 4x4 block) */
   for (int i = 0; i < 4; i++)
     for (int j = 0; j < 4; j++) S[i * 4 + j] = P[i * 7 + j] + ((i == j) ? R_DIAG[i] : 0.0);
@@ -384,7 +402,7 @@ int w2t_oracle_linear_assignment(const float *cost, int D, int T, int32_t *pairs
 /* association (sort.py:193-230)                                       */
 /* ------------------------------------------------------------------ */
 
-int w2t_oracle_associate(const float *dets, int D, const double *trks, int T, double iou_threshold,
+int w2t_oracle_associate(const float *dets, int D, const double *trks, int T, double iou_threshold, int promotion,
                          int32_t *matched_det_of_trk, int32_t *new_order) {
   int n_new = 0;
   for (int t = 0; t < T; t++) matched_det_of_trk[t] = -1;
@@ -404,10 +422,14 @@ int w2t_oracle_associate(const float *dets, int D, const double *trks, int T, do
   for (int i = 0; i < k; i++) assigned[pairs[2 * i]] = 1;
   for (int d = 0; d < D; d++)
     if (!assigned[d]) new_order[n_new++] = d;
-  const float thr = (float)iou_threshold; /* NEP 50: the python float adopts float32, sort.py:220 */
+  /* sort.py:220: NumPy 1.x compares the float32 entry with the python float in float64; under NEP 50 the
+   * python float adopts float32 */
+  const float thr = (float)iou_threshold;
   for (int i = 0; i < k; i++) {
     int d = pairs[2 * i], t = pairs[2 * i + 1];
-    if (M[(size_t)d * T + t] < thr) new_order[n_new++] = d;
+    const float o = M[(size_t)d * T + t];
+    const int rejected = (promotion == W2T_PROMOTION_NEP50) ? (o < thr) : ((double)o < iou_threshold);
+    if (rejected) new_order[n_new++] = d;
     else matched_det_of_trk[t] = d;
   }
   free(M); free(cost); free(pairs); free(assigned);
@@ -481,14 +503,14 @@ static int track_substream(const w2t_sort_problem_t *p, w2t_sort_result_t *r, in
       new_cap = D + 64;
       new_order = (int32_t *)realloc(new_order, sizeof(int32_t) * new_cap);
     }
-    int n_new = w2t_oracle_associate(dets, D, boxes, T, p->iou_thr[c], match, new_order);
+    int n_new = w2t_oracle_associate(dets, D, boxes, T, p->iou_thr[c], p->promotion, match, new_order);
     /* sort.py:270-273 */
     for (int t = 0; t < T; t++)
       if (match[t] >= 0) {
         trk_t *k = &trk[t];
         k->tsu = 0;
         k->hit_streak += 1;
-        w2t_oracle_kf_update(k->x, k->P, dets + 4 * match[t]);
+        w2t_oracle_kf_update(k->x, k->P, dets + 4 * match[t], p->promotion);
       }
     /* sort.py:276-278 */
     if (T + n_new > cap) {
@@ -497,7 +519,7 @@ static int track_substream(const w2t_sort_problem_t *p, w2t_sort_result_t *r, in
     }
     for (int i = 0; i < n_new; i++) {
       trk_t *k = &trk[T + i];
-      w2t_oracle_kf_init(dets + 4 * new_order[i], k->x, k->P);
+      w2t_oracle_kf_init(dets + 4 * new_order[i], k->x, k->P, p->promotion);
       k->tsu = 0;
       k->hit_streak = 0;
       k->birth_g = g;

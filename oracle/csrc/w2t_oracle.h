@@ -25,14 +25,16 @@ extern "C" {
 
 /* sort.py:50-62 on a float32 row (NEP 50): z = x, y, s, r all float32 */
 void w2t_oracle_bbox_to_z(const float det[4], float z[4]);
+/* the same under either NumPy promotion regime (W2T_PROMOTION_*), as the float64 values the filter receives */
+void w2t_oracle_bbox_to_z_d(const float det[4], int promotion, double z[4]);
 /* sort.py:65-75 */
 void w2t_oracle_x_to_bbox(const double x[7], double box[4]);
 /* sort.py:97-137: x0 = [z,0,0,0], P0 = diag(10,10,10,10,1e4,1e4,1e4) */
-void w2t_oracle_kf_init(const float det[4], double x[7], double P[49]);
+void w2t_oracle_kf_init(const float det[4], double x[7], double P[49], int promotion);
 /* sort.py:170-172 + filterpy predict */
 void w2t_oracle_kf_predict(double x[7], double P[49]);
 /* sort.py:164 + filterpy update (Joseph form, LAPACK-order 4x4 inverse) */
-void w2t_oracle_kf_update(double x[7], double P[49], const float det[4]);
+void w2t_oracle_kf_update(double x[7], double P[49], const float det[4], int promotion);
 /* numpy.linalg.inv of a 4x4 (row-major) in OpenBLAS dgesv operation order */
 void w2t_oracle_inv4(const double S[16], double out[16]);
 
@@ -45,7 +47,7 @@ int w2t_oracle_linear_assignment(const float *cost, int D, int T, int32_t *pairs
 
 /* sort.py:193-230.  matched_det_of_trk[T] = detection index or -1;
  * new_order[D] = detections that start a new tracker, in the reference's order; returns their count. */
-int w2t_oracle_associate(const float *dets, int D, const double *trks, int T, double iou_threshold,
+int w2t_oracle_associate(const float *dets, int D, const double *trks, int T, double iou_threshold, int promotion,
                          int32_t *matched_det_of_trk, int32_t *new_order);
 
 /* tracking/utils.py:25-60 for all streams (host pointers). */

@@ -144,14 +144,47 @@ def stable_torch_sort():
         torch.Tensor.sort = orig
 
 
-def ref_track_all(predictions, iou_thresholds, max_age, min_hits):
-    """tracking/track.py:42-47 executed with the reference's own modules."""
+def _legacy_convert_bbox_to_z(bbox):
+    """sort.py:50-62 statement by statement, with the one thing NumPy 2 no longer does spelled out: under NumPy
+    1.x (the reference's pinned environment) a float32 SCALAR combined with a python float gives float64, so
+    ``w / 2.``, ``bbox[0] + ...`` and ``w / float(h)`` are float64 operations; ``w``, ``h`` and ``s`` stay float32."""
+    import numpy as np
+    w = bbox[2] - bbox[0]
+    h = bbox[3] - bbox[1]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        x = np.float64(bbox[0]) + np.float64(w) / 2.
+        y = np.float64(bbox[1]) + np.float64(h) / 2.
+        s = w * h  # scale is just area
+        r = np.float64(w) / float(h)
+    return np.array([x, y, s, r]).reshape((4, 1))
+
+
+def ref_track_all(predictions, iou_thresholds, max_age, min_hits, promotion="nep50"):
+    """tracking/track.py:42-47 executed with the reference's own modules.
+
+    ``promotion="nep50"``: the files exactly as they are, under this container's NumPy 2.
+    ``promotion="legacy"``: EMULATION of the reference's pinned NumPy 1.x environment, which cannot be installed
+    here — the reference's files still run, with two substitutions that restore value-based casting where the hot
+    path depends on it: ``convert_bbox_to_z`` is replaced by ``_legacy_convert_bbox_to_z`` and the IoU thresholds
+    are passed as ``numpy.float64`` scalars, so that ``iou_matrix[..] < iou_threshold`` (sort.py:220) compares in
+    float64 as it did under NumPy 1.x."""
+    import numpy as np
     ref_utils, ref_sort, _ = load_tracking()
     ref_sort.KalmanBoxTracker.count = 0
+    legacy = str(promotion).lower() == "legacy"
+    if not legacy and str(promotion).lower() != "nep50":
+        raise ValueError("promotion must be 'legacy' or 'nep50'")
+    saved = ref_sort.convert_bbox_to_z
+    if legacy:
+        ref_sort.convert_bbox_to_z = _legacy_convert_bbox_to_z
+        iou_thresholds = [np.float64(t) for t in iou_thresholds]
     out = []
-    for segment_id in predictions.keys():
-        for camera_id in predictions[segment_id]:
-            out += ref_utils.track_sort(predictions, segment_id, camera_id, iou_thresholds, max_age, min_hits)
+    try:
+        for segment_id in predictions.keys():
+            for camera_id in predictions[segment_id]:
+                out += ref_utils.track_sort(predictions, segment_id, camera_id, iou_thresholds, max_age, min_hits)
+    finally:
+        ref_sort.convert_bbox_to_z = saved
     return out
 
 

@@ -4,24 +4,50 @@ TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Follows, function by
 function, ``/root/reference/tracking/sort/sort.py:33-296``,
 ``tracking/sort/tracker_sort.py:10-51`` and ``tracking/utils.py:11-96`` with the
 third-party solver / filter restated in ``munkres.py`` / ``kalman.py``.
-Every dtype decision is an explicit cast (NEP 50 semantics) so
-the port does not depend on the installed NumPy's promotion rules.  Checked
+Every dtype decision is an explicit cast so the port does not depend on the
+installed NumPy's promotion rules; ``PROMOTION`` / ``promotion()`` select which
+regime the casts restate: "legacy" (NumPy 1.x value-based casting, the reference's
+pinned environment, ``/root/reference/environment.yml:7``) or "nep50" (NumPy 2,
+what the reference's files do when executed in this container).  Checked
 against the reference's own files executed through ``ref_shim`` by
 ``tests/golden/make_golden.py`` and ``tests/test_oracle.py``.
 
 The per-object Python / small-NumPy-array structure of the reference is kept
 on purpose: this port is also the timed CPU baseline (``bench.py``).
 """
+import contextlib
 import json
 import math
 
 import numpy as np
+
+from waymo_2d_tracking_b200 import _abi
 
 from .kalman import KalmanFilter
 from .munkres import linear_assignment
 
 f32 = np.float32
 f64 = np.float64
+
+PROMOTION = _abi.DEFAULT_PROMOTION     # "legacy" | "nep50"
+
+
+@contextlib.contextmanager
+def promotion(name):
+    """Run the port under the given promotion regime (None = leave the current one)."""
+    global PROMOTION
+    prev = PROMOTION
+    if name is not None:
+        _abi.promotion_code(name)       # validates
+        PROMOTION = name
+    try:
+        yield
+    finally:
+        PROMOTION = prev
+
+
+def _legacy():
+    return _abi.promotion_code(PROMOTION) == _abi.W2T_PROMOTION_LEGACY
 
 # tracking/utils.py:11-17
 IMAGE_SIZES = {
@@ -74,10 +100,19 @@ def iou_matrix(dets, trks):
 
 
 def bbox_to_z(bbox):
-    """sort.py:50-62 on a float32 row under NEP 50: every component is float32."""
+    """sort.py:50-62 on a float32 row.  NEP 50: every component is float32.  Legacy (NumPy 1.x): ``w``, ``h``
+    and ``s = w * h`` are float32 scalars, but float32-scalar (op) python-float is float64, so
+    ``x = bbox[0] + w / 2.``, ``y`` and ``r = w / float(h)`` are float64 computations."""
     b0, b1, b2, b3 = f32(bbox[0]), f32(bbox[1]), f32(bbox[2]), f32(bbox[3])
     w = f32(b2 - b0)
     h = f32(b3 - b1)
+    if _legacy():
+        with np.errstate(divide='ignore', invalid='ignore'):
+            x = f64(b0) + f64(w) / f64(2.)
+            y = f64(b1) + f64(h) / f64(2.)
+            s = f64(f32(w * h))
+            r = f64(w) / f64(h)
+        return np.array([x, y, s, r], dtype=f64).reshape((4, 1))
     x = f32(b0 + f32(w / f32(2.)))
     y = f32(b1 + f32(h / f32(2.)))
     s = f32(w * h)
@@ -158,10 +193,11 @@ def associate(dets, trks, iou_threshold=0.3, return_iou=False):
     used_t = set(pairs[:, 1].tolist())
     free_d = [d for d in range(len(dets)) if d not in used_d]
     free_t = [t for t in range(len(trks)) if t not in used_t]
-    thr = f32(iou_threshold)                      # NEP 50: python float adopts float32
+    # sort.py:220: NEP 50 - the python float adopts float32; legacy - float32 scalar vs python float compares in float64
+    thr = f64(iou_threshold) if _legacy() else f32(iou_threshold)
     keep = []
     for d, t in pairs:
-        if M[d, t] < thr:
+        if (f64(M[d, t]) if _legacy() else M[d, t]) < thr:
             free_d.append(int(d))
             free_t.append(int(t))
         else:
@@ -303,12 +339,13 @@ def read_data_file(file_name, score_threshold):
         return group_entries(json.load(fp), score_threshold)
 
 
-def track_all(predictions, iou_thresholds, max_age, min_hits, reset_ids=True):
+def track_all(predictions, iou_thresholds, max_age, min_hits, reset_ids=True, promotion=None):
     """tracking/track.py:42-47 — the reference's own timed region."""
     if reset_ids:
         BoxTracker.count = 0
     out = []
-    for segment_id in predictions.keys():
-        for camera_id in predictions[segment_id]:
-            out += track_sort(predictions, segment_id, camera_id, iou_thresholds, max_age, min_hits)
+    with globals()["promotion"](promotion):
+        for segment_id in predictions.keys():
+            for camera_id in predictions[segment_id]:
+                out += track_sort(predictions, segment_id, camera_id, iou_thresholds, max_age, min_hits)
     return out

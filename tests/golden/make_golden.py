@@ -118,7 +118,10 @@ def scene_inputs(scene):
     return d
 
 
-def run_reference_tracking(dets, max_age, min_hits):
+def run_reference_tracking(dets, max_age, min_hits, promotion="nep50"):
+    """``promotion="nep50"``: the reference's files as they are under this container's NumPy 2 (keys ``out_*``);
+    ``"legacy"``: the shim's emulation of the reference's pinned NumPy 1.x environment (keys ``leg_*``), see
+    ``oracle.ref_shim.ref_track_all``."""
     ref_utils, ref_sort, _ = ref_shim.load_tracking()
     with tempfile.NamedTemporaryFile("wt", suffix=".json", delete=False) as fp:
         json.dump(dets, fp)
@@ -127,7 +130,78 @@ def run_reference_tracking(dets, max_age, min_hits):
         predictions = ref_utils.read_data_file(path, SCORE_THR)
     finally:
         os.unlink(path)
-    return ref_shim.ref_track_all(predictions, IOU_THR, max_age, min_hits)
+    return ref_shim.ref_track_all(predictions, IOU_THR, max_age, min_hits, promotion=promotion)
+
+
+# Full-size cases (BASELINE.json configs C1 / C2: one whole segment).  Inputs are regenerated from the seeded
+# synthetic scene; of the outputs the fixture keeps ids / counts for every row and boxes / scores for the rows of
+# every SAMPLE-th image, which keeps the files small.
+BIG_SAMPLE = 8
+BIG_TRACK = {"big_c1": dict(preset="c1", seed=4101, max_age=2, min_hits=0)}
+BIG_ENSEMBLE = {"big_c2": dict(preset="c2", seed=4102, min_score=0.01, iou_thresh=0.5, cut=0.9)}
+
+
+def big_track_arrays(rows, image_ids, prefix):
+    a = golden_io.tracks_to_arrays(rows, image_ids)
+    keep = (a["img"] % BIG_SAMPLE) == 0
+    return {prefix + "img": a["img"], prefix + "cat": a["cat"].astype(np.int8), prefix + "oid": a["oid"].astype(np.int32),
+            prefix + "bbox_s": a["bbox"][keep], prefix + "score_s": a["score"][keep]}
+
+
+def main_big():
+    for name, case in BIG_TRACK.items():
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path):
+            continue
+        scene = synth.make_scene(synth.preset(case["preset"], n_segments=1, seed=case["seed"]))
+        dets = synth.to_json_list(scene, scene.submissions[0])
+        out = {"preset": np.asarray(case["preset"]), "seed": np.int64(case["seed"]), "sample": np.int64(BIG_SAMPLE),
+               "max_age": np.int64(case["max_age"]), "min_hits": np.int64(case["min_hits"])}
+        for promotion, prefix in (("nep50", "out_"), ("legacy", "leg_")):
+            rows = run_reference_tracking(dets, case["max_age"], case["min_hits"], promotion)
+            out.update(big_track_arrays(rows, scene.image_ids(), prefix))
+            print(name, promotion, "dets", len(dets), "rows", len(rows))
+        np.savez_compressed(path, **out)
+    for name, case in BIG_ENSEMBLE.items():
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path):
+            continue
+        scene = synth.make_scene(synth.preset(case["preset"], n_segments=1, seed=case["seed"]))
+        subs = [synth.to_json_list(scene, s) for s in scene.submissions]
+        rows = ref_shim.ref_ensemble_all(subs, None, case["min_score"], case["iou_thresh"], case["cut"])
+        a = golden_io.dets_to_arrays(rows, scene.image_ids())
+        keep = (a["img"] % BIG_SAMPLE) == 0
+        out = {"preset": np.asarray(case["preset"]), "seed": np.int64(case["seed"]), "sample": np.int64(BIG_SAMPLE),
+               "min_score": np.float64(case["min_score"]), "iou_thresh": np.float64(case["iou_thresh"]),
+               "cut": np.float64(case["cut"]), "out_img": a["img"], "out_cat": a["cat"].astype(np.int8),
+               "out_bbox_s": a["bbox"][keep].astype(np.int16), "out_score_s": a["score"][keep]}
+        assert np.array_equal(out["out_bbox_s"], a["bbox"][keep])
+        np.savez_compressed(path, **out)
+        print(name, "in", sum(len(s) for s in subs), "out", len(rows))
+
+
+def add_legacy():
+    """Adds the ``leg_*`` outputs (legacy promotion) to the tracking fixtures that do not have them yet."""
+    for name, case in TRACK_CASES.items():
+        path = os.path.join(HERE, name + ".npz")
+        g = golden_io.load(name)
+        if "leg_oid" in g:
+            continue
+        scene = synth.make_scene(synth.SynthConfig(**case["cfg"]))
+        dets = synth.to_json_list(scene, scene.submissions[0])
+        rows = run_reference_tracking(dets, case["max_age"], case["min_hits"], "legacy")
+        g.update({"leg_" + k: v for k, v in golden_io.tracks_to_arrays(rows, scene.image_ids()).items()})
+        np.savez_compressed(path, **g)
+        print(name, "legacy rows", len(rows), "ids equal to nep50:", np.array_equal(g["leg_oid"], g["out_oid"]))
+    g = golden_io.load("pipeline_small")
+    if "leg_oid" not in g:
+        scene = synth.make_scene(synth.SynthConfig(**json.loads(str(g["cfg"]))))
+        subs = [synth.to_json_list(scene, s) for s in scene.submissions]
+        ens = ref_shim.ref_ensemble_all(subs, None, 0.01, 0.5, 0.9)
+        rows = run_reference_tracking(ens, 2, 0, "legacy")
+        g.update({"leg_" + k: v for k, v in golden_io.tracks_to_arrays(rows, scene.image_ids()).items()})
+        np.savez_compressed(os.path.join(HERE, "pipeline_small.npz"), **g)
+        print("pipeline_small legacy rows", len(rows))
 
 
 def main_methods():
@@ -159,8 +233,11 @@ def main_methods():
 def main():
     assert ref_shim.available(), "reference not mounted at %s" % ref_shim.REF_ROOT
     if "--new-only" in sys.argv:
-        return main_methods()
+        main_methods()
+        add_legacy()
+        return main_big()
     main_methods()
+    main_big()
     for name, case in TRACK_CASES.items():
         scene = synth.make_scene(synth.SynthConfig(**case["cfg"]))
         dets = synth.to_json_list(scene, scene.submissions[0])
@@ -201,6 +278,7 @@ def main():
     out["cfg"] = np.asarray(json.dumps(cfg))
     np.savez_compressed(os.path.join(HERE, "pipeline_small.npz"), **out)
     print("pipeline_small ens", len(ens), "rows", len(rows))
+    add_legacy()
 
 
 if __name__ == "__main__":

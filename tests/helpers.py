@@ -8,6 +8,17 @@ from waymo_2d_tracking_b200 import packing, synth
 
 SCORE_THR = [0.95, 0.6, 1.0, 0.9]
 IOU_THR = [0.01, 0.01, 1.0, 0.0]
+PROMOTIONS = ("legacy", "nep50")
+
+
+def golden_tracks(g, promotion=None):
+    """Tracker outputs of a fixture: ``out_*`` = the reference's files under this container's NumPy 2 (NEP 50),
+    ``leg_*`` = the shim's emulation of the reference's pinned NumPy 1.x environment (tests/golden/make_golden.py).
+    ``promotion=None``: the regime the product runs by default."""
+    from waymo_2d_tracking_b200 import _abi
+    legacy = _abi.promotion_code(promotion) == _abi.W2T_PROMOTION_LEGACY
+    prefix = "leg_" if legacy else "out_"
+    return {k[4:]: v for k, v in g.items() if k.startswith(prefix)}
 
 
 def golden_scene(g):
@@ -67,3 +78,30 @@ def ensemble_rows_as_arrays(group_offsets, res, n_img, n_classes=4, image_order=
 
 def sorted_image_order(image_ids):
     return sorted(range(len(image_ids)), key=lambda i: image_ids[i])
+
+
+def assert_big_tracks_equal(got, g, promotion, box_exact=True):
+    """Full-size tracking fixture (tests/golden/make_golden.py, BIG_TRACK): ids / images / categories of every
+    row, boxes and confidences of the rows of every ``sample``-th image."""
+    from waymo_2d_tracking_b200 import _abi
+    pre = "leg_" if _abi.promotion_code(promotion) == _abi.W2T_PROMOTION_LEGACY else "out_"
+    assert len(got["img"]) == len(g[pre + "img"])
+    np.testing.assert_array_equal(got["img"], g[pre + "img"])
+    np.testing.assert_array_equal(got["cat"], g[pre + "cat"])
+    np.testing.assert_array_equal(got["oid"], g[pre + "oid"])          # track ids: bit-exact
+    keep = (got["img"] % int(g["sample"])) == 0
+    if box_exact:
+        np.testing.assert_array_equal(got["bbox"][keep], g[pre + "bbox_s"])
+    else:
+        np.testing.assert_allclose(got["bbox"][keep], g[pre + "bbox_s"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got["score"][keep], g[pre + "score_s"], rtol=1e-9, atol=0)
+
+
+def assert_big_ensemble_equal(got, g):
+    """Full-size ensemble fixture (BIG_ENSEMBLE): images / categories of every row, boxes and scores of the rows
+    of every ``sample``-th image; all bit-exact."""
+    np.testing.assert_array_equal(got["img"], g["out_img"])
+    np.testing.assert_array_equal(got["cat"], g["out_cat"])
+    keep = (got["img"] % int(g["sample"])) == 0
+    np.testing.assert_array_equal(got["bbox"][keep], g["out_bbox_s"])
+    np.testing.assert_array_equal(got["score"][keep], g["out_score_s"])

@@ -170,7 +170,7 @@ def test_track_cli_matches_reference_golden(name, tmp_path, capsys):
     assert "duration:" in printed and scene.segments[0] in printed
     rows = json.loads(out.read_text())
     got = golden_io.tracks_to_arrays(rows, scene.image_ids())
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g)      # the product's default promotion regime
     helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)
     assert isinstance(rows[0]['object_id'], str)
 
@@ -185,7 +185,7 @@ def test_track_sort_per_stream_continues_the_global_id_counter():
         for cam in pred[seg]:
             rows += trk_utils.track_sort(pred, seg, cam, helpers.IOU_THR, 2, 0)
     got = golden_io.tracks_to_arrays(rows, scene.image_ids())
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g)      # the product's default promotion regime
     helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)
     assert sort_mod.KalmanBoxTracker.count == want["oid"].max()
     # --segment-id filter of the CLI == tracking that segment alone from a fresh counter
@@ -296,7 +296,7 @@ def test_sort_building_blocks_python_surface():
     assert sort_mod.iou(d, t) == float(np.float32(sort_port.iou(d, t)))
     np.testing.assert_array_equal(sort_mod.iou_batch(d[None], t[None]), sort_port.iou_matrix(d[None], t[None]))
     z = sort_mod.convert_bbox_to_z(d)
-    assert z.shape == (4, 1) and z.dtype == np.float32
+    assert z.shape == (4, 1) and z.dtype == (np.float64 if runtime.promotion_code() == 0 else np.float32)
     np.testing.assert_array_equal(z, sort_port.bbox_to_z(d).reshape(4, 1))
     x = np.array([30., 50., 2400., 0.66, 0, 0, 0])
     np.testing.assert_array_equal(sort_mod.convert_x_to_bbox(x), sort_port.x_to_bbox(x).reshape(1, 4))

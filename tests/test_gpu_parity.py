@@ -25,15 +25,19 @@ def rand_boxes(rng, n, lo=0, hi=800, smin=2, smax=250):
 
 # ---- building blocks ------------------------------------------------------------------------
 
-def test_kalman_bit_exact_vs_c_oracle():
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
+def test_kalman_bit_exact_vs_c_oracle(promotion):
     rng = np.random.default_rng(0)
     n = 257
     dets = rand_boxes(rng, n).astype(np.float32)
-    x, P = runtime.kf_init(dets)
+    x, P = runtime.kf_init(dets, promotion=promotion)
     ox = np.zeros_like(x)
     oP = np.zeros_like(P)
     for i in range(n):
-        ox[i], oP[i] = c_oracle.kf_init(dets[i])
+        ox[i], oP[i] = c_oracle.kf_init(dets[i], promotion=promotion)
+    z = runtime.bbox_to_z(dets, promotion=promotion)
+    assert z.dtype == (np.float64 if promotion == "legacy" else np.float32)
+    np.testing.assert_array_equal(z, np.stack([c_oracle.bbox_to_z(d, promotion=promotion) for d in dets]))
     np.testing.assert_array_equal(x, ox)
     np.testing.assert_array_equal(P, oP)
     for step in range(12):
@@ -45,9 +49,9 @@ def test_kalman_bit_exact_vs_c_oracle():
         np.testing.assert_array_equal(boxes, np.stack([c_oracle.x_to_bbox(v) for v in ox]))
         dets = (dets + rng.normal(0, 3, dets.shape)).astype(np.float32)
         dets[:, 2:] = np.maximum(dets[:, 2:], dets[:, :2] + 1)
-        x, P, _ = runtime.kf_update(x, P, dets)
+        x, P, _ = runtime.kf_update(x, P, dets, promotion=promotion)
         for i in range(n):
-            ox[i], oP[i] = c_oracle.kf_update(ox[i], oP[i], dets[i])
+            ox[i], oP[i] = c_oracle.kf_update(ox[i], oP[i], dets[i], promotion=promotion)
         np.testing.assert_array_equal(x, ox)                     # bit-exact, far inside the 1e-9 bar
         np.testing.assert_array_equal(P, oP)
 
@@ -102,9 +106,9 @@ def test_linear_assignment_large_crowded():
 
 # ---- SORT stage -------------------------------------------------------------------------------
 
-def compare_sort(packed, iou_thr, max_age, min_hits, final_cap=0):
-    got = runtime.sort_track(packed, iou_thr, max_age, min_hits, final_cap=final_cap)
-    want = c_oracle.sort_track(packed, iou_thr, max_age, min_hits, final_cap=final_cap)
+def compare_sort(packed, iou_thr, max_age, min_hits, final_cap=0, promotion=None):
+    got = runtime.sort_track(packed, iou_thr, max_age, min_hits, final_cap=final_cap, promotion=promotion)
+    want = c_oracle.sort_track(packed, iou_thr, max_age, min_hits, final_cap=final_cap, promotion=promotion)
     assert want["status"] == 0
     np.testing.assert_array_equal(got["out_count"], want["out_count"])
     np.testing.assert_array_equal(got["created"], want["created"])
@@ -137,15 +141,41 @@ def compare_sort(packed, iou_thr, max_age, min_hits, final_cap=0):
     return got
 
 
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
 @pytest.mark.parametrize("name", TRACK_CASES)
-def test_sort_matches_reference_golden(name):
+def test_sort_matches_reference_golden(name, promotion):
     g = golden_io.load(name)
     scene = helpers.golden_scene(g)
     packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
-    res = compare_sort(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), final_cap=64)
+    res = compare_sort(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), final_cap=64, promotion=promotion)
     got = helpers.track_rows_as_arrays(packed, res, scene.image_ids(), ids=res["ids"])
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g, promotion)
     helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)
+
+
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
+def test_sort_full_size_c1_matches_reference_golden(promotion):
+    """BASELINE.json config C1 at full size (one segment: 5 cameras x 200 frames, ~110 detections per frame in)
+    against the reference's own output (tests/golden/big_c1.npz) and, row for row, against the C oracle."""
+    g = golden_io.load("big_c1")
+    scene = synth.make_scene(synth.preset(str(g["preset"]), n_segments=1, seed=int(g["seed"])))
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    res = compare_sort(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), promotion=promotion)
+    got = helpers.track_rows_as_arrays(packed, res, scene.image_ids(), ids=res["ids"])
+    helpers.assert_big_tracks_equal(got, g, promotion)
+
+
+def test_ensemble_full_size_c2_matches_reference_golden():
+    """BASELINE.json config C2 at full size (3 submissions of one segment, 274 k boxes in) against the reference's own
+    output (tests/golden/big_c2.npz)."""
+    g = golden_io.load("big_c2")
+    scene = synth.make_scene(synth.preset(str(g["preset"]), n_segments=1, seed=int(g["seed"])))
+    groups = synth.groups_from_scene(scene, None, float(g["min_score"]))
+    res = runtime.softnms_groups(groups.group_offsets, groups.rows, float(g["iou_thresh"]), float(g["cut"]),
+                                 float(g["min_score"]), 4, helpers.SCORE_THR, max_group=groups.max_group)
+    got = helpers.ensemble_rows_as_arrays(groups.group_offsets, res, scene.n_img,
+                                          image_order=helpers.sorted_image_order(scene.image_ids()))
+    helpers.assert_big_ensemble_equal(got, g)
 
 
 @pytest.mark.parametrize("seed,max_age,min_hits", [(101, 2, 0), (102, 1, 3), (103, 0, 0), (104, 5, 1)])
@@ -173,7 +203,8 @@ def test_sort_random_configurations_vs_oracle(seed):
     score_thr = [float(rng.choice([0.0, 0.3, 0.6, 0.9, 0.95])) for _ in range(4)]
     iou_thr = [float(rng.choice([0.0, 0.01, 0.3, 0.5, 1.0])) for _ in range(4)]
     packed = synth.tracks_from_submission(scene, scene.submissions[0], score_thr)
-    compare_sort(packed, iou_thr, int(rng.integers(0, 5)), int(rng.integers(0, 4)), final_cap=128)
+    compare_sort(packed, iou_thr, int(rng.integers(0, 5)), int(rng.integers(0, 4)), final_cap=128,
+                 promotion=helpers.PROMOTIONS[seed % 2])
 
 
 def test_sort_ragged_and_empty_streams():
@@ -315,14 +346,15 @@ def test_softnms_rejects_unsupported_scores_loudly():
 
 # ---- ensemble -> SORT on the device ----------------------------------------------------------------
 
-def test_pipeline_matches_reference_golden_end_to_end():
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
+def test_pipeline_matches_reference_golden_end_to_end(promotion):
     import test_oracle as T
     g = golden_io.load("pipeline_small")
     scene = helpers.golden_scene(g)
     groups = synth.groups_from_scene(scene, None, 0.01)
     res = runtime.ensemble_and_track(groups.group_offsets, groups.rows, scene.stream_img_offsets, scene.cam_wh(), 4,
                                      0.5, 0.9, 0.01, helpers.SCORE_THR, helpers.IOU_THR, 2, 0,
-                                     max_group=groups.max_group)
+                                     max_group=groups.max_group, promotion=promotion)
     ens = helpers.ensemble_rows_as_arrays(groups.group_offsets, res, scene.n_img,
                                           image_order=helpers.sorted_image_order(scene.image_ids()))
     for k in ("img", "cat", "bbox", "score"):
@@ -334,7 +366,7 @@ def test_pipeline_matches_reference_golden_end_to_end():
         class_rank=None, n_rows=len(groups.rows))
     order = T.stream_order_of_sorted_images(scene)
     got = T.rows_in_stream_order(packed, res, scene, order)
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g, promotion)
     helpers.assert_tracks_equal(got, want, score_rtol=1e-9, box_exact=True)
 
 

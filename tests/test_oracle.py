@@ -12,29 +12,55 @@ TRACK_CASES = ["track_c1_small", "track_minhits", "track_cyclist_ties", "track_d
 ENS_CASES = ["ensemble_c2_small", "ensemble_weighted", "ensemble_ties"]
 
 
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
 @pytest.mark.parametrize("name", TRACK_CASES)
-def test_c_oracle_tracking_matches_reference_golden(name):
+def test_c_oracle_tracking_matches_reference_golden(name, promotion):
     g = golden_io.load(name)
     scene = helpers.golden_scene(g)
     packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
-    res = c_oracle.sort_track(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]))
+    res = c_oracle.sort_track(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), promotion=promotion)
     assert res["status"] == 0
     got = helpers.track_rows_as_arrays(packed, res, scene.image_ids())
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g, promotion)
     # boxes are bit-exact: the C oracle reproduces the BLAS/LAPACK operation order
     helpers.assert_tracks_equal(got, want, score_rtol=1e-12, box_exact=True)
 
 
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
 @pytest.mark.parametrize("name", TRACK_CASES[:2])
-def test_numpy_port_tracking_matches_reference_golden(name):
+def test_numpy_port_tracking_matches_reference_golden(name, promotion):
     g = golden_io.load(name)
     scene = helpers.golden_scene(g)
     dets = synth.to_json_list(scene, scene.submissions[0])
     pred = sort_port.group_entries(dets, helpers.SCORE_THR)
-    rows = sort_port.track_all(pred, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]))
+    rows = sort_port.track_all(pred, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), promotion=promotion)
     got = golden_io.tracks_to_arrays(rows, scene.image_ids())
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g, promotion)
     helpers.assert_tracks_equal(got, want, score_rtol=0, box_exact=True)
+
+
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
+def test_c_oracle_full_size_c1_matches_reference_golden(promotion):
+    """Config C1 at full size (5 cameras x 200 frames): C oracle vs the reference's own output."""
+    g = golden_io.load("big_c1")
+    scene = synth.make_scene(synth.preset(str(g["preset"]), n_segments=1, seed=int(g["seed"])))
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    res = c_oracle.sort_track(packed, helpers.IOU_THR, int(g["max_age"]), int(g["min_hits"]), promotion=promotion)
+    assert res["status"] == 0
+    got = helpers.track_rows_as_arrays(packed, res, scene.image_ids())
+    helpers.assert_big_tracks_equal(got, g, promotion)
+
+
+def test_c_oracle_full_size_c2_matches_reference_golden():
+    """Config C2 at full size (3 submissions, one segment): C oracle vs the reference's own output."""
+    g = golden_io.load("big_c2")
+    scene = synth.make_scene(synth.preset(str(g["preset"]), n_segments=1, seed=int(g["seed"])))
+    groups = synth.groups_from_scene(scene, None, float(g["min_score"]))
+    res = c_oracle.softnms_groups(groups.group_offsets, groups.rows, float(g["iou_thresh"]), float(g["cut"]),
+                                  float(g["min_score"]), 4, helpers.SCORE_THR)
+    got = helpers.ensemble_rows_as_arrays(groups.group_offsets, res, scene.n_img,
+                                          image_order=helpers.sorted_image_order(scene.image_ids()))
+    helpers.assert_big_ensemble_equal(got, g)
 
 
 def test_dict_packer_equals_vectorised_packer():
@@ -76,7 +102,8 @@ def test_numpy_port_ensemble_matches_reference_golden(name):
         np.testing.assert_array_equal(got[k], g["out_" + k])
 
 
-def test_c_oracle_pipeline_matches_reference_golden():
+@pytest.mark.parametrize("promotion", helpers.PROMOTIONS)
+def test_c_oracle_pipeline_matches_reference_golden(promotion):
     """ensemble -> (int / 5-decimal rounding) -> tracker, against the reference run end to end."""
     g = golden_io.load("pipeline_small")
     scene = helpers.golden_scene(g)
@@ -91,11 +118,11 @@ def test_c_oracle_pipeline_matches_reference_golden():
         stream_img_offsets=scene.stream_img_offsets, det_start=groups.group_offsets[:-1].copy(),
         det_count=nms["trk_count"], det_box=nms["trk_box"], cam_wh=scene.cam_wh(), img_exists=nms["img_exists"],
         class_rank=None, n_rows=len(groups.rows))
-    res = c_oracle.sort_track(packed, helpers.IOU_THR, 2, 0)
+    res = c_oracle.sort_track(packed, helpers.IOU_THR, 2, 0, promotion=promotion)
     # the reference tracked streams in sorted-image_id order of the ensemble JSON
     order = stream_order_of_sorted_images(scene)
     got = rows_in_stream_order(packed, res, scene, order)
-    want = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    want = helpers.golden_tracks(g, promotion)
     helpers.assert_tracks_equal(got, want, score_rtol=1e-12, box_exact=True)
 
 
@@ -252,12 +279,13 @@ def test_reference_itself_agrees_with_ports_on_a_fresh_seed():
     ens_port = ensemble_port.ensemble_all(subs, None, 0.01, 0.5, 0.9)
     assert ens_ref == ens_port
     pred = sort_port.group_entries(ens_ref, helpers.SCORE_THR)
-    a = ref_shim.ref_track_all(pred, helpers.IOU_THR, 2, 0)
-    b = sort_port.track_all(pred, helpers.IOU_THR, 2, 0)
-    assert len(a) == len(b)
-    for x, y in zip(a, b):
-        assert x["image_id"] == y["image_id"] and x["object_id"] == y["object_id"]
-        assert [float(v) for v in x["bbox"]] == [float(v) for v in y["bbox"]] and float(x["score"]) == float(y["score"])
+    for promotion in helpers.PROMOTIONS:
+        a = ref_shim.ref_track_all(pred, helpers.IOU_THR, 2, 0, promotion=promotion)
+        b = sort_port.track_all(pred, helpers.IOU_THR, 2, 0, promotion=promotion)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert x["image_id"] == y["image_id"] and x["object_id"] == y["object_id"]
+            assert [float(v) for v in x["bbox"]] == [float(v) for v in y["bbox"]] and float(x["score"]) == float(y["score"])
 
 
 # ---- the CLI's other two methods and the general nms() signature -------------------------------
@@ -360,11 +388,13 @@ def _random_tracking_case(seed, n_frames=14):
 @pytest.mark.parametrize("seed", range(300, 310))
 def test_c_oracle_equals_numpy_port_on_random_configurations(seed):
     scene, score_thr, iou_thr, max_age, min_hits = _random_tracking_case(seed)
+    promotion = helpers.PROMOTIONS[seed % 2]
     packed = synth.tracks_from_submission(scene, scene.submissions[0], score_thr)
-    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits)
+    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits, promotion=promotion)
     got = helpers.track_rows_as_arrays(packed, res, scene.image_ids())
     pred = sort_port.group_entries(synth.to_json_list(scene, scene.submissions[0]), score_thr)
-    want = golden_io.tracks_to_arrays(sort_port.track_all(pred, iou_thr, max_age, min_hits), scene.image_ids())
+    want = golden_io.tracks_to_arrays(sort_port.track_all(pred, iou_thr, max_age, min_hits, promotion=promotion),
+                                      scene.image_ids())
     helpers.assert_tracks_equal(got, want, score_rtol=1e-12, box_exact=False)
 
 
@@ -372,9 +402,11 @@ def test_c_oracle_equals_numpy_port_on_random_configurations(seed):
 @pytest.mark.parametrize("seed", [400, 401, 402])
 def test_reference_itself_equals_c_oracle_on_random_configurations(seed):
     scene, score_thr, iou_thr, max_age, min_hits = _random_tracking_case(seed, n_frames=10)
+    promotion = helpers.PROMOTIONS[seed % 2]
     packed = synth.tracks_from_submission(scene, scene.submissions[0], score_thr)
-    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits)
+    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits, promotion=promotion)
     got = helpers.track_rows_as_arrays(packed, res, scene.image_ids())
     pred = sort_port.group_entries(synth.to_json_list(scene, scene.submissions[0]), score_thr)
-    want = golden_io.tracks_to_arrays(ref_shim.ref_track_all(pred, iou_thr, max_age, min_hits), scene.image_ids())
+    want = golden_io.tracks_to_arrays(ref_shim.ref_track_all(pred, iou_thr, max_age, min_hits, promotion=promotion),
+                                      scene.image_ids())
     helpers.assert_tracks_equal(got, want, score_rtol=1e-12, box_exact=False)

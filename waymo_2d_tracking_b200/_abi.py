@@ -4,6 +4,7 @@ Only declarations live here: the structs, the status codes and the argument
 types of every exported symbol.  ``_lib.py`` binds them to ``libw2t.so``.
 """
 import ctypes as C
+import os
 
 W2T_MAX_CLASSES = 8
 
@@ -105,6 +106,20 @@ class NmsProblem(C.Structure):
 W2T_WIDE_DETS = 320          # include/w2t_types.h
 W2T_NARROW_DETS = 128
 W2T_PROMOTION_LEGACY, W2T_PROMOTION_NEP50 = 0, 1
+# NumPy promotion regime the tracker reproduces unless a call says otherwise: "legacy" = NumPy 1.x value-based
+# casting, the reference's pinned environment (python 3.7, /root/reference/environment.yml:7 — scikit-learn 0.22.2
+# and filterpy do not even import under NumPy 2); "nep50" = NumPy 2.  Environment variable W2T_PROMOTION overrides.
+DEFAULT_PROMOTION = os.environ.get("W2T_PROMOTION", "legacy")
+
+
+def promotion_code(promotion=None):
+    name = DEFAULT_PROMOTION if promotion is None else promotion
+    if name in (W2T_PROMOTION_LEGACY, W2T_PROMOTION_NEP50):
+        return int(name)
+    try:
+        return {"legacy": W2T_PROMOTION_LEGACY, "nep50": W2T_PROMOTION_NEP50}[str(name).lower()]
+    except KeyError:
+        raise ValueError("promotion must be 'legacy' or 'nep50', not %r" % (name,))
 
 
 def sort_aux_bytes(n_substreams):
@@ -154,9 +169,9 @@ EXPORTS = {
     "w2t_iou_matrix": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p, _p]),
     "w2t_linear_assignment_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "w2t_linear_assignment": (C.c_int, [_p, C.c_int32, C.c_int32, _p, _p, _p, _p]),
-    "w2t_kf_init": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
+    "w2t_kf_init": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, _p]),
     "w2t_kf_predict": (C.c_int, [_p, _p, _p, C.c_int32, _p]),
-    "w2t_kf_update": (C.c_int, [_p, _p, _p, _p, C.c_int32, _p]),
+    "w2t_kf_update": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int32, _p]),
     "w2t_json_load": (C.c_int, [C.c_char_p, C.POINTER(_p)]),
     "w2t_json_count": (C.c_int64, [_p]),
     "w2t_json_n_images": (C.c_int64, [_p]),
@@ -165,7 +180,7 @@ EXPORTS = {
     "w2t_json_free": (None, [_p]),
     "w2t_json_write_tracks": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p, _p]),
     "w2t_json_write_detections": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p]),
-    "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, _p]),
+    "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p]),
     "w2t_x_to_bbox": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
 }
 

@@ -87,13 +87,13 @@ __global__ void __launch_bounds__(BLOCK) lap_kernel(const float *cost, int D, in
   }
 }
 
-__global__ void kf_init_kernel(double *x, double *P, const float4 *dets, int n) {
+__global__ void kf_init_kernel(double *x, double *P, const float4 *dets, int n, bool nep50) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 d4 = dets[i];
   const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
   double xv[7], Pv[49];
-  kf_init(dd, xv, Pv);
+  kf_init(dd, xv, Pv, nep50);
   for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
   for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
 }
@@ -120,7 +120,7 @@ __global__ void kf_predict_kernel(double *x, double *P, double *boxes, int n) {
   }
 }
 
-__global__ void kf_update_kernel(double *x, double *P, const float4 *dets, double *boxes, int n) {
+__global__ void kf_update_kernel(double *x, double *P, const float4 *dets, double *boxes, int n, bool nep50) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 d4 = dets[i];
@@ -130,10 +130,10 @@ __global__ void kf_update_kernel(double *x, double *P, const float4 *dets, doubl
   for (int k = 0; k < 49; k++) Pv[k] = P[49 * (size_t)i + k];
   double pb[kBlockP];
   if (kfb_from_dense(Pv, pb)) {  // the tracker's path: block form
-    kfb_update(xv, pb, dd);
+    kfb_update(xv, pb, dd, nep50);
     kfb_to_dense(pb, Pv);
   } else {
-    kf_update(xv, Pv, dd);
+    kf_update(xv, Pv, dd, nep50);
   }
   for (int k = 0; k < 7; k++) x[7 * (size_t)i + k] = xv[k];
   for (int k = 0; k < 49; k++) P[49 * (size_t)i + k] = Pv[k];
@@ -144,14 +144,13 @@ __global__ void kf_update_kernel(double *x, double *P, const float4 *dets, doubl
   }
 }
 
-__global__ void bbox_to_z_kernel(const float4 *dets, float4 *z, int n) {
+__global__ void bbox_to_z_kernel(const float4 *dets, double *z, int n, bool nep50) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 d4 = dets[i];
-  const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-  float zz[4];
-  bbox_to_z(dd, zz);
-  z[i] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+  double zz[4];
+  bbox_to_z_d(d4.x, d4.y, d4.z, d4.w, nep50, zz);
+  for (int k = 0; k < 4; k++) z[4 * (size_t)i + k] = zz[k];
 }
 
 __global__ void x_to_bbox_kernel(const double *x, int ldx, double *boxes, int n) {
@@ -165,12 +164,12 @@ __global__ void x_to_bbox_kernel(const double *x, int ldx, double *boxes, int n)
 
 }  // namespace
 
-extern "C" int w2t_bbox_to_z(const float *dets, float *z, int32_t n, w2t_stream_t stream) {
+extern "C" int w2t_bbox_to_z(const float *dets, double *z, int32_t n, int32_t promotion, w2t_stream_t stream) {
   if (n < 0) return W2T_ERR_ARG;
   if (n == 0) return W2T_OK;
   if (!dets || !z) return W2T_ERR_ARG;
-  bbox_to_z_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(dets),
-                                                                    reinterpret_cast<float4 *>(z), n);
+  bbox_to_z_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(dets), z, n,
+                                                                    promotion == W2T_PROMOTION_NEP50);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
 }
@@ -218,11 +217,12 @@ extern "C" int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, in
   return W2T_OK;
 }
 
-extern "C" int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, w2t_stream_t stream) {
+extern "C" int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, int32_t promotion, w2t_stream_t stream) {
   if (n < 0) return W2T_ERR_ARG;
   if (n == 0) return W2T_OK;
   if (!x || !P || !dets) return W2T_ERR_ARG;
-  kf_init_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), n);
+  kf_init_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), n,
+                                                                 promotion == W2T_PROMOTION_NEP50);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
 }
@@ -236,12 +236,13 @@ extern "C" int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2
   return W2T_OK;
 }
 
-extern "C" int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n,
+extern "C" int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n, int32_t promotion,
                              w2t_stream_t stream) {
   if (n < 0) return W2T_ERR_ARG;
   if (n == 0) return W2T_OK;
   if (!x || !P || !dets) return W2T_ERR_ARG;
-  kf_update_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), boxes, n);
+  kf_update_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), boxes, n,
+                                                                   promotion == W2T_PROMOTION_NEP50);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
 }

@@ -54,20 +54,9 @@ def collect_profile():
     return {k: sum(v) / len(v) for k, v in acc.items()}
 
 
-# NumPy promotion regime the tracker reproduces (include/w2t_types.h, W2T_PROMOTION_*): "legacy" = NumPy 1.x
-# value-based casting, the reference's pinned environment (python 3.7, environment.yml:7); "nep50" = NumPy 2.
-# Module default, overridable per call (``promotion=``) and by the environment variable W2T_PROMOTION.
-PROMOTION = os.environ.get("W2T_PROMOTION", "nep50")
-
-
-def promotion_code(promotion=None):
-    name = PROMOTION if promotion is None else promotion
-    if name in (_abi.W2T_PROMOTION_LEGACY, _abi.W2T_PROMOTION_NEP50):
-        return int(name)
-    try:
-        return {"legacy": _abi.W2T_PROMOTION_LEGACY, "nep50": _abi.W2T_PROMOTION_NEP50}[str(name).lower()]
-    except KeyError:
-        raise ValueError("promotion must be 'legacy' or 'nep50', not %r" % (name,))
+# NumPy promotion regime the tracker reproduces (include/w2t_types.h, W2T_PROMOTION_*; default and meaning:
+# _abi.DEFAULT_PROMOTION), overridable per call with ``promotion="legacy" | "nep50"``.
+promotion_code = _abi.promotion_code
 
 
 def require_cuda():
@@ -464,24 +453,36 @@ def _collect(trk, rows, raw, extra=None):
     return res
 
 
-def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0, raw=True, promotion=None):
+def upload_tracks(packed):
+    """Device copies of a ``packing.PackedTracks`` (for callers that keep the inputs resident in HBM)."""
+    device = require_cuda()
+    return dict(offsets=_dev(packed.stream_img_offsets, np.int32, device), start=_dev(packed.det_start, np.int32, device),
+                count=_dev(packed.det_count, np.int32, device),
+                box=_dev(packed.det_box, np.float32, device).reshape(-1, 4),
+                exists=_dev(packed.img_exists, np.uint8, device), cam=_dev(packed.cam_wh, np.float64, device),
+                rank=_dev(packed.class_rank, np.int32, device))
+
+
+def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_base=0, raw=True, promotion=None,
+               dev=None, to_host=True):
     """SORT over every stream of ``packed`` (``packing.PackedTracks``).
 
     Returns the dense output list (``rows_box/score/id/img/cat`` in the reference's order, ids
     assigned on the device) and, with ``raw``, the per-slot arrays of ``w2t_sort_result_t``.
+    ``dev``: device copies from :func:`upload_tracks` (skips the host->device copies);
+    ``to_host=False``: leave the results in HBM and return the device tensors (``trk``, ``rows``).
     """
-    device = require_cuda()
+    require_cuda()
     S, NC = packed.n_streams, packed.n_classes
     plan = make_plan(S, NC, packed.stream_img_offsets, packed.det_count, packed.img_exists, max_age)
-    d_offsets = _dev(packed.stream_img_offsets, np.int32, device)
-    d_start = _dev(packed.det_start, np.int32, device)
-    trk = sort_track_device(
-        S, NC, d_offsets, d_start, _dev(packed.det_count, np.int32, device),
-        _dev(packed.det_box, np.float32, device).reshape(-1, 4), _dev(packed.img_exists, np.uint8, device),
-        _dev(packed.cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan, final_cap,
-        promotion=promotion)
-    rows = finalize_device(S, NC, d_offsets, d_start, trk, _dev(packed.class_rank, np.int32, device), id_base,
+    d = dev if dev is not None else upload_tracks(packed)
+    d_offsets, d_start = d["offsets"], d["start"]
+    trk = sort_track_device(S, NC, d_offsets, d_start, d["count"], d["box"], d["exists"], d["cam"], iou_thresholds,
+                            max_age, min_hits, plan, final_cap, promotion=promotion)
+    rows = finalize_device(S, NC, d_offsets, d_start, trk, d["rank"], id_base,
                            int(np.asarray(packed.det_count, np.int64).sum()))
+    if not to_host:
+        return {"trk": trk, "rows": rows, "launches": 6}
     res = _collect(trk, rows, raw)
     res["id_next"] = int(id_base + res["totals"][0])
     if raw:
@@ -1030,13 +1031,13 @@ def linear_assignment(cost):
     return pairs[:k].cpu().numpy().astype(int).reshape(-1, 2)
 
 
-def kf_init(dets):
+def kf_init(dets, promotion=None):
     device = require_cuda()
     d = _dev(np.asarray(dets, np.float32).reshape(-1, 4), np.float32, device)
     n = int(d.shape[0])
     x = torch.zeros((n, 7), dtype=torch.float64, device=device)
     P = torch.zeros((n, 49), dtype=torch.float64, device=device)
-    check(lib().w2t_kf_init(_ptr(x), _ptr(P), _ptr(d), n, _stream()), "w2t_kf_init")
+    check(lib().w2t_kf_init(_ptr(x), _ptr(P), _ptr(d), n, promotion_code(promotion), _stream()), "w2t_kf_init")
     return x.cpu().numpy(), P.cpu().numpy().reshape(n, 7, 7)
 
 
@@ -1050,24 +1051,29 @@ def kf_predict(x, P):
     return xd.cpu().numpy(), Pd.cpu().numpy().reshape(n, 7, 7), boxes.cpu().numpy()
 
 
-def kf_update(x, P, dets):
+def kf_update(x, P, dets, promotion=None):
     device = require_cuda()
     xd = _dev(np.asarray(x, np.float64).reshape(-1, 7), np.float64, device).clone()
     n = int(xd.shape[0])
     Pd = _dev(np.asarray(P, np.float64).reshape(n, 49), np.float64, device).clone()
     d = _dev(np.asarray(dets, np.float32).reshape(n, 4), np.float32, device)
     boxes = torch.zeros((n, 4), dtype=torch.float64, device=device)
-    check(lib().w2t_kf_update(_ptr(xd), _ptr(Pd), _ptr(d), _ptr(boxes), n, _stream()), "w2t_kf_update")
+    check(lib().w2t_kf_update(_ptr(xd), _ptr(Pd), _ptr(d), _ptr(boxes), n, promotion_code(promotion), _stream()),
+          "w2t_kf_update")
     return xd.cpu().numpy(), Pd.cpu().numpy().reshape(n, 7, 7), boxes.cpu().numpy()
 
 
-def bbox_to_z(dets):
-    """``convert_bbox_to_z`` (sort.py:50-62) of n float32 boxes -> float32 [n,4]."""
+def bbox_to_z(dets, promotion=None):
+    """``convert_bbox_to_z`` (sort.py:50-62) of n float32 boxes -> [n,4]: float64 under legacy promotion (x, y
+    and r are float64 computations, s a float32 product), float32 under NEP 50 — the dtypes the reference's
+    ``np.array([x, y, s, r])`` has in either environment."""
     device = require_cuda()
     d = _dev(np.asarray(dets, np.float32).reshape(-1, 4), np.float32, device)
-    z = torch.zeros_like(d)
-    check(lib().w2t_bbox_to_z(_ptr(d), _ptr(z), int(d.shape[0]), _stream()), "w2t_bbox_to_z")
-    return z.cpu().numpy()
+    z = torch.zeros(d.shape, dtype=torch.float64, device=device)
+    code = promotion_code(promotion)
+    check(lib().w2t_bbox_to_z(_ptr(d), _ptr(z), int(d.shape[0]), code, _stream()), "w2t_bbox_to_z")
+    out = z.cpu().numpy()
+    return out.astype(np.float32) if code == _abi.W2T_PROMOTION_NEP50 else out
 
 
 def x_to_bbox(x):

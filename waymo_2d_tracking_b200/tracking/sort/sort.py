@@ -10,8 +10,10 @@ exactly as the reference orders it.  This frame-by-frame API exists for compatib
 call costs a handful of small launches; whole streams belong to ``tracking.utils.track_all``.
 There is no CPU fallback.
 
-Semantics pinned: NumPy 2 / NEP 50 — ``convert_bbox_to_z`` of a float32 row is
-float32 in every component, and the IoU threshold is compared in float32.  The solver is the
+NumPy promotion (``_abi.DEFAULT_PROMOTION``): by default the reference's pinned NumPy 1.x
+environment — in ``convert_bbox_to_z`` of a float32 row x, y and r are float64 computations and only s is a
+float32 product, and the IoU threshold is compared in float64; ``W2T_PROMOTION=nep50`` selects NumPy 2
+semantics (all four components float32, threshold compared in float32).  The solver is the
 scikit-learn 0.22.2 Munkres emulation (``csrc/munkres.cuh``), the filter the filterpy
 ``KalmanFilter`` restatement (``csrc/kalman.cuh``).
 """
@@ -43,7 +45,8 @@ def iou_batch(bb_test, bb_gt):
 
 
 def convert_bbox_to_z(bbox):
-    """[x1,y1,x2,y2] -> [x,y,s,r] as a (4,1) float32 array (sort.py:50-62 on a float32 row)."""
+    """[x1,y1,x2,y2] -> [x,y,s,r] as a (4,1) array (sort.py:50-62 on a float32 row): float64 under legacy
+    promotion, float32 under NEP 50."""
     return runtime.bbox_to_z(np.asarray(bbox, np.float32)[:4]).reshape(4, 1)
 
 
@@ -117,10 +120,13 @@ def associate_detections_to_trackers(detections, trackers, iou_threshold=0.3):
     matched_indices = runtime.linear_assignment(-iou_matrix)
     unmatched_detections = [d for d in range(len(detections)) if d not in matched_indices[:, 0]]
     unmatched_trackers = [t for t in range(len(trackers)) if t not in matched_indices[:, 1]]
-    thr = np.float32(iou_threshold)           # NEP 50: the Python float adopts the matrix dtype
+    # sort.py:220: NumPy 1.x compares the float32 entry with the python float in float64; under NEP 50 the python
+    # float adopts the matrix dtype
+    legacy = runtime.promotion_code() == 0
+    thr = np.float64(iou_threshold) if legacy else np.float32(iou_threshold)
     matches = []
     for d, t in matched_indices:
-        if iou_matrix[d, t] < thr:
+        if (np.float64(iou_matrix[d, t]) if legacy else iou_matrix[d, t]) < thr:
             unmatched_detections.append(d)
             unmatched_trackers.append(t)
         else:
