@@ -39,16 +39,39 @@ METRIC = "tracked frames/sec (ensemble+SORT)"
 UNIT = "frames/s"
 
 
+CONFIGS = {
+    # BASELINE.json:configs, in order.  `stages`: what one step runs; `segments`: default size of the job
+    "c1": dict(stages="sort", segments=1,
+               name="C1 SORT on one segment: %d segment(s) x 5 cameras x 200 frames, ~110 dets/frame in, 4 classes, max-age 2 min-hits 0"),
+    "c2": dict(stages="nms", segments=1,
+               name="C2 soft-NMS ensemble of 3 submissions (min-score .01, soft-nms-cut .9) on %d segment(s) x 5 cameras x 200 frames"),
+    "c3": dict(stages="both", segments=150,
+               name="C3 full test-scale per GPU: %d segments x 5 cameras x 200 frames, 3 submissions, "
+                    "soft-NMS(iou .5, cut .9, min-score .01) + SORT(max-age 2, min-hits 0)"),
+    "c4": dict(stages="sort", segments=1,
+               name="C4 crowded-scene stress: %d segment(s) x 5 cameras x 200 frames, ~1000 dets/frame, ~300 live tracks per class (large Hungarian solves)"),
+    "c5": dict(stages="both", segments=1,
+               name="C5 5-way TTA ensemble (~3000 boxes/frame) + SORT end to end on %d segment(s) x 5 cameras x 200 frames"),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20; 3 for --impl reference, whose steps take seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--segments", type=int, default=150, help="segments per GPU (150 = configuration C3)")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c3",
+                    help="configuration of BASELINE.json (default c3: the one the metric is quoted on)")
+    ap.add_argument("--segments", type=int, default=None, help="segments per GPU (default: the configuration's own size; "
+                    "with --scaling strong: segments of the whole job)")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="weak: every GPU gets --segments segments; strong: ONE job of --segments segments split over the GPUs")
     ap.add_argument("--seed", type=int, default=1000)
-    ap.add_argument("--cpu-sample-frames", type=int, default=200)
+    ap.add_argument("--cpu-sample-frames", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-streams", type=int, default=16,
+                    help="streams of the timed output checked against the C oracle after the timed region (0 = off)")
     ap.add_argument("--chunks", type=int, default=8, help="pipeline depth of the end-to-end leg")
     ap.add_argument("--skip-e2e", action="store_true",
                     help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
@@ -57,12 +80,15 @@ def parse_args():
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 3 if args.impl == "reference" else 20
+    if args.segments is None:
+        args.segments = CONFIGS[args.config]["segments"]
+    if args.cpu_sample_frames is None:
+        args.cpu_sample_frames = {"c1": 200, "c2": 100, "c3": 200, "c4": 12, "c5": 16}[args.config]
     return args
 
 
-def workload_name(segments):
-    return ("C3 full test-scale per GPU: %d segments x 5 cameras x 200 frames, 3 submissions, "
-            "soft-NMS(iou .5, cut .9, min-score .01) + SORT(max-age 2, min-hits 0)" % segments)
+def workload_name(config, segments):
+    return CONFIGS[config]["name"] % segments
 
 
 # ---------------------------------------------------------------------------------------------
@@ -70,11 +96,12 @@ def workload_name(segments):
 # ---------------------------------------------------------------------------------------------
 
 def _cpu_stream_job(job):
-    """One (segment, camera) stream, `frames` images: ensemble of the submissions, then SORT."""
-    seed, stream, frames = job
+    """One (segment, camera) stream, `frames` images, through the stages of the configuration."""
+    config, seed, stream, frames = job
     from oracle import ensemble_port, sort_port
     from waymo_2d_tracking_b200 import synth
-    scene = synth.make_scene(synth.preset("c3", n_segments=1, seed=seed))
+    stages = CONFIGS[config]["stages"]
+    scene = synth.make_scene(synth.preset(config, n_segments=1, seed=seed))
     F = scene.cfg.n_frames
     lo, hi = stream * F, stream * F + frames
     ids = scene.image_ids()
@@ -84,19 +111,28 @@ def _cpu_stream_job(job):
         subs.append([{'image_id': ids[int(i)], 'category_id': int(c), 'bbox': [int(v) for v in b], 'score': float(s)}
                      for i, c, b, s in zip(sub.image_index[m], sub.category[m], sub.bbox[m], sub.score[m])])
     t0 = time.perf_counter()
-    ens = ensemble_port.ensemble_all(subs, None, NMS["min_score"], NMS["iou_thresh"], NMS["soft_nms_cut"])
-    pred = sort_port.group_entries(ens, SCORE_THR)
-    rows = sort_port.track_all(pred, IOU_THR, MAX_AGE, MIN_HITS)
+    if stages == "sort":
+        ens = subs[0]
+    else:
+        ens = ensemble_port.ensemble_all(subs, None, NMS["min_score"], NMS["iou_thresh"], NMS["soft_nms_cut"])
+    n_rows = len(ens)
+    if stages != "nms":
+        pred = sort_port.group_entries(ens, SCORE_THR)
+        n_rows = len(sort_port.track_all(pred, IOU_THR, MAX_AGE, MIN_HITS))
     dt = time.perf_counter() - t0
-    return frames, dt, len(rows)
+    return frames, dt, n_rows
 
 
-def cpu_baseline_single(seed, frames):
-    n, dt, rows = _cpu_stream_job((seed, 0, frames))
+PORT_NOTE = ("oracle/ NumPy port of the reference path (ensemble_port + sort_port); the reference's own files, which "
+             "cannot travel to the GPU box, measured 3-4x SLOWER than this port in the dev container (10 vs 38 frames/s "
+             "per core on the same 400 frames), so ratios against it are conservative")
+
+
+def cpu_baseline_single(config, seed, frames):
+    n, dt, rows = _cpu_stream_job((config, seed, 0, frames))
     return dict(value=n / dt, unit=UNIT, cores=1, kind="port",
-                sample="1 stream (segment seed %d, camera FRONT), first %d of 200 frames, oracle/ NumPy port of the "
-                       "reference path, single thread as tracking/track.py runs it; %.1f s of CPU work"
-                       % (seed, frames, dt))
+                sample="1 stream (segment seed %d, camera FRONT), first %d of 200 frames, single thread as "
+                       "tracking/track.py runs it; %.1f s of CPU work; %s" % (seed, frames, dt, PORT_NOTE))
 
 
 def run_reference_arm(args, rank, world):
@@ -111,7 +147,9 @@ def run_reference_arm(args, rank, world):
     per_step = []
     with ctx.Pool(cores) as pool:
         for step in range(args.warmup + args.steps):
-            jobs = [(args.seed + step, w % 5, frames) for w in range(cores)]
+            # every worker gets its own stream: camera w % 5 of segment seed + step * ceil(cores / 5) + w // 5
+            seg0 = args.seed + step * ((cores + 4) // 5)
+            jobs = [(args.config, seg0 + w // 5, w % 5, frames) for w in range(cores)]
             res = pool.map(_cpu_stream_job, jobs)
             # the workers run concurrently: the step takes as long as the slowest one's timed region
             # (synthetic-data generation inside the worker is not part of the path and is excluded)
@@ -123,12 +161,12 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.segments),
-                   "sample": "each step: %d streams x first %d of 200 frames, one stream per host process" % (cores, frames)},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.segments),
+                   "sample": "each step: %d DISTINCT streams x first %d of 200 frames, one stream per host process" % (cores, frames)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d worker processes, each one (segment, camera) stream x %d frames per step, "
-                                   "ensemble_port + sort_port (NumPy restatement of the reference)" % (cores, frames)},
+                         "sample": "%d worker processes, each its own (segment, camera) stream x %d frames per step; %s"
+                                   % (cores, frames, PORT_NOTE)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,6 +232,93 @@ class ClockSampler(threading.Thread):
 # our arm
 # ---------------------------------------------------------------------------------------------
 
+# ---------------------------------------------------------------------------------------------
+# parity sample: streams of the timed output against the C oracle (test infrastructure; the checker only)
+# ---------------------------------------------------------------------------------------------
+
+def _rows_of_images(rows, img0, img1):
+    """Dense output rows (dict of arrays in the reference's order) restricted to images [img0, img1)."""
+    m = (rows["rows_img"] >= img0) & (rows["rows_img"] < img1)
+    return {k: np.asarray(rows[k])[m] for k in ("rows_img", "rows_cat", "rows_box", "rows_score", "rows_id")}
+
+
+def parity_sample(stages, scene, groups, packed, rows, ens, n_streams, seed):
+    """Checks `n_streams` randomly chosen streams of the FULL-SIZE output against oracle/ (plain-C restatement):
+    kept ensemble rows bit-exact; track images / categories / boxes bit-exact, ids exact relative to the stream's
+    first id (the absolute base is the creation count of all earlier streams), confidences within 1e-9."""
+    from oracle import c_oracle
+    from waymo_2d_tracking_b200 import packing
+    NC = 4
+    S = scene.n_streams
+    rng = np.random.default_rng(seed)
+    pick = sorted(rng.choice(S, size=min(n_streams, S), replace=False).tolist())
+    offs = scene.stream_img_offsets
+    bad, n_rows = 0, 0
+    for s_ in pick:
+        img0, img1 = int(offs[s_]), int(offs[s_ + 1])
+        g0, g1 = img0 * NC, img1 * NC
+        if stages == "sort":
+            sub = packing.PackedTracks(
+                n_streams=1, n_classes=NC, streams=[packed.streams[s_]], frame_ids=packed.frame_ids[img0:img1],
+                stream_img_offsets=np.asarray([0, img1 - img0], np.int32),
+                det_start=(packed.det_start[g0:g1] - packed.det_start[g0]).astype(np.int32),
+                det_count=packed.det_count[g0:g1], cam_wh=packed.cam_wh[s_:s_ + 1],
+                det_box=packed.det_box[int(packed.det_start[g0]):int(packed.det_start[g1 - 1] + packed.det_count[g1 - 1])],
+                img_exists=None if packed.img_exists is None else packed.img_exists[img0:img1],
+                class_rank=None if packed.class_rank is None else packed.class_rank[s_ * NC:(s_ + 1) * NC],
+                n_rows=int(packed.det_count[g0:g1].sum()))
+        else:
+            go = groups.group_offsets
+            r0, r1 = int(go[g0]), int(go[g1])
+            loc = (go[g0:g1 + 1] - r0).astype(np.int32)
+            nms = c_oracle.softnms_groups(loc, groups.rows[r0:r1], NMS["iou_thresh"], NMS["soft_nms_cut"], NMS["min_score"],
+                                          NC, SCORE_THR)
+            if ens is not None:
+                for k in ("ens_count",):
+                    bad += int(np.count_nonzero(nms[k] != ens[k][g0:g1]))
+                for g in range(g1 - g0):
+                    c, o = int(nms["ens_count"][g]), int(loc[g])
+                    bad += int(np.count_nonzero(nms["ens_box"][o:o + c] != ens["ens_box"][r0 + o:r0 + o + c]))
+                    bad += int(np.count_nonzero(nms["ens_score"][o:o + c] != ens["ens_score"][r0 + o:r0 + o + c]))
+                    n_rows += c
+            if stages == "nms":
+                continue
+            sub = packing.PackedTracks(
+                n_streams=1, n_classes=NC, streams=[scene.streams()[s_]], frame_ids=scene.frame_ids[img0:img1],
+                stream_img_offsets=np.asarray([0, img1 - img0], np.int32), det_start=loc[:-1].copy(),
+                det_count=nms["trk_count"], det_box=nms["trk_box"], cam_wh=scene.cam_wh()[s_:s_ + 1],
+                img_exists=nms["img_exists"], class_rank=None, n_rows=r1 - r0)
+        want = c_oracle.sort_track(sub, IOU_THR, MAX_AGE, MIN_HITS)
+        ids, _ = packing.assign_ids(sub.stream_img_offsets, NC, sub.det_start, want["out_count"], want["created"],
+                                    want["first_img"], sub.class_rank, want["out_birth"])
+        dense = packing.unpack_tracks(sub, want["out_box"], want["out_score"], want["out_count"], want["first_img"], ids)
+        got = _rows_of_images(rows, img0, img1)
+        n_rows += len(dense)
+        if len(dense) != len(got["rows_id"]):
+            bad += abs(len(dense) - len(got["rows_id"])) + 1
+            continue
+        if not dense:
+            continue
+        index = {iid: i for i, iid in enumerate(packing.image_id_strings(sub))}
+        w_img = np.array([index[r["image_id"]] for r in dense]) + img0
+        w_cat = np.array([r["category_id"] for r in dense])
+        w_box = np.array([r["bbox"] for r in dense], np.float64).reshape(-1, 4)
+        w_score = np.array([r["score"] for r in dense], np.float64)
+        w_id = np.array([int(r["object_id"]) for r in dense], np.int64)
+        bad += int(np.count_nonzero(w_img != got["rows_img"])) + int(np.count_nonzero(w_cat != got["rows_cat"]))
+        bad += int(np.count_nonzero(w_box != got["rows_box"]))
+        bad += int(np.count_nonzero(~np.isclose(w_score, got["rows_score"], rtol=1e-9, atol=0)))
+        bad += int(np.count_nonzero((w_id - w_id.min()) != (got["rows_id"] - got["rows_id"].min())))
+    return {"streams": len(pick), "rows": int(n_rows), "mismatches": int(bad), "oracle": "oracle/csrc (plain-C restatement)",
+            "checked": "full-size output of the timed configuration: " + (
+                "kept ensemble rows bit-exact" if stages == "nms" else
+                "track rows (image, category, box bit-exact; ids exact relative to the stream's first id; confidence rtol 1e-9)")}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -204,7 +329,7 @@ def main():
         return
 
     import torch
-    from waymo_2d_tracking_b200 import runtime, synth
+    from waymo_2d_tracking_b200 import packing, runtime, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -218,39 +343,77 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic workload (per rank: its own 150 segments) ----------------------------------
-    t0 = time.time()
-    scene = synth.make_scene(synth.preset("c3", n_segments=args.segments, seed=args.seed + rank))
-    groups = synth.groups_from_scene(scene, None, NMS["min_score"])
-    gen_s = time.time() - t0
-    n_frames = scene.n_img
-    # the synthetic submissions carry integer pixel boxes like real detector output (detnet/data/coco.py:250),
-    # so the packer emits 16-byte compact rows (double score + 4 x int16) instead of 5 doubles
-    from waymo_2d_tracking_b200 import packing
-    # ... and 5-decimal scores (coco.py:249), so 8-byte packed rows hold them exactly (packing.packed_rows
-    # verifies that bit for bit and returns None otherwise)
-    packed = None if (args.wide_rows or args.compact_rows) else packing.packed_rows(groups.rows)
-    compact = None if (args.wide_rows or packed is not None) else packing.compact_rows(groups.rows)
-    if packed is not None:
-        h_rows = torch.from_numpy(packed.view(np.uint8).reshape(-1, 8)).pin_memory()
-    elif compact is not None:
-        h_rows = torch.from_numpy(compact.view(np.uint8).reshape(-1, 16)).pin_memory()
+    stages = CONFIGS[args.config]["stages"]
+    # ---- synthetic workload.  weak: every rank its own --segments segments; strong: the job's segments are split
+    if args.scaling == "strong":
+        lo, hi = args.segments * rank // world, args.segments * (rank + 1) // world
+        n_seg = max(hi - lo, 1)
     else:
-        h_rows = torch.from_numpy(groups.rows).pin_memory()
-    h_offs = torch.from_numpy(groups.group_offsets).pin_memory()
-    d_rows, d_offs = h_rows.cuda(), h_offs.cuda()
-    cam_wh = scene.cam_wh()
-    kw = dict(stream_img_offsets=scene.stream_img_offsets, cam_wh=cam_wh, n_classes=4, score_thr=SCORE_THR,
-              iou_thresholds=IOU_THR, max_age=MAX_AGE, min_hits=MIN_HITS, max_group=groups.max_group, **NMS)
+        n_seg = args.segments
+    t0 = time.time()
+    scene = synth.make_scene(synth.preset(args.config, n_segments=n_seg, seed=args.seed + rank))
+    n_frames = scene.n_img
+    groups = packed_trk = None
+    if stages == "sort":
+        packed_trk = synth.tracks_from_submission(scene, scene.submissions[0], SCORE_THR)
+        n_in = int(packed_trk.det_box.shape[0])
+    else:
+        groups = synth.groups_from_scene(scene, None, NMS["min_score"])
+        n_in = int(groups.rows.shape[0])
+    gen_s = time.time() - t0
 
-    def step_device():
-        # inputs resident in HBM, outputs left in HBM, no host round trip inside the step
-        return runtime.ensemble_and_track(d_offs, d_rows, to_host=False, want_ensemble=False, raw=False,
-                                          host_group_offsets=groups.group_offsets, **kw)
+    input_rows = None
+    if stages == "sort":
+        dev_in = runtime.upload_tracks(packed_trk)
+        h2d = int(packed_trk.det_box.nbytes + packed_trk.det_count.nbytes + packed_trk.det_start.nbytes)
+        input_rows = "16 B (4 x float32 corner boxes, already filtered by read_data_file)"
 
-    def step_e2e():
-        # public API with HOST buffers: chunked so that H2D, kernels and D2H overlap (runtime.py)
-        return runtime.ensemble_and_track_pipelined(h_offs, h_rows, n_chunks=args.chunks, **kw)
+        def step_device():
+            return runtime.sort_track(packed_trk, IOU_THR, MAX_AGE, MIN_HITS, raw=False, dev=dev_in, to_host=False)
+
+        def step_e2e():
+            return runtime.sort_track(packed_trk, IOU_THR, MAX_AGE, MIN_HITS, raw=False)
+    else:
+        # the synthetic submissions carry integer pixel boxes and 5-decimal scores like real detector output
+        # (detnet/data/coco.py:249-250), so 8-byte packed rows hold them exactly (packing.packed_rows verifies that
+        # bit for bit and returns None otherwise); --compact-rows / --wide-rows ship 16 B / 40 B rows instead
+        packed = None if (args.wide_rows or args.compact_rows) else packing.packed_rows(groups.rows)
+        compact = None if (args.wide_rows or packed is not None) else packing.compact_rows(groups.rows)
+        if packed is not None:
+            h_rows = torch.from_numpy(packed.view(np.uint8).reshape(-1, 8)).pin_memory()
+            input_rows = "8 B packed (17-bit score*1e5 + 13/12/11/11-bit box, verified lossless by the packer)"
+        elif compact is not None:
+            h_rows = torch.from_numpy(compact.view(np.uint8).reshape(-1, 16)).pin_memory()
+            input_rows = "16 B compact (f64 score + 4 x int16 box)"
+        else:
+            h_rows = torch.from_numpy(groups.rows).pin_memory()
+            input_rows = "40 B (5 x f64)"
+        h_offs = torch.from_numpy(groups.group_offsets).pin_memory()
+        d_rows, d_offs = h_rows.cuda(), h_offs.cuda()
+        h2d = int(h_rows.numel() * h_rows.element_size() + h_offs.numel() * 4)
+        fmt = runtime._host_rows(h_rows)[1]
+        G = int(groups.group_offsets.shape[0]) - 1
+        if stages == "nms":
+            def step_device():
+                return {"nms": runtime.softnms_groups_device(d_offs, d_rows, G, groups.max_group, NMS["iou_thresh"],
+                                                             NMS["soft_nms_cut"], NMS["min_score"], 4, None,
+                                                             want_merged=False, box_format=fmt), "launches": 1}
+
+            def step_e2e():
+                return runtime.softnms_groups(h_offs, h_rows, NMS["iou_thresh"], NMS["soft_nms_cut"], NMS["min_score"], 4,
+                                              None, max_group=groups.max_group, want_merged=False)
+        else:
+            kw = dict(stream_img_offsets=scene.stream_img_offsets, cam_wh=scene.cam_wh(), n_classes=4, score_thr=SCORE_THR,
+                      iou_thresholds=IOU_THR, max_age=MAX_AGE, min_hits=MIN_HITS, max_group=groups.max_group, **NMS)
+
+            def step_device():
+                # inputs resident in HBM, outputs left in HBM, no host round trip inside the step
+                return runtime.ensemble_and_track(d_offs, d_rows, to_host=False, want_ensemble=False, raw=False,
+                                                  host_group_offsets=groups.group_offsets, **kw)
+
+            def step_e2e():
+                # public API with HOST buffers: chunked so that H2D, kernels and D2H overlap (runtime.py)
+                return runtime.ensemble_and_track_pipelined(h_offs, h_rows, n_chunks=min(args.chunks, scene.n_streams), **kw)
 
     def timed(fn, steps):
         barrier()
@@ -276,8 +439,9 @@ def main():
     ms_dev, out = timed(step_device, args.steps)
     kernel_ms = runtime.collect_profile()
     runtime.PROFILE = None
+    out_e2e = None
     if args.skip_e2e:
-        ms_e2e, out_e2e = float("nan"), {"n_rows": int(out["rows"]["totals"][1].item()), "d2h_bytes": 0}
+        ms_e2e = float("nan")
     else:
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
@@ -286,36 +450,52 @@ def main():
 
     # ---- bookkeeping -------------------------------------------------------------------------------
     K = args.steps
-    total_frames = n_frames * world
+    frames_all = torch.tensor([float(n_frames)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(frames_all)
+    total_frames = int(frames_all.item())
     value = total_frames * K / (ms_dev / 1e3)
     e2e_value = total_frames * K / (ms_e2e / 1e3)
-    n_in = int(groups.rows.shape[0])
     torch.cuda.synchronize()
     for stage in ("nms", "trk"):
-        if int(out[stage]["status"].item()) != 0:
+        if stage in out and int(out[stage]["status"].item()) != 0:
             raise SystemExit("bench.py: %s kernel reported status %d" % (stage, int(out[stage]["status"].item())))
-    n_trk = int(out["nms"]["trk_count"].sum().item())
-    n_dev_rows = int(out["rows"]["totals"][1].item())
-    if n_dev_rows != int(out_e2e["n_rows"]):
-        raise SystemExit("bench.py: device-resident and end-to-end legs disagree on the number of rows")
-    parity = None
-    if not args.skip_e2e:
-        # full-size consistency of the two legs (single launch vs chunked pipeline): every row's track id,
-        # image, category and box must be identical, bit for bit
+    n_trk = n_in if stages == "sort" else (int(out["nms"]["trk_count"].sum().item()) if stages == "both" else 0)
+    if stages == "nms":
+        n_out = int(out["nms"]["ens_count"].sum().item())
+    else:
+        n_out = int(out["rows"]["totals"][1].item())
+    consistency = None
+    if out_e2e is not None and stages != "nms":
+        # full-size consistency of the two legs (single launch vs chunked pipeline / host-buffer call): every row's
+        # track id, image, category, box and confidence must be identical, bit for bit
+        if n_out != int(out_e2e["n_rows"]):
+            raise SystemExit("bench.py: device-resident and end-to-end legs disagree on the number of rows")
         dev_rows = out["rows"]
         same = True
-        for key, host_arr in (("rows_id", out_e2e["rows_id"]), ("rows_img", out_e2e["rows_img"]),
-                              ("rows_cat", out_e2e["rows_cat"]), ("rows_box", out_e2e["rows_box"]),
-                              ("rows_score", out_e2e["rows_score"])):
-            same = same and bool(torch.equal(dev_rows[key][:n_dev_rows].cpu(), torch.from_numpy(np.asarray(host_arr))))
+        for key in ("rows_id", "rows_img", "rows_cat", "rows_box", "rows_score"):
+            same = same and bool(torch.equal(dev_rows[key][:n_out].cpu(), torch.from_numpy(np.asarray(out_e2e[key]))))
         if not same:
-            raise SystemExit("bench.py: the chunked end-to-end leg and the single-launch leg produced different rows")
-        parity = "all %d rows of the e2e leg (%d chunks) bit-identical to the single-launch leg" % (n_dev_rows, args.chunks)
-    n_out = int(out_e2e["n_rows"])
-    h2d = int(h_rows.numel() * h_rows.element_size() + h_offs.numel() * 4)
-    d2h = int(out_e2e["d2h_bytes"])
+            raise SystemExit("bench.py: the end-to-end leg and the device-resident leg produced different rows")
+        consistency = "all %d rows of the e2e leg bit-identical to the device-resident leg" % n_out
+    # ---- full-size parity sample against the oracle (after the timed region; rank 0's share of the job)
+    parity = None
+    if rank == 0 and args.parity_streams > 0:
+        if stages == "nms":
+            ens = {k: out["nms"][k].cpu().numpy() for k in ("ens_count", "ens_box", "ens_score")}
+            rows_h = None
+        else:
+            ens = None
+            rows_h = {k: out["rows"][k][:n_out].cpu().numpy() for k in ("rows_img", "rows_cat", "rows_box", "rows_score", "rows_id")}
+        parity = parity_sample(stages, scene, groups, packed_trk, rows_h, ens, args.parity_streams, args.seed)
+    d2h = 0 if out_e2e is None else int(out_e2e.get("d2h_bytes", 0) if stages != "nms" else
+                                        sum(np.asarray(v).nbytes for v in out_e2e.values() if v is not None))
     # algorithmic bytes: soft-NMS 88 B per input box; SORT 24 B per tracked detection + 60 B per row
-    alg = {"softnms_kernel": 88.0 * n_in, "sort_track_kernel": 24.0 * n_trk + 60.0 * n_out}
+    alg = {}
+    if stages != "sort":
+        alg["softnms_kernel"] = 88.0 * n_in
+    if stages != "nms":
+        alg["sort_track_kernel"] = 24.0 * n_trk + 60.0 * n_out
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -324,42 +504,48 @@ def main():
     dominant = max(alg, key=lambda k: kernel_ms.get(k, 0.0)) if kernel_ms else None
     roofline = None
     if dominant:
-        traffic = None
+        traffic, ncu = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dominant)
+        if os.path.exists(tpath) and args.config == "c3":
+            tj = json.load(open(tpath))
+            traffic, ncu = tj.get(dominant), tj.get("ncu", {}).get(dominant)
         achieved = alg[dominant] / (kernel_ms[dominant] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "kernel_ms": kernel_ms, "algorithmic_bytes": alg,
+                    "kernel_ms": kernel_ms, "algorithmic_bytes": alg, "ncu": ncu,
                     "note": "dependency/latency-bound path (sequential frames per stream, serial Munkres): "
                             "HBM fraction is expected to be small; see DESIGN.md"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.segments), "frames_per_gpu": n_frames,
-                   "boxes_in_per_gpu": n_in, "tracked_dets_per_gpu": n_trk, "track_rows_per_gpu": n_out,
-                   "input_rows": ("8 B packed (17-bit score*1e5 + 13/12/11/11-bit box, verified lossless by the packer)" if packed is not None else
-                                  "16 B compact (f64 score + 4 x int16 box)" if compact is not None else "40 B (5 x f64)"),
-                   "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (h2d / 1e9),
+        "config": {"workload": workload_name(args.config, args.segments), "name": args.config, "stages": stages,
+                   "frames_per_gpu": n_frames, "frames_total": total_frames,
+                   "boxes_in_per_gpu": n_in, "tracked_dets_per_gpu": n_trk, "rows_out_per_gpu": n_out,
+                   "input_rows": input_rows,
+                   "l2": ("inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (h2d / 1e9)) if h2d > 126e6
+                   else "inputs (%.1f MB per step) fit the 126 MB L2: the step is bound by serial chain latency, not by HBM "
+                        "(no flush: every kernel of a step writes its outputs, 2-7x the input size, in between)" % (h2d / 1e6),
                    "parallelism": "streams sharded by segment, %d rank(s), no collective" % world,
-                   "generate_s": round(gen_s, 1), "full_size_check": parity},
+                   "generate_s": round(gen_s, 1), "full_size_check": consistency},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(out["launches"]) * K,
         "clocks": clocks,
         "roofline": roofline,
+        "parity_sample": parity,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single(args.seed, args.cpu_sample_frames)
+        line["cpu_baseline"] = cpu_baseline_single(args.config, args.seed, args.cpu_sample_frames)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and parity["mismatches"] != 0:
+        raise SystemExit("bench.py: %d mismatches against the oracle on the parity sample" % parity["mismatches"])
 
 
 if __name__ == "__main__":
