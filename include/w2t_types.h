@@ -53,12 +53,14 @@ typedef struct w2t_sort_plan_t {
   /* w2t_stream_wait_value32 and post-process it while the rest of the launch is still running.  */
   const int32_t *chunk_of;
   int32_t *chunk_done;
-  /* Launch classes.  `order` is [wide | mid | narrow]:                                             */
-  /*   the first n_wide entries are sub-streams with more than W2T_WIDE_DETS detections in some     */
-  /*   image (crowded scenes): 512-thread CTAs; the next n_mid entries have more than              */
-  /*   W2T_NARROW_DETS: 128-thread CTAs; the rest are tracked by one WARP each (persistent warps    */
-  /*   that pull sub-streams from a queue in this order).  A narrow sub-stream whose live trackers  */
-  /*   outgrow W2T_NARROW_DETS is tracked again by a 128-thread CTA (flag in the aux area).         */
+  /* Launch classes, by the most detections a sub-stream MAY have in one image (det_cap can be an  */
+  /* upper bound; the kernels classify again from the actual counts).  `order` is                   */
+  /* [wide | mid | narrow]: the first n_wide entries have det_cap > W2T_WIDE_DETS, the next n_mid    */
+  /* entries det_cap > W2T_NARROW_DETS.  Narrow sub-streams are tracked by warps (persistent warps   */
+  /* that pull sub-streams from queues in this order); crowded ones (more than W2T_NARROW_DETS       */
+  /* detections in some image, or live trackers beyond the warp kernel's reach) by clusters of 8     */
+  /* CTAs with the cost matrix in distributed shared memory; anything beyond that by single CTAs     */
+  /* with the matrix in global memory.                                                               */
   int32_t  n_wide;
   int32_t  n_mid;
   /* byte offset, inside the workspace, of the auxiliary area of the warp kernel (w2t_sort_plan     */
@@ -71,7 +73,7 @@ typedef struct w2t_sort_plan_t {
 } w2t_sort_plan_t;
 
 #define W2T_WIDE_DETS 320
-#define W2T_NARROW_DETS 128
+#define W2T_NARROW_DETS 96
 #define W2T_SORT_AUX_BYTES(n_substreams) (64 + 12 * (int64_t)(n_substreams))
 
 /* NumPy promotion regime the tracker reproduces (w2t_sort_problem_t.promotion):                     */

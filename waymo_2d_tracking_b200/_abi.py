@@ -104,7 +104,7 @@ class NmsProblem(C.Structure):
 
 
 W2T_WIDE_DETS = 320          # include/w2t_types.h
-W2T_NARROW_DETS = 128
+W2T_NARROW_DETS = 96
 W2T_PROMOTION_LEGACY, W2T_PROMOTION_NEP50 = 0, 1
 # NumPy promotion regime the tracker reproduces unless a call says otherwise: "legacy" = NumPy 1.x value-based
 # casting, the reference's pinned environment (python 3.7, /root/reference/environment.yml:7 — scikit-learn 0.22.2

@@ -8,6 +8,7 @@
 
 #include "sort_kernel.cuh"
 #include "sort_warp.cuh"
+#include "sort_crowd.cuh"
 
 using namespace w2t;
 
@@ -182,14 +183,31 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
         W2T_CUDA_TRY(cudaEventRecord(ev_fork[dev], st));
         W2T_CUDA_TRY(cudaStreamWaitEvent(sb, ev_fork[dev], 0));
       }
-      if (n_wide > 0) {
-        P.bail_want = kClsWide;
-        sort_track_kernel<512, 1, false><<<n_wide, 512, 0, sb>>>(P);
+      static bool crowd_attr[16] = {false};
+      const size_t crowd_smem = (size_t)kCrowdSmemBytes;
+      if (dev >= 16 || !crowd_attr[dev]) {
+        W2T_CUDA_TRY(cudaFuncSetAttribute(sort_crowd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)crowd_smem));
+        W2T_CUDA_TRY(cudaFuncSetAttribute(sort_crowd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (dev < 16) crowd_attr[dev] = true;
       }
-      if (n_big > 0) {
-        P.bail_want = kClsMid;
-        sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<n_big, kSortBlock, 0, sb>>>(P);
-      }
+      // clusters of `ctas` CTAs over the first `entries` sub-streams of the launch order, serving two class flags
+      auto launch_crowd = [&](int entries, int ctas, int want_a, int want_b, int overflow, cudaStream_t s_) -> cudaError_t {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(entries * ctas));
+        cfg.blockDim = dim3(kCrowdWarps * 32);
+        cfg.dynamicSmemBytes = crowd_smem;
+        cfg.stream = s_;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)ctas;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, sort_crowd_kernel, P, want_a, want_b, overflow);
+      };
+      if (n_wide > 0) W2T_CUDA_TRY(launch_crowd(n_wide, 16, kClsWide, kClsWide, kClsHuge, sb));
+      if (n_big > 0) W2T_CUDA_TRY(launch_crowd(n_big, 8, kClsMid, kClsMid, kClsOver8, sb));
       if (fork) W2T_CUDA_TRY(cudaEventRecord(ev_join[dev], sb));
       {
         static bool attr_set[16] = {false};
@@ -203,10 +221,12 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
         if (tm) sort_warp_kernel<true><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
         else sort_warp_kernel<false><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
       }
-      // second pass: sub-streams that outgrew the warp kernel are tracked again by CTAs
-      P.bail_want = kClsBailed;
-      sort_track_kernel<kSortBlock, kSortMinBlocks, false><<<nq, kSortBlock, 0, st>>>(P);
+      // second pass: sub-streams that outgrew the warp kernel are tracked again by clusters ...
+      W2T_CUDA_TRY(launch_crowd(nq, 16, kClsBailed, kClsOver8, kClsHuge, st));
       if (fork) W2T_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[dev], 0));
+      // ... and what outgrew those, by CTAs that keep the cost matrix in global memory
+      P.bail_want = kClsHuge;
+      sort_track_kernel<512, 1, false><<<nq, 512, 0, st>>>(P);
     }
   }
   W2T_CUDA_TRY(cudaGetLastError());

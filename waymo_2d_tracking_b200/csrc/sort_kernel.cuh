@@ -113,7 +113,15 @@ struct SortParams {
 };
 
 // values of SortParams::bail[q] (aux area of the workspace): who tracks sub-stream q
-enum { kClsWarp = 0, kClsBailed = 1, kClsWide = 2, kClsMid = 3 };
+enum {
+  kClsWarp = 0,    // the warp kernel tracks it (sort_warp.cuh)
+  kClsBailed = 1,  // outgrew the warp kernel: a 16-CTA cluster tracks it again (second pass)
+  kClsWide = 2,    // very crowded (more than W2T_WIDE_DETS detections in some image): 16-CTA clusters (sort_crowd.cuh)
+  kClsMid = 3,     // crowded (more than W2T_NARROW_DETS): 8-CTA clusters
+  kClsHuge = 4,    // beyond the cluster kernel: CTAs with the cost matrix in global memory (sort_kernel.cuh, last pass)
+  kClsDone = 5,    // tracked by a cluster
+  kClsOver8 = 6    // outgrew an 8-CTA cluster: a 16-CTA cluster tracks it again (second pass)
+};
 
 // iou() of sort.py:33-47 as numba compiles it for (float32[:], float64[:]): the detection's
 // own area is a float32 product, everything else float64; the result is stored as float32.

@@ -41,6 +41,7 @@ constexpr int kWarpSmemBytes = 232448;  // 227 KB: the most dynamic shared memor
 constexpr int kTeamsPerCta = 8;     // sub-streams in flight per SM: 4 pairs + 4 single warps
 constexpr int kWarpsPerCta = 12;
 constexpr int kBigCols = 384, kSmallCols = 128;  // TMEM columns (= cell words of the cost matrix) of a pair / a single warp
+constexpr int kClassifyHuge = 896;  // = kCrowdM (sort_crowd.cuh): more detections than the cluster kernel takes
 
 // The cost matrix of a team's current image lives in TENSOR MEMORY (256 KB per SM, 128 lanes x 512 columns x
 // 32 bit, reached with tcgen05.ld / tcgen05.st; SASS: LDTM / STTM).  A warp can only touch the 32 TMEM lanes of
@@ -856,7 +857,7 @@ __global__ void __launch_bounds__(1024) sort_classify_kernel(const w2t_sort_prob
       int dmax = 0;
       for (int img = p.stream_img_offsets[s]; img < p.stream_img_offsets[s + 1]; img++)
         if (p.img_exists == nullptr || p.img_exists[img]) dmax = max(dmax, p.det_count[img * NC + c]);
-      const int cls = dmax > W2T_WIDE_DETS ? kClsWide : dmax > W2T_NARROW_DETS ? kClsMid : kClsWarp;
+      const int cls = dmax > kClassifyHuge ? kClsHuge : dmax > W2T_WIDE_DETS ? kClsWide : dmax > W2T_NARROW_DETS ? kClsMid : kClsWarp;
       Q.cls[q] = cls;
       // a crowd of D detections meets about 1.3 D trackers (max_age 2): ceil8(D) rows x ceil32(1.3 D + 8) / 32 words
       const int words = (min(kWarpDim, dmax + dmax / 3 + 8) + 31) >> 5;
