@@ -328,8 +328,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # one process per GPU: keep each rank's host threads within its share of the cores
+    share = max(1, (os.cpu_count() or 1) // max(world, 1))
+    os.environ.setdefault("W2T_PLAN_THREADS", str(max(1, min(4, share - 1))))
     import torch
     from waymo_2d_tracking_b200 import packing, runtime, synth
+    torch.set_num_threads(max(1, min(4, share)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)

@@ -97,6 +97,13 @@ int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t *stream_im
                   const int32_t *det_count, const uint8_t *img_exists, int32_t max_age,
                   w2t_sort_plan_t *plan);
 
+/* The same from the group offsets of the rows alone (group g holds rows group_offsets[g] ..
+ * group_offsets[g+1]): capacities from the group SIZES, an image counted as present when it has any
+ * row.  For callers that plan before the ensemble has run (sizes before soft-NMS are upper bounds of
+ * what reaches the tracker), without materialising the count arrays. */
+int w2t_sort_plan_offsets(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                          const int32_t *group_offsets, int32_t max_age, w2t_sort_plan_t *plan);
+
 /* Replaces the loop of tracking/track.py:42-47: track_sort()
  * (tracking/utils.py:25-60) -> MultiClassTrackerSort.track()
  * (tracking/sort/tracker_sort.py:22-51) -> Sort.update()

@@ -154,6 +154,7 @@ EXPORTS = {
     "w2t_fusion_groups": (C.c_int, [C.POINTER(NmsProblem), _p, C.c_int32, C.POINTER(NmsResult), C.c_int, _p, _p]),
     "w2t_fusion_max_group": (C.c_int, []),
     "w2t_sort_plan": (C.c_int, [C.c_int32, C.c_int32, _p, _p, _p, C.c_int32, C.POINTER(SortPlan)]),
+    "w2t_sort_plan_offsets": (C.c_int, [C.c_int32, C.c_int32, _p, _p, C.c_int32, C.POINTER(SortPlan)]),
     "w2t_sort_track": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortPlan), C.POINTER(SortResult), _p, _p, _p]),
     "w2t_sort_step": (C.c_int, [C.POINTER(SortProblem), C.POINTER(SortPlan), C.POINTER(SortResult), _p, _p, C.c_int32,
                                 _p, _p]),

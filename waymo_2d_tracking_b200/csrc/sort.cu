@@ -12,10 +12,27 @@
 
 using namespace w2t;
 
+static int sort_plan_impl(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                          const int32_t *det_count, const int32_t *group_offsets, const uint8_t *img_exists,
+                          int32_t max_age, w2t_sort_plan_t *plan);
+
 extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
                              const int32_t *det_count, const uint8_t *img_exists, int32_t max_age,
                              w2t_sort_plan_t *plan) {
-  if (!stream_img_offsets || !det_count || !plan || !plan->order || !plan->track_cap || !plan->det_cap ||
+  return sort_plan_impl(n_streams, n_classes, stream_img_offsets, det_count, nullptr, img_exists, max_age, plan);
+}
+
+extern "C" int w2t_sort_plan_offsets(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                                     const int32_t *group_offsets, int32_t max_age, w2t_sort_plan_t *plan) {
+  return sort_plan_impl(n_streams, n_classes, stream_img_offsets, nullptr, group_offsets, nullptr, max_age, plan);
+}
+
+// det_count[g], or — when only the group offsets of the rows are known (upper bounds, e.g. the group sizes before
+// the ensemble) — group_offsets[g + 1] - group_offsets[g], with an image counted as present when it has any row
+static int sort_plan_impl(int32_t n_streams, int32_t n_classes, const int32_t *stream_img_offsets,
+                          const int32_t *det_count, const int32_t *group_offsets, const uint8_t *img_exists,
+                          int32_t max_age, w2t_sort_plan_t *plan) {
+  if (!stream_img_offsets || (!det_count && !group_offsets) || !plan || !plan->order || !plan->track_cap || !plan->det_cap ||
       !plan->ws_offset || n_streams < 0 || n_classes < 1 || n_classes > W2T_MAX_CLASSES || max_age < 0) {
     set_last_error("w2t_sort_plan: bad argument");
     return W2T_ERR_ARG;
@@ -35,7 +52,13 @@ extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t
       int pos = 0;
       for (int img = stream_img_offsets[s]; img < stream_img_offsets[s + 1]; img++) {
         if (img_exists && !img_exists[img]) continue;
-        const int32_t *cnt = det_count + (size_t)img * NC;
+        int32_t from_offsets[W2T_MAX_CLASSES];
+        const int32_t *cnt = det_count ? det_count + (size_t)img * NC : from_offsets;
+        if (!det_count) {
+          const int32_t *go = group_offsets + (size_t)img * NC;
+          if (go[NC] == go[0]) continue;  // no row at all: the image does not exist for the tracker
+          for (int c = 0; c < NC; c++) from_offsets[c] = go[c + 1] - go[c];
+        }
         int *slot = ring.data() + (size_t)pos * NC;
         for (int c = 0; c < NC; c++) {
           const int d = cnt[c];
@@ -56,7 +79,9 @@ extern "C" int w2t_sort_plan(int32_t n_streams, int32_t n_classes, const int32_t
     }
   };
   const int n_img_total = n_streams > 0 ? stream_img_offsets[n_streams] : 0;
-  const int n_threads = (n_img_total >= 40000 && n_streams >= 8) ? 4 : 1;
+  // a few host threads for large jobs; W2T_PLAN_THREADS caps them (one process per GPU: cores / ranks)
+  int n_threads = (n_img_total >= 40000 && n_streams >= 8) ? 4 : 1;
+  if (const char *e = getenv("W2T_PLAN_THREADS")) n_threads = std::max(1, std::min(n_threads, atoi(e)));
   if (n_threads == 1) {
     plan_streams(0, n_streams);
   } else {

@@ -286,7 +286,9 @@ def hardnms_groups(group_offsets, rows, iou_thresh=0.5, top_k=0, max_group=None,
 # SORT
 # ---------------------------------------------------------------------------
 
-def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age):
+def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age, group_offsets=None):
+    """``w2t_sort_plan`` on host arrays.  With ``group_offsets`` (int32 [G+1]) instead of ``h_count`` /
+    ``h_exists``: ``w2t_sort_plan_offsets`` — capacities from the group sizes (upper bounds before the ensemble)."""
     nq = n_streams * n_classes
     arrays = dict(order=np.zeros(nq, np.int32), track_cap=np.zeros(nq, np.int32),
                   det_cap=np.zeros(nq, np.int32), ws_offset=np.zeros(nq, np.int64))
@@ -294,12 +296,18 @@ def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age):
     for k, v in arrays.items():
         setattr(plan, k, v.ctypes.data_as(C.c_void_p))
     h_offsets = np.ascontiguousarray(h_offsets, np.int32)
-    h_count = np.ascontiguousarray(h_count, np.int32)
-    h_exists = None if h_exists is None else np.ascontiguousarray(h_exists, np.uint8)
-    check(lib().w2t_sort_plan(int(n_streams), int(n_classes), h_offsets.ctypes.data_as(C.c_void_p),
-                              h_count.ctypes.data_as(C.c_void_p),
-                              None if h_exists is None else h_exists.ctypes.data_as(C.c_void_p),
-                              int(max_age), C.byref(plan)), "w2t_sort_plan")
+    if group_offsets is not None:
+        go = np.ascontiguousarray(group_offsets, np.int32)
+        check(lib().w2t_sort_plan_offsets(int(n_streams), int(n_classes), h_offsets.ctypes.data_as(C.c_void_p),
+                                          go.ctypes.data_as(C.c_void_p), int(max_age), C.byref(plan)),
+              "w2t_sort_plan_offsets")
+    else:
+        h_count = np.ascontiguousarray(h_count, np.int32)
+        h_exists = None if h_exists is None else np.ascontiguousarray(h_exists, np.uint8)
+        check(lib().w2t_sort_plan(int(n_streams), int(n_classes), h_offsets.ctypes.data_as(C.c_void_p),
+                                  h_count.ctypes.data_as(C.c_void_p),
+                                  None if h_exists is None else h_exists.ctypes.data_as(C.c_void_p),
+                                  int(max_age), C.byref(plan)), "w2t_sort_plan")
     arrays["ws_bytes"] = int(plan.ws_bytes)
     arrays["n_wide"] = int(plan.n_wide)
     arrays["n_mid"] = int(plan.n_mid)
@@ -527,9 +535,7 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     if host_group_offsets is not None and not to_host and n_groups:
         # no round trip: capacities from the input sizes; W2T_ERR_CAPACITY (only possible when the
         # ensemble drops every box of an image) is left in trk["status"] for the caller to check
-        sizes = np.diff(np.asarray(host_group_offsets)).astype(np.int32)
-        exists_ub = (sizes.reshape(-1, NC).sum(1) > 0).astype(np.uint8)
-        plan = make_plan(S, NC, h_offsets, sizes, exists_ub, max_age)
+        plan = make_plan(S, NC, h_offsets, None, None, max_age, group_offsets=np.asarray(host_group_offsets))
         trk = sort_track_device(S, NC, d_offsets, d_start, nms["trk_count"], nms["trk_box"], nms["img_exists"],
                                 _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan,
                                 promotion=promotion)
@@ -738,12 +744,10 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                      "status": nms_out["status"]}
             softnms_groups_device(d_goff[g0:g1 + 1], d_rows, g1 - g0, max_group, iou_thresh, soft_nms_cut, min_score,
                                   NC, score_thr, out=nms_k, box_format=fmt)
-    if sizes is None:
-        sizes = np.diff(go_np).astype(np.int32)
-    exists_ub = (np.diff(go_np[::NC]) > 0).astype(np.uint8)      # an image exists if any of its groups has a row
-    # one plan for all streams (slab capacities and offsets, heaviest-first order); the launch order is then
-    # regrouped chunk by chunk, heaviest first inside a chunk
-    plan_all = make_plan(S, NC, h_offsets, sizes, exists_ub, max_age)
+    # one plan for all streams (slab capacities and offsets, heaviest-first order) from the INPUT group sizes
+    # (an image exists if any of its groups has a row); the launch order is then regrouped chunk by chunk,
+    # heaviest first inside a chunk
+    plan_all = make_plan(S, NC, h_offsets, None, None, max_age, group_offsets=go_np)
     chunk_of_stream = np.zeros(S, np.int32)
     for k, (s0, s1) in enumerate(chunks):
         chunk_of_stream[s0:s1] = k
