@@ -229,6 +229,14 @@ int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_
  * x, y and r are float64 computations and only s = w*h is a float32 product (w2t_types.h). */
 int w2t_bbox_to_z(const float *dets, double *z, int32_t n, int32_t promotion, w2t_stream_t stream);
 
+/* bbox_vote (detnet/utils/box_utils.py:401-430), the box-voting step of the detector head
+ * (detnet/nn/modules/detection.py:69-71): out[i] = sum_j s_j * all_boxes[j] / sum_j s_j over the boxes j with
+ * IoU(nms_boxes[i], all_boxes[j]) >= thresh.  Boxes are [.,4] x1,y1,x2,y2 in float64 storage; compute_f32 = 1
+ * does the arithmetic in float32 (the head's tensors).  The summation order of torch.sum is not reproduced:
+ * agreement is to rounding (1e-6 relative in float32, 1e-12 in float64), not bit-exact. */
+int w2t_bbox_vote(const double *nms_boxes, int32_t n, const double *all_boxes, const double *all_scores, int32_t m,
+                  double thresh, int32_t compute_f32, double *out, w2t_stream_t stream);
+
 /* convert_x_to_bbox (sort.py:65-75) of n states: row i is x[i*ldx .. i*ldx+3] = x, y, s, r (ldx >= 4);
  * boxes[n,4] = x1, y1, x2, y2. */
 int w2t_x_to_bbox(const double *x, int32_t ldx, double *boxes, int32_t n, w2t_stream_t stream);

@@ -186,6 +186,10 @@ typedef struct w2t_nms_problem_t {
   double conf_thresh;            /* > 0: a box whose running score drops below it is removed  */
                                  /*   and neither output nor suppresses later ones            */
                                  /*   (box_utils.py:379-381)                                  */
+  int32_t compute_f32;           /* 1: decay / suppression arithmetic in float32 — the detector */
+                                 /*   head's call of nms() with float32 tensors                */
+                                 /*   (detnet/nn/modules/detection.py:59-77); rows then hold     */
+                                 /*   float32 values widened to float64.  0: float64 (ensemble) */
 } w2t_nms_problem_t;
 
 /* Outputs of the ensemble stage.  Row k of group g is at group_offsets[g] + k, in the

@@ -108,6 +108,39 @@ def nms_api_cases():
     return out
 
 
+def nms_f32_cases():
+    """The detector head's call pattern (detnet/nn/modules/detection.py:59-77): float32 point-form boxes and
+    float32 scores through box_utils.nms (soft / hard, top_k, conf_thresh) and box_utils.bbox_vote; outputs of the
+    reference's own functions (torch CPU, float32 arithmetic).  Also two float64 bbox_vote cases."""
+    import torch
+    _, _, bu = ref_shim.load_ensemble()
+    rng = np.random.default_rng(91)
+    out = {}
+    n_cases = 0
+    for trial in range(32):
+        n = int(rng.integers(2, 90))
+        xy = rng.uniform(0, 300, (n, 2))
+        dt = np.float32 if trial < 28 else np.float64
+        boxes = np.c_[xy, xy + rng.uniform(8, 150, (n, 2))].astype(dt)
+        scores = rng.uniform(0.05, 1, n).astype(dt)          # distinct with probability 1
+        kw = dict(overlap=[0.5, 0.3, 0.45][trial % 3], top_k=[0, 200, 9][trial % 3], soft=bool(trial % 2),
+                  conf_thresh=[0.05, 0.2][(trial // 2) % 2], soft_nms_cut=[1.0, 0.9][(trial // 4) % 2])
+        tb, ts = torch.from_numpy(boxes), torch.from_numpy(scores)
+        with ref_shim.stable_torch_sort():
+            keep, sc = bu.nms(tb, ts, **kw)
+        keep_t = torch.as_tensor([int(k) for k in keep], dtype=torch.long)
+        voted = bu.bbox_vote(tb[keep_t], sc, tb, ts, 0.6) if len(keep_t) else torch.zeros((0, 4), dtype=tb.dtype)
+        p = "c%d_" % n_cases
+        out[p + "boxes"], out[p + "scores"] = boxes, scores
+        out[p + "args"] = np.asarray([kw["overlap"], kw["top_k"], float(kw["soft"]), kw["conf_thresh"], kw["soft_nms_cut"]])
+        out[p + "keep"] = np.asarray([int(k) for k in keep], np.int64)
+        out[p + "out_scores"] = sc.numpy().copy()
+        out[p + "voted"] = voted.numpy().copy()
+        n_cases += 1
+    out["n_cases"] = np.int64(n_cases)
+    return out
+
+
 def scene_inputs(scene):
     d = {"image_ids": np.asarray(scene.image_ids()), "n_sub": np.int64(len(scene.submissions))}
     for k, sub in enumerate(scene.submissions):
@@ -228,6 +261,11 @@ def main_methods():
         out = nms_api_cases()
         np.savez_compressed(path, **out)
         print("nms_api", int(out["n_cases"]), "cases")
+    path = os.path.join(HERE, "nms_f32.npz")
+    if not os.path.exists(path):
+        out = nms_f32_cases()
+        np.savez_compressed(path, **out)
+        print("nms_f32", int(out["n_cases"]), "cases")
 
 
 def main():

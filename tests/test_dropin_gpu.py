@@ -99,6 +99,25 @@ def test_nms_api_matches_reference_golden():
         np.testing.assert_array_equal(sc.numpy(), g[p + "out_scores"])     # decayed scores bit-exact
 
 
+def test_detector_head_nms_float32_and_bbox_vote_match_reference_golden():
+    """The Detect call pattern (detnet/nn/modules/detection.py:59-77): float32 boxes / scores through nms (arithmetic
+    in float32 like torch: kept indices and decayed scores bit-exact) and bbox_vote (agreement to rounding: the
+    reference's torch.sum order is not reproduced); the last cases are float64."""
+    g = golden_io.load("nms_f32")
+    for i in range(int(g["n_cases"])):
+        p = "c%d_" % i
+        overlap, top_k, soft, conf, cut = g[p + "args"]
+        tb, ts = torch.from_numpy(g[p + "boxes"]), torch.from_numpy(g[p + "scores"])
+        keep, sc = box_utils.nms(tb, ts, overlap=overlap, top_k=int(top_k), soft=bool(soft), conf_thresh=conf, soft_nms_cut=cut)
+        assert [int(k) for k in keep] == g[p + "keep"].tolist(), i
+        assert sc.dtype == ts.dtype
+        np.testing.assert_array_equal(sc.numpy(), g[p + "out_scores"])
+        keep_t = torch.as_tensor([int(k) for k in keep], dtype=torch.long)
+        voted = box_utils.bbox_vote(tb[keep_t], sc, tb, ts, 0.6)
+        assert voted.dtype == tb.dtype and tuple(voted.shape) == g[p + "voted"].shape
+        np.testing.assert_allclose(voted.numpy(), g[p + "voted"], rtol=2e-6 if tb.dtype == torch.float32 else 1e-12, atol=0)
+
+
 def test_nms_detections_and_merge_detections_vs_oracle():
     rng = np.random.default_rng(8)
     for trial in range(12):
@@ -126,8 +145,10 @@ def test_box_conversions_and_dtype_guard():
     pf = box_utils.point_form(b)
     assert pf.tolist() == [[8., 17., 12., 23.], [0., -1.25, 1., 1.75]]
     assert box_utils.center_size(pf).tolist() == b.tolist()
+    with pytest.raises(TypeError):      # mixed dtypes: torch itself would refuse `sorted_scores *= weights`
+        box_utils.nms(pf.float(), torch.tensor([0.5, 0.4], dtype=torch.float64), soft=True)
     with pytest.raises(TypeError):
-        box_utils.nms(pf.float(), torch.tensor([0.5, 0.4]), soft=True)
+        box_utils.nms(pf.half(), torch.tensor([0.5, 0.4]).half(), soft=True)
     keep, sc = box_utils.nms(pf[:0], torch.zeros(0, dtype=torch.float64), soft=True)
     assert keep == [] and sc.numel() == 0
 

@@ -100,6 +100,7 @@ class NmsProblem(C.Structure):
         ("box_format", C.c_int32),
         ("top_k", C.c_int32),
         ("conf_thresh", C.c_double),
+        ("compute_f32", C.c_int32),
     ]
 
 
@@ -182,6 +183,7 @@ EXPORTS = {
     "w2t_json_write_tracks": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p, _p]),
     "w2t_json_write_detections": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p]),
     "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p]),
+    "w2t_bbox_vote": (C.c_int, [_p, C.c_int32, _p, _p, C.c_int32, C.c_double, C.c_int32, _p, _p]),
     "w2t_x_to_bbox": (C.c_int, [_p, C.c_int32, _p, C.c_int32, _p]),
 }
 

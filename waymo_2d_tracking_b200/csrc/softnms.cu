@@ -56,15 +56,19 @@ __device__ __forceinline__ uint32_t strip_mask(double x1, double y1, double x2, 
   return (mx & 0xffffu) | (my << 16);
 }
 
-template <int BLOCK, bool HARD>
+// T: the arithmetic type of the decay / suppression.  double: the ensemble path (ensemble.py:54, tta.py:11-12 are
+// float64 end to end).  float: the detector head's call (detnet/nn/modules/detection.py:59-77 passes float32
+// boxes and scores, and torch keeps every op of box_utils.py:335-391 in float32); inputs arrive as float64 rows
+// holding float32 values, results are widened back.
+template <int BLOCK, bool HARD, typename T>
 __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_scan[2 * (BLOCK / 32)];
   const int cap = P.cap;
   double *raw = reinterpret_cast<double *>(smem_raw);  // [cap] scores in input order
-  double *sx1 = raw + cap, *sy1 = sx1 + cap, *sx2 = sy1 + cap, *sy2 = sx2 + cap;
-  double *sar = sy2 + cap, *ssc = sar + cap;
-  int *src = reinterpret_cast<int *>(ssc + cap);
+  T *sx1 = reinterpret_cast<T *>(raw + cap), *sy1 = sx1 + cap, *sx2 = sy1 + cap, *sy2 = sx2 + cap;
+  T *sar = sy2 + cap, *ssc = sar + cap;
+  int *src = reinterpret_cast<int *>(raw + 7 * (size_t)cap);  // same layout for both arithmetic types
   uint32_t *smk = reinterpret_cast<uint32_t *>(src + cap);  // coarse occupancy masks, see strip_mask()
 
   const int tid = threadIdx.x;
@@ -151,58 +155,60 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
       const int sel = E < m - G ? E : m - G;
       rank = G + L - (E - sel);
     }
-    double b0, b1, b2, b3;
-    row_box(i, b0, b1, b2, b3);
-    double x1, y1, x2, y2;
+    double d0, d1, d2, d3;
+    row_box(i, d0, d1, d2, d3);
+    const T b0 = (T)d0, b1 = (T)d1, b2 = (T)d2, b3 = (T)d3;
+    T x1, y1, x2, y2;
     if (fmt == W2T_BOX_XYXY) {
       x1 = b0; y1 = b1; x2 = b2; y2 = b3;
     } else {
-      const double w = b2, h = b3;
-      double cx = b0, cy = b1;
+      const T w = b2, h = b3;
+      T cx = b0, cy = b1;
       if (fmt != W2T_BOX_CXCYWH) { cx = cx + w / 2; cy = cy + h / 2; }  // lxly2cxcy, ensemble.py:19-22
-      const double hw = w * 0.5, hh = h * 0.5;                         // point_form, box_utils.py:32-35
+      const T hw = w * (T)0.5, hh = h * (T)0.5;                         // point_form, box_utils.py:32-35
       x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
     }
-    const double area = (x2 - x1) * (y2 - y1);            // box_utils.py:342
-    if (!HARD && !(area > 0.)) bad = true;  // 0/0 weights: the reference would drop the box as NaN
+    const T area = (x2 - x1) * (y2 - y1);            // box_utils.py:342
+    if (!HARD && !(area > (T)0)) bad = true;  // 0/0 weights: the reference would drop the box as NaN
     sx1[rank] = x1; sy1[rank] = y1; sx2[rank] = x2; sy2[rank] = y2;
     sar[rank] = area;
-    ssc[rank] = si;
+    ssc[rank] = (T)si;
     src[rank] = i;
-    smk[rank] = strip_mask(x1, y1, x2, y2);
+    smk[rank] = strip_mask((double)x1, (double)y1, (double)x2, (double)y2);
   }
   if (bad && P.status) atomicMax(P.status, W2T_ERR_ARG);
   __syncthreads();
 
   // 3. decay
-  const double cut = P.p.soft_nms_cut;
-  const double denom = cut - P.p.iou_thresh;
-  double wt0 = (cut - 0.0) / denom;  // weight of a pair with IoU = +0
-  if (wt0 < 0.) wt0 = 0.;
-  if (wt0 > 1.) wt0 = 1.;
-  const bool skip_disjoint = (wt0 == 1.0);
+  // the python floats of box_utils.py:368 enter the tensor arithmetic in the tensor's dtype
+  const T cut = (T)P.p.soft_nms_cut;
+  const T denom = (T)(P.p.soft_nms_cut - P.p.iou_thresh);
+  T wt0 = (cut - (T)0) / denom;  // weight of a pair with IoU = +0
+  if (wt0 < (T)0) wt0 = (T)0;
+  if (wt0 > (T)1) wt0 = (T)1;
+  const bool skip_disjoint = (wt0 == (T)1);
   // weight box i (kept, higher ranked) applies to box j; box_utils.py:349-370
-  auto pair_weight = [&](int i, double x1, double y1, double x2, double y2, double area, bool &one) -> double {
-    const double ix1 = sx1[i], iy1 = sy1[i], ix2 = sx2[i], iy2 = sy2[i];
+  auto pair_weight = [&](int i, T x1, T y1, T x2, T y2, T area, bool &one) -> T {
+    const T ix1 = sx1[i], iy1 = sy1[i], ix2 = sx2[i], iy2 = sy2[i];
     // strictly separated boxes: the clamped width or height below is 0, so inter = +0 (sufficient,
     // not necessary: touching or degenerate cases fall through to the full computation)
-    if (skip_disjoint && (x2 <= ix1 || ix2 <= x1 || y2 <= iy1 || iy2 <= y1)) { one = true; return 1.0; }
-    const double xx1 = x1 > ix1 ? x1 : ix1;
-    const double yy1 = y1 > iy1 ? y1 : iy1;
-    const double xx2 = x2 < ix2 ? x2 : ix2;
-    const double yy2 = y2 < iy2 ? y2 : iy2;
-    double w = xx2 - xx1;
-    double h = yy2 - yy1;
-    if (w < 0.) w = 0.;
-    if (h < 0.) h = 0.;
-    const double inter = w * h;
-    if (inter == 0. && skip_disjoint) { one = true; return 1.0; }  // IoU = +0 (areas are positive), weight 1.0
+    if (skip_disjoint && (x2 <= ix1 || ix2 <= x1 || y2 <= iy1 || iy2 <= y1)) { one = true; return (T)1; }
+    const T xx1 = x1 > ix1 ? x1 : ix1;
+    const T yy1 = y1 > iy1 ? y1 : iy1;
+    const T xx2 = x2 < ix2 ? x2 : ix2;
+    const T yy2 = y2 < iy2 ? y2 : iy2;
+    T w = xx2 - xx1;
+    T h = yy2 - yy1;
+    if (w < (T)0) w = (T)0;
+    if (h < (T)0) h = (T)0;
+    const T inter = w * h;
+    if (inter == (T)0 && skip_disjoint) { one = true; return (T)1; }  // IoU = +0 (areas are positive), weight 1.0
     one = false;
-    const double uni = (area - inter) + sar[i];
-    const double iou = inter / uni;
-    double wt = (cut - iou) / denom;
-    if (wt < 0.) wt = 0.;
-    if (wt > 1.) wt = 1.;
+    const T uni = (area - inter) + sar[i];
+    const T iou = inter / uni;
+    T wt = (cut - iou) / denom;
+    if (wt < (T)0) wt = (T)0;
+    if (wt > (T)1) wt = (T)1;
     return wt;
   };
   // separated pairs leave box j untouched: weight exactly 1.0 (soft) / overlap 0 <= threshold (hard)
@@ -211,8 +217,8 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   if (!sequential) {
     // fixed-order triangular product: thread j multiplies the weights of every i ranked above it
     for (int j = tid; j < m; j += BLOCK) {
-      const double x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j], area = sar[j];
-      double live = ssc[j];
+      const T x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j], area = sar[j];
+      T live = ssc[j];
       const uint32_t mj = smk[j];
       // 32 higher ranked boxes at a time: a divergence-free integer loop collects the candidates whose
       // strip masks meet this box's in x and in y (a few percent of the pairs); only those go through
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
           const int i = i0 + __ffs(cand) - 1;
           cand &= cand - 1u;
           bool one;
-          const double wt = pair_weight(i, x1, y1, x2, y2, area, one);
+          const T wt = pair_weight(i, x1, y1, x2, y2, area, one);
           if (!one) live = live * wt;
         }
       }
@@ -259,28 +265,28 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
         const bool apart = mask_skip && ((both & 0xffffu) == 0u || (both >> 16) == 0u);
         if (apart) {
           // soft branch: the score is unchanged but still has to pass `ge(conf_thresh)` (box_utils.py:379)
-          if (!HARD && !(ssc[j] >= conf)) alive[j] = 0;
+          if (!HARD && !(ssc[j] >= (T)conf)) alive[j] = 0;
           continue;
         }
         if (HARD) {
           // torchvision nms_kernel_impl: ovr = inter / (iarea + areas[j] - inter); suppress if > thr
-          const double kx1 = sx1[k], ky1 = sy1[k], kx2 = sx2[k], ky2 = sy2[k];
-          const double xx1 = kx1 > sx1[j] ? kx1 : sx1[j];
-          const double yy1 = ky1 > sy1[j] ? ky1 : sy1[j];
-          const double xx2 = kx2 < sx2[j] ? kx2 : sx2[j];
-          const double yy2 = ky2 < sy2[j] ? ky2 : sy2[j];
-          double w = xx2 - xx1, h = yy2 - yy1;
-          if (!(w > 0.)) w = 0.;   // std::max(0, w): a NaN difference yields 0
-          if (!(h > 0.)) h = 0.;
-          const double inter = w * h;
-          const double ovr = inter / ((sar[k] + sar[j]) - inter);
-          if (ovr > P.p.iou_thresh) alive[j] = 0;
+          const T kx1 = sx1[k], ky1 = sy1[k], kx2 = sx2[k], ky2 = sy2[k];
+          const T xx1 = kx1 > sx1[j] ? kx1 : sx1[j];
+          const T yy1 = ky1 > sy1[j] ? ky1 : sy1[j];
+          const T xx2 = kx2 < sx2[j] ? kx2 : sx2[j];
+          const T yy2 = ky2 < sy2[j] ? ky2 : sy2[j];
+          T w = xx2 - xx1, h = yy2 - yy1;
+          if (!(w > (T)0)) w = (T)0;   // std::max(0, w): a NaN difference yields 0
+          if (!(h > (T)0)) h = (T)0;
+          const T inter = w * h;
+          const T ovr = inter / ((sar[k] + sar[j]) - inter);
+          if ((double)ovr > P.p.iou_thresh) alive[j] = 0;  // torchvision compares with its double threshold
         } else {
           bool one;
-          const double wt = pair_weight(k, sx1[j], sy1[j], sx2[j], sy2[j], sar[j], one);
-          const double live = one ? ssc[j] : ssc[j] * wt;
+          const T wt = pair_weight(k, sx1[j], sy1[j], sx2[j], sy2[j], sar[j], one);
+          const T live = one ? ssc[j] : ssc[j] * wt;
           ssc[j] = live;
-          if (!(live >= conf)) alive[j] = 0;
+          if (!(live >= (T)conf)) alive[j] = 0;
         }
       }
       __syncthreads();
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     int bx = 0, by = 0, bw = 0, bh = 0;
     double rs = 0.;
     if (f_keep) {
-      const double x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j];
-      const double live = ssc[j];
+      const double x1 = (double)sx1[j], y1 = (double)sy1[j], x2 = (double)sx2[j], y2 = (double)sy2[j];
+      const double live = (double)ssc[j];
       // center_size (box_utils.py:57-69) then cxcy2lxly (ensemble.py:25-28)
       const double cx = (x1 + x2) * 0.5, cy = (y1 + y2) * 0.5;
       const double w = x2 - x1, h = y2 - y1;
@@ -350,14 +356,20 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   }
 }
 
-template <int BLOCK, bool HARD>
-int launch(const NmsParams &P, int n_groups, size_t smem, cudaStream_t stream) {
+template <int BLOCK, bool HARD, typename T>
+int launch_t(const NmsParams &P, int n_groups, size_t smem, cudaStream_t stream) {
   if (smem > 48 * 1024)
-    W2T_CUDA_TRY(cudaFuncSetAttribute(softnms_kernel<BLOCK, HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    W2T_CUDA_TRY(cudaFuncSetAttribute(softnms_kernel<BLOCK, HARD, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-  softnms_kernel<BLOCK, HARD><<<n_groups, BLOCK, smem, stream>>>(P);
+  softnms_kernel<BLOCK, HARD, T><<<n_groups, BLOCK, smem, stream>>>(P);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
+}
+
+template <int BLOCK, bool HARD>
+int launch(const NmsParams &P, int n_groups, size_t smem, cudaStream_t stream) {
+  return P.p.compute_f32 ? launch_t<BLOCK, HARD, float>(P, n_groups, smem, stream)
+                         : launch_t<BLOCK, HARD, double>(P, n_groups, smem, stream);
 }
 
 template <bool HARD>

@@ -162,7 +162,60 @@ __global__ void x_to_bbox_kernel(const double *x, int ldx, double *boxes, int n)
   for (int k = 0; k < 4; k++) boxes[4 * (size_t)i + k] = b[k];
 }
 
+// bbox_vote (detnet/utils/box_utils.py:401-430): one CTA per kept box; the boxes that overlap it by IoU >= thresh
+// vote with their scores.  T = the tensors' dtype.  The reference's torch.sum order is not reproduced (tree
+// reduction here), so results agree to rounding, not bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(128) bbox_vote_kernel(const double *nms_boxes, int n, const double *all_boxes,
+                                                        const double *all_scores, int m, double thresh, double *out) {
+  __shared__ T red[5][4];
+  const int i = blockIdx.x;
+  const T b0 = (T)nms_boxes[4 * i], b1 = (T)nms_boxes[4 * i + 1], b2 = (T)nms_boxes[4 * i + 2], b3 = (T)nms_boxes[4 * i + 3];
+  const T nms_area = (b2 - b0) * (b3 - b1);
+  T acc[5] = {(T)0, (T)0, (T)0, (T)0, (T)0};
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const T x1 = (T)all_boxes[4 * j], y1 = (T)all_boxes[4 * j + 1], x2 = (T)all_boxes[4 * j + 2], y2 = (T)all_boxes[4 * j + 3];
+    const T area = (x2 - x1) * (y2 - y1);
+    const T xx1 = x1 < b0 ? b0 : x1, yy1 = y1 < b1 ? b1 : y1;   // clamp(min=...)
+    const T xx2 = x2 > b2 ? b2 : x2, yy2 = y2 > b3 ? b3 : y2;   // clamp(max=...)
+    T w = xx2 - xx1, h = yy2 - yy1;
+    if (w < (T)0) w = (T)0;
+    if (h < (T)0) h = (T)0;
+    const T inter = w * h;
+    const T uni = (area + nms_area) - inter;
+    const T iou = inter / uni;
+    if (iou >= (T)thresh) {
+      const T sc = (T)all_scores[j];
+      acc[0] += x1 * sc; acc[1] += y1 * sc; acc[2] += x2 * sc; acc[3] += y2 * sc; acc[4] += sc;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    T v = acc[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const T tot = (red[4][0] + red[4][1]) + (red[4][2] + red[4][3]);
+    const T sum = (red[threadIdx.x][0] + red[threadIdx.x][1]) + (red[threadIdx.x][2] + red[threadIdx.x][3]);
+    out[4 * i + threadIdx.x] = (double)(sum / tot);
+  }
+}
+
 }  // namespace
+
+extern "C" int w2t_bbox_vote(const double *nms_boxes, int32_t n, const double *all_boxes, const double *all_scores,
+                             int32_t m, double thresh, int32_t compute_f32, double *out, w2t_stream_t stream) {
+  if (n < 0 || m < 0) return W2T_ERR_ARG;
+  if (n == 0) return W2T_OK;
+  if (!nms_boxes || !out || (m > 0 && (!all_boxes || !all_scores))) return W2T_ERR_ARG;
+  if (compute_f32) bbox_vote_kernel<float><<<n, 128, 0, (cudaStream_t)stream>>>(nms_boxes, n, all_boxes, all_scores, m, thresh, out);
+  else bbox_vote_kernel<double><<<n, 128, 0, (cudaStream_t)stream>>>(nms_boxes, n, all_boxes, all_scores, m, thresh, out);
+  W2T_CUDA_TRY(cudaGetLastError());
+  return W2T_OK;
+}
 
 extern "C" int w2t_bbox_to_z(const float *dets, double *z, int32_t n, int32_t promotion, w2t_stream_t stream) {
   if (n < 0) return W2T_ERR_ARG;

@@ -134,7 +134,7 @@ def _np(t):
 
 def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
                           n_classes=0, score_thr=None, want_merged=True, box_format=_abi.W2T_BOX_LTWH, top_k=0,
-                          conf_thresh=0.0, want_ensemble=True, hard=False, out=None):
+                          conf_thresh=0.0, want_ensemble=True, hard=False, out=None, compute_f32=False):
     """Launch on device tensors; returns device tensors (no synchronisation).
     ``hard`` selects ``w2t_hardnms_groups`` (the ``-m nms`` method) instead of the soft branch.
     ``out``: preallocated result tensors to write into (all keys below; rows are indexed by the
@@ -144,7 +144,7 @@ def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, so
     N = int(d_rows.shape[0])
     if out is not None:
         return _launch_nms(dict(out), d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
-                           n_classes, score_thr, box_format, top_k, conf_thresh, hard)
+                           n_classes, score_thr, box_format, top_k, conf_thresh, hard, compute_f32)
     out = {
         "merged": torch.empty((N, 5), dtype=torch.float64, device=device) if want_merged else None,
         "src_index": torch.empty(N, dtype=torch.int32, device=device) if want_merged else None,
@@ -162,11 +162,11 @@ def softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, so
         out["trk_box"] = torch.empty((N, 4), dtype=torch.float32, device=device)
         out["img_exists"] = torch.zeros(max(n_groups // n_classes, 1), dtype=torch.uint8, device=device)
     return _launch_nms(out, d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, n_classes,
-                       score_thr, box_format, top_k, conf_thresh, hard)
+                       score_thr, box_format, top_k, conf_thresh, hard, compute_f32)
 
 
 def _launch_nms(out, d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score, n_classes,
-                score_thr, box_format, top_k, conf_thresh, hard):
+                score_thr, box_format, top_k, conf_thresh, hard, compute_f32=False):
     thr = None
     if score_thr is not None:
         thr = (C.c_double * n_classes)(*[float(v) for v in score_thr[:n_classes]])
@@ -178,6 +178,7 @@ def _launch_nms(out, d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nm
     prob.n_classes = int(n_classes)
     prob.score_thr = C.cast(thr, C.c_void_p) if thr is not None else None
     prob.box_format, prob.top_k, prob.conf_thresh = int(box_format), int(top_k), float(conf_thresh)
+    prob.compute_f32 = 1 if compute_f32 else 0
     res = _abi.NmsResult()
     for k in ("merged", "src_index", "kept_count", "ens_count", "ens_box", "ens_score", "trk_count", "trk_box",
               "img_exists"):
@@ -191,7 +192,7 @@ def _launch_nms(out, d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nm
 
 def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_score=0.0, n_classes=0,
                    score_thr=None, max_group=None, want_merged=True, box_format=_abi.W2T_BOX_LTWH, top_k=0,
-                   conf_thresh=0.0, want_ensemble=True, hard=False):
+                   conf_thresh=0.0, want_ensemble=True, hard=False, compute_f32=False):
     """Soft-NMS (or, with ``hard``, plain NMS) merge of every (image, category) group; NumPy in, NumPy out."""
     device = require_cuda()
     offs_np = group_offsets if isinstance(group_offsets, np.ndarray) else None
@@ -207,7 +208,7 @@ def softnms_groups(group_offsets, rows, iou_thresh=0.5, soft_nms_cut=1.0, min_sc
     d_rows = t_rows.to(device, non_blocking=True).contiguous()
     out = softnms_groups_device(d_offsets, d_rows, n_groups, max_group, iou_thresh, soft_nms_cut, min_score,
                                 n_classes, score_thr, want_merged, box_format, top_k, conf_thresh, want_ensemble,
-                                hard)
+                                hard, compute_f32=compute_f32)
     host = {k: _host(v) for k, v in out.items()}
     torch.cuda.current_stream().synchronize()
     check_device_status(int(host["status"][0]), "soft-NMS")
@@ -271,11 +272,12 @@ def fusion_groups(group_offsets, rows, sub_counts, iou_thresh=0.5, min_score=0.0
     return {k: _np(v) for k, v in host.items()}
 
 
-def hardnms_groups(group_offsets, rows, iou_thresh=0.5, top_k=0, max_group=None, box_format=_abi.W2T_BOX_XYXY):
+def hardnms_groups(group_offsets, rows, iou_thresh=0.5, top_k=0, max_group=None, box_format=_abi.W2T_BOX_XYXY,
+                   compute_f32=False):
     """``nms(soft=False)`` of every group: ``keep`` holds, per group from its first row on, the kept
     input rows (group-local indices) in descending score order; ``kept_count`` how many."""
     res = softnms_groups(group_offsets, rows, iou_thresh, 1.0, -np.inf, max_group=max_group, box_format=box_format,
-                         top_k=top_k, want_ensemble=False, hard=True)
+                         top_k=top_k, want_ensemble=False, hard=True, compute_f32=compute_f32)
     offs = np.asarray(group_offsets, np.int64)
     local = res["src_index"].astype(np.int64) - np.repeat(offs[:-1], np.diff(offs))
     res["keep"] = local
@@ -1078,6 +1080,18 @@ def bbox_to_z(dets, promotion=None):
     check(lib().w2t_bbox_to_z(_ptr(d), _ptr(z), int(d.shape[0]), code, _stream()), "w2t_bbox_to_z")
     out = z.cpu().numpy()
     return out.astype(np.float32) if code == _abi.W2T_PROMOTION_NEP50 else out
+
+
+def bbox_vote(nms_boxes, all_boxes, all_scores, thresh, compute_f32=False):
+    """``bbox_vote`` (box_utils.py:401-430) on NumPy / torch inputs -> float64 [n,4] (``w2t_bbox_vote``)."""
+    device = require_cuda()
+    nb = _dev(np.asarray(nms_boxes, np.float64).reshape(-1, 4), np.float64, device)
+    ab = _dev(np.asarray(all_boxes, np.float64).reshape(-1, 4), np.float64, device)
+    sc = _dev(np.asarray(all_scores, np.float64).reshape(-1), np.float64, device)
+    out = torch.zeros((nb.shape[0], 4), dtype=torch.float64, device=device)
+    check(lib().w2t_bbox_vote(_ptr(nb), int(nb.shape[0]), _ptr(ab), _ptr(sc), int(ab.shape[0]), float(thresh),
+                              1 if compute_f32 else 0, _ptr(out), _stream()), "w2t_bbox_vote")
+    return out.cpu().numpy()
 
 
 def x_to_bbox(x):
