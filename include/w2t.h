@@ -82,7 +82,9 @@ int w2t_fusion_groups(const w2t_nms_problem_t *problem, const int32_t *sub_count
                       w2t_nms_result_t *result, int max_group_size, int32_t *status, w2t_stream_t stream);
 int w2t_fusion_max_group(void);
 
-/* Largest group the NMS kernels accept (shared-memory resident). */
+/* Largest group the NMS kernels keep in shared memory (3401 boxes).  Larger groups are not an error: a second
+ * launch of a few persistent CTAs runs the same kernel over arrays in global memory (stream-ordered scratch from
+ * cudaMallocAsync, freed behind the launch) for just those groups. */
 int w2t_softnms_max_group(void);
 
 /* ---- SORT --------------------------------------------------------------- */

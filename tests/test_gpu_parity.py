@@ -104,6 +104,17 @@ def test_linear_assignment_large_crowded():
     np.testing.assert_array_equal(runtime.linear_assignment(cost.T.copy()), c_oracle.linear_assignment(cost.T.copy()))
 
 
+def test_linear_assignment_beyond_2048():
+    # past the old 2048 limit of the solver's mask words (now 4096): 300 detections against 2500 trackers, and the
+    # transposed problem (a full 2500 x 2500 solve takes the C oracle two minutes, so the square case stays out)
+    rng = np.random.default_rng(5)
+    trks = rand_boxes(rng, 2500, 0, 6000, 20, 90)
+    dets = np.r_[trks[:250] + rng.normal(0, 4, (250, 4)), rand_boxes(rng, 50, 0, 6000, 20, 90)].astype(np.float32)
+    cost = -c_oracle.iou_matrix(dets, trks)
+    np.testing.assert_array_equal(runtime.linear_assignment(cost), c_oracle.linear_assignment(cost))
+    np.testing.assert_array_equal(runtime.linear_assignment(cost.T.copy()), c_oracle.linear_assignment(cost.T.copy()))
+
+
 # ---- SORT stage -------------------------------------------------------------------------------
 
 def compare_sort(packed, iou_thr, max_age, min_hits, final_cap=0, promotion=None):
@@ -336,6 +347,32 @@ def test_softnms_large_group_tta_shaped():
     groups = synth.groups_from_scene(scene, None, 0.01)
     assert groups.max_group > 1000
     compare_nms(groups, 0.5, 0.9, 0.01)
+
+
+def test_softnms_group_beyond_shared_memory():
+    # a group of 5000 boxes (shared memory holds 3401): the global-memory pass takes it, its neighbours stay on the
+    # regular launch; soft and hard branch against the C oracle, bit for bit
+    rng = np.random.default_rng(12)
+    sizes = [7, 5000, 0, 120, 3600]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    n = int(offs[-1])
+    c = rng.uniform(0, 1900, (n, 2))
+    rows = np.c_[np.round(rng.uniform(0.02, 1, n), 5), c.astype(np.int64), rng.integers(8, 160, (n, 2))].astype(np.float64)
+    got = runtime.softnms_groups(offs, rows, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR, max_group=max(sizes))
+    want = c_oracle.softnms_groups(offs, rows, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR)
+    for k in ("ens_count", "trk_count", "kept_count"):
+        np.testing.assert_array_equal(got[k], want[k])
+    for g in range(len(sizes)):
+        o, cnt = int(offs[g]), int(want["ens_count"][g])
+        np.testing.assert_array_equal(got["ens_box"][o:o + cnt], want["ens_box"][o:o + cnt])
+        np.testing.assert_array_equal(got["ens_score"][o:o + cnt], want["ens_score"][o:o + cnt])
+        np.testing.assert_array_equal(got["merged"][o:o + sizes[g]], want["merged"][o:o + sizes[g]])
+    got = runtime.hardnms_groups(offs, rows, 0.5, max_group=max(sizes), box_format=0)
+    want = c_oracle.softnms_groups(offs, rows, 0.5, 1.0, -np.inf, box_format=0, hard=True)
+    np.testing.assert_array_equal(got["kept_count"], want["kept_count"])
+    for g in range(len(sizes)):
+        o, cnt = int(offs[g]), int(want["kept_count"][g])
+        np.testing.assert_array_equal(got["merged"][o:o + cnt], want["merged"][o:o + cnt])
 
 
 def test_softnms_rejects_unsupported_scores_loudly():

@@ -45,7 +45,7 @@
 
 namespace w2t {
 
-constexpr int kMunkresMaxWords = 64;                      // mask words kept in shared memory
+constexpr int kMunkresMaxWords = 128;                     // mask words kept in shared memory
 constexpr int kMunkresMaxDim = kMunkresMaxWords * 32;     // largest max(D, T)
 
 struct MunkresShared {

@@ -34,8 +34,15 @@ struct NmsParams {
   w2t_nms_result_t r;
   double score_thr[W2T_MAX_CLASSES];
   int has_thr;
-  int cap;  // boxes the shared-memory arrays hold
+  int cap;  // boxes the arrays hold
   int32_t *status;
+  // oversized groups (more boxes than shared memory holds): a second launch of a few persistent CTAs keeps the
+  // arrays in global memory (`work`, one slice of `work_stride` bytes per CTA) and serves only groups with more
+  // than `small_cap` boxes; the regular launch skips those (`skip_big`)
+  unsigned char *work;
+  size_t work_stride;
+  int small_cap;
+  int skip_big;
 };
 
 // HARD = false: the soft branch (box_utils.py:335-391).  HARD = true: the hard branch
@@ -65,24 +72,30 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_scan[2 * (BLOCK / 32)];
   const int cap = P.cap;
-  double *raw = reinterpret_cast<double *>(smem_raw);  // [cap] scores in input order
+  unsigned char *mem = P.work ? P.work + (size_t)blockIdx.x * P.work_stride : smem_raw;
+  double *raw = reinterpret_cast<double *>(mem);  // [cap] scores in input order
   T *sx1 = reinterpret_cast<T *>(raw + cap), *sy1 = sx1 + cap, *sx2 = sy1 + cap, *sy2 = sx2 + cap;
   T *sar = sy2 + cap, *ssc = sar + cap;
   int *src = reinterpret_cast<int *>(raw + 7 * (size_t)cap);  // same layout for both arithmetic types
   uint32_t *smk = reinterpret_cast<uint32_t *>(src + cap);  // coarse occupancy masks, see strip_mask()
 
   const int tid = threadIdx.x;
-  const int g = blockIdx.x;
+  // one group per CTA (regular launch: gridDim = groups); the oversized pass strides a few CTAs over all groups
+#pragma unroll 1
+  for (int g = blockIdx.x; g < P.p.n_groups; g += gridDim.x) {
+  __syncthreads();  // the previous group's arrays are free
   const int base = P.p.group_offsets[g];
   const int n = P.p.group_offsets[g + 1] - base;
+  if (P.work != nullptr && n <= P.small_cap) continue;  // the regular launch has it
   if (n > cap) {
+    if (P.skip_big) continue;  // the oversized pass has it
     if (tid == 0) {
       if (P.status) atomicMax(P.status, W2T_ERR_CAPACITY);
       P.r.ens_count[g] = 0;
       if (P.r.trk_count) P.r.trk_count[g] = 0;
       if (P.r.kept_count) P.r.kept_count[g] = 0;
     }
-    return;
+    continue;
   }
   const int fmt = P.p.box_format;
   // row i of the group: score and the four box columns, from 40-byte double rows or 16-byte compact rows
@@ -354,6 +367,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
     if (P.r.trk_count) P.r.trk_count[g] = n_trk;
     if (P.r.img_exists && P.p.n_classes > 0 && n_ens > 0) P.r.img_exists[g / P.p.n_classes] = 1;
   }
+  }  // groups
 }
 
 template <int BLOCK, bool HARD, typename T>
@@ -390,24 +404,40 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
     set_last_error("%s: score_thr given without trk_count/trk_box/n_classes", who);
     return W2T_ERR_ARG;
   }
-  if (max_group_size > w2t_softnms_max_group()) {
-    set_last_error("%s: group of %d boxes exceeds the shared-memory limit of %d", who, max_group_size,
-                   w2t_softnms_max_group());
-    return W2T_ERR_CAPACITY;
-  }
+  const int smem_cap = w2t_softnms_max_group();
   NmsParams P;
+  P.work = nullptr;
+  P.work_stride = 0;
+  P.small_cap = 0;
+  P.skip_big = max_group_size > smem_cap ? 1 : 0;
   P.p = *problem;
   P.r = *result;
   P.has_thr = problem->score_thr != nullptr;
   for (int i = 0; i < W2T_MAX_CLASSES; i++)
     P.score_thr[i] = (P.has_thr && i < problem->n_classes) ? problem->score_thr[i] : 0.0;
   P.p.score_thr = nullptr;
-  P.cap = (std::max(max_group_size, 1) + 3) & ~3;  // multiple of 4: keeps the int arrays 16-byte aligned
+  const int regular_max = std::min(max_group_size, smem_cap);
+  P.cap = (std::max(regular_max, 1) + 3) & ~3;  // multiple of 4: keeps the int arrays 16-byte aligned
   P.status = status;
   const size_t smem = (size_t)P.cap * kBytesPerBox + 4 * kMaskPad;
-  if (max_group_size <= 96) return launch<64, HARD>(P, problem->n_groups, smem, stream);
-  if (max_group_size <= 768) return launch<128, HARD>(P, problem->n_groups, smem, stream);
-  return launch<256, HARD>(P, problem->n_groups, smem, stream);
+  int rc;
+  if (regular_max <= 96) rc = launch<64, HARD>(P, problem->n_groups, smem, stream);
+  else if (regular_max <= 768) rc = launch<128, HARD>(P, problem->n_groups, smem, stream);
+  else rc = launch<256, HARD>(P, problem->n_groups, smem, stream);
+  if (rc != W2T_OK || max_group_size <= smem_cap) return rc;
+  // oversized groups: the same kernel over arrays in global memory (stream-ordered scratch, freed behind the
+  // launch), a few persistent CTAs striding over the groups
+  const int ctas = std::min(problem->n_groups, 296);
+  P.small_cap = P.cap;
+  P.skip_big = 0;
+  P.cap = (max_group_size + 3) & ~3;
+  P.work_stride = (((size_t)P.cap * kBytesPerBox + 4 * kMaskPad) + 255) / 256 * 256;
+  void *work = nullptr;
+  W2T_CUDA_TRY(cudaMallocAsync(&work, P.work_stride * (size_t)ctas, stream));
+  P.work = static_cast<unsigned char *>(work);
+  rc = launch<256, HARD>(P, ctas, 0, stream);
+  W2T_CUDA_TRY(cudaFreeAsync(work, stream));
+  return rc;
 }
 
 }  // namespace
