@@ -438,7 +438,8 @@ def main():
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("W2T_BENCH_NO_SAMPLER"):      # debug aid
+        sampler.start()
     runtime.PROFILE = []
     ms_dev, out = timed(step_device, args.steps)
     kernel_ms = runtime.collect_profile()

@@ -128,3 +128,51 @@ def test_array_packers_equal_the_dict_packers(tmp_path):
     assert a.image_ids == b.image_ids and a.category_ids == b.category_ids and a.max_group == b.max_group
     for k in ("group_offsets", "rows", "sub_counts"):
         np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+
+
+def test_threaded_reader_and_writers_equal_the_sequential_ones(tmp_path, monkeypatch):
+    """Files large enough for the multi-threaded paths (csrc/json_io.cpp: the list is split at record boundaries,
+    rows are formatted in ranges): same arrays, byte-identical files; a file whose strings contain the split
+    pattern falls back to the sequential parse."""
+    import dataclasses
+    rng = np.random.default_rng(3)
+    n = 70000
+    rows = [{"image_id": "seg%d/%d/FRONT" % (i % 7, i % 997), "category_id": int(1 + i % 4),
+             "bbox": [int(v) for v in rng.integers(0, 1900, 4)], "score": round(float(rng.uniform(0, 1)), 5)}
+            for i in range(n)]
+    path = tmp_path / "big.json"
+    path.write_text(json.dumps(rows))
+    assert path.stat().st_size > 6 << 20
+    monkeypatch.setenv("W2T_JSON_THREADS", "1")
+    seq = native_json.load(path)
+    monkeypatch.setenv("W2T_JSON_THREADS", "3")
+    par = native_json.load(path)
+    for f in dataclasses.fields(seq):
+        a, b = getattr(seq, f.name), getattr(par, f.name)
+        assert np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b, f.name
+    assert len(par) == n and par.image_ids[:3] == ["seg0/0/FRONT", "seg1/1/FRONT", "seg2/2/FRONT"]
+    box = rng.uniform(0, 1900, (n, 4))
+    score = rng.uniform(0.2, 1, n)
+    oid = rng.integers(1, 10 ** 6, n)
+    for thr in ("1", "3"):
+        monkeypatch.setenv("W2T_JSON_THREADS", thr)
+        native_json.write_tracks(tmp_path / ("t%s.json" % thr), seq.image_ids, seq.image_index, box, score, seq.category, oid)
+        native_json.write_detections(tmp_path / ("d%s.json" % thr), seq.image_ids, seq.image_index, seq.category,
+                                     seq.bbox.astype(np.int32), seq.score)
+    assert (tmp_path / "t1.json").read_bytes() == (tmp_path / "t3.json").read_bytes()
+    assert (tmp_path / "d1.json").read_bytes() == (tmp_path / "d3.json").read_bytes()
+    assert json.loads((tmp_path / "d3.json").read_text())[n - 1]["score"] == rows[n - 1]["score"]
+    tricky = [{"image_id": 's}, {"x/%d/FRONT' % i, "category_id": 1, "bbox": [1, 2, 3, 4], "score": 0.5} for i in range(60000)]
+    (tmp_path / "tricky.json").write_text(json.dumps(tricky))
+    t = native_json.load(tmp_path / "tricky.json")
+    assert len(t) == 60000 and t.image_ids[7] == 's}, {"x/7/FRONT'
+
+
+def test_reader_is_as_strict_as_json_load(tmp_path):
+    for bad in ('[{"image_id": "a", "category_id": 1, "bbox": [1-2, 2, 3, 4], "score": 0.5}]',
+                '[{"image_id": "a", "category_id": 1, "bbox": [1e, 2, 3, 4], "score": 0.5}]',
+                '[{"image_id": "a", "category_id": 1.5, "bbox": [1, 2, 3, 4], "score": 0.5}]'):
+        p = tmp_path / "bad.json"
+        p.write_text(bad)
+        with pytest.raises(Exception):
+            native_json.load(p)

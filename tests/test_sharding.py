@@ -43,6 +43,42 @@ def make_inputs():
     return scene, [synth.to_json_list(scene, s) for s in scene.submissions]
 
 
+def oracle_track_packed(packed, iou_thr, max_age, min_hits):
+    """C oracle on packed streams -> dense rows like runtime.sort_track(raw=False), ids counted from 1."""
+    from oracle import c_oracle
+    from waymo_2d_tracking_b200 import packing
+    res = c_oracle.sort_track(packed, iou_thr, max_age, min_hits)
+    ids, nxt = packing.assign_ids(packed.stream_img_offsets, packed.n_classes, packed.det_start, res["out_count"],
+                                  res["created"], res["first_img"], packed.class_rank, res["out_birth"])
+    dense = packing.unpack_tracks(packed, res["out_box"], res["out_score"], res["out_count"], res["first_img"], ids)
+    index = {iid: i for i, iid in enumerate(packing.image_id_strings(packed))}
+    rows = dict(rows_img=np.array([index[r['image_id']] for r in dense], np.int32),
+                rows_cat=np.array([r['category_id'] for r in dense], np.int32),
+                rows_box=np.array([r['bbox'] for r in dense], np.float64).reshape(-1, 4),
+                rows_score=np.array([r['score'] for r in dense], np.float64),
+                rows_id=np.array([int(r['object_id']) for r in dense], np.int64), n_rows=len(dense))
+    return rows, int(nxt)
+
+
+def array_worker(rank, world, port, json_path, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from waymo_2d_tracking_b200 import native_json
+    dets = native_json.load(json_path)
+    image_ids, rows, nxt = sharding.track_arrays_sharded(dets, helpers.SCORE_THR, helpers.IOU_THR, 2, 0,
+                                                         track_fn=oracle_track_packed)
+    if rank == 0:
+        native_json.write_tracks(out_path, image_ids, rows["rows_img"], rows["rows_box"], rows["rows_score"],
+                                 rows["rows_cat"], rows["rows_id"])
+    else:
+        assert rows is None and image_ids is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def worker(rank, world, port, out_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -91,3 +127,23 @@ def test_world_size_2_sharded_tracking_and_ensemble_equal_single_process(tmp_pat
         assert a[0] == b['image_id'] and a[1] == b['object_id'] and a[2] == b['category_id']
         assert a[3] == [float(v) for v in b['bbox']] and a[4] == float(b['score'])
     assert got["ens"] == json.loads(json.dumps(ensemble_port.ensemble_all(subs, [2, 1], 0.01, 0.5, 0.9)))
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_array_path_of_the_tracking_cli_equals_single_process(tmp_path):
+    """``sharding.track_arrays_sharded`` (what ``tracking/track.py`` runs under torchrun): native reader -> each rank
+    packs and tracks its block of segments -> arrays gathered to rank 0 -> native writer; same file as one process."""
+    from oracle import sort_port
+    scene, subs = make_inputs()
+    src = tmp_path / "sub.json"
+    src.write_text(json.dumps(subs[0]))
+    out = tmp_path / "tracks.json"
+    mp.spawn(array_worker, args=(2, free_port(), str(src), str(out)), nprocs=2, join=True)
+    got = json.loads(out.read_text())
+    pred = sort_port.group_entries(subs[0], helpers.SCORE_THR)
+    want = sort_port.track_all(pred, helpers.IOU_THR, 2, 0, reset_ids=True)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a['image_id'] == b['image_id'] and a['object_id'] == b['object_id'] and a['category_id'] == b['category_id']
+        assert a['bbox'] == [float(v) for v in b['bbox']]
+        assert a['score'] == pytest.approx(float(b['score']), rel=1e-12)

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -138,6 +139,7 @@ struct Parser {
     const char *b = (*s == '+') ? s + 1 : s;
     const auto r = std::from_chars(b, p, v);  // correctly rounded, like Python's float()
     if (r.ec != std::errc() && r.ec != std::errc::result_out_of_range) return fail("bad number");
+    if (r.ptr != p) return fail("bad number");  // "1-2", "1e": json.load raises as well
     return true;
   }
   bool skip_value() {
@@ -222,6 +224,7 @@ struct Parser {
     } else {
       idx = it->second;
     }
+    if (!(cat == (double)(int32_t)cat)) return fail("category_id must be an integer");
     out.image_index.push_back(idx);
     out.category.push_back((int32_t)cat);
     out.bbox.insert(out.bbox.end(), box, box + 4);
@@ -230,10 +233,117 @@ struct Parser {
     return true;
   }
 
+  // The list of detections, split over host threads: candidate split points are places where one record ends
+  // and the next begins (`}` `,` `{`); a thread parses from its split point up to exactly the next one.  A split
+  // point that fell inside a string shows up as a parse error or a missed rendezvous, and the caller then parses
+  // sequentially — so the result never depends on the split.
+  bool list_parallel(w2t_json_dets &out, int T) {
+    std::vector<const char *> starts(1, p);
+    const size_t total = (size_t)(end - p);
+    for (int t = 1; t < T; t++) {
+      const char *q = p + total * (size_t)t / (size_t)T;
+      if (q <= starts.back()) continue;
+      const char *hit = nullptr;
+      for (; q + 1 < end; q++) {
+        if (*q != '}') continue;
+        const char *r = q + 1;
+        while (r < end && (*r == ' ' || *r == '\n' || *r == '\t' || *r == '\r')) r++;
+        if (r >= end || *r != ',') continue;
+        r++;
+        while (r < end && (*r == ' ' || *r == '\n' || *r == '\t' || *r == '\r')) r++;
+        if (r < end && *r == '{') { hit = r; break; }
+      }
+      if (hit == nullptr) break;
+      if (hit > starts.back()) starts.push_back(hit);
+    }
+    const int n = (int)starts.size();
+    if (n < 2) return false;
+    std::vector<w2t_json_dets> part((size_t)n);
+    std::vector<const char *> stop((size_t)n, nullptr);
+    std::vector<char> good((size_t)n, 0);
+    auto work = [&](int t) {
+      Parser sub{starts[t], end};
+      const char *limit = (t + 1 < n) ? starts[t + 1] : nullptr;
+      w2t_json_dets &o = part[t];
+      const size_t guess = (size_t)((limit ? limit : end) - starts[t]) / 90 + 16;
+      o.image_index.reserve(guess); o.category.reserve(guess); o.bbox.reserve(4 * guess);
+      o.score.reserve(guess); o.has_score.reserve(guess);
+      for (;;) {
+        if (!sub.detection(o)) return;
+        sub.ws();
+        if (sub.p < sub.end && *sub.p == ',') {
+          sub.p++;
+          sub.ws();
+          if (limit != nullptr) {
+            if (sub.p == limit) break;       // rendezvous with the next thread's first record
+            if (sub.p > limit) return;       // ran past it: the split point was not a record boundary
+          }
+          continue;
+        }
+        if (limit != nullptr) return;        // the list ended inside a middle chunk?!
+        if (!sub.expect(']')) return;
+        break;
+      }
+      stop[t] = sub.p;
+      good[t] = 1;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < n; t++)
+      if (!good[t]) return false;
+    // merge: image ids keep first-appearance order
+    for (int t = 0; t < n; t++) {
+      w2t_json_dets &o = part[t];
+      std::vector<int32_t> remap(o.image_ids.size());
+      for (size_t i = 0; i < o.image_ids.size(); i++) {
+        auto it = out.lookup.find(o.image_ids[i]);
+        if (it == out.lookup.end()) {
+          const int32_t idx = (int32_t)out.image_ids.size();
+          out.image_ids.push_back(o.image_ids[i]);
+          out.lookup.emplace(out.image_ids.back(), idx);
+          remap[i] = idx;
+        } else {
+          remap[i] = it->second;
+        }
+      }
+      const size_t base = out.image_index.size();
+      out.image_index.resize(base + o.image_index.size());
+      for (size_t i = 0; i < o.image_index.size(); i++) out.image_index[base + i] = remap[o.image_index[i]];
+      out.category.insert(out.category.end(), o.category.begin(), o.category.end());
+      out.bbox.insert(out.bbox.end(), o.bbox.begin(), o.bbox.end());
+      out.score.insert(out.score.end(), o.score.begin(), o.score.end());
+      out.has_score.insert(out.has_score.end(), o.has_score.begin(), o.has_score.end());
+    }
+    p = stop[n - 1];
+    return true;
+  }
+
+  static int list_threads(size_t bytes) {
+    int T = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("W2T_JSON_THREADS")) T = atoi(e);
+    T = std::min(T, 32);
+    T = std::min<int>(T, (int)(bytes >> 21));  // at least 2 MB of text per thread
+    return std::max(T, 1);
+  }
+
   bool list(w2t_json_dets &out) {
     if (!expect('[')) return false;
     ws();
     if (p < end && *p == ']') { p++; return true; }
+    {
+      const int T = list_threads((size_t)(end - p));
+      const char *p0 = p;
+      const size_t rows0 = out.image_index.size(), ids0 = out.image_ids.size();
+      if (T > 1) {
+        if (list_parallel(out, T)) return true;
+        // undo anything a failed attempt merged (it merges only after every thread succeeded: nothing), reparse
+        p = p0;
+        err = nullptr;
+        (void)rows0; (void)ids0;
+      }
+    }
     for (;;) {
       if (!detection(out)) return false;
       ws();
@@ -366,7 +476,7 @@ bool write_all(const char *path, const std::string &data, bool append) {
 }  // namespace
 
 extern "C" int w2t_json_load(const char *path, w2t_json_dets_t **out) {
-  if (!path || !out) return W2T_ERR_ARG;
+  if (!path || !out) { w2t::set_last_error("w2t_json_load: bad argument"); return W2T_ERR_ARG; }
   *out = nullptr;
   std::string buf;
   if (!read_file(path, buf)) {
@@ -399,7 +509,7 @@ extern "C" int64_t w2t_json_n_images(const w2t_json_dets_t *h) { return h ? (int
 
 extern "C" int w2t_json_copy(const w2t_json_dets_t *h, int32_t *image_index, int32_t *category, double *bbox,
                              double *score, uint8_t *has_score) {
-  if (!h) return W2T_ERR_ARG;
+  if (!h) { w2t::set_last_error("w2t_json_copy: null handle"); return W2T_ERR_ARG; }
   const size_t n = h->image_index.size();
   if (image_index) memcpy(image_index, h->image_index.data(), 4 * n);
   if (category) memcpy(category, h->category.data(), 4 * n);
@@ -423,11 +533,64 @@ extern "C" const char *w2t_json_image_ids(w2t_json_dets_t *h, int64_t *bytes) {
 
 extern "C" void w2t_json_free(w2t_json_dets_t *h) { delete h; }
 
+namespace {
+// rows [0, n) formatted by `row(out, i)` on a few host threads (each its own range and buffer), written in order
+template <class ROW>
+bool write_rows_parallel(const char *path, int64_t n, ROW row) {
+  int T = (int)std::thread::hardware_concurrency();
+  if (const char *e = getenv("W2T_JSON_THREADS")) T = atoi(e);
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(T, 32), n / 20000));
+  std::vector<std::string> buf((size_t)T);
+  auto work = [&](int t) {
+    const int64_t i0 = n * t / T, i1 = n * (t + 1) / T;
+    std::string &out = buf[t];
+    out.reserve((size_t)(i1 - i0) * 160 + 16);
+    if (t == 0) out += '[';
+    for (int64_t i = i0; i < i1; i++) {
+      if (i) out += ", ";
+      row(out, i);
+    }
+    if (t == T - 1) out += ']';
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+  work(0);
+  for (auto &th : pool) th.join();
+  FILE *f = fopen(path, "wb");
+  if (!f) return false;
+  bool ok = true;
+  for (int t = 0; t < T && ok; t++) ok = fwrite(buf[t].data(), 1, buf[t].size(), f) == buf[t].size();
+  return (fclose(f) == 0) && ok;
+}
+}  // namespace
+
 extern "C" int w2t_json_write_tracks(const char *path, int64_t n, const char *const *image_ids, const int32_t *image,
                                      const double *bbox, const double *score, const int32_t *category,
                                      const int64_t *object_id) {
-  if (!path || n < 0 || (n > 0 && (!image_ids || !image || !bbox || !score || !category || !object_id)))
+  if (!path || n < 0 || (n > 0 && (!image_ids || !image || !bbox || !score || !category || !object_id))) {
+    w2t::set_last_error("w2t_json_write_tracks: bad argument");
     return W2T_ERR_ARG;
+  }
+  if (n >= 40000) {
+    const bool ok = write_rows_parallel(path, n, [&](std::string &out, int64_t i) {
+      out += "{\"image_id\": ";
+      py_string(out, image_ids[image[i]]);
+      out += ", \"bbox\": [";
+      for (int k = 0; k < 4; k++) {
+        if (k) out += ", ";
+        py_float(out, bbox[4 * i + k]);
+      }
+      out += "], \"score\": ";
+      py_float(out, score[i]);
+      out += ", \"category_id\": ";
+      out += std::to_string(category[i]);
+      out += ", \"object_id\": \"";
+      out += std::to_string((long long)object_id[i]);
+      out += "\"}";
+    });
+    if (!ok) { w2t::set_last_error("w2t_json_write_tracks: cannot write %s", path); return W2T_ERR_ARG; }
+    return W2T_OK;
+  }
   std::string out;
   out.reserve(1 << 22);
   out += '[';
@@ -462,7 +625,28 @@ extern "C" int w2t_json_write_tracks(const char *path, int64_t n, const char *co
 extern "C" int w2t_json_write_detections(const char *path, int64_t n, const char *const *image_ids,
                                          const int32_t *image, const int32_t *category, const int32_t *bbox,
                                          const double *score) {
-  if (!path || n < 0 || (n > 0 && (!image_ids || !image || !category || !bbox || !score))) return W2T_ERR_ARG;
+  if (!path || n < 0 || (n > 0 && (!image_ids || !image || !category || !bbox || !score))) {
+    w2t::set_last_error("w2t_json_write_detections: bad argument");
+    return W2T_ERR_ARG;
+  }
+  if (n >= 40000) {
+    const bool ok = write_rows_parallel(path, n, [&](std::string &out, int64_t i) {
+      out += "{\"image_id\": ";
+      py_string(out, image_ids[image[i]]);
+      out += ", \"category_id\": ";
+      out += std::to_string(category[i]);
+      out += ", \"bbox\": [";
+      for (int k = 0; k < 4; k++) {
+        if (k) out += ", ";
+        out += std::to_string(bbox[4 * i + k]);
+      }
+      out += "], \"score\": ";
+      py_float(out, score[i]);
+      out += '}';
+    });
+    if (!ok) { w2t::set_last_error("w2t_json_write_detections: cannot write %s", path); return W2T_ERR_ARG; }
+    return W2T_OK;
+  }
   std::string out;
   out.reserve(1 << 22);
   out += '[';

@@ -194,6 +194,7 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
       P.queue = Q.hdr;
       P.bail = Q.cls;
       P.n_items = nq;
+      sort_dmax_kernel<<<(nq + 63) / 64, 64, 0, st>>>(P.p, Q.cls);
       sort_classify_kernel<<<1, 1024, 0, st>>>(P.p, plan->order, Q);
       const int n_big = n_wide + n_mid;  // leading entries of the order that may be too crowded for a warp
       const bool fork = n_big > 0 && dev < 16;
@@ -231,8 +232,9 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, sort_crowd_kernel, P, want_a, want_b, overflow);
       };
-      if (n_wide > 0) W2T_CUDA_TRY(launch_crowd(n_wide, 16, kClsWide, kClsWide, kClsHuge, sb));
-      if (n_big > 0) W2T_CUDA_TRY(launch_crowd(n_big, 8, kClsMid, kClsMid, kClsOver8, sb));
+      const bool dbg_no16 = getenv("W2T_DBG_NO_CROWD16") != nullptr, dbg_no8 = getenv("W2T_DBG_NO_CROWD8") != nullptr;
+      if (n_wide > 0 && !dbg_no16) W2T_CUDA_TRY(launch_crowd(n_wide, 16, kClsWide, kClsWide, kClsHuge, sb));
+      if (n_big > 0 && !dbg_no8) W2T_CUDA_TRY(launch_crowd(n_big, 8, kClsMid, kClsMid, kClsOver8, sb));
       if (fork) W2T_CUDA_TRY(cudaEventRecord(ev_join[dev], sb));
       {
         static bool attr_set[16] = {false};
@@ -247,7 +249,7 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
         else sort_warp_kernel<false><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
       }
       // second pass: sub-streams that outgrew the warp kernel are tracked again by clusters ...
-      W2T_CUDA_TRY(launch_crowd(nq, 16, kClsBailed, kClsOver8, kClsHuge, st));
+      if (!dbg_no16) W2T_CUDA_TRY(launch_crowd(nq, 16, kClsBailed, kClsOver8, kClsHuge, st));
       if (fork) W2T_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[dev], 0));
       // ... and what outgrew those, by CTAs that keep the cost matrix in global memory
       P.bail_want = kClsHuge;

@@ -838,8 +838,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
 }
 
 // Actual crowding of every sub-stream (the launch plan may have been computed from upper bounds, e.g. the group
-// sizes BEFORE the ensemble): most detections in one image -> class flag (kCls*) for the kernels above, and the two
-// queues of the warp kernel, both in the plan's launch order (heaviest first).  One block.
+// sizes BEFORE the ensemble): most detections in one image (sort_dmax_kernel, one thread per sub-stream, left in
+// Q.cls) -> class flag (kCls*) for the kernels above, and the two queues of the warp kernel, both in the plan's
+// launch order (heaviest first; sort_classify_kernel, one block).
+__global__ void sort_dmax_kernel(const w2t_sort_problem_t p, int32_t *dmax_out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NC = p.n_classes;
+  if (q >= p.n_streams * NC) return;
+  const int s = q / NC, c = q - s * NC;
+  int dmax = 0;
+  for (int img = p.stream_img_offsets[s]; img < p.stream_img_offsets[s + 1]; img++)
+    if (p.img_exists == nullptr || p.img_exists[img]) dmax = max(dmax, p.det_count[img * NC + c]);
+  dmax_out[q] = dmax;
+}
+
 __global__ void __launch_bounds__(1024) sort_classify_kernel(const w2t_sort_problem_t p, const int32_t *order, WarpQueues Q) {
   __shared__ int s_tot[2][32];
   __shared__ int s_base[2];
@@ -853,10 +865,7 @@ __global__ void __launch_bounds__(1024) sort_classify_kernel(const w2t_sort_prob
     int q = 0;
     if (i < nq) {
       q = order[i];
-      const int s = q / NC, c = q - s * NC;
-      int dmax = 0;
-      for (int img = p.stream_img_offsets[s]; img < p.stream_img_offsets[s + 1]; img++)
-        if (p.img_exists == nullptr || p.img_exists[img]) dmax = max(dmax, p.det_count[img * NC + c]);
+      const int dmax = Q.cls[q];  // left there by sort_dmax_kernel
       const int cls = dmax > kClassifyHuge ? kClsHuge : dmax > W2T_WIDE_DETS ? kClsWide : dmax > W2T_NARROW_DETS ? kClsMid : kClsWarp;
       Q.cls[q] = cls;
       // a crowd of D detections meets about 1.3 D trackers (max_age 2): ceil8(D) rows x ceil32(1.3 D + 8) / 32 words

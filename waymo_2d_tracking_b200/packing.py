@@ -314,12 +314,13 @@ def packed_rows(rows):
 # array paths (native JSON reader -> packed arrays, no per-detection Python objects)
 # ---------------------------------------------------------------------------
 
-def pack_detections(dets, score_threshold, n_classes, segment_id=None):
+def pack_detections(dets, score_threshold, n_classes, segment_id=None, segment_block=None):
     """``read_data_file`` (tracking/utils.py:63-96) + :func:`pack_predictions` on the flat arrays of
     ``native_json.load``: same streams (segments, then cameras, in first-appearance order of the
     file), same frames (every frame that occurs in the file, filtered or not), same surviving rows
     in the same order, same category first-appearance ranks.  ``segment_id`` keeps one segment only
-    (``track.py --segment-id``)."""
+    (``track.py --segment-id``); ``segment_block=(rank, world)`` keeps this rank's contiguous block of the
+    (remaining) segments in first-appearance order (``sharding.block``): one process per GPU."""
     NC = int(n_classes)
     thr = np.asarray(score_threshold, np.float64)
     # image id -> (segment, frame, camera); ValueError for anything but two slashes, like utils.py:70
@@ -344,6 +345,14 @@ def pack_detections(dets, score_threshold, n_classes, segment_id=None):
     stream_pairs = upair[order]
     if segment_id is not None:
         mask = np.asarray([segments[int(p) // n_cam] == segment_id for p in stream_pairs], bool)
+        stream_pairs = stream_pairs[mask] if len(stream_pairs) else stream_pairs
+    if segment_block is not None:
+        seg_order = list(dict.fromkeys(int(p) // n_cam for p in stream_pairs))   # first-appearance order
+        r, w = segment_block
+        q, rem = divmod(len(seg_order), int(w))
+        lo = r * q + min(r, rem)
+        mine = set(seg_order[lo:lo + q + (1 if r < rem else 0)])
+        mask = np.asarray([int(p) // n_cam in mine for p in stream_pairs], bool)
         stream_pairs = stream_pairs[mask] if len(stream_pairs) else stream_pairs
     stream_of_pair = {int(p): s for s, p in enumerate(stream_pairs)}
     streams = [(segments[int(p) // n_cam], cameras[int(p) % n_cam]) for p in stream_pairs]

@@ -95,6 +95,53 @@ def track_all_sharded(predictions, iou_thresholds, max_age, min_hits, track_fn=N
     return merged, id_base + total
 
 
+def _device_track_packed(packed, iou_thresholds, max_age, min_hits):
+    """Track packed streams on this rank's GPU with ids counted from 1; returns (dense rows, trackers created)."""
+    from . import runtime
+    res = runtime.sort_track(packed, list(iou_thresholds)[:packed.n_classes], max_age, min_hits, id_base=0, raw=False)
+    return res, int(res["id_next"])
+
+
+def track_arrays_sharded(dets, score_threshold, iou_thresholds, max_age, min_hits, segment_id=None, track_fn=None,
+                         group=None, id_base=0):
+    """The tracking CLI's work over all ranks of ``group``, on flat arrays from end to end.
+
+    ``dets``: ``native_json.Detections`` of the whole input file (every rank parses it: the native reader does
+    that at hundreds of MB/s).  Rank r packs and tracks its block of segments
+    (``track_fn(packed, iou_thresholds, max_age, min_hits) -> (rows, n_created)``: dense ``rows_*`` arrays with ids
+    counted from 1; default: the CUDA path), ids are rebased by the exclusive scan of ``n_created`` and the
+    ARRAYS — not lists of dicts — are gathered to rank 0 in rank order.  Returns, on rank 0,
+    ``(image_ids, rows, next_id_base)`` with ``rows["rows_img"]`` indexing ``image_ids``; ``(None, None,
+    next_id_base)`` elsewhere.  The rows are identical to a single-process run."""
+    import numpy as np
+    from . import packing
+    if track_fn is None:
+        track_fn = _device_track_packed
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    packed = packing.pack_detections(dets, score_threshold, len(iou_thresholds), segment_id=segment_id,
+                                     segment_block=(rank, world))
+    res, created = track_fn(packed, iou_thresholds, max_age, min_hits)
+    before, total = exclusive_scan_int(created, group)
+    n = int(res["n_rows"]) if "n_rows" in res else len(res["rows_id"])
+    part = {"image_ids": packing.image_id_strings(packed),
+            "rows_img": np.asarray(res["rows_img"][:n], np.int32), "rows_cat": np.asarray(res["rows_cat"][:n], np.int32),
+            "rows_box": np.asarray(res["rows_box"][:n], np.float64).reshape(-1, 4),
+            "rows_score": np.asarray(res["rows_score"][:n], np.float64),
+            "rows_id": np.asarray(res["rows_id"][:n], np.int64) + (id_base + before)}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(part, gathered, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None, None, id_base + total
+    image_ids, shift = [], 0
+    for p in gathered:
+        p["rows_img"] = p["rows_img"] + shift
+        shift += len(p["image_ids"])
+        image_ids += p["image_ids"]
+    rows = {k: np.concatenate([p[k] for p in gathered]) for k in ("rows_img", "rows_cat", "rows_box", "rows_score", "rows_id")}
+    rows["n_rows"] = len(rows["rows_id"])
+    return image_ids, rows, id_base + total
+
+
 def ensemble_sharded(submissions, weights, method, iou_thresh, soft_nms_cut, min_score, merge_fn=None, group=None):
     """``detnet.ensemble.ensemble_submissions`` over all ranks: images are sharded in sorted order
     (contiguous blocks, so a segment's images stay together), merged independently and gathered to

@@ -7,7 +7,8 @@ Same flags, same input / output JSON, same prints (the parsed args, every segmen
 duration of the tracking loop) as ``track.py:13-50``.  The reference tracks one (segment, camera)
 stream after the other in Python; here all streams are tracked by one launch of the persistent
 CUDA kernel, so the per-segment prints precede the single call.  Under ``torchrun`` (WORLD_SIZE > 1)
-segments are sharded over the ranks / GPUs and rank 0 writes the output (``sharding.py``).  The ground-truth file is loaded
+segments are sharded over the ranks / GPUs — every rank parses the file with the native reader, packs and tracks its own
+block of segments, and rank 0 gathers the result ARRAYS and writes the output (``sharding.track_arrays_sharded``).  The ground-truth file is loaded
 (and must exist) like in the reference although its content is not used (``track.py:32-35``).
 """
 import argparse
@@ -60,22 +61,23 @@ def main(argv=None):
             image_id2path[image['id']] = join(ground_truth_dir, image['file_name'])
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        # launched by torchrun: one rank per GPU, segments sharded, rank 0 gathers and writes
-        predictions = read_data_file(args.input, args.score_threshold)
-        if args.segment_id:
-            predictions = {k: v for k, v in predictions.items() if k == args.segment_id}
-        start_time = time.time()
-        for segment_id in predictions.keys():
-            print(segment_id)
+        # launched by torchrun: one rank per GPU, each packs and tracks its block of segments from the flat arrays,
+        # rank 0 gathers ARRAYS and writes the file
         sharding.init_from_env()
-        tracked_predictions, _ = sharding.track_all_sharded(predictions, args.iou_threshold, args.max_age,
-                                                            args.min_hits)
-        if tracked_predictions is None:
+        start_time = time.time()
+        if sharding.dist.get_rank() == 0:
+            whole = packing.pack_detections(dets, args.score_threshold, len(args.iou_threshold),
+                                            segment_id=args.segment_id or None)
+            for segment_id in dict.fromkeys(seg for seg, _ in whole.streams):
+                print(segment_id)
+        image_ids, rows, _ = sharding.track_arrays_sharded(dets, args.score_threshold, args.iou_threshold, args.max_age,
+                                                           args.min_hits, segment_id=args.segment_id or None)
+        if rows is None:
             return None
         print("duration: %.2fs" % (time.time() - start_time))
-        with open(args.output, 'wt') as fp:
-            json.dump(tracked_predictions, fp)
-        return len(tracked_predictions)
+        native_json.write_tracks(args.output, image_ids, rows["rows_img"], rows["rows_box"], rows["rows_score"],
+                                 rows["rows_cat"], rows["rows_id"])
+        return int(rows["n_rows"])
 
     n_classes = len(args.iou_threshold)
     packed = packing.pack_detections(dets, args.score_threshold, n_classes, segment_id=args.segment_id or None)
