@@ -60,6 +60,28 @@ def oracle_track_packed(packed, iou_thr, max_age, min_hits):
     return rows, int(nxt)
 
 
+def oracle_merge_groups(groups, method, iou_thresh, cut, min_score):
+    from oracle import c_oracle
+    return c_oracle.softnms_groups(groups.group_offsets, groups.rows, iou_thresh, cut, min_score)
+
+
+def ensemble_array_worker(rank, world, port, paths, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from waymo_2d_tracking_b200 import native_json
+    out = sharding.ensemble_arrays_sharded([native_json.load(p) for p in paths], [1.0, 0.5], "soft_nms", 0.5, 0.9, 0.01,
+                                           merge_fn=oracle_merge_groups)
+    if rank == 0:
+        native_json.write_detections(out_path, *out)
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def array_worker(rank, world, port, json_path, out_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -147,3 +169,20 @@ def test_world_size_2_array_path_of_the_tracking_cli_equals_single_process(tmp_p
         assert a['image_id'] == b['image_id'] and a['object_id'] == b['object_id'] and a['category_id'] == b['category_id']
         assert a['bbox'] == [float(v) for v in b['bbox']]
         assert a['score'] == pytest.approx(float(b['score']), rel=1e-12)
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_array_path_of_the_ensemble_cli_equals_single_process(tmp_path):
+    """``sharding.ensemble_arrays_sharded`` (what ``detnet/ensemble.py`` runs under torchrun) against the oracle port."""
+    from oracle import ensemble_port
+    scene, subs = make_inputs()
+    paths = []
+    for k, sub in enumerate(subs):
+        p = tmp_path / ("sub%d.json" % k)
+        p.write_text(json.dumps(sub))
+        paths.append(str(p))
+    out = tmp_path / "ens.json"
+    mp.spawn(ensemble_array_worker, args=(2, free_port(), paths, str(out)), nprocs=2, join=True)
+    got = json.loads(out.read_text())
+    want = json.loads(json.dumps(ensemble_port.ensemble_all(subs, [2, 1], 0.01, 0.5, 0.9)))
+    assert got == want

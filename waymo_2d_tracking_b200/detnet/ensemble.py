@@ -261,15 +261,17 @@ def main(argv=None):
 
     import os
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        submissions = [json.load(Path(f).open()) for f in input_files]
-        # launched by torchrun: images sharded over the ranks / GPUs, rank 0 gathers and writes
+        # launched by torchrun: every rank parses the files natively and merges its block of images; the kept rows
+        # travel to rank 0 as arrays, which writes the file
         sharding.init_from_env()
-        output_json = sharding.ensemble_sharded(submissions, list(input_weights), args.method, args.iou_thresh,
-                                                args.soft_nms_cut, args.min_score)
-        if output_json is not None:
-            with output_file.open('wt') as fp:
-                json.dump(output_json, fp)
-        return output_json
+        out = sharding.ensemble_arrays_sharded([native_json.load(f) for f in input_files], list(input_weights),
+                                               args.method, args.iou_thresh, args.soft_nms_cut, args.min_score)
+        if out is None:
+            return None
+        image_ids, img, cat, box, score = out
+        print('No. Images:', len(image_ids))
+        native_json.write_detections(output_file, image_ids, img, cat, box, score)
+        return len(score)
     # native reader / writer: files <-> flat arrays, no per-detection Python objects
     groups = packing.pack_detection_files([native_json.load(f) for f in input_files], input_weights, args.min_score)
     print('No. Images:', len(groups.image_ids))

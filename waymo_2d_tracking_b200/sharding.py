@@ -142,6 +142,45 @@ def track_arrays_sharded(dets, score_threshold, iou_thresholds, max_age, min_hit
     return image_ids, rows, id_base + total
 
 
+def ensemble_arrays_sharded(files, weights, method, iou_thresh, soft_nms_cut, min_score, merge_fn=None, group=None):
+    """The ensemble CLI's work over all ranks of ``group``, on flat arrays from end to end.
+
+    ``files``: one ``native_json.Detections`` per input file (every rank parses them with the native reader).
+    All ranks build the same grouping (``packing.pack_detection_files``: images sorted, categories ascending);
+    rank r merges its contiguous block of images (``merge_fn(groups, method, iou_thresh, soft_nms_cut, min_score)``
+    -> ``ens_count / ens_box / ens_score`` at the group offsets; default: the CUDA path) and the kept rows travel to
+    rank 0 as ARRAYS.  Returns ``(image_ids, image_index, category, bbox, score)`` on rank 0 — the arguments of
+    ``native_json.write_detections`` — and ``None`` elsewhere; identical to a single-process run."""
+    import numpy as np
+    from . import packing
+    if merge_fn is None:
+        from .detnet import ensemble as ens
+        merge_fn = ens.merge_groups
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    groups = packing.pack_detection_files(files, weights, min_score)
+    ncat = max(len(groups.category_ids), 1)
+    lo, hi = block(len(groups.image_ids), rank, world)
+    g0, g1 = lo * ncat, hi * ncat
+    go = np.asarray(groups.group_offsets, np.int64)
+    part = {"img": np.zeros(0, np.int32), "cat": np.zeros(0, np.int32), "box": np.zeros((0, 4), np.int32), "score": np.zeros(0)}
+    if hi > lo:
+        r0, r1 = int(go[g0]), int(go[g1])
+        sizes = np.diff(go[g0:g1 + 1])
+        mine = packing.PackedGroups(groups.image_ids[lo:hi], groups.category_ids, (go[g0:g1 + 1] - r0).astype(np.int32),
+                                    groups.rows[r0:r1], int(sizes.max()) if len(sizes) else 0,
+                                    None if groups.sub_counts is None else groups.sub_counts[g0:g1])
+        res = merge_fn(mine, method, iou_thresh, soft_nms_cut, min_score)
+        rows, grp = packing.valid_row_index(np.asarray(mine.group_offsets, np.int64)[:-1], res["ens_count"])
+        part = {"img": (grp // ncat + lo).astype(np.int32), "cat": np.asarray(groups.category_ids, np.int32)[grp % ncat],
+                "box": np.asarray(res["ens_box"])[rows].astype(np.int32), "score": np.asarray(res["ens_score"])[rows]}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(part, gathered, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+    cat = lambda k: np.concatenate([p[k] for p in gathered])
+    return groups.image_ids, cat("img"), cat("cat"), cat("box"), cat("score")
+
+
 def ensemble_sharded(submissions, weights, method, iou_thresh, soft_nms_cut, min_score, merge_fn=None, group=None):
     """``detnet.ensemble.ensemble_submissions`` over all ranks: images are sharded in sorted order
     (contiguous blocks, so a segment's images stay together), merged independently and gathered to
