@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-streams", type=int, default=16,
                     help="streams of the timed output checked against the C oracle after the timed region (0 = off)")
+    ap.add_argument("--cli-segments", type=int, default=8,
+                    help="segments of the JSON->JSON command-line record (c3, N=1 only; 0 = skip)")
     ap.add_argument("--chunks", type=int, default=8, help="pipeline depth of the end-to-end leg")
     ap.add_argument("--skip-e2e", action="store_true",
                     help="profiling aid: only the device-resident leg (the launch list then shows one step's kernels)")
@@ -319,6 +321,58 @@ def parity_sample(stages, scene, groups, packed, rows, ens, n_streams, seed):
 # our arm
 # ---------------------------------------------------------------------------------------------
 
+def cli_record(n_segments, seed):
+    """JSON -> JSON through the command lines (README.md:41,54 of the reference): submission files on disk in,
+    tracks.json out.  The fused CLI (``python -m waymo_2d_tracking_b200.pipeline``) and the two drop-in CLIs run on
+    the same files; the outputs must be byte-identical.  A bounded sample of the C3 workload (file parsing is
+    per-segment work, so frames/s does not depend on the sample size beyond launch overheads)."""
+    import contextlib
+    import tempfile
+    from waymo_2d_tracking_b200 import native_json, pipeline, synth
+    from waymo_2d_tracking_b200.detnet import ensemble as ens_cli
+    from waymo_2d_tracking_b200.tracking import track as track_cli
+    from waymo_2d_tracking_b200.tracking.sort import sort as sort_mod
+    scene = synth.make_scene(synth.preset("c3", n_segments=n_segments, seed=seed + 77))
+    ids = scene.image_ids()
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(sys.stderr):
+        files = []
+        for k, sub in enumerate(scene.submissions):
+            files.append(os.path.join(tmp, "sub%d.json" % k))
+            native_json.write_detections(files[-1], ids, sub.image_index, sub.category, sub.bbox, sub.score)
+        gt = os.path.join(tmp, "images.json")
+        with open(gt, "w") as fp:
+            fp.write("[]")
+        in_bytes = sum(os.path.getsize(f) for f in files)
+        nms = ["--min-score=%r" % NMS["min_score"], "--soft-nms-cut=%r" % NMS["soft_nms_cut"]]
+        trk = ["--max-age=%d" % MAX_AGE, "--min-hits=%d" % MIN_HITS]
+        fused_out, ens_out, two_out = (os.path.join(tmp, n) for n in ("fused.json", "ens.json", "two.json"))
+        best_fused, best_two = float("inf"), float("inf")
+        for _ in range(2):                                  # first pass warms the page cache and the pinned pools
+            sort_mod.KalmanBoxTracker.count = 0
+            t0 = time.perf_counter()
+            pipeline.main(files + ["-o", fused_out] + nms + trk)
+            best_fused = min(best_fused, time.perf_counter() - t0)
+            sort_mod.KalmanBoxTracker.count = 0
+            if os.path.exists(ens_out):
+                os.remove(ens_out)                          # the reference refuses to overwrite (ensemble.py:134)
+            t0 = time.perf_counter()
+            ens_cli.main(files + ["-o", ens_out, "-m", "soft_nms"] + nms)
+            track_cli.main(["--ground-truth", gt, "--input", ens_out, "--output", two_out] + trk)
+            best_two = min(best_two, time.perf_counter() - t0)
+        sort_mod.KalmanBoxTracker.count = 0
+        out_bytes = os.path.getsize(fused_out)
+        with open(fused_out, "rb") as a, open(two_out, "rb") as b:
+            same = a.read() == b.read()
+    if not same:
+        raise SystemExit("bench.py: the fused CLI and the two-command path wrote different tracks.json files")
+    return {"value": scene.n_img / best_fused, "unit": UNIT, "path": "python -m waymo_2d_tracking_b200.pipeline (fused, opt-in)",
+            "two_command_value": scene.n_img / best_two,
+            "two_command_path": "detnet.ensemble -m soft_nms && tracking/track.py (the reference's commands)",
+            "sample": "%d segments = %d frames, %.0f MB of submission JSON in, %.0f MB of tracks JSON out; best of 2 "
+                      "in-process runs, files on local disk" % (n_segments, scene.n_img, in_bytes / 1e6, out_bytes / 1e6),
+            "json_in_mb_s": in_bytes / 1e6 / best_fused, "outputs_byte_identical": same}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -545,6 +599,8 @@ def main():
         line["cpu_baseline"] = cpu_baseline_single(args.config, args.seed, args.cpu_sample_frames)
     elif rank == 0:
         line["cpu_baseline"] = None
+    if rank == 0 and world == 1 and args.config == "c3" and args.cli_segments > 0:
+        line["cli"] = cli_record(args.cli_segments, args.seed)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -180,6 +180,31 @@ int w2t_json_copy(const w2t_json_dets_t *dets, int32_t *image_index, int32_t *ca
 const char *w2t_json_image_ids(w2t_json_dets_t *dets, int64_t *bytes);
 void w2t_json_free(w2t_json_dets_t *dets);
 
+/* load_input_submissions + the grouping of ensemble_detections (detnet/ensemble.py:31-47,78-95) on files: parses
+ * the n_files submissions (concurrently), drops rows with width or height <= 0 or score * weight < min_score
+ * (ensemble.py:37-42), and groups the rest by (image, category): images that keep a row, in sorted image_id order
+ * (W2T_LAYOUT_ENSEMBLE, columns = the category ids that occur, ascending) or — for the tracker behind the ensemble —
+ * as the streams read_data_file + track.py (tracking/utils.py:63-96, track.py:36-44) would form from the ensemble's
+ * output file: segments and cameras in first-appearance order of the sorted list, frames in numeric order, columns =
+ * categories 1..n_classes (W2T_LAYOUT_STREAMS).  Rows of a group: file order, then JSON order (tta.py:9-12).
+ * weights may be NULL (all 1).  W2T_ERR_UNSUPPORTED: use the general (Python) packer.  HOST functions. */
+typedef struct w2t_json_groups w2t_json_groups_t;
+int w2t_json_group_files(const char *const *paths, int32_t n_files, const double *weights, double min_score,
+                         int32_t layout, int32_t n_classes, w2t_json_groups_t **out);
+/* info: [0] images, [1] columns per image, [2] rows, [3] largest group, [4] streams (W2T_LAYOUT_STREAMS),
+ *       [5] 1 if every row fits the 8-byte W2T_BOX_LTWH_P64 format exactly, [6] category ids, [7] files */
+int w2t_json_groups_info(const w2t_json_groups_t *groups, int64_t info[8]);
+/* any pointer may be NULL.  category_ids [info 6]; image_order [images]: layout position -> index into the sorted
+ * image ids; stream_img_offsets [streams+1] and frame_ids [images] (W2T_LAYOUT_STREAMS only); group_offsets
+ * [images*columns+1]; sub_counts [images*columns, files]; rows [rows,5] = score*weight, left, top, width, height;
+ * packed [rows] (only written when info[5] is 1) */
+int w2t_json_groups_copy(const w2t_json_groups_t *groups, int32_t *category_ids, int32_t *image_order,
+                         int32_t *stream_img_offsets, int64_t *frame_ids, int32_t *group_offsets, int32_t *sub_counts,
+                         double *rows, uint64_t *packed);
+/* the sorted image ids, each followed by '\n'; valid until w2t_json_groups_free */
+const char *w2t_json_groups_image_ids(const w2t_json_groups_t *groups, int64_t *bytes);
+void w2t_json_groups_free(w2t_json_groups_t *groups);
+
 /* Replace json.dump of tracking/track.py:50 (rows of tracking/utils.py:52-58) and of
  * detnet/ensemble.py:159-160 (rows of :61-62).  Byte-identical to the reference's files: default
  * separators, ensure_ascii, floats as Python's float.__repr__.  image_ids[k] = NUL-terminated

@@ -35,9 +35,15 @@ enum {
   W2T_ERR_ARG = 1,        /* bad argument (null pointer, negative size, too many classes) */
   W2T_ERR_CAPACITY = 2,   /* a plan capacity (tracks / detections per frame) was exceeded */
   W2T_ERR_CUDA = 3,       /* CUDA runtime error; see w2t_last_error() */
-  W2T_ERR_NONFINITE = 4   /* a tracker box became +-inf (unreachable with finite inputs; the
+  W2T_ERR_NONFINITE = 4,  /* a tracker box became +-inf (unreachable with finite inputs; the
                              reference mis-indexes its tracker list there, sort.py:261-265) */
+  W2T_ERR_UNSUPPORTED = 5 /* host packers only: an input this fast path does not cover (the caller uses the
+                             general path, which reproduces the reference's behaviour or its exception) */
 };
+
+/* image layouts of w2t_json_group_files */
+#define W2T_LAYOUT_ENSEMBLE 0 /* images in sorted image_id order, one column per category id that occurs  */
+#define W2T_LAYOUT_STREAMS 1  /* images stream by stream in frame order, columns = categories 1..n_classes */
 
 /* Per-sub-stream launch plan, computed on the host from the detection counts
  * (w2t_sort_plan).  All arrays have n_streams * n_classes entries. */

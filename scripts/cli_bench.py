@@ -30,6 +30,15 @@ with tempfile.TemporaryDirectory() as tmp:
     track_cli.main(["--ground-truth", gt, "--input", os.path.join(tmp, "ens.json"), "--output", os.path.join(tmp, "trk.json"), "--max-age=2", "--min-hits=0"])
     t2 = time.perf_counter()
     print("native CLIs : ensemble %.2f s, track %.2f s -> %.0f frames/s JSON to JSON" % (t1 - t0, t2 - t1, scene.n_img / (t2 - t0)))
+    # the opt-in fused command: no intermediate file
+    from waymo_2d_tracking_b200 import pipeline
+    for _ in range(2):
+        sort_mod.KalmanBoxTracker.count = 0
+        t0 = time.perf_counter()
+        pipeline.main(files + ["-o", os.path.join(tmp, "fused.json"), "--min-score=0.01", "--soft-nms-cut=0.9", "--max-age=2", "--min-hits=0"])
+        t1 = time.perf_counter()
+    print("fused CLI   : %.2f s -> %.0f frames/s JSON to JSON; same tracks.json: %s" % (
+        t1 - t0, scene.n_img / (t1 - t0), open(os.path.join(tmp, "fused.json"), "rb").read() == open(os.path.join(tmp, "trk.json"), "rb").read()))
     # the same kernels behind Python's json + dict loops (what a pure-Python host layer costs)
     t0 = time.perf_counter()
     subs = [json.load(open(f)) for f in files]

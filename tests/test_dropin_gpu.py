@@ -332,3 +332,31 @@ def test_sort_building_blocks_python_surface():
     np.testing.assert_allclose(trk.kf.x, ref.kf.x, rtol=1e-9, atol=1e-9)
     assert trk.get_error() == pytest.approx(ref.get_error(), rel=1e-9)
     assert trk.hits == 1 and trk.time_since_update == 0 and trk.age == 1
+
+
+# ---- fused CLI -------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("with_ens", [False, True])
+def test_fused_cli_writes_the_same_files_as_the_two_reference_commands(with_ens, tmp_path):
+    # python -m detnet.ensemble ... -o ens.json && python tracking/track.py --input ens.json ... (README.md:41,54)
+    # against the opt-in one-process pipeline: tracks.json (and ens.json) byte for byte
+    from waymo_2d_tracking_b200 import pipeline
+    cfg = synth.SynthConfig(n_segments=3, cameras=("FRONT", "FRONT_LEFT", "SIDE_RIGHT"), n_frames=25, n_submissions=3,
+                            objects_per_frame=35.0, seed=77)
+    scene = synth.make_scene(cfg)
+    files = write_submissions(scene, tmp_path)
+    gt = tmp_path / "images.json"
+    gt.write_text(json.dumps([{'id': 'x', 'file_name': 'x.jpg'}]))
+    ens_a, trk_a = tmp_path / "ens_a.json", tmp_path / "trk_a.json"
+    ens.main(files + ['-o', str(ens_a), '-m', 'soft_nms', '--min-score=0.01', '--soft-nms-cut=0.9', '-j', '-1'])
+    sort_mod.KalmanBoxTracker.count = 0
+    track_cli.main(['--ground-truth', str(gt), '--input', str(ens_a), '--output', str(trk_a), '--max-age=2',
+                    '--min-hits=0'])
+    ens_b, trk_b = tmp_path / "ens_b.json", tmp_path / "trk_b.json"
+    sort_mod.KalmanBoxTracker.count = 0
+    argv = files + ['-o', str(trk_b), '--min-score=0.01', '--soft-nms-cut=0.9', '--max-age=2', '--min-hits=0']
+    n = pipeline.main(argv + (['--ensemble-output', str(ens_b)] if with_ens else []))
+    assert n == len(json.loads(trk_a.read_text())) and n > 1000
+    assert trk_b.read_bytes() == trk_a.read_bytes()
+    if with_ens:
+        assert ens_b.read_bytes() == ens_a.read_bytes()

@@ -176,3 +176,76 @@ def test_reader_is_as_strict_as_json_load(tmp_path):
         p.write_text(bad)
         with pytest.raises(Exception):
             native_json.load(p)
+
+
+def _write_files(scene, tmp_path, tweak=None):
+    files = []
+    for k, sub in enumerate(scene.submissions):
+        rows = synth.to_json_list(scene, sub)
+        if tweak:
+            tweak(k, rows)
+        p = tmp_path / ("sub%d.json" % k)
+        p.write_text(json.dumps(rows))
+        files.append(str(p))
+    return files
+
+
+@pytest.mark.parametrize("weights", [[1.0, 1.0, 1.0], [1.0, 0.5, 0.25]])
+def test_native_grouping_equals_the_array_packer(tmp_path, weights):
+    # w2t_json_group_files (parse + filter + group in one native call) against load + pack_detection_files
+    from waymo_2d_tracking_b200 import _abi, pipeline
+    cfg = synth.SynthConfig(n_segments=3, cameras=("FRONT", "FRONT_LEFT", "SIDE_RIGHT"), n_frames=12, n_submissions=3,
+                            objects_per_frame=20.0, seed=31)
+    scene = synth.make_scene(cfg)
+
+    def tweak(k, rows):
+        rows[3]['bbox'][2] = 0                      # dropped by the width filter
+        rows[5]['score'] = 0.001                    # dropped by min_score
+        if k == 1:                                  # an image that only this file holds
+            rows.append({'image_id': 'zz_seg/17/FRONT', 'category_id': 4, 'bbox': [1, 2, 30, 40], 'score': 0.5})
+    files = _write_files(scene, tmp_path, tweak)
+    want = packing.pack_detection_files([native_json.load(f) for f in files], weights, 0.01)
+    got = native_json.group_files(files, weights, 0.01)
+    assert got.image_ids == want.image_ids and got.category_ids == want.category_ids
+    np.testing.assert_array_equal(got.group_offsets, want.group_offsets)
+    np.testing.assert_array_equal(got.rows, want.rows)
+    np.testing.assert_array_equal(got.sub_counts, want.sub_counts)
+    assert got.max_group == want.max_group and got.columns == len(want.category_ids)
+    np.testing.assert_array_equal(got.image_order, np.arange(len(want.image_ids)))
+    packed = packing.packed_rows(want.rows)
+    if packed is None:
+        assert got.packed is None
+    else:
+        np.testing.assert_array_equal(got.packed, packed)
+    # the tracker's layout: the native call against the general path of pipeline.load_groups
+    fast = pipeline.load_groups(files, weights, 0.01, 4)
+    orig = native_json.group_files
+    try:
+        native_json.group_files = lambda *a, **k: None
+        slow = pipeline.load_groups(files, weights, 0.01, 4)
+    finally:
+        native_json.group_files = orig
+    assert fast[0] == slow[0] and fast[7] == slow[7]
+    for a, b in zip(fast[1:6], slow[1:6]):
+        np.testing.assert_array_equal(a, b)
+    assert (fast[6] is None) == (slow[6] is None)
+    if fast[6] is not None:
+        np.testing.assert_array_equal(fast[6], slow[6])
+    assert (weights[1] == 1.0) == (fast[6] is not None)       # weighted scores leave the 5-decimal grid
+
+
+def test_native_grouping_leaves_unusual_inputs_to_the_general_path(tmp_path):
+    from waymo_2d_tracking_b200 import _abi
+    rows = [{'image_id': 'seg/1_0/FRONT', 'category_id': 1, 'bbox': [1, 2, 3, 4], 'score': 0.5}]
+    p = tmp_path / "odd.json"
+    p.write_text(json.dumps(rows))
+    assert native_json.group_files([p], [1.0], 0.0, _abi.W2T_LAYOUT_STREAMS, 4) is None     # int('1_0') == 10
+    assert native_json.group_files([p], [1.0], 0.0).image_ids == ['seg/1_0/FRONT']
+    rows[0]['image_id'], rows[0]['category_id'] = 'seg/3/FRONT', 7
+    p.write_text(json.dumps(rows))
+    assert native_json.group_files([p], [1.0], 0.0, _abi.W2T_LAYOUT_STREAMS, 4) is None     # IndexError territory
+    with pytest.raises(W2TError):
+        native_json.group_files([tmp_path / "missing.json"], [1.0], 0.0)
+    p.write_text("[]")
+    empty = native_json.group_files([p], [1.0], 0.0, _abi.W2T_LAYOUT_STREAMS, 4)
+    assert empty.image_ids == [] and len(empty.rows) == 0 and list(empty.group_offsets) == [0]

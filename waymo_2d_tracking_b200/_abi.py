@@ -13,6 +13,8 @@ W2T_ERR_ARG = 1
 W2T_ERR_CAPACITY = 2
 W2T_ERR_CUDA = 3
 W2T_ERR_NONFINITE = 4
+W2T_ERR_UNSUPPORTED = 5
+W2T_LAYOUT_ENSEMBLE, W2T_LAYOUT_STREAMS = 0, 1
 
 STATUS_NAMES = {
     W2T_OK: "ok",
@@ -20,6 +22,7 @@ STATUS_NAMES = {
     W2T_ERR_CAPACITY: "plan capacity exceeded",
     W2T_ERR_CUDA: "CUDA error",
     W2T_ERR_NONFINITE: "tracker box became infinite",
+    W2T_ERR_UNSUPPORTED: "input outside the fast host path",
 }
 
 _p = C.c_void_p
@@ -180,6 +183,11 @@ EXPORTS = {
     "w2t_json_copy": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "w2t_json_image_ids": (_p, [_p, C.POINTER(C.c_int64)]),
     "w2t_json_free": (None, [_p]),
+    "w2t_json_group_files": (C.c_int, [_p, C.c_int32, _p, C.c_double, C.c_int32, C.c_int32, C.POINTER(_p)]),
+    "w2t_json_groups_info": (C.c_int, [_p, _p]),
+    "w2t_json_groups_copy": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "w2t_json_groups_image_ids": (_p, [_p, C.POINTER(C.c_int64)]),
+    "w2t_json_groups_free": (None, [_p]),
     "w2t_json_write_tracks": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p, _p]),
     "w2t_json_write_detections": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p]),
     "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p]),

@@ -273,7 +273,7 @@ def main(argv=None):
         native_json.write_detections(output_file, image_ids, img, cat, box, score)
         return len(score)
     # native reader / writer: files <-> flat arrays, no per-detection Python objects
-    groups = packing.pack_detection_files([native_json.load(f) for f in input_files], input_weights, args.min_score)
+    groups = packing.pack_files(input_files, input_weights, args.min_score)
     print('No. Images:', len(groups.image_ids))
     print('No. categories:', len(groups.category_ids))
     if not len(groups.image_ids):

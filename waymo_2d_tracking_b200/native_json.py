@@ -9,10 +9,11 @@ written are byte-identical to what the reference's ``json.dump`` produces.
 import ctypes as C
 import os
 from dataclasses import dataclass
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
+from . import _abi
 from ._lib import check, lib
 
 
@@ -80,3 +81,58 @@ def write_detections(path, image_ids, image, category, bbox, score):
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     check(lib().w2t_json_write_detections(os.fsencode(str(path)), len(image), C.cast(table, C.c_void_p), vp(image),
                                           vp(category), vp(bbox), vp(score)), "w2t_json_write_detections")
+
+
+@dataclass
+class FileGroups:
+    """``w2t_json_group_files``: the submissions of an ensemble parsed and grouped by (image, category) natively."""
+    image_ids: List[str]            # images that keep a row, sorted
+    category_ids: List[int]         # every category id of the files, ascending
+    image_order: np.ndarray         # [n_img] layout position -> index into image_ids
+    group_offsets: np.ndarray       # [n_img * columns + 1] int32
+    sub_counts: np.ndarray          # [n_img * columns, files] int32
+    rows: Optional[np.ndarray]      # [N,5] float64 (None: not asked for, see ``packed``)
+    packed: Optional[np.ndarray]    # [N] uint64 (``packing.packed_rows`` format) or None
+    max_group: int
+    columns: int
+    stream_img_offsets: Optional[np.ndarray] = None   # W2T_LAYOUT_STREAMS only
+    frame_ids: Optional[np.ndarray] = None
+
+
+def group_files(paths, weights, min_score, layout=_abi.W2T_LAYOUT_ENSEMBLE, n_classes=0, want_rows=True):
+    """Parse and group submission files in one native call; ``None`` when the input needs the general packer
+    (``packing.pack_detection_files``: odd frame spellings, categories outside the tracker's list, ...).
+    ``want_rows=False`` skips the float64 rows when the 8-byte packed rows hold them exactly."""
+    encoded = [os.fsencode(str(q)) for q in paths]
+    table = (C.c_char_p * len(encoded))(*encoded)
+    w = np.ascontiguousarray(weights, np.float64)
+    handle = C.c_void_p()
+    status = lib().w2t_json_group_files(C.cast(table, C.c_void_p), len(encoded), w.ctypes.data_as(C.c_void_p),
+                                        float(min_score), int(layout), int(n_classes), C.byref(handle))
+    if status == _abi.W2T_ERR_UNSUPPORTED:
+        return None
+    check(status, "w2t_json_group_files")
+    try:
+        info = (C.c_int64 * 8)()
+        check(lib().w2t_json_groups_info(handle, info), "w2t_json_groups_info")
+        n_img, cols, n_rows, max_group, n_streams, packable, n_cat, n_files = (int(v) for v in info)
+        G = n_img * cols
+        streams = layout == _abi.W2T_LAYOUT_STREAMS
+        out = FileGroups([], [], np.empty(n_img, np.int32), np.empty(G + 1, np.int32), np.empty((G, n_files), np.int32),
+                         np.empty((n_rows, 5), np.float64) if (want_rows or not packable) else None,
+                         np.empty(n_rows, np.uint64) if packable else None,
+                         max_group, cols, np.empty(n_streams + 1, np.int32) if streams else None,
+                         np.empty(n_img, np.int64) if streams else None)
+        cats = np.empty(n_cat, np.int32)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib().w2t_json_groups_copy(handle, vp(cats), vp(out.image_order), vp(out.stream_img_offsets),
+                                         vp(out.frame_ids), vp(out.group_offsets), vp(out.sub_counts), vp(out.rows),
+                                         vp(out.packed)), "w2t_json_groups_copy")
+        out.category_ids = [int(c) for c in cats]
+        nbytes = C.c_int64(0)
+        ptr = lib().w2t_json_groups_image_ids(handle, C.byref(nbytes))
+        text = C.string_at(ptr, nbytes.value).decode("utf-8") if nbytes.value else ""
+        out.image_ids = text.split("\n")[:-1] if text else []
+        return out
+    finally:
+        lib().w2t_json_groups_free(handle)

@@ -434,3 +434,13 @@ def pack_detection_files(files, weights, min_score):
         sub_counts = np.zeros((0, max(len(files), 1)), np.int32)
     return PackedGroups(image_ids, category_ids, offsets.astype(np.int32), np.ascontiguousarray(rows[order]),
                         int(counts.max()) if G else 0, sub_counts)
+
+
+def pack_files(paths, weights, min_score):
+    """:func:`pack_detection_files` straight from the files: one native call parses and groups them
+    (``w2t_json_group_files``); inputs it does not cover go through ``native_json.load`` + the array packer."""
+    from . import native_json
+    fast = native_json.group_files(paths, weights, min_score)
+    if fast is None:
+        return pack_detection_files([native_json.load(f) for f in paths], weights, min_score)
+    return PackedGroups(fast.image_ids, fast.category_ids, fast.group_offsets, fast.rows, fast.max_group, fast.sub_counts)
