@@ -382,8 +382,13 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    # one process per GPU: keep each rank's host threads within its share of the cores
-    share = max(1, (os.cpu_count() or 1) // max(world, 1))
+    # one process per GPU: keep each rank's host threads within its share of the cores (and, before torch starts
+    # its thread pools, pin the process to that share)
+    bound = None
+    if world > 1:
+        from waymo_2d_tracking_b200 import _bind
+        bound = _bind.bind_rank_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    share = len(bound) if bound else max(1, (os.cpu_count() or 1) // max(world, 1))
     os.environ.setdefault("W2T_PLAN_THREADS", str(max(1, min(4, share - 1))))
     import torch
     from waymo_2d_tracking_b200 import packing, runtime, synth
@@ -478,10 +483,16 @@ def main():
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         out = None
+        host_ms = []
         for _ in range(steps):
+            t_host = time.perf_counter()
             out = fn()
+            host_ms.append((time.perf_counter() - t_host) * 1e3)
         end.record()
         barrier()
+        if os.environ.get("W2T_BENCH_STEP_TIMES"):      # debug aid: host time of every call, per rank
+            print("rank %d %s host ms per call: %s" % (rank, fn.__name__, " ".join("%.1f" % v for v in host_ms)),
+                  file=sys.stderr, flush=True)
         ms = start.elapsed_time(end)
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
@@ -497,6 +508,11 @@ def main():
     runtime.PROFILE = []
     ms_dev, out = timed(step_device, args.steps)
     kernel_ms = runtime.collect_profile()
+    if os.environ.get("W2T_BENCH_STEP_TIMES") and runtime.PROFILE:   # debug aid: device timeline of the timed steps
+        first = runtime.PROFILE[0][1]
+        print("rank %d device timeline (ms from the first kernel): %s" % (rank, "  ".join(
+            "%s@%.1f+%.1f" % (name.split("_")[0], first.elapsed_time(a), a.elapsed_time(b)) for name, a, b in runtime.PROFILE)),
+            file=sys.stderr, flush=True)
     runtime.PROFILE = None
     out_e2e = None
     if args.skip_e2e:
@@ -587,6 +603,7 @@ def main():
                    else "inputs (%.1f MB per step) fit the 126 MB L2: the step is bound by serial chain latency, not by HBM "
                         "(no flush: every kernel of a step writes its outputs, 2-7x the input size, in between)" % (h2d / 1e6),
                    "parallelism": "streams sharded by segment, %d rank(s), no collective" % world,
+                   "host_cores_per_rank": share,
                    "generate_s": round(gen_s, 1), "full_size_check": consistency},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},

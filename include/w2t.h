@@ -30,6 +30,9 @@ typedef struct CUstream_st *w2t_stream_t; /* == cudaStream_t */
 const char *w2t_version(void);
 /* message of the last failing call on this host thread ("" if none) */
 const char *w2t_last_error(void);
+/* forget it (callers that report a message call this afterwards, so that a later failure which sets no message of
+ * its own is not reported with a stale one) */
+void w2t_clear_error(void);
 /* SM count and compute capability of the current device */
 int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor);
 

@@ -71,7 +71,8 @@ typedef struct w2t_sort_plan_t {
   int32_t  n_mid;
   /* byte offset, inside the workspace, of the auxiliary area of the warp kernel (w2t_sort_plan     */
   /* sets it and includes its W2T_SORT_AUX_BYTES(n_substreams) in ws_bytes): work-queue counters,    */
-  /* one class flag per sub-stream and the two queues.  < 0 = no aux area: CTAs track everything.    */
+  /* one class flag per sub-stream, the two queues, and the warp kernel's spill areas.               */
+  /* < 0 = no aux area: CTAs track everything.                                                       */
   int64_t  aux_offset;
   /* most detections any NARROW sub-stream has in one image: picks how many warps (= sub-streams)   */
   /* share an SM's shared memory, i.e. how large a cost matrix each can hold (0 = unknown)          */
@@ -80,7 +81,11 @@ typedef struct w2t_sort_plan_t {
 
 #define W2T_WIDE_DETS 320
 #define W2T_NARROW_DETS 96
-#define W2T_SORT_AUX_BYTES(n_substreams) (64 + 12 * (int64_t)(n_substreams))
+#define W2T_SORT_QUEUE_BYTES(n_substreams) (((64 + 12 * (int64_t)(n_substreams)) + 255) / 256 * 256)
+/* + the spill areas of the warp kernel: 160 CTAs x 8 teams x 64 KB for the rare cost matrix that outgrows a team's */
+/* share of tensor memory                                                                                           */
+#define W2T_SORT_SPILL_BYTES (160 * 8 * (int64_t)65536)
+#define W2T_SORT_AUX_BYTES(n_substreams) (W2T_SORT_QUEUE_BYTES(n_substreams) + W2T_SORT_SPILL_BYTES)
 
 /* NumPy promotion regime the tracker reproduces (w2t_sort_problem_t.promotion):                     */
 /*   LEGACY  NumPy 1.x value-based casting — the reference's pinned environment (python 3.7,         */
@@ -122,7 +127,10 @@ typedef struct w2t_sort_result_t {
   int32_t *out_count;    /* [n_img*n_classes] rows emitted (<= det_count)                     */
   int32_t *created;      /* [n_img*n_classes] trackers created at this (image, category)      */
   int32_t *first_img;    /* [n_streams*n_classes] stream-local index of the image where the   */
-                         /*   category first appeared (tracker_sort.py:32-33) or -1           */
+                         /*   category first appeared (tracker_sort.py:32-33) or -1.          */
+                         /*   w2t_sort_step (optional there): the smallest `group` of          */
+                         /*   out_birth any live tracker of the sub-stream still refers to     */
+                         /*   (INT32_MAX: none) — id bases of older calls can be forgotten     */
   /* optional (may be NULL): final filter state of every sub-stream, for parity tests */
   int32_t *final_count;  /* [n_streams*n_classes] live trackers after the last image          */
   double  *final_state;  /* [n_streams*n_classes, final_cap, 56] x[7] then P[49] row-major,    */

@@ -311,6 +311,30 @@ def test_sort_stepper_two_streams_in_lockstep():
     assert stepper.count == sort_port.BoxTracker.count and total > 100
 
 
+def test_sort_stepper_long_run_forgets_old_id_bases():
+    """400 calls with short-lived tracks: the per-call id-base table is trimmed to the oldest live track (the kernel
+    reports it) and the ids still equal the port's."""
+    sc = synth.make_scene(synth.SynthConfig(n_segments=1, cameras=("FRONT",), n_frames=400, n_submissions=1,
+                                            objects_per_frame=12.0, mean_life=8.0, seed=77))
+    pred = sort_port.group_entries(synth.to_json_list(sc, sc.submissions[0]), helpers.SCORE_THR)
+    f = pred[sc.segments[0]][sc.cameras[0]]
+    frames = [f[k] for k in sorted(f)]
+    sort_port.BoxTracker.count = 0
+    ref = sort_port.MultiClassTracker(max_age=2, min_hits=0)
+    stepper = runtime.SortStepper(helpers.IOU_THR, max_age=2, min_hits=0, n_streams=1, track_cap=128, det_cap=64)
+    for entries in frames:
+        rows = [[e['bbox'][0], e['bbox'][1], e['bbox'][0] + e['bbox'][2], e['bbox'][1] + e['bbox'][3], e['score'],
+                 e['category_id']] for e in entries]
+        want = ref.track(rows, helpers.IOU_THR)
+        got = stepper.step([(np.asarray([r[:5] for r in rows], np.float64).reshape(-1, 5),
+                             np.asarray([r[5] - 1 for r in rows], np.int64))])[0]
+        assert [c + 1 for c in got] == list(want.keys())
+        for c, v in got.items():
+            np.testing.assert_array_equal(v[:, 4], want[c + 1][:, 4])
+    assert stepper.count == sort_port.BoxTracker.count > 300
+    assert stepper._base_lo >= 256 and len(stepper._bases) <= 256
+
+
 def test_sort_building_blocks_python_surface():
     d = np.array([10, 20, 50, 80, 0.9], np.float32)
     t = np.array([12.5, 18.0, 55.0, 77.0])

@@ -256,6 +256,19 @@ def test_sort_medium_density_matches_oracle():
     compare_sort(packed, helpers.IOU_THR, 2, 0)
 
 
+@pytest.mark.parametrize("opf,seed,top", [(160.0, 2, 103), (170.0, 1, 104), (170.0, 6, 110)])
+def test_sort_images_that_outgrow_tensor_memory_match_oracle(opf, seed, top):
+    # vehicles peak just above W2T_NARROW_DETS at a few images: the warp kernel keeps the sub-stream and spills those
+    # images' cost matrices to its global-memory area (top <= 104), or leaves it to the cluster kernel (110)
+    cfg = synth.SynthConfig(n_segments=1, cameras=("FRONT", "SIDE_LEFT"), n_frames=80, n_submissions=1,
+                            objects_per_frame=opf, class_mix=(0.7, 0.25, 0.0, 0.05), seed=seed)
+    scene = synth.make_scene(cfg)
+    packed = synth.tracks_from_submission(scene, scene.submissions[0], helpers.SCORE_THR)
+    vehicles = packed.det_count.reshape(-1, 4)[:, 0]
+    assert vehicles.max() == top and 0 < (vehicles > 96).sum() <= 32
+    compare_sort(packed, helpers.IOU_THR, 2, 0)
+
+
 def test_sort_crowded_matches_oracle():
     # C4-shaped miniature: ~1000 dets/frame, hundreds of live tracks per category
     cfg = synth.preset("c4", cameras=("FRONT",), n_frames=8, seed=9)

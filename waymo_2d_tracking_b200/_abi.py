@@ -127,8 +127,8 @@ def promotion_code(promotion=None):
 
 
 def sort_aux_bytes(n_substreams):
-    """W2T_SORT_AUX_BYTES of include/w2t_types.h."""
-    return 64 + 12 * int(n_substreams)
+    """W2T_SORT_AUX_BYTES of include/w2t_types.h: queue area (rounded to 256) + the warp kernel's spill areas."""
+    return (64 + 12 * int(n_substreams) + 255) // 256 * 256 + 160 * 8 * 65536
 W2T_BOX_LTWH, W2T_BOX_CXCYWH, W2T_BOX_XYXY, W2T_BOX_LTWH_I16, W2T_BOX_LTWH_P64 = 0, 1, 2, 3, 4
 
 
@@ -150,6 +150,7 @@ class NmsResult(C.Structure):
 EXPORTS = {
     "w2t_version": (C.c_char_p, []),
     "w2t_last_error": (C.c_char_p, []),
+    "w2t_clear_error": (None, []),
     "w2t_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "w2t_stream_wait_value32": (C.c_int, [_p, _p, C.c_int32]),
     "w2t_softnms_groups": (C.c_int, [C.POINTER(NmsProblem), C.POINTER(NmsResult), C.c_int, _p, _p]),

@@ -33,6 +33,7 @@ def lib():
 def check(status, what):
     if status != _abi.W2T_OK:
         msg = lib().w2t_last_error().decode() or _abi.STATUS_NAMES.get(status, "status %d" % status)
+        lib().w2t_clear_error()              # a later failure without a message of its own must not show this one
         raise W2TError("%s failed: %s" % (what, msg))
 
 

@@ -28,6 +28,8 @@ extern "C" const char *w2t_version(void) { return "w2t 0.1 (sm_100a)"; }
 
 extern "C" const char *w2t_last_error(void) { return w2t::g_last_error; }
 
+extern "C" void w2t_clear_error(void) { w2t::g_last_error[0] = '\0'; }
+
 extern "C" int w2t_device_info(int *sm_count, int *cc_major, int *cc_minor) {
   int dev = 0;
   W2T_CUDA_TRY(cudaGetDevice(&dev));

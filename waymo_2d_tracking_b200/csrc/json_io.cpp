@@ -30,6 +30,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -51,6 +52,16 @@ struct w2t_json_dets {
 };
 
 namespace {
+
+// host threads this process may use: the affinity mask (one rank per GPU binds itself to a share of the cores),
+// capped by W2T_JSON_THREADS
+int usable_cores() {
+  int T = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) T = std::max(1, CPU_COUNT(&set));
+  if (const char *e = getenv("W2T_JSON_THREADS")) T = atoi(e);
+  return std::max(T, 1);
+}
 
 // W2T_JSON_TIMING=1: phase times of the host packers / writers on stderr
 struct Lap {
@@ -379,9 +390,7 @@ struct Parser {
   }
 
   static int list_threads(size_t bytes) {
-    int T = (int)std::thread::hardware_concurrency();
-    if (const char *e = getenv("W2T_JSON_THREADS")) T = atoi(e);
-    T = std::min(T, 32);
+    int T = std::min(usable_cores(), 32);
     T = std::min<int>(T, (int)(bytes >> 21));  // at least 2 MB of text per thread
     return std::max(T, 1);
   }
@@ -722,6 +731,11 @@ extern "C" int w2t_json_group_files(const char *const *paths, int32_t n_files, c
       w2t::set_last_error("w2t_json_load: %s", errors[f].c_str());
       return W2T_ERR_ARG;
     }
+  for (int f = 0; f < K; f++)
+    if (std::find(files[f]->has_score.begin(), files[f]->has_score.end(), (uint8_t)0) != files[f]->has_score.end()) {
+      w2t::set_last_error("w2t_json_group_files: a row of %s has no \"score\"", paths[f]);
+      return W2T_ERR_UNSUPPORTED;  // the general path raises the reference's KeyError
+    }
   g->n_files = K;
   lap("parse");
   // 2. filters of convert_submission (ensemble.py:37-42): width and height > 0, score * weight >= min_score
@@ -951,7 +965,7 @@ extern "C" int w2t_json_groups_copy(const w2t_json_groups_t *g, int32_t *categor
     // gather from the parsed files, group ranges dealt to a few threads
     const int K = g->n_files;
     const int64_t G = (int64_t)g->group_offsets.size() - 1;
-    int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int>((int)std::thread::hardware_concurrency(), 16),
+    int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int>(usable_cores(), 16),
                                                          g->n_rows / 100000));
     auto job = [&](int t) {
       const int64_t q0 = G * t / T, q1 = G * (t + 1) / T;
@@ -988,9 +1002,7 @@ namespace {
 // rows [0, n) formatted by `row(out, i)` on a few host threads (each its own range and buffer), written in order
 template <class ROW>
 bool write_rows_parallel(const char *path, int64_t n, ROW row) {
-  int T = (int)std::thread::hardware_concurrency();
-  if (const char *e = getenv("W2T_JSON_THREADS")) T = atoi(e);
-  T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(T, 32), n / 20000));
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(usable_cores(), 32), n / 20000));
   std::vector<std::string> buf((size_t)T);
   Lap lap;
   auto work = [&](int t) {

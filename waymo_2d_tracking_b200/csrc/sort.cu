@@ -189,8 +189,10 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
       W2T_CUDA_TRY(cudaGetDevice(&dev));
       if (sm_count == 0) W2T_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
       char *aux = P.ws + plan->aux_offset;
-      W2T_CUDA_TRY(cudaMemsetAsync(aux, 0, (size_t)W2T_SORT_AUX_BYTES(nq), st));
+      W2T_CUDA_TRY(cudaMemsetAsync(aux, 0, (size_t)W2T_SORT_QUEUE_BYTES(nq), st));
       const WarpQueues Q = warp_queues(aux, nq);
+      static_assert((int64_t)kSpillCtas * kTeamsPerCta * kSpillFloats * 4 == W2T_SORT_SPILL_BYTES, "spill area size");
+      P.spill = reinterpret_cast<float *>(aux + W2T_SORT_QUEUE_BYTES(nq));
       P.queue = Q.hdr;
       P.bail = Q.cls;
       P.n_items = nq;
@@ -244,7 +246,7 @@ static int launch_sort(const char *who, const w2t_sort_problem_t *problem, const
           W2T_CUDA_TRY(cudaFuncSetAttribute(sort_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           if (dev < 16) attr_set[dev] = true;
         }
-        const int ctas = std::min(sm_count, nq);  // one CTA per SM; the first round is dealt across them
+        const int ctas = std::min(std::min(sm_count, kSpillCtas), nq);  // one CTA per SM; the first round is dealt across them
         if (tm) sort_warp_kernel<true><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
         else sort_warp_kernel<false><<<ctas, kWarpsPerCta * 32, smem, st>>>(P);
       }

@@ -90,6 +90,7 @@ struct SortParams {
   const int64_t *ws_offset;
   char *ws;
   int32_t *status;
+  float *spill;       // warp kernel: per-team spill areas for cost matrices that outgrow tensor memory (sort_warp.cuh)
   long long *timers;  // optional [n_substreams,16] phase cycle counters (debug aid, may be NULL)
   const int32_t *chunk_of;  // optional completion tracking, see w2t_sort_plan_t
   int32_t *chunk_done;
@@ -673,6 +674,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) sort_track_kernel(const SortParam
   if (STEP) {
     __syncthreads();
     if (tid == 0) reinterpret_cast<int4 *>(P.sub_state)[q] = make_int4(T, frame_count, started ? 1 : 0, (s_nan ? 1 : 0) | 2);
+    if (P.r.first_img != nullptr) {
+      // frame-by-frame mode: the oldest birth group any live tracker of the sub-stream refers to (INT_MAX: none),
+      // so that the caller can forget the id bases of older calls
+      int oldest = 0x7fffffff;
+      for (int t = tid; t < T; t += BLOCK) oldest = min(oldest, bgA[list[t]]);
+      oldest = __reduce_min_sync(0xffffffffu, oldest);
+      __syncthreads();
+      if ((tid & 31) == 0) s_scan[tid >> 5] = oldest;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < BLOCK / 32; w++) oldest = min(oldest, s_scan[w]);
+        P.r.first_img[q] = oldest;
+      }
+      __syncthreads();
+    }
   }
 
   // optional: filter state of every live tracker, already predicted one step past the last image

@@ -41,6 +41,10 @@ constexpr int kWarpSmemBytes = 232448;  // 227 KB: the most dynamic shared memor
 constexpr int kTeamsPerCta = 8;     // sub-streams in flight per SM: 4 pairs + 4 single warps
 constexpr int kWarpsPerCta = 12;
 constexpr int kBigCols = 384, kSmallCols = 128;  // TMEM columns (= cell words of the cost matrix) of a pair / a single warp
+constexpr int kSpillFloats = 512 * 32;  // a team's spill area: the largest matrix (ceil8(128) rows x 4 column words)
+constexpr int kSpillCtas = 160;          // CTAs the spill area is sized for (the grid is one CTA per SM, at most this)
+constexpr int kSpillImages = 32;         // a sub-stream may spill at this many images and still be served by warps
+constexpr int kSpillDets = 104;          // ... if it never holds more detections than this (its trackers: ~1.25x)
 constexpr int kClassifyHuge = 896;  // = kCrowdM (sort_crowd.cuh): more detections than the cluster kernel takes
 
 // The cost matrix of a team's current image lives in TENSOR MEMORY (256 KB per SM, 128 lanes x 512 columns x
@@ -93,6 +97,37 @@ __device__ __forceinline__ void tm_st8(const uint32_t taddr, const float (&v)[8]
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// The cost matrix of one image lives in the team's share of tensor memory — or, for the rare image whose matrix
+// outgrows that share (ceil8(n) * ceil32(m) / 32 columns > kBigCols / kSmallCols), in the team's spill area in
+// global memory (L2), laid out the same way: column c of lane l at spill[c * 32 + l].
+// SPILL is a compile-time property of the code path: the common path carries no trace of the other one.
+template <bool SPILL>
+struct Cells {
+  uint32_t tm;
+  float *spill;
+  __device__ __forceinline__ void ld8(const int col, float (&v)[8]) const {
+    if (SPILL) {
+      const float *p = spill + col * 32 + lane_id();
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = __ldcg(p + j * 32);
+    } else {
+      tm_ld8(tm + (uint32_t)col, v);
+    }
+  }
+  __device__ __forceinline__ void st8(const int col, const float (&v)[8]) const {
+    if (SPILL) {
+      float *p = spill + col * 32 + lane_id();
+#pragma unroll
+      for (int j = 0; j < 8; j++) __stcg(p + j * 32, v[j]);
+    } else {
+      tm_st8(tm + (uint32_t)col, v);
+    }
+  }
+  __device__ __forceinline__ void wait_st() const {
+    if (!SPILL) tm_wait_st();  // global stores are ordered by the team's barrier
+  }
+};
+
 // A team: one warp, or a pair (leader = half 0, helper = half 1) that meets at a 64-thread named barrier.
 struct Team {
   int half, nh, bar;
@@ -129,7 +164,8 @@ __device__ __forceinline__ uint32_t strip_mask_checked(const double x1, const do
 // of `uc`: column 32k + lane is uncovered, bit k of `ucw`: word k has an uncovered column at all); rows go eight
 // at a time, one TMEM access per eight cell words, the blocks of eight dealt out between the warps of the team
 // (the matrix holds ceil8(n) rows: the padding rows are computed on and never read).
-__device__ __forceinline__ void cost_shift(WarpShared &S, const uint32_t tm, const int n, const int m, const Team &team) {
+template <bool SPILL>
+__device__ __forceinline__ void cost_shift(WarpShared &S, const Cells<SPILL> tm, const int n, const int m, const Team &team) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = lane_id();
   const int mw = (m + 31) >> 5, NP = (n + 7) & ~7;
@@ -152,7 +188,7 @@ __device__ __forceinline__ void cost_shift(WarpShared &S, const uint32_t tm, con
     for (uint32_t w = ucw; w; w &= w - 1u) {
       const int k = __ffs(w) - 1;
       float v[8];
-      tm_ld8(tm + k * NP + r0, v);
+      tm.ld8(k * NP + r0, v);
       if ((uc >> k) & 1u) {
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -178,7 +214,7 @@ __device__ __forceinline__ void cost_shift(WarpShared &S, const uint32_t tm, con
         const bool colv = k * 32 + lane < m;
         const bool u = (uc >> k) & 1u;
         float v[8];
-        tm_ld8(tm + k * NP + r0, v);
+        tm.ld8(k * NP + r0, v);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           if ((cr >> j) & 1u) v[j] = v[j] + mn;
@@ -186,10 +222,10 @@ __device__ __forceinline__ void cost_shift(WarpShared &S, const uint32_t tm, con
           const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
           if (lane == 0) zp[j * kWarpZS + k] = word;
         }
-        tm_st8(tm + k * NP + r0, v);
+        tm.st8(k * NP + r0, v);
       }
     }
-    tm_wait_st();
+    tm.wait_st();
   }
   team.sync();
 }
@@ -200,8 +236,8 @@ __device__ __forceinline__ void cost_shift(WarpShared &S, const uint32_t tm, con
 // as munkres.cuh (see there for why each shortcut is exact).  Runs in the team's leading warp; lane k holds
 // word k of every mask.  A helper warp follows in solver_helper().  Returns 0, or 9 when the iteration budget
 // ran out (NaN costs).
-template <bool TIMERS>
-__device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, const int n, const int m, const Team &team,
+template <bool TIMERS, bool SPILL>
+__device__ __forceinline__ int warp_munkres(WarpShared &S, const Cells<SPILL> tm, const int n, const int m, const Team &team,
                                             long long *ph) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = lane_id();
@@ -351,7 +387,8 @@ __device__ __forceinline__ int warp_munkres(WarpShared &S, const uint32_t tm, co
 }
 
 // the helper's side of warp_munkres: cost shifts until the leader reports the outcome
-__device__ __forceinline__ int solver_helper(WarpShared &S, const uint32_t tm, const int n, const int m, const Team &team) {
+template <bool SPILL>
+__device__ __forceinline__ int solver_helper(WarpShared &S, const Cells<SPILL> tm, const int n, const int m, const Team &team) {
 #pragma unroll 1
   for (;;) {
     team.sync();
@@ -407,7 +444,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
   asm volatile("tcgen05.fence::after_thread_sync;");
   // this team's share: the 32 lanes of its quarter; pairs take the low columns, single warps the rest
   const int kCols = bigw ? kBigCols : kSmallCols;
-  const uint32_t tm = s_tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(bigw ? 0 : kBigCols);
+  const uint32_t tm_base = s_tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(bigw ? 0 : kBigCols);
+  float *const spill = P.spill + ((size_t)blockIdx.x * kTeamsPerCta + (size_t)(bigw ? wq : 4 + wq)) * kSpillFloats;
   const int NC = P.p.n_classes;
   const float4 *det_box = reinterpret_cast<const float4 *>(P.p.det_box);
   const int max_age = P.p.max_age, min_hits = P.p.min_hits;
@@ -528,7 +566,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
         const bool flipped = D > T;  // the solver transposes when there are more rows than columns
         const int n = flipped ? T : D, m = flipped ? D : T;
         const int mw = (m + 31) >> 5, NP = (n + 7) & ~7;
-        if (mw * NP > kCols) { bail = true; break; }  // the matrix does not fit this team's share of tensor memory
         auto mask_of = [&](const bool is_det, const int i) -> uint32_t {
           if (is_det) {
             const float4 b = S.det[i];
@@ -563,78 +600,84 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sort_warp_kernel(const S
         //    the solver).  Every other pair is strictly disjoint and costs -0.0f.
         //    Then the team, lanes own columns: reduced costs -> tensor memory, zero bit words -> S.Z, eight rows
         //    at a time.
+        // the matrix goes to the team's share of tensor memory, or — the rare image that outgrows it — to the
+        // team's spill area (a second, cold instance of the same code)
+        auto build_and_solve = [&](const auto tm) -> int {
 #pragma unroll 1
-        for (int rb = 0; rb < n; rb += 32) {
-          const int r = rb + lane;
-          if (lead && r < n) {
-            const uint32_t rm = mask_of(!flipped, r);
-            uint4 cx = make_uint4(0u, 0u, 0u, 0u), cy = cx;
+          for (int rb = 0; rb < n; rb += 32) {
+            const int r = rb + lane;
+            if (lead && r < n) {
+              const uint32_t rm = mask_of(!flipped, r);
+              uint4 cx = make_uint4(0u, 0u, 0u, 0u), cy = cx;
 #pragma unroll 1
-            for (uint32_t w = rm & 0xffffu; w; w &= w - 1u) {
-              const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[__ffs(w) - 1]);
-              cx.x |= v.x; cx.y |= v.y; cx.z |= v.z; cx.w |= v.w;
+              for (uint32_t w = rm & 0xffffu; w; w &= w - 1u) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[__ffs(w) - 1]);
+                cx.x |= v.x; cx.y |= v.y; cx.z |= v.z; cx.w |= v.w;
+              }
+#pragma unroll 1
+              for (uint32_t w = rm >> 16; w; w &= w - 1u) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[16 + __ffs(w) - 1]);
+                cy.x |= v.x; cy.y |= v.y; cy.z |= v.z; cy.w |= v.w;
+              }
+              uint32_t *zr = S.Z + r * kWarpZS;
+              zr[0] = cx.x & cy.x; zr[1] = cx.y & cy.y; zr[2] = cx.z & cy.z; zr[3] = cx.w & cy.w;
+              const int ncand = __popc(zr[0]) + __popc(zr[1]) + __popc(zr[2]) + __popc(zr[3]);
+              // minimum on the order-preserving integer image of the float (NaN sorts last, like fminf ignores it)
+              uint32_t mn_u = (ncand < m) ? Munkres<32>::ordered(-0.0f) : 0xffffffffu;
+              float *row = S.raw + lane * m;
+#pragma unroll 1
+              for (int k = 0; k < mw; k++) {
+#pragma unroll 1
+                for (uint32_t w = zr[k]; w; w &= w - 1u) {
+                  const int cc = k * 32 + __ffs(w) - 1;
+                  const int di = flipped ? cc : r, ti = flipped ? r : cc;
+                  const float v = -iou_pair_call(S.det[di], S.box[0][ti], S.box[1][ti], S.box[2][ti], S.box[3][ti]);
+                  row[cc] = v;
+                  mn_u = min(mn_u, Munkres<32>::ordered(v));
+                }
+              }
+              S.rowmin[r] = Munkres<32>::unordered(mn_u);
+              S.row_star[r] = -1;
+              S.row_prime[r] = -1;
             }
+            team.sync();
+            const int r_end = min(rb + 32, NP);
 #pragma unroll 1
-            for (uint32_t w = rm >> 16; w; w &= w - 1u) {
-              const uint4 v = *reinterpret_cast<const uint4 *>(S.strip[16 + __ffs(w) - 1]);
-              cy.x |= v.x; cy.y |= v.y; cy.z |= v.z; cy.w |= v.w;
-            }
-            uint32_t *zr = S.Z + r * kWarpZS;
-            zr[0] = cx.x & cy.x; zr[1] = cx.y & cy.y; zr[2] = cx.z & cy.z; zr[3] = cx.w & cy.w;
-            const int ncand = __popc(zr[0]) + __popc(zr[1]) + __popc(zr[2]) + __popc(zr[3]);
-            // minimum on the order-preserving integer image of the float (NaN sorts last, like fminf ignores it)
-            uint32_t mn_u = (ncand < m) ? Munkres<32>::ordered(-0.0f) : 0xffffffffu;
-            float *row = S.raw + lane * m;
+            for (int r0 = rb + team.half * 8; r0 < r_end; r0 += 8 * team.nh) {
+              float mn[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) mn[j] = S.rowmin[r0 + j];
+              const float *p = S.raw + (r0 - rb) * m + lane;
+              uint32_t *zp = S.Z + r0 * kWarpZS;
 #pragma unroll 1
-            for (int k = 0; k < mw; k++) {
-#pragma unroll 1
-              for (uint32_t w = zr[k]; w; w &= w - 1u) {
-                const int cc = k * 32 + __ffs(w) - 1;
-                const int di = flipped ? cc : r, ti = flipped ? r : cc;
-                const float v = -iou_pair_call(S.det[di], S.box[0][ti], S.box[1][ti], S.box[2][ti], S.box[3][ti]);
-                row[cc] = v;
-                mn_u = min(mn_u, Munkres<32>::ordered(v));
+              for (int k = 0; k < mw; k++) {
+                const bool colv = k * 32 + lane < m;
+                const float *pk = p + k * 32;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  const uint32_t cw = zp[j * kWarpZS + k];
+                  v[j] = -0.0f;
+                  if ((cw >> lane) & 1u) v[j] = pk[j * m];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  v[j] = v[j] - mn[j];
+                  const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
+                  if (lane == 0) zp[j * kWarpZS + k] = word;
+                }
+                tm.st8(k * NP + r0, v);
               }
             }
-            S.rowmin[r] = Munkres<32>::unordered(mn_u);
-            S.row_star[r] = -1;
-            S.row_prime[r] = -1;
+            tm.wait_st();
+            team.sync();
           }
-          team.sync();
-          const int r_end = min(rb + 32, NP);
-#pragma unroll 1
-          for (int r0 = rb + team.half * 8; r0 < r_end; r0 += 8 * team.nh) {
-            float mn[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) mn[j] = S.rowmin[r0 + j];
-            const float *p = S.raw + (r0 - rb) * m + lane;
-            uint32_t *zp = S.Z + r0 * kWarpZS;
-#pragma unroll 1
-            for (int k = 0; k < mw; k++) {
-              const bool colv = k * 32 + lane < m;
-              const float *pk = p + k * 32;
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const uint32_t cw = zp[j * kWarpZS + k];
-                v[j] = -0.0f;
-                if ((cw >> lane) & 1u) v[j] = pk[j * m];
-              }
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                v[j] = v[j] - mn[j];
-                const uint32_t word = __ballot_sync(FULL, colv && v[j] == 0.0f);
-                if (lane == 0) zp[j * kWarpZS + k] = word;
-              }
-              tm_st8(tm + k * NP + r0, v);
-            }
-          }
-          tm_wait_st();
-          team.sync();
-        }
-        W2T_WTICK(2);
-        if (TIMERS && lane == 0) ph[13]++;
-        const int act = lead ? warp_munkres<TIMERS>(S, tm, n, m, team, ph) : solver_helper(S, tm, n, m, team);
+          W2T_WTICK(2);
+          if (TIMERS && lane == 0) ph[13]++;
+            return lead ? warp_munkres<TIMERS>(S, tm, n, m, team, ph) : solver_helper(S, tm, n, m, team);
+        };
+        const int act = (mw * NP > kCols) ? build_and_solve(Cells<true>{tm_base, spill})
+                                          : build_and_solve(Cells<false>{tm_base, spill});
         if (act != 0) err = W2T_ERR_ARG;
         W2T_WTICK(5);
         if (lead) {
@@ -846,10 +889,14 @@ __global__ void sort_dmax_kernel(const w2t_sort_problem_t p, int32_t *dmax_out) 
   const int NC = p.n_classes;
   if (q >= p.n_streams * NC) return;
   const int s = q / NC, c = q - s * NC;
-  int dmax = 0;
+  int dmax = 0, over = 0;
   for (int img = p.stream_img_offsets[s]; img < p.stream_img_offsets[s + 1]; img++)
-    if (p.img_exists == nullptr || p.img_exists[img]) dmax = max(dmax, p.det_count[img * NC + c]);
-  dmax_out[q] = dmax;
+    if (p.img_exists == nullptr || p.img_exists[img]) {
+      const int d = p.det_count[img * NC + c];
+      dmax = max(dmax, d);
+      over += d > W2T_NARROW_DETS;
+    }
+  dmax_out[q] = min(dmax, 0xffff) | (min(over, 0x7fff) << 16);  // images whose matrix may outgrow a pair's tensor memory
 }
 
 __global__ void __launch_bounds__(1024) sort_classify_kernel(const w2t_sort_problem_t p, const int32_t *order, WarpQueues Q) {
@@ -865,8 +912,10 @@ __global__ void __launch_bounds__(1024) sort_classify_kernel(const w2t_sort_prob
     int q = 0;
     if (i < nq) {
       q = order[i];
-      const int dmax = Q.cls[q];  // left there by sort_dmax_kernel
-      const int cls = dmax > kClassifyHuge ? kClsHuge : dmax > W2T_WIDE_DETS ? kClsWide : dmax > W2T_NARROW_DETS ? kClsMid : kClsWarp;
+      const int dmax = Q.cls[q] & 0xffff, over = Q.cls[q] >> 16;  // left there by sort_dmax_kernel
+      // warps take a sub-stream whose matrices fit a pair's tensor memory at all but a few images (those spill)
+      const bool warps = dmax <= W2T_NARROW_DETS || (dmax <= kSpillDets && over <= kSpillImages);
+      const int cls = dmax > kClassifyHuge ? kClsHuge : dmax > W2T_WIDE_DETS ? kClsWide : !warps ? kClsMid : kClsWarp;
       Q.cls[q] = cls;
       // a crowd of D detections meets about 1.3 D trackers (max_age 2): ceil8(D) rows x ceil32(1.3 D + 8) / 32 words
       const int words = (min(kWarpDim, dmax + dmax / 3 + 8) + 31) >> 5;

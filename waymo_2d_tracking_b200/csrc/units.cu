@@ -208,9 +208,15 @@ __global__ void __launch_bounds__(128) bbox_vote_kernel(const double *nms_boxes,
 
 extern "C" int w2t_bbox_vote(const double *nms_boxes, int32_t n, const double *all_boxes, const double *all_scores,
                              int32_t m, double thresh, int32_t compute_f32, double *out, w2t_stream_t stream) {
-  if (n < 0 || m < 0) return W2T_ERR_ARG;
+  if (n < 0 || m < 0) {
+    set_last_error("w2t_bbox_vote: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (n == 0) return W2T_OK;
-  if (!nms_boxes || !out || (m > 0 && (!all_boxes || !all_scores))) return W2T_ERR_ARG;
+  if (!nms_boxes || !out || (m > 0 && (!all_boxes || !all_scores))) {
+    set_last_error("w2t_bbox_vote: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   if (compute_f32) bbox_vote_kernel<float><<<n, 128, 0, (cudaStream_t)stream>>>(nms_boxes, n, all_boxes, all_scores, m, thresh, out);
   else bbox_vote_kernel<double><<<n, 128, 0, (cudaStream_t)stream>>>(nms_boxes, n, all_boxes, all_scores, m, thresh, out);
   W2T_CUDA_TRY(cudaGetLastError());
@@ -218,9 +224,15 @@ extern "C" int w2t_bbox_vote(const double *nms_boxes, int32_t n, const double *a
 }
 
 extern "C" int w2t_bbox_to_z(const float *dets, double *z, int32_t n, int32_t promotion, w2t_stream_t stream) {
-  if (n < 0) return W2T_ERR_ARG;
+  if (n < 0) {
+    set_last_error("w2t_bbox_to_z: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (n == 0) return W2T_OK;
-  if (!dets || !z) return W2T_ERR_ARG;
+  if (!dets || !z) {
+    set_last_error("w2t_bbox_to_z: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   bbox_to_z_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(dets), z, n,
                                                                     promotion == W2T_PROMOTION_NEP50);
   W2T_CUDA_TRY(cudaGetLastError());
@@ -228,9 +240,15 @@ extern "C" int w2t_bbox_to_z(const float *dets, double *z, int32_t n, int32_t pr
 }
 
 extern "C" int w2t_x_to_bbox(const double *x, int32_t ldx, double *boxes, int32_t n, w2t_stream_t stream) {
-  if (n < 0 || ldx < 4) return W2T_ERR_ARG;
+  if (n < 0 || ldx < 4) {
+    set_last_error("w2t_x_to_bbox: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (n == 0) return W2T_OK;
-  if (!x || !boxes) return W2T_ERR_ARG;
+  if (!x || !boxes) {
+    set_last_error("w2t_x_to_bbox: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   x_to_bbox_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, ldx, boxes, n);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
@@ -238,9 +256,15 @@ extern "C" int w2t_x_to_bbox(const double *x, int32_t ldx, double *boxes, int32_
 
 extern "C" int w2t_iou_matrix(const float *dets, int32_t D, const double *trks, int32_t T, float *out,
                               w2t_stream_t stream) {
-  if (D < 0 || T < 0) return W2T_ERR_ARG;
+  if (D < 0 || T < 0) {
+    set_last_error("w2t_iou_matrix: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (D == 0 || T == 0) return W2T_OK;
-  if (!dets || !trks || !out) return W2T_ERR_ARG;
+  if (!dets || !trks || !out) {
+    set_last_error("w2t_iou_matrix: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   const size_t total = (size_t)D * T;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
   iou_matrix_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(dets), D, trks, T, out);
@@ -255,12 +279,18 @@ extern "C" size_t w2t_linear_assignment_workspace(int32_t D, int32_t T) {
 
 extern "C" int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, int32_t *pairs, int32_t *n_pairs,
                                      void *workspace, w2t_stream_t stream) {
-  if (D < 0 || T < 0 || !n_pairs) return W2T_ERR_ARG;
+  if (D < 0 || T < 0 || !n_pairs) {
+    set_last_error("w2t_linear_assignment: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (D == 0 || T == 0) {
     W2T_CUDA_TRY(cudaMemsetAsync(n_pairs, 0, sizeof(int32_t), (cudaStream_t)stream));
     return W2T_OK;
   }
-  if (!cost || !pairs || !workspace) return W2T_ERR_ARG;
+  if (!cost || !pairs || !workspace) {
+    set_last_error("w2t_linear_assignment: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   if (std::max(D, T) > kMunkresMaxDim) {
     set_last_error("w2t_linear_assignment: max(D,T)=%d exceeds %d", std::max(D, T), kMunkresMaxDim);
     return W2T_ERR_CAPACITY;
@@ -271,9 +301,15 @@ extern "C" int w2t_linear_assignment(const float *cost, int32_t D, int32_t T, in
 }
 
 extern "C" int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, int32_t promotion, w2t_stream_t stream) {
-  if (n < 0) return W2T_ERR_ARG;
+  if (n < 0) {
+    set_last_error("w2t_kf_init: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (n == 0) return W2T_OK;
-  if (!x || !P || !dets) return W2T_ERR_ARG;
+  if (!x || !P || !dets) {
+    set_last_error("w2t_kf_init: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   kf_init_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), n,
                                                                  promotion == W2T_PROMOTION_NEP50);
   W2T_CUDA_TRY(cudaGetLastError());
@@ -281,9 +317,15 @@ extern "C" int w2t_kf_init(double *x, double *P, const float *dets, int32_t n, i
 }
 
 extern "C" int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2t_stream_t stream) {
-  if (n < 0) return W2T_ERR_ARG;
+  if (n < 0) {
+    set_last_error("w2t_kf_predict: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (n == 0) return W2T_OK;
-  if (!x || !P) return W2T_ERR_ARG;
+  if (!x || !P) {
+    set_last_error("w2t_kf_predict: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   kf_predict_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, boxes, n);
   W2T_CUDA_TRY(cudaGetLastError());
   return W2T_OK;
@@ -291,9 +333,15 @@ extern "C" int w2t_kf_predict(double *x, double *P, double *boxes, int32_t n, w2
 
 extern "C" int w2t_kf_update(double *x, double *P, const float *dets, double *boxes, int32_t n, int32_t promotion,
                              w2t_stream_t stream) {
-  if (n < 0) return W2T_ERR_ARG;
+  if (n < 0) {
+    set_last_error("w2t_kf_update: bad argument (negative size)");
+    return W2T_ERR_ARG;
+  }
   if (n == 0) return W2T_OK;
-  if (!x || !P || !dets) return W2T_ERR_ARG;
+  if (!x || !P || !dets) {
+    set_last_error("w2t_kf_update: bad argument (null pointer)");
+    return W2T_ERR_ARG;
+  }
   kf_update_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x, P, reinterpret_cast<const float4 *>(dets), boxes, n,
                                                                    promotion == W2T_PROMOTION_NEP50);
   W2T_CUDA_TRY(cudaGetLastError());

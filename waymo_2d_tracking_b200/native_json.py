@@ -110,6 +110,7 @@ def group_files(paths, weights, min_score, layout=_abi.W2T_LAYOUT_ENSEMBLE, n_cl
     status = lib().w2t_json_group_files(C.cast(table, C.c_void_p), len(encoded), w.ctypes.data_as(C.c_void_p),
                                         float(min_score), int(layout), int(n_classes), C.byref(handle))
     if status == _abi.W2T_ERR_UNSUPPORTED:
+        lib().w2t_clear_error()
         return None
     check(status, "w2t_json_group_files")
     try:

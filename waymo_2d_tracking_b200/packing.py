@@ -402,7 +402,10 @@ def pack_detections(dets, score_threshold, n_classes, segment_id=None, segment_b
 def pack_detection_files(files, weights, min_score):
     """``load_input_submissions`` (detnet/ensemble.py:78-84) + grouping on the flat arrays of
     ``native_json.load``: one ``Detections`` per input file -> :class:`PackedGroups` with images in
-    sorted order and categories ascending, rows of a group in (file, JSON) order."""
+    sorted order and categories ascending, rows of a group in (file, JSON) order.  A row without "score" raises
+    ``KeyError('score')`` like ``det['score']`` does there (ensemble.py:38)."""
+    if any(len(d.has_score) and not d.has_score.all() for d in files):
+        raise KeyError('score')
     category_ids = sorted(set(int(c) for d in files for c in np.unique(d.category)))
     cat_index = np.full((max(category_ids) + 1) if category_ids else 1, -1, np.int64)
     for i, c in enumerate(category_ids):

@@ -900,7 +900,11 @@ class SortStepper:
         self._cam = torch.zeros((self.S, 2), dtype=torch.float64, device=self.device)   # unused by the raw rows
         self.count = int(id_base)            # KalmanBoxTracker.count
         self.calls = 0
-        self._bases = np.zeros((64, nq), np.int64)   # [call, group]: id of the first tracker the group created
+        # [call - _base_lo, group]: id of the first tracker the group created at that call; calls no live tracker
+        # refers to any more are dropped (the kernel reports the oldest birth still alive), so the table stays as
+        # long as the oldest live track, not as long as the run
+        self._bases = np.zeros((64, nq), np.int64)
+        self._base_lo = 0
         self.class_order = [[] for _ in range(self.S)]   # categories (0-based) in first-appearance order
 
     def step(self, boxes, exists=None):
@@ -956,7 +960,10 @@ class SortStepper:
                "out_birth": torch.zeros((max(N, 1), 2), dtype=torch.int32, device=dev),
                "out_count": torch.zeros(G, dtype=torch.int32, device=dev),
                "created": torch.zeros(G, dtype=torch.int32, device=dev),
+               "first_img": torch.zeros(G, dtype=torch.int32, device=dev),   # step mode: oldest live birth group
                "status": torch.zeros(1, dtype=torch.int32, device=dev)}
+        if (self.calls + 1) * G >= 2 ** 31:
+            raise W2TError("SortStepper: birth records are int32 (call * groups); %d calls of %d groups reached" % (self.calls, G))
         prob = _abi.SortProblem()
         prob.n_streams, prob.n_classes = S, NC
         prob.stream_img_offsets = _ptr(d_offsets)
@@ -972,7 +979,7 @@ class SortStepper:
         cplan.ws_bytes, cplan.n_wide = self._ws_bytes, self._n_wide
         cplan.n_mid, cplan.aux_offset, cplan.narrow_cap = 0, -1, 0
         res = _abi.SortResult()
-        for k in ("out_box", "out_score", "out_birth", "out_count", "created"):
+        for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img"):
             setattr(res, k, _ptr(out[k]))
         check(lib().w2t_sort_step(C.byref(prob), C.byref(cplan), C.byref(res), _ptr(self._workspace),
                                   _ptr(self._sub_state), int(self.calls * G), _ptr(out["status"]), _stream()),
@@ -986,9 +993,9 @@ class SortStepper:
             for c in self.class_order[s]:
                 base[s, c] = self.count
                 self.count += int(created[s, c])
-        if self.calls == len(self._bases):
+        if self.calls - self._base_lo == len(self._bases):
             self._bases = np.concatenate([self._bases, np.zeros_like(self._bases)])
-        self._bases[self.calls] = base.reshape(-1)
+        self._bases[self.calls - self._base_lo] = base.reshape(-1)
         self.calls += 1
         result = []
         for s in range(S):
@@ -999,11 +1006,18 @@ class SortStepper:
                 g = s * NC + c
                 o, m = int(start[g]), int(h["out_count"][g])
                 birth = h["out_birth"][o:o + m]
-                ids = self._bases[birth[:, 0] // G, birth[:, 0] % G] + birth[:, 1] + 1
+                ids = self._bases[birth[:, 0] // G - self._base_lo, birth[:, 0] % G] + birth[:, 1] + 1
                 rows = np.concatenate([h["out_box"][o:o + m], ids[:, None].astype(np.float64),
                                        h["out_score"][o:o + m, None]], axis=1)
                 tracked[c] = rows[::-1].copy() if m else np.empty((0, 6))
             result.append(tracked)
+        # forget the id bases of calls no live tracker was born in
+        oldest = min(int(h["first_img"].min()) // G if G else self.calls, self.calls)
+        drop = oldest - self._base_lo
+        if drop >= 64:
+            keep = self.calls - oldest
+            self._bases[:keep] = self._bases[drop:drop + keep].copy()
+            self._base_lo = oldest
         return result
 
 

@@ -13,6 +13,8 @@ import os
 
 import torch.distributed as dist
 
+from ._bind import bind_rank_cores  # noqa: F401  (re-exported)
+
 
 def block(n_items, rank, world):
     """Contiguous block [lo, hi) of ``n_items`` for ``rank``; sizes differ by at most one."""
@@ -43,6 +45,7 @@ def init_from_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         return 0, 1
+    bind_rank_cores()
     import torch
     if not dist.is_initialized():
         if torch.cuda.is_available():
