@@ -565,6 +565,32 @@ def main():
         parity = parity_sample(stages, scene, groups, packed_trk, rows_h, ens, args.parity_streams, args.seed)
     d2h = 0 if out_e2e is None else int(out_e2e.get("d2h_bytes", 0) if stages != "nms" else
                                         sum(np.asarray(v).nbytes for v in out_e2e.values() if v is not None))
+    # ---- what the copies of one end-to-end step cost on their own, all ranks at once: the same byte counts from / to
+    # pinned memory on two streams, no kernels.  On a box whose host memory system caps the aggregate DMA rate this
+    # floor grows with the number of ranks and bounds the e2e leg from below ("multi-GPU").
+    copy_floor_ms = None
+    if out_e2e is not None and h2d > 0 and d2h > 0:
+        src, dst = torch.empty(h2d, dtype=torch.uint8).pin_memory(), torch.empty(d2h, dtype=torch.uint8).pin_memory()
+        d_src, d_dst = torch.empty(h2d, dtype=torch.uint8, device="cuda"), torch.empty(d2h, dtype=torch.uint8, device="cuda")
+        s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def step_copies():
+            cur = torch.cuda.current_stream()
+            s_a.wait_stream(cur)
+            s_b.wait_stream(cur)
+            with torch.cuda.stream(s_a):
+                d_src.copy_(src, non_blocking=True)
+            with torch.cuda.stream(s_b):
+                dst.copy_(d_dst, non_blocking=True)
+            cur.wait_stream(s_a)
+            cur.wait_stream(s_b)
+            return None
+
+        for _ in range(2):
+            step_copies()
+        ms_copy, _ = timed(step_copies, args.steps)
+        copy_floor_ms = ms_copy / args.steps
+        del src, dst, d_src, d_dst
     # algorithmic bytes: soft-NMS 88 B per input box; SORT 24 B per tracked detection + 60 B per row
     alg = {}
     if stages != "sort":
@@ -606,7 +632,9 @@ def main():
                    "host_cores_per_rank": share,
                    "generate_s": round(gen_s, 1), "full_size_check": consistency},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K},
+                "ms_per_step": ms_e2e / K, "copies_alone_ms_per_step": copy_floor_ms,
+                "copies_alone_note": "the step's host<->device copies by themselves (pinned memory, both directions at "
+                                     "once, all ranks together, max over ranks): the floor the host's memory system sets"},
         "gpu_launches": int(out["launches"]) * K,
         "clocks": clocks,
         "roofline": roofline,

@@ -127,12 +127,30 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   // removals make the result order-dependent (box_utils.py:379-381; always for hard NMS)
   const bool sequential = HARD || conf > 0.;
   bool bad = false;
-  for (int i = tid; i < n; i += BLOCK) {
-    const double sc = row_score(i);
-    raw[i] = sc;
-    // without removals the reference keeps every box only if no score ever fails `ge(conf_thresh)`
-    if (!HARD && !sequential && !(sc >= (conf < 0. ? conf : 0.))) bad = true;
-    if (sc != sc) bad = true;
+  // Packed rows carry the score as a 17-bit integer (score * 1e5): (score, input position) then fits one 32-bit
+  // key whose order IS the canonical order — score descending, later position first among equals — and the rank
+  // of a box is a single count of larger keys.  (Soft branch without removals, groups of at most 1024 boxes.)
+  const bool int_keys = !HARD && !sequential && fmt == W2T_BOX_LTWH_P64 && n <= 1024;
+  uint32_t *ukey = reinterpret_cast<uint32_t *>(raw);  // instead of the input-order scores
+  if (int_keys) {
+    const int n4 = (n + 3) & ~3;  // the rank loop reads four keys at a time; 0 is never "larger"
+    for (int i = tid; i < n4; i += BLOCK) {
+      uint32_t key = 0u;
+      if (i < n) {
+        const unsigned long long q = *reinterpret_cast<const unsigned long long *>(bytes + 8 * ((size_t)base + i));
+        key = ((uint32_t)(q & 0x1ffffu) << 10) | (uint32_t)i;
+      }
+      ukey[i] = key;
+    }
+    // scores are finite and >= 0 here; `ge(conf_thresh)` with conf <= 0 never fails
+  } else {
+    for (int i = tid; i < n; i += BLOCK) {
+      const double sc = row_score(i);
+      raw[i] = sc;
+      // without removals the reference keeps every box only if no score ever fails `ge(conf_thresh)`
+      if (!HARD && !sequential && !(sc >= (conf < 0. ? conf : 0.))) bad = true;
+      if (sc != sc) bad = true;
+    }
   }
   __syncthreads();
 
@@ -140,21 +158,33 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   //    top_k boxes take part (box_utils.py:325-327)
   const int m = (P.p.top_k > 0 && P.p.top_k < n) ? P.p.top_k : n;
   for (int i = tid; i < n; i += BLOCK) {
-    const double si = raw[i];
+    double si;
     // G boxes score higher; of the equal ones L come earlier and H later in the input.  Ties are
     // rare, so the main loop only counts "greater" and "greater or equal" (two compares per box)
     // and the positions of the equal ones are looked at only when there are any.
     int G = 0, GE = 0, L = 0, H = 0;
-    for (int k = 0; k < n; k++) {
-      const double sk = raw[k];
-      G += (sk > si) ? 1 : 0;
-      GE += (sk >= si) ? 1 : 0;
-    }
-    if (GE - G > 1) {
+    if (int_keys) {
+      const uint32_t ui = ukey[i];
+      const uint4 *k4 = reinterpret_cast<const uint4 *>(ukey);
+      const int n4 = (n + 3) >> 2;
+      for (int k = 0; k < n4; k++) {
+        const uint4 v = k4[k];  // broadcast
+        G += (v.x > ui) + (v.y > ui) + (v.z > ui) + (v.w > ui);
+      }
+      si = (double)(ui >> 10) / 100000.0;  // = row_score(i)
+    } else {
+      si = raw[i];
       for (int k = 0; k < n; k++) {
         const double sk = raw[k];
-        L += (sk == si && k < i) ? 1 : 0;
-        H += (sk == si && k > i) ? 1 : 0;
+        G += (sk > si) ? 1 : 0;
+        GE += (sk >= si) ? 1 : 0;
+      }
+      if (GE - G > 1) {
+        for (int k = 0; k < n; k++) {
+          const double sk = raw[k];
+          L += (sk == si && k < i) ? 1 : 0;
+          H += (sk == si && k > i) ? 1 : 0;
+        }
       }
     }
     // The reference sorts ascending (stable, canonical rule) and consumes from the end, so among
@@ -228,17 +258,50 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   const bool mask_skip = HARD ? (P.p.iou_thresh >= 0.) : skip_disjoint;
   int *alive = reinterpret_cast<int *>(raw);  // the input-order scores are no longer needed
   if (!sequential) {
-    // fixed-order triangular product: thread j multiplies the weights of every i ranked above it
-    for (int j = tid; j < m; j += BLOCK) {
+    // Who can overlap whom: one bit set over the ranks per strip (32 strips x W words, in place of the scores) —
+    // bit j of strip b: box j touches strip b.  Built 32 ranks at a time by a 32 x 32 bit transpose of the masks.
+    uint32_t *strips = reinterpret_cast<uint32_t *>(raw);
+    const int W = (m + 31) >> 5;  // 32 * W words <= cap + 31 words: inside the 2 * cap words of `raw` for cap >= 32
+    const bool use_strips = mask_skip && 32 * W <= 2 * cap;
+    if (use_strips) {
+      const int lane = tid & 31;
+      for (int j0 = (tid >> 5) * 32; j0 < m; j0 += BLOCK) {
+        const uint32_t mj = (j0 + lane < m) ? smk[j0 + lane] : 0u;
+        uint32_t mine = 0u;
+#pragma unroll 8
+        for (int b = 0; b < 32; b++) {
+          const uint32_t w = __ballot_sync(0xffffffffu, (mj >> b) & 1u);
+          if (lane == b) mine = w;
+        }
+        strips[lane * W + (j0 >> 5)] = mine;
+      }
+      __syncthreads();
+    }
+    // fixed-order triangular product: box j multiplies the weights of every i ranked above it — j units of work, so
+    // a thread takes the boxes p and m-1-p together (m-1 units for every thread) instead of one box each
+    const int n_pairs = (m + 1) >> 1;
+#pragma unroll 1
+    for (int u = tid; u < 2 * n_pairs; u += BLOCK) {
+      // slots [0, n_pairs) = the light halves; after them the heavy halves in the same thread order (same tid for
+      // BLOCK >= n_pairs; otherwise still m-1 units per consecutive pair of rounds)
+      const int pq = u < n_pairs ? u : u - n_pairs;
+      const int j = u < n_pairs ? pq : m - 1 - pq;
+      if (u >= n_pairs && j == pq) continue;  // the middle box of an odd group was done in the first half
       const T x1 = sx1[j], y1 = sy1[j], x2 = sx2[j], y2 = sy2[j], area = sar[j];
       T live = ssc[j];
       const uint32_t mj = smk[j];
-      // 32 higher ranked boxes at a time: a divergence-free integer loop collects the candidates whose
-      // strip masks meet this box's in x and in y (a few percent of the pairs); only those go through
-      // the FP64 arithmetic, in rank order, so the product is multiplied in the reference's order.
+      // 32 higher ranked boxes at a time: the candidates are the boxes that share an x strip AND a y strip with
+      // this one (a few percent of the pairs); only those go through the FP64 arithmetic, in rank order, so the
+      // product is multiplied in the reference's order.
       for (int i0 = 0; i0 < j; i0 += 32) {
         uint32_t cand = 0xffffffffu;
-        if (mask_skip) {
+        if (use_strips) {
+          const uint32_t *col = strips + (i0 >> 5);
+          uint32_t cx = 0u, cy = 0u;
+          for (uint32_t w = mj & 0xffffu; w; w &= w - 1u) cx |= col[(__ffs(w) - 1) * W];
+          for (uint32_t w = mj >> 16; w; w &= w - 1u) cy |= col[(16 + __ffs(w) - 1) * W];
+          cand = cx & cy;
+        } else if (mask_skip) {
           cand = 0u;
           const uint4 *mk4 = reinterpret_cast<const uint4 *>(smk + i0);  // broadcast loads; padded past m
 #pragma unroll
