@@ -11,16 +11,19 @@ tail -3 $out/${tag}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log
 timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"; cat $out/${tag}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err; cat $out/${tag}_bench_ref.json
-for c in c1 c2 c4 c5; do
-  timeout 900 python bench.py --config $c --steps 5 --warmup 3 > $out/${tag}_bench_$c.json 2>> $out/${tag}_bench.err; echo "bench $c rc=$?"
+for c in c1 c2; do
+  timeout 900 python bench.py --config $c --steps 10 --warmup 3 > $out/${tag}_bench_$c.json 2>> $out/${tag}_bench.err; echo "bench $c rc=$?"
+done
+for c in c4 c5; do   # crowded configurations: the oracle side of the parity sample is slow, check 2 streams
+  timeout 900 python bench.py --config $c --steps 5 --warmup 3 --parity-streams 2 > $out/${tag}_bench_$c.json 2>> $out/${tag}_bench.err; echo "bench $c rc=$?"
 done
 # launch list of the same command (shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-e2e --parity-streams 0 > $out/${tag}_bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skip-e2e --parity-streams 0 --cli-segments 0 > $out/${tag}_bench_under_ncu.log 2>&1
 # full captures of one launch of each kernel at the bench's own size (ncu replays the launch ~40 times)
 SEG=${2:-150}
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sort_warp_kernel -s 1 -c 1 -f -o $out/${tag}_prof_sort \
-    python bench.py --segments $SEG --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e --parity-streams 0 > $out/${tag}_ncu_sort.log 2>&1
+    python bench.py --segments $SEG --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e --parity-streams 0 --cli-segments 0 > $out/${tag}_ncu_sort.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:softnms_kernel -s 1 -c 1 -f -o $out/${tag}_prof_nms \
-    python bench.py --segments $SEG --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e --parity-streams 0 > $out/${tag}_ncu_nms.log 2>&1
+    python bench.py --segments $SEG --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e --parity-streams 0 --cli-segments 0 > $out/${tag}_ncu_nms.log 2>&1
 ls -la $out | tail -20
