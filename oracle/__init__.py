@@ -27,6 +27,12 @@ Parity status
   covariance identities.  Everything around them is pinned by executing the
   reference's own code.
 
-NumPy semantics: NEP 50 (NumPy 2) — see SURVEY.md §8c.  The ports use explicit
-casts so they do not depend on the installed NumPy's promotion rules.
+NumPy semantics: two promotion regimes, selected per call (``promotion="legacy"``
+— NumPy 1.x value-based casting, the reference's pinned environment and the
+product's default — or ``"nep50"``, NumPy 2).  The ports use explicit casts so they
+do not depend on the installed NumPy's promotion rules.  The ``nep50`` goldens are
+the reference's files executed as they are under this image's NumPy 2; for
+``legacy`` the two promotion-sensitive spots of that execution are emulated
+(``ref_shim._legacy_convert_bbox_to_z`` and float64 thresholds), because NumPy 1.x
+cannot be installed here — see DESIGN.md §3.
 """
