@@ -359,6 +359,22 @@ def cli_record(n_segments, seed):
             ens_cli.main(files + ["-o", ens_out, "-m", "soft_nms"] + nms)
             track_cli.main(["--ground-truth", gt, "--input", ens_out, "--output", two_out] + trk)
             best_two = min(best_two, time.perf_counter() - t0)
+        # level (iii) of SURVEY.md §8d: parsed arrays in host memory (what the JSON reader hands over) -> packing on
+        # the host (filters, grouping, stream layout, 8-byte rows: NumPy) -> kernels -> dense rows on the host
+        from waymo_2d_tracking_b200 import packing, runtime
+        dets = [native_json.load(f) for f in files]
+        best_arrays = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ids_s, perm, s_off, _frames, go, rows, packed, max_group = pipeline.groups_from_detections(dets, [1.0] * len(dets), NMS["min_score"], 4)
+            cams = [ids_s[int(perm[int(o)])].split('/')[2] for o in s_off[:-1]]
+            res = runtime.ensemble_and_track_pipelined(
+                go.astype(np.int32), packed if packed is not None else rows, stream_img_offsets=s_off,
+                cam_wh=np.asarray([packing.camera_size(c) for c in cams], np.float64).reshape(-1, 2), n_classes=4,
+                score_thr=SCORE_THR, iou_thresholds=IOU_THR, max_age=MAX_AGE, min_hits=MIN_HITS, max_group=max_group,
+                n_chunks=min(8, len(cams)), **NMS)
+            best_arrays = min(best_arrays, time.perf_counter() - t0)
+        arrays_rows = int(res["n_rows"])
         sort_mod.KalmanBoxTracker.count = 0
         out_bytes = os.path.getsize(fused_out)
         with open(fused_out, "rb") as a, open(two_out, "rb") as b:
@@ -370,7 +386,11 @@ def cli_record(n_segments, seed):
             "two_command_path": "detnet.ensemble -m soft_nms && tracking/track.py (the reference's commands)",
             "sample": "%d segments = %d frames, %.0f MB of submission JSON in, %.0f MB of tracks JSON out; best of 2 "
                       "in-process runs, files on local disk" % (n_segments, scene.n_img, in_bytes / 1e6, out_bytes / 1e6),
-            "json_in_mb_s": in_bytes / 1e6 / best_fused, "outputs_byte_identical": same}
+            "json_in_mb_s": in_bytes / 1e6 / best_fused, "outputs_byte_identical": same,
+            "arrays_in_rows_out_value": scene.n_img / best_arrays,
+            "arrays_in_rows_out_path": "parsed arrays in host memory -> NumPy packing (filters, grouping, stream layout, "
+                                       "8-byte rows) -> ensemble_and_track_pipelined -> %d dense rows on the host; the "
+                                       "level the CPU arm is timed at (dicts in, dicts out)" % arrays_rows}
 
 
 def main():

@@ -87,7 +87,13 @@ def load_groups(files, weights, min_score, NC, want_rows=True):
     if fast is not None:
         return (fast.image_ids, fast.image_order.astype(np.int64), fast.stream_img_offsets, fast.frame_ids,
                 fast.group_offsets.astype(np.int64), fast.rows, fast.packed, fast.max_group)
-    groups = packing.pack_detection_files([native_json.load(f) for f in files], weights, min_score)
+    return groups_from_detections([native_json.load(f) for f in files], weights, min_score, NC)
+
+
+def groups_from_detections(dets, weights, min_score, NC):
+    """The general path of :func:`load_groups` on parsed files (``native_json.Detections``, one per submission):
+    ``packing.pack_detection_files`` + the regrouping into the tracker's layout, in NumPy.  Same return value."""
+    groups = packing.pack_detection_files(dets, weights, min_score)
     if any(not (1 <= c <= NC) for c in groups.category_ids):
         raise IndexError("list index out of range: category ids %r with %d IoU thresholds" % (groups.category_ids, NC))
     ncat = len(groups.category_ids)
