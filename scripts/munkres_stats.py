@@ -7,7 +7,7 @@ from waymo_2d_tracking_b200 import synth
 import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 kw = dict(n_segments=1)
-if name == "c4":
+if name in ("c4", "c5"):
     kw.update(cameras=("FRONT",), n_frames=12)
 scene = synth.make_scene(synth.preset(name, seed=1000, **kw))
 lib = c_oracle.lib()
