@@ -480,7 +480,8 @@ def main():
             def step_device():
                 return {"nms": runtime.softnms_groups_device(d_offs, d_rows, G, groups.max_group, NMS["iou_thresh"],
                                                              NMS["soft_nms_cut"], NMS["min_score"], 4, None,
-                                                             want_merged=False, box_format=fmt), "launches": 1}
+                                                             want_merged=False, box_format=fmt),
+                        "launches": runtime.nms_launch_count(G, groups.max_group)}
 
             def step_e2e():
                 return runtime.softnms_groups(h_offs, h_rows, NMS["iou_thresh"], NMS["soft_nms_cut"], NMS["min_score"], 4,
@@ -520,8 +521,22 @@ def main():
             ms = float(t.item())
         return ms, out
 
+    # warm up exactly the code the timed loop runs (per-kernel CUDA events included), then keep Python's cyclic
+    # garbage collector out of the timed regions: a generation-2 pass over the scene's objects is a host stall of
+    # tens of milliseconds that has nothing to do with the path being measured
+    import gc
+    runtime.PROFILE = []
+    held = None
     for _ in range(args.warmup):
-        step_device()
+        # like the timed loop: the previous step's outputs stay alive while the next step allocates its own, so both
+        # sets of device buffers exist before the timing starts (a first-time cudaMalloc of ~2 GB inside the timed
+        # region stalls the host for 50-80 ms: the "intermittent" stall of earlier bench lines)
+        held = step_device()
+    del held
+    torch.cuda.synchronize()
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     sampler = ClockSampler(local_rank)
     if not os.environ.get("W2T_BENCH_NO_SAMPLER"):      # debug aid
         sampler.start()
@@ -538,10 +553,13 @@ def main():
     if args.skip_e2e:
         ms_e2e = float("nan")
     else:
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e()
+        held = None
+        for _ in range(max(2, min(args.warmup, 3))):
+            held = step_e2e()
+        del held
         ms_e2e, out_e2e = timed(step_e2e, args.steps)
     clocks = sampler.summary()
+    gc.enable()
 
     # ---- bookkeeping -------------------------------------------------------------------------------
     K = args.steps

@@ -18,6 +18,9 @@
 // Tie rule: the reference's sort is unstable; the canonical order used here
 // and by the oracle is (score descending, concatenation index descending).
 #include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -43,6 +46,9 @@ struct NmsParams {
   size_t work_stride;
   int small_cap;
   int skip_big;
+  // size classes: a launch serves the groups with n_lo < boxes <= n_hi (n_lo = -1: from empty groups on), so that
+  // small groups get small CTAs (one warp for up to 32 boxes) and waste neither lanes nor block-wide barriers
+  int n_lo, n_hi;
 };
 
 // HARD = false: the soft branch (box_utils.py:335-391).  HARD = true: the hard branch
@@ -87,6 +93,7 @@ __global__ void __launch_bounds__(BLOCK) softnms_kernel(const NmsParams P) {
   const int base = P.p.group_offsets[g];
   const int n = P.p.group_offsets[g + 1] - base;
   if (P.work != nullptr && n <= P.small_cap) continue;  // the regular launch has it
+  if (n <= P.n_lo || n > P.n_hi) continue;  // another size class has it
   if (n > cap) {
     if (P.skip_big) continue;  // the oversized pass has it
     if (tid == 0) {
@@ -472,6 +479,8 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
   P.work = nullptr;
   P.work_stride = 0;
   P.small_cap = 0;
+  P.n_lo = -1;
+  P.n_hi = INT_MAX;
   P.skip_big = max_group_size > smem_cap ? 1 : 0;
   P.p = *problem;
   P.r = *result;
@@ -484,9 +493,34 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
   P.status = status;
   const size_t smem = (size_t)P.cap * kBytesPerBox + 4 * kMaskPad;
   int rc;
-  if (regular_max <= 96) rc = launch<64, HARD>(P, problem->n_groups, smem, stream);
-  else if (regular_max <= 768) rc = launch<128, HARD>(P, problem->n_groups, smem, stream);
-  else rc = launch<256, HARD>(P, problem->n_groups, smem, stream);
+  // many groups of mixed sizes (a Waymo-shaped job: vehicles ~200 boxes per group, pedestrians ~80, cyclists and
+  // signs < 35): one launch per size class, each with CTAs and shared memory of its own size.  A CTA whose group
+  // belongs to another class exits at once.  W2T_NMS_CLASSES="a,b" overrides the class bounds (debug aid; "" = one).
+  int bounds[2] = {32, 96};
+  int n_bounds = (regular_max > 64 && problem->n_groups >= 1024) ? 2 : 0;
+  if (const char *e = getenv("W2T_NMS_CLASSES")) {
+    n_bounds = 0;
+    int a = 0, b2 = 0;
+    const int got = sscanf(e, "%d,%d", &a, &b2);
+    if (got >= 1 && a > 0) bounds[n_bounds++] = a;
+    if (got >= 2 && b2 > a) bounds[n_bounds++] = b2;
+  }
+  while (n_bounds > 0 && bounds[n_bounds - 1] >= regular_max) n_bounds--;
+  rc = W2T_OK;
+  int lo = -1;
+  for (int k = 0; k <= n_bounds && rc == W2T_OK; k++) {
+    NmsParams Q = P;
+    Q.n_lo = lo;
+    Q.n_hi = (k < n_bounds) ? bounds[k] : INT_MAX;
+    const int top = (k < n_bounds) ? bounds[k] : regular_max;   // largest group this launch serves
+    Q.cap = (std::max(top, 1) + 3) & ~3;
+    const size_t sm = (size_t)Q.cap * kBytesPerBox + 4 * kMaskPad;
+    if (top <= 32) rc = launch<32, HARD>(Q, problem->n_groups, sm, stream);
+    else if (top <= 96) rc = launch<64, HARD>(Q, problem->n_groups, sm, stream);
+    else if (top <= 768) rc = launch<128, HARD>(Q, problem->n_groups, sm, stream);
+    else rc = launch<256, HARD>(Q, problem->n_groups, sm, stream);
+    lo = Q.n_hi;
+  }
   if (rc != W2T_OK || max_group_size <= smem_cap) return rc;
   // oversized groups: the same kernel over arrays in global memory (stream-ordered scratch, freed behind the
   // launch), a few persistent CTAs striding over the groups

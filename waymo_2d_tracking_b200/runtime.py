@@ -318,6 +318,30 @@ def make_plan(n_streams, n_classes, h_offsets, h_count, h_exists, max_age, group
     return arrays
 
 
+FINALIZE_LAUNCHES = 5      # order, scan sums / offsets / apply, rows (csrc/finalize.cu)
+
+
+def nms_launch_count(n_groups, max_group):
+    """Kernels one ``w2t_softnms_groups`` call launches (``run_groups`` in csrc/softnms.cu): one launch per size
+    class (up to 32 boxes, up to 96, the rest) when the job mixes sizes, plus the pass over global scratch for
+    groups beyond shared memory."""
+    cap = int(lib().w2t_softnms_max_group())
+    regular = min(int(max_group), cap)
+    classes = 1
+    if regular > 64 and int(n_groups) >= 1024 and "W2T_NMS_CLASSES" not in os.environ:
+        classes += int(regular > 32) + int(regular > 96)
+    return classes + int(int(max_group) > cap)
+
+
+def sort_launch_count(plan, n_substreams):
+    """Kernels one ``w2t_sort_track`` call launches (``launch_sort`` in csrc/sort.cu, warp path): dmax, classify,
+    the cluster kernel over the plan's wide / wide+mid classes, the warp kernel, the cluster kernel's second
+    pass, the CTA kernel for what is left."""
+    if plan.get("aux_offset", -1) < 0:
+        return int(plan["n_wide"] > 0) + int(n_substreams > plan["n_wide"])
+    return 2 + int(plan["n_wide"] > 0) + int(plan["n_wide"] + plan["n_mid"] > 0) + 3
+
+
 def launch_classes(plan, order):
     """Reorder ``order`` into the launch classes of ``w2t_sort_plan_t`` — [wide | mid | narrow], each part
     keeping its relative order — and return (order, n_wide, n_mid)."""
@@ -492,7 +516,7 @@ def sort_track(packed, iou_thresholds, max_age=1, min_hits=0, final_cap=0, id_ba
     rows = finalize_device(S, NC, d_offsets, d_start, trk, d["rank"], id_base,
                            int(np.asarray(packed.det_count, np.int64).sum()))
     if not to_host:
-        return {"trk": trk, "rows": rows, "launches": 6}
+        return {"trk": trk, "rows": rows, "launches": sort_launch_count(plan, S * NC) + FINALIZE_LAUNCHES}
     res = _collect(trk, rows, raw)
     res["id_next"] = int(id_base + res["totals"][0])
     if raw:
@@ -542,7 +566,8 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
                                 _dev(cam_wh, np.float64, device), iou_thresholds, max_age, min_hits, plan,
                                 promotion=promotion)
         out_rows = finalize_device(S, NC, d_offsets, d_start, trk, None, id_base, int(d_rows.shape[0]))
-        return {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": None, "launches": 6}
+        return {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": None,
+                "launches": nms_launch_count(n_groups, max_group) + sort_launch_count(plan, S * NC) + FINALIZE_LAUNCHES}
     # the plan needs the surviving counts on the host: one small D2H between the stages
     h_cnt, h_exists, h_nms_status = _host(nms["trk_count"], "trk_count"), _host(nms["img_exists"], "img_exists"), \
         _host(nms["status"], "nms_status")
@@ -556,12 +581,14 @@ def ensemble_and_track(group_offsets, rows, stream_img_offsets, cam_wh, n_classe
     n_trk = int(h_cnt.numpy().sum(dtype=np.int64))
     if not to_host:
         # results stay in HBM (bench.py's device-resident leg); 1 soft-NMS + 1 SORT + 4 finalize kernels
-        dev = {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": n_trk, "launches": 6}
+        dev = {"nms": nms, "trk": trk, "rows": out_rows, "n_trk": n_trk,
+               "launches": nms_launch_count(n_groups, max_group) + sort_launch_count(plan, S * NC) + FINALIZE_LAUNCHES}
         return dev
     extra = {k: nms[k] for k in ("ens_count", "ens_box", "ens_score")} if want_ensemble else {}
     res = _collect(trk, out_rows, raw, extra)
     res["d2h_bytes"] += h_cnt.numel() * 4 + h_exists.numel() + 4
-    res["n_trk"], res["launches"] = n_trk, 6
+    res["n_trk"] = n_trk
+    res["launches"] = nms_launch_count(n_groups, max_group) + sort_launch_count(plan, S * NC) + FINALIZE_LAUNCHES
     res["trk_count"], res["img_exists"] = h_cnt.numpy(), h_exists.numpy()
     res["id_next"] = int(id_base + res["totals"][0])
     if raw:
@@ -848,7 +875,8 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
     check_device_status(int(h_status[0]), "soft-NMS")
     check_device_status(int(h_status[1]), "SORT")
     res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 24 * len(chunks) + 8,
-           "launches": 5 * len(chunks) + 1, "n_chunks": len(chunks)}
+           "launches": len(chunks) * (nms_launch_count(max(G // len(chunks), 1), max_group) + FINALIZE_LAUNCHES)
+           + sort_launch_count(plan_all, S * NC), "n_chunks": len(chunks)}
     for key in _ROW_KEYS[:-1]:
         pool = _PINNED[("pipe_" + key, {"rows_box": f64, "rows_score": f64, "rows_id": torch.int64,
                                          "rows_img": i32, "rows_cat": i32}[key])]
