@@ -670,7 +670,12 @@ def main():
                    "host_cores_per_rank": share,
                    "generate_s": round(gen_s, 1), "full_size_check": consistency},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K, "copies_alone_ms_per_step": copy_floor_ms,
+                "ms_per_step": ms_e2e / K,
+                "result": None if stages != "both" else
+                "dense rows in pinned host memory, 48 B each: 4 x f64 box, f64 confidence, int32 object id - id_base, "
+                "int32 image * 8 + category - 1 (runtime.HostRows decodes int64 ids / image / category arrays on first "
+                "access, outside the timed step; the JSON writer consumes them)",
+                "copies_alone_ms_per_step": copy_floor_ms,
                 "copies_alone_note": "the step's host<->device copies by themselves (pinned memory, both directions at "
                                      "once, all ranks together, max over ranks): the floor the host's memory system sets"},
         "gpu_launches": int(out["launches"]) * K,

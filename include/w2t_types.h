@@ -158,6 +158,10 @@ typedef struct w2t_rows_t {
   int64_t  birth_group_base; /* subtracted from out_birth's group index: set it to the first    */
                        /*   group of the shard when w2t_sort_track ran over the whole job but   */
                        /*   w2t_sort_finalize is called per shard with shard-local arrays       */
+  int32_t *compact;    /* optional [capacity,2]: 8 bytes per row INSTEAD of object_id / image /  */
+                       /*   category (those may then be NULL), for rows that travel to the host: */
+                       /*   [0] object id minus the host-side id_base argument, [1] image * 8 +  */
+                       /*   category_id - 1 (n_classes <= 8)                                     */
 } w2t_rows_t;
 
 /* layout of the four box columns of w2t_nms_problem_t.rows */

@@ -87,6 +87,7 @@ class Rows(C.Structure):
         ("capacity", C.c_int64),
         ("image_base", C.c_int32),
         ("birth_group_base", C.c_int64),
+        ("compact", _p),
     ]
 
 

@@ -31,6 +31,7 @@ struct FinParams {
   double *rows_box, *rows_score;
   int64_t *rows_id;
   int32_t *rows_img, *rows_cat;
+  int2 *rows_compact;  // optional: (id - id_base, image * 8 + category - 1) instead of the three arrays above
   int64_t rows_cap;
   int32_t image_base;
   int64_t birth_base;
@@ -168,9 +169,14 @@ __global__ void rows_kernel(const FinParams P) {
       reinterpret_cast<double4 *>(P.rows_box)[dst] = b;
       P.rows_score[dst] = P.out_score[src];
       const int bg = (int)(P.out_birth[2 * src] - P.birth_base), bk = P.out_birth[2 * src + 1];
-      P.rows_id[dst] = id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
-      P.rows_img[dst] = img + P.image_base;
-      P.rows_cat[dst] = c + 1;
+      const int64_t id = id_base + P.scan_created[(bg / NC) * NC + k] + bk + 1;
+      if (P.rows_compact != nullptr) {
+        P.rows_compact[dst] = make_int2((int)(id - P.id_base), (img + P.image_base) * 8 + c);
+      } else {
+        P.rows_id[dst] = id;
+        P.rows_img[dst] = img + P.image_base;
+        P.rows_cat[dst] = c + 1;
+      }
     }
   }
 }
@@ -204,7 +210,8 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
       W2T_CUDA_TRY(cudaMemcpyAsync(rows->totals + 2, &id_base, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     return W2T_OK;
   }
-  if (!workspace || !rows->box || !rows->score || !rows->object_id || !rows->image || !rows->category) {
+  if (!workspace || !rows->box || !rows->score ||
+      (!rows->compact && (!rows->object_id || !rows->image || !rows->category))) {
     set_last_error("w2t_sort_finalize: null buffer");
     return W2T_ERR_ARG;
   }
@@ -234,6 +241,7 @@ extern "C" int w2t_sort_finalize(const w2t_sort_problem_t *problem, const w2t_so
   P.rows_id = rows->object_id;
   P.rows_img = rows->image;
   P.rows_cat = rows->category;
+  P.rows_compact = reinterpret_cast<int2 *>(rows->compact);
   P.rows_cap = rows->capacity;
   P.image_base = rows->image_base;
   P.birth_base = rows->birth_group_base;

@@ -426,21 +426,25 @@ def assign_ids(n_streams, n_classes, h_offsets, h_start, h_out_count, h_created,
 
 
 def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank, id_base, rows_cap, image_base=0,
-                    rows=None, id_base_device=None, birth_group_base=0):
+                    rows=None, id_base_device=None, birth_group_base=0, compact=False):
     """Device-side ids + dense rows (``w2t_sort_finalize``) on the tensors ``sort_track_device`` returned.
-    ``rows``: preallocated output tensors (same keys) to write into instead of allocating."""
+    ``rows``: preallocated output tensors (same keys) to write into instead of allocating.  ``compact``: 8 bytes
+    per row (``rows_compact`` [cap,2] int32: id - id_base, image * 8 + category - 1) instead of ``rows_id`` /
+    ``rows_img`` / ``rows_cat`` (16 bytes): what the pipelined path sends home (:class:`HostRows` decodes it)."""
     device = trk["out_box"].device
     NC = int(n_classes)
     n_groups = int(d_start.shape[0])
     cap = max(int(rows_cap), 1)
-    rows = rows if rows is not None else {
-        "rows_box": torch.empty((cap, 4), dtype=torch.float64, device=device),
-        "rows_score": torch.empty(cap, dtype=torch.float64, device=device),
-        "rows_id": torch.empty(cap, dtype=torch.int64, device=device),
-        "rows_img": torch.empty(cap, dtype=torch.int32, device=device),
-        "rows_cat": torch.empty(cap, dtype=torch.int32, device=device),
-        "totals": torch.zeros(3, dtype=torch.int64, device=device),
-    }
+    if rows is None:
+        rows = {"rows_box": torch.empty((cap, 4), dtype=torch.float64, device=device),
+                "rows_score": torch.empty(cap, dtype=torch.float64, device=device),
+                "totals": torch.zeros(3, dtype=torch.int64, device=device)}
+        if compact:
+            rows["rows_compact"] = torch.empty((cap, 2), dtype=torch.int32, device=device)
+        else:
+            rows.update({"rows_id": torch.empty(cap, dtype=torch.int64, device=device),
+                         "rows_img": torch.empty(cap, dtype=torch.int32, device=device),
+                         "rows_cat": torch.empty(cap, dtype=torch.int32, device=device)})
     ws = torch.empty(int(lib().w2t_sort_finalize_workspace(int(n_streams), NC, n_groups)), dtype=torch.uint8,
                      device=device)
     prob = _abi.SortProblem()
@@ -450,8 +454,9 @@ def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank,
     for k in ("out_box", "out_score", "out_birth", "out_count", "created", "first_img"):
         setattr(res, k, _ptr(trk[k]))
     crows = _abi.Rows()
-    crows.box, crows.score, crows.object_id = _ptr(rows["rows_box"]), _ptr(rows["rows_score"]), _ptr(rows["rows_id"])
-    crows.image, crows.category, crows.totals = _ptr(rows["rows_img"]), _ptr(rows["rows_cat"]), _ptr(rows["totals"])
+    crows.box, crows.score, crows.totals = _ptr(rows["rows_box"]), _ptr(rows["rows_score"]), _ptr(rows["totals"])
+    crows.object_id, crows.image, crows.category = (_ptr(rows.get(k)) for k in ("rows_id", "rows_img", "rows_cat"))
+    crows.compact = _ptr(rows.get("rows_compact"))
     crows.capacity = cap
     crows.image_base = int(image_base)
     crows.id_base_device = _ptr(id_base_device)
@@ -464,6 +469,26 @@ def finalize_device(n_streams, n_classes, d_offsets, d_start, trk, d_class_rank,
 
 
 _ROW_KEYS = ("rows_box", "rows_score", "rows_id", "rows_img", "rows_cat", "totals")
+_COMPACT_ROW_KEYS = ("rows_box", "rows_score", "rows_compact")
+
+
+class HostRows(dict):
+    """Result of the pipelined path.  The device sends 48 bytes per row home — box, confidence and 8 bytes holding
+    (object id - ``id_base``, image * 8 + category - 1) — and ``rows_id`` (int64), ``rows_img`` and ``rows_cat``
+    (int32) are decoded from them on first access."""
+
+    def __missing__(self, key):
+        pair = dict.__getitem__(self, "rows_compact")
+        if key == "rows_id":
+            value = pair[:, 0].astype(np.int64) + np.int64(dict.__getitem__(self, "id_base"))
+        elif key == "rows_img":
+            value = pair[:, 1] >> 3
+        elif key == "rows_cat":
+            value = (pair[:, 1] & 7) + 1
+        else:
+            raise KeyError(key)
+        self[key] = value
+        return value
 _RAW_KEYS = ("out_box", "out_score", "out_birth", "out_count", "created", "first_img", "final_count", "final_state")
 
 
@@ -832,9 +857,10 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
             trk_k = {"out_box": trk_out["out_box"], "out_score": trk_out["out_score"], "out_birth": trk_out["out_birth"],
                      "out_count": trk_out["out_count"][g0:g1], "created": trk_out["created"][g0:g1],
                      "first_img": trk_out["first_img"][s0 * NC:s1 * NC]}
-            rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk_k, None, id_base if k == 0 else 0,
+            # ids relative to id_base all along the chain (the compact rows hold them as int32; HostRows adds id_base)
+            rows_k = finalize_device(ns, NC, d_loc, d_goff[g0:g1], trk_k, None, 0,
                                      int(go_np[g1] - go_np[g0]), image_base=img0, birth_group_base=g0,
-                                     id_base_device=None if prev_totals is None else prev_totals[2:])
+                                     id_base_device=None if prev_totals is None else prev_totals[2:], compact=True)
             prev_totals = rows_k["totals"]
             h_totals[3 * k:3 * k + 3].copy_(rows_k["totals"], non_blocking=True)
             ev = torch.cuda.Event()
@@ -852,7 +878,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
         n_k = int(h_totals[3 * k + 1])
         with torch.cuda.stream(s_out):
             s_out.wait_event(fin_done[k])
-            for key in _ROW_KEYS[:-1]:
+            for key in _COMPACT_ROW_KEYS:
                 src = rows_of[k][key][:n_k]
                 width = src.shape[1] if src.dim() > 1 else 1
                 pool = _pinned_pool("pipe_" + key, src.dtype, (n_rows_total + n_k) * width, n_rows_total * width,
@@ -861,7 +887,7 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                 d2h_bytes += src.numel() * src.element_size()
             _trace("d2h queued %d" % k, s_out)
         n_rows_total += n_k
-    created_total = int(h_totals[3 * (len(chunks) - 1) + 2]) - int(id_base)
+    created_total = int(h_totals[3 * (len(chunks) - 1) + 2])
     for cs in comp + [fin, s_in]:
         main.wait_stream(cs)
     h_status = _host(torch.stack([nms_out["status"][0], trk_out["status"][0]]), "pipe_status")
@@ -874,14 +900,14 @@ def ensemble_and_track_pipelined(group_offsets, rows, stream_img_offsets, cam_wh
                                   raw=False, promotion=promotion)
     check_device_status(int(h_status[0]), "soft-NMS")
     check_device_status(int(h_status[1]), "SORT")
-    res = {"n_rows": n_rows_total, "id_next": int(id_base + created_total), "d2h_bytes": d2h_bytes + 24 * len(chunks) + 8,
+    res = HostRows({"n_rows": n_rows_total, "id_next": int(id_base + created_total), "id_base": int(id_base),
+           "d2h_bytes": d2h_bytes + 24 * len(chunks) + 8,
            "launches": len(chunks) * (nms_launch_count(max(G // len(chunks), 1), max_group) + FINALIZE_LAUNCHES)
-           + sort_launch_count(plan_all, S * NC), "n_chunks": len(chunks)}
-    for key in _ROW_KEYS[:-1]:
-        pool = _PINNED[("pipe_" + key, {"rows_box": f64, "rows_score": f64, "rows_id": torch.int64,
-                                         "rows_img": i32, "rows_cat": i32}[key])]
-        width = 4 if key == "rows_box" else 1
-        res[key] = pool[:n_rows_total * width].view((n_rows_total, 4) if width == 4 else (n_rows_total,)).numpy()
+           + sort_launch_count(plan_all, S * NC), "n_chunks": len(chunks)})
+    for key in _COMPACT_ROW_KEYS:
+        pool = _PINNED[("pipe_" + key, {"rows_box": f64, "rows_score": f64, "rows_compact": i32}[key])]
+        width = {"rows_box": 4, "rows_compact": 2}.get(key, 1)
+        res[key] = pool[:n_rows_total * width].view((n_rows_total, width) if width > 1 else (n_rows_total,)).numpy()
     return res
 
 
