@@ -151,3 +151,18 @@ def test_rows_to_dicts_matches_unpack_tracks():
                  rows_img=np.array([index[r['image_id']] for r in want]),
                  rows_cat=np.array([r['category_id'] for r in want]))
     assert packing.rows_to_dicts(packed, dense) == want
+
+
+def test_host_rows_decode_the_compact_pairs_lazily():
+    # runtime.HostRows: (object id - id_base, image * 8 + category - 1) pairs -> int64 ids, int32 image / category
+    from waymo_2d_tracking_b200 import runtime
+    pair = np.array([[0, 5 * 8 + 0], [41, 5 * 8 + 3], [2 ** 31 - 1, (2 ** 28 - 1) * 8 + 7]], np.int32)
+    rows = runtime.HostRows({"rows_compact": pair, "id_base": 2 ** 40, "n_rows": 3})
+    assert "rows_id" not in rows
+    np.testing.assert_array_equal(rows["rows_id"], np.array([2 ** 40, 2 ** 40 + 41, 2 ** 40 + 2 ** 31 - 1], np.int64))
+    np.testing.assert_array_equal(rows["rows_img"], [5, 5, 2 ** 28 - 1])
+    np.testing.assert_array_equal(rows["rows_cat"], [1, 4, 8])
+    assert rows["rows_id"].dtype == np.int64 and rows["rows_img"].dtype == np.int32 and rows["rows_cat"].dtype == np.int32
+    assert "rows_id" in rows                       # decoded once, then kept
+    with pytest.raises(KeyError):
+        rows["no_such_key"]
