@@ -388,6 +388,44 @@ def test_softnms_group_beyond_shared_memory():
         np.testing.assert_array_equal(got["merged"][o:o + cnt], want["merged"][o:o + cnt])
 
 
+def test_softnms_size_classes_and_their_boundaries():
+    # >= 1024 groups of mixed sizes: one launch per size class (<= 32 boxes: one-warp CTAs, <= 96, the rest).  Sizes
+    # on both sides of every bound, empty groups, tied scores (the integer-key ranking of packed rows must break
+    # ties like the canonical rule), every branch of the kernel: soft, soft with removals, top_k, hard.
+    rng = np.random.default_rng(77)
+    sizes = rng.choice([0, 1, 2, 31, 32, 33, 64, 95, 96, 97, 128, 129, 150], size=1400)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    n = int(offs[-1])
+    xy = rng.integers(0, 1700, (n, 2))
+    wh = rng.integers(10, 220, (n, 2))
+    score = np.round(rng.uniform(0.02, 1, n), 2)          # 2 decimals: plenty of ties inside a group
+    rows = np.c_[score, xy, wh].astype(np.float64)
+    packed = packing.packed_rows(rows)
+    assert packed is not None and int(sizes.max()) > 96
+    mg = int(sizes.max())
+    want = c_oracle.softnms_groups(offs, rows, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR)
+    for data in (rows, packed):
+        got = runtime.softnms_groups(offs, data, 0.5, 0.9, 0.01, 4, helpers.SCORE_THR, max_group=mg)
+        for k in ("merged", "src_index", "ens_count", "trk_count", "kept_count", "img_exists"):
+            np.testing.assert_array_equal(got[k], want[k])
+        idx, _ = packing.valid_row_index(offs[:-1].astype(np.int64), want["ens_count"])
+        np.testing.assert_array_equal(got["ens_box"][idx], want["ens_box"][idx])
+        np.testing.assert_array_equal(got["ens_score"][idx], want["ens_score"][idx])
+    # removals (conf_thresh > 0) and top_k: the order-dependent branch
+    want = c_oracle.softnms_groups(offs, rows, 0.4, 0.8, 0.0, top_k=40, conf_thresh=0.3)
+    got = runtime.softnms_groups(offs, rows, 0.4, 0.8, 0.0, max_group=mg, top_k=40, conf_thresh=0.3)
+    np.testing.assert_array_equal(got["kept_count"], want["kept_count"])
+    idx, _ = packing.valid_row_index(offs[:-1].astype(np.int64), want["kept_count"])
+    np.testing.assert_array_equal(got["merged"][idx], want["merged"][idx])
+    np.testing.assert_array_equal(got["src_index"][idx], want["src_index"][idx])
+    # hard NMS
+    want = c_oracle.softnms_groups(offs, rows, 0.5, 1.0, -np.inf, box_format=0, hard=True)
+    got = runtime.hardnms_groups(offs, rows, 0.5, max_group=mg, box_format=0)
+    np.testing.assert_array_equal(got["kept_count"], want["kept_count"])
+    idx, _ = packing.valid_row_index(offs[:-1].astype(np.int64), want["kept_count"])
+    np.testing.assert_array_equal(got["merged"][idx], want["merged"][idx])
+
+
 def test_softnms_rejects_unsupported_scores_loudly():
     rows = np.array([[-0.5, 0, 0, 10, 10], [0.5, 0, 0, 10, 10]], np.float64)
     with pytest.raises(Exception):
