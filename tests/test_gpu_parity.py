@@ -389,11 +389,11 @@ def test_softnms_group_beyond_shared_memory():
 
 
 def test_softnms_size_classes_and_their_boundaries():
-    # >= 1024 groups of mixed sizes: one launch per size class (<= 32 boxes: one-warp CTAs, <= 96, the rest).  Sizes
+    # >= 16384 groups of mixed sizes: one launch per size class (<= 32 boxes: one-warp CTAs, <= 96, the rest).  Sizes
     # on both sides of every bound, empty groups, tied scores (the integer-key ranking of packed rows must break
     # ties like the canonical rule), every branch of the kernel: soft, soft with removals, top_k, hard.
     rng = np.random.default_rng(77)
-    sizes = rng.choice([0, 1, 2, 31, 32, 33, 64, 95, 96, 97, 128, 129, 150], size=1400)
+    sizes = rng.choice([0, 1, 2, 31, 32, 33, 64, 95, 96, 97, 128, 129, 150], size=17000, p=[.3, .2, .2, .05, .05, .05, .03, .02, .02, .02, .02, .02, .02])
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     n = int(offs[-1])
     xy = rng.integers(0, 1700, (n, 2))

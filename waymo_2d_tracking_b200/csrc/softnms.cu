@@ -497,7 +497,8 @@ int run_groups(const w2t_nms_problem_t *problem, w2t_nms_result_t *result, int m
   // signs < 35): one launch per size class, each with CTAs and shared memory of its own size.  A CTA whose group
   // belongs to another class exits at once.  W2T_NMS_CLASSES="a,b" overrides the class bounds (debug aid; "" = one).
   int bounds[2] = {32, 96};
-  int n_bounds = (regular_max > 64 && problem->n_groups >= 1024) ? 2 : 0;
+  // (a small job is bound by launch latency instead: one launch)
+  int n_bounds = (regular_max > 64 && problem->n_groups >= 16384) ? 2 : 0;
   if (const char *e = getenv("W2T_NMS_CLASSES")) {
     n_bounds = 0;
     int a = 0, b2 = 0;

@@ -328,7 +328,7 @@ def nms_launch_count(n_groups, max_group):
     cap = int(lib().w2t_softnms_max_group())
     regular = min(int(max_group), cap)
     classes = 1
-    if regular > 64 and int(n_groups) >= 1024 and "W2T_NMS_CLASSES" not in os.environ:
+    if regular > 64 and int(n_groups) >= 16384 and "W2T_NMS_CLASSES" not in os.environ:
         classes += int(regular > 32) + int(regular > 96)
     return classes + int(int(max_group) > cap)
 
