@@ -166,3 +166,41 @@ def test_host_rows_decode_the_compact_pairs_lazily():
     assert "rows_id" in rows                       # decoded once, then kept
     with pytest.raises(KeyError):
         rows["no_such_key"]
+
+
+def test_rank_core_binding_splits_the_affinity_mask(monkeypatch):
+    import os
+    from waymo_2d_tracking_b200 import _bind
+    if not hasattr(os, "sched_setaffinity"):
+        pytest.skip("no sched_setaffinity on this platform")
+    before = os.sched_getaffinity(0)
+    cores = sorted(before)
+    try:
+        monkeypatch.setenv("W2T_BIND_CORES", "0")
+        assert _bind.bind_rank_cores(0, 2) is None and os.sched_getaffinity(0) == before
+        monkeypatch.delenv("W2T_BIND_CORES")
+        assert _bind.bind_rank_cores(0, 1) is None                       # a single rank keeps every core
+        if len(cores) >= 2:
+            share = len(cores) // 2
+            mine = _bind.bind_rank_cores(1, 2)
+            assert mine == cores[share:2 * share] and os.sched_getaffinity(0) == set(mine)
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_launch_counts_follow_the_library_rules():
+    # runtime.nms_launch_count / sort_launch_count restate run_groups (csrc/softnms.cu) and launch_sort (csrc/sort.cu):
+    # the bench line's gpu_launches is built from them
+    from waymo_2d_tracking_b200 import runtime
+    cap = int(runtime.lib().w2t_softnms_max_group())
+    assert runtime.nms_launch_count(4000, 280) == 1              # a small job: one launch
+    assert runtime.nms_launch_count(600000, 280) == 3            # size classes <= 32, <= 96, the rest
+    assert runtime.nms_launch_count(600000, 90) == 2             # no group beyond 96 boxes
+    assert runtime.nms_launch_count(600000, 60) == 1
+    assert runtime.nms_launch_count(10, cap + 1) == 2            # + the pass over global scratch
+    plan = {"aux_offset": 4096, "n_wide": 0, "n_mid": 0}
+    assert runtime.sort_launch_count(plan, 3000) == 5            # dmax, classify, warps, clusters' second pass, CTAs
+    plan = {"aux_offset": 4096, "n_wide": 2, "n_mid": 5}
+    assert runtime.sort_launch_count(plan, 3000) == 7
+    plan = {"aux_offset": -1, "n_wide": 2, "n_mid": 0}
+    assert runtime.sort_launch_count(plan, 8) == 2 and runtime.sort_launch_count(plan, 2) == 1
