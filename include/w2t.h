@@ -208,6 +208,28 @@ int w2t_json_groups_copy(const w2t_json_groups_t *groups, int32_t *category_ids,
 const char *w2t_json_groups_image_ids(const w2t_json_groups_t *groups, int64_t *bytes);
 void w2t_json_groups_free(w2t_json_groups_t *groups);
 
+/* read_data_file (tracking/utils.py:63-96) and the packing of its result for w2t_sort_track, straight from the file:
+ * parses `path` (a detection list or {"annotations": [...]}), drops rows with width or height < 1 and rows whose
+ * score is below score_thr[category_id - 1] (utils.py:79-87, in that order), and lays the rest out as the tracker
+ * wants them: streams = (segment, camera) pairs in first-appearance order of the file (segments, then cameras
+ * inside a segment), every image of a stream in frame order whether or not a row of it survives, group g = image *
+ * n_classes + category_id - 1 with rows in file order, boxes x, y, x+w, y+h rounded to float32
+ * (tracker_sort.py:45), class_rank = position of the category in the stream's tracker dict (order of the first
+ * surviving row).  segment_id (may be NULL): keep that segment only (track.py --segment-id); block_world > 1:
+ * keep this rank's contiguous block of the remaining segments (one process per GPU).  W2T_ERR_UNSUPPORTED: use the
+ * general (Python) packer, which reproduces the reference's behaviour or its exception.  HOST functions. */
+typedef struct w2t_json_tracks w2t_json_tracks_t;
+int w2t_json_pack_tracks(const char *path, const double *score_thr, int32_t n_thr, int32_t n_classes,
+                         const char *segment_id, int32_t block_rank, int32_t block_world, w2t_json_tracks_t **out);
+/* info: [0] streams, [1] images, [2] rows, [3] bytes of the stream names ("segment\tcamera\n" per stream) */
+int w2t_json_tracks_info(const w2t_json_tracks_t *tracks, int64_t info[4]);
+/* any pointer may be NULL: stream_img_offsets [streams+1], frame_ids [images], det_start / det_count
+ * [images*n_classes], det_box [rows,4] float32, class_rank [streams*n_classes], stream_names [info 3] */
+int w2t_json_tracks_copy(const w2t_json_tracks_t *tracks, int32_t *stream_img_offsets, int64_t *frame_ids,
+                         int32_t *det_start, int32_t *det_count, float *det_box, int32_t *class_rank,
+                         char *stream_names);
+void w2t_json_tracks_free(w2t_json_tracks_t *tracks);
+
 /* Replace json.dump of tracking/track.py:50 (rows of tracking/utils.py:52-58) and of
  * detnet/ensemble.py:159-160 (rows of :61-62).  Byte-identical to the reference's files: default
  * separators, ensure_ascii, floats as Python's float.__repr__.  image_ids[k] = NUL-terminated

@@ -249,3 +249,70 @@ def test_native_grouping_leaves_unusual_inputs_to_the_general_path(tmp_path):
     p.write_text("[]")
     empty = native_json.group_files([p], [1.0], 0.0, _abi.W2T_LAYOUT_STREAMS, 4)
     assert empty.image_ids == [] and len(empty.rows) == 0 and list(empty.group_offsets) == [0]
+
+
+def _same_packed(a, b):
+    assert a.streams == [tuple(s) for s in b.streams] and a.n_rows == b.n_rows and a.n_classes == b.n_classes
+    for k in ("frame_ids", "stream_img_offsets", "det_start", "det_count", "det_box", "cam_wh", "class_rank"):
+        x, y = np.asarray(getattr(a, k)), np.asarray(getattr(b, k))
+        assert x.dtype == y.dtype or k in ("frame_ids",), k
+        np.testing.assert_array_equal(x, y, err_msg=k)
+
+
+def test_native_track_packer_equals_the_array_packer(tmp_path):
+    # w2t_json_pack_tracks (parse + read_data_file's filters + stream layout in one native call) against
+    # native_json.load + packing.pack_detections: every array, every option
+    cfg = synth.SynthConfig(n_segments=4, cameras=("SIDE_LEFT", "FRONT", "FRONT_RIGHT"), n_frames=9, n_submissions=1,
+                            objects_per_frame=30.0, seed=13)
+    scene = synth.make_scene(cfg)
+    rows = synth.to_json_list(scene, scene.submissions[0])
+    rng = np.random.default_rng(3)
+    rng.shuffle(rows)                                   # streams / frames / categories first appear in file order
+    rows[7]['bbox'][2] = 0.5                            # dropped: width < 1
+    rows[9]['score'] = 0.0                              # dropped: below every threshold
+    del rows[11]['score']                               # ground-truth style row: score 1.0
+    p = tmp_path / "dets.json"
+    p.write_text(json.dumps(rows))
+    dets = native_json.load(p)
+    thr = [0.95, 0.6, 1.0, 0.9]
+    _same_packed(packing.pack_track_file(p, thr, 4), packing.pack_detections(dets, thr, 4))
+    seg = scene.segments[2]
+    _same_packed(packing.pack_track_file(p, thr, 4, segment_id=seg), packing.pack_detections(dets, thr, 4, segment_id=seg))
+    assert packing.pack_track_file(p, thr, 4, segment_id="no-such-segment").n_streams == 0
+    for world in (2, 3, 5):
+        for rank in range(world):
+            _same_packed(packing.pack_track_file(p, thr, 4, segment_block=(rank, world)),
+                         packing.pack_detections(dets, thr, 4, segment_block=(rank, world)))
+    # {"annotations": [...]} wrapper, more categories than the file uses
+    p2 = tmp_path / "gt.json"
+    p2.write_text(json.dumps({"annotations": rows, "images": []}))
+    _same_packed(packing.pack_track_file(p2, thr + [0.5, 0.5], 6), packing.pack_detections(native_json.load(p2), thr + [0.5, 0.5], 6))
+    # empty file
+    p3 = tmp_path / "empty.json"
+    p3.write_text("[]")
+    empty = packing.pack_track_file(p3, thr, 4)
+    assert empty.n_streams == 0 and empty.n_rows == 0 and list(empty.stream_img_offsets) == [0]
+
+
+def test_native_track_packer_leaves_exceptions_to_the_general_path(tmp_path):
+    thr = [0.95, 0.6, 1.0, 0.9]
+    row = {'image_id': 'seg/5/FRONT', 'category_id': 5, 'bbox': [1, 2, 30, 40], 'score': 0.99}
+    p = tmp_path / "d.json"
+    p.write_text(json.dumps([row]))
+    assert native_json.pack_tracks(p, thr, 4) is None
+    with pytest.raises(IndexError):                      # thresholds[4] in the reference (utils.py:85)
+        packing.pack_track_file(p, thr, 4)
+    row.update(category_id=1, image_id='seg/5')
+    p.write_text(json.dumps([row]))
+    with pytest.raises(ValueError):                      # image_id.split('/') unpacking (utils.py:70)
+        packing.pack_track_file(p, thr, 4)
+    row.update(image_id='seg/5/NOT_A_CAMERA')
+    p.write_text(json.dumps([row]))
+    with pytest.raises(KeyError):                        # IMAGE_SIZES[camera_id] (utils.py:21)
+        packing.pack_track_file(p, thr, 4)
+    row.update(image_id='seg/1_0/FRONT')                 # int('1_0') == 10: Python's spelling, general path
+    p.write_text(json.dumps([row]))
+    assert native_json.pack_tracks(p, thr, 4) is None
+    assert list(packing.pack_track_file(p, thr, 4).frame_ids) == [10]
+    with pytest.raises(W2TError):
+        packing.pack_track_file(tmp_path / "missing.json", thr, 4)

@@ -190,6 +190,11 @@ EXPORTS = {
     "w2t_json_groups_copy": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "w2t_json_groups_image_ids": (_p, [_p, C.POINTER(C.c_int64)]),
     "w2t_json_groups_free": (None, [_p]),
+    "w2t_json_pack_tracks": (C.c_int, [C.c_char_p, _p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32,
+                                       C.POINTER(_p)]),
+    "w2t_json_tracks_info": (C.c_int, [_p, _p]),
+    "w2t_json_tracks_copy": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p]),
+    "w2t_json_tracks_free": (None, [_p]),
     "w2t_json_write_tracks": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p, _p]),
     "w2t_json_write_detections": (C.c_int, [C.c_char_p, C.c_int64, _p, _p, _p, _p, _p]),
     "w2t_bbox_to_z": (C.c_int, [_p, _p, C.c_int32, C.c_int32, _p]),

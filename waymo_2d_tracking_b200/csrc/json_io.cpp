@@ -998,6 +998,211 @@ extern "C" const char *w2t_json_groups_image_ids(const w2t_json_groups_t *g, int
 
 extern "C" void w2t_json_groups_free(w2t_json_groups_t *g) { delete g; }
 
+// ---- the tracker's input from one file: read_data_file + the packing of its result (tracking/utils.py:63-96) ----
+
+struct w2t_json_tracks {
+  std::string stream_names;                 // "segment\tcamera\n" per stream
+  std::vector<int32_t> stream_img_offsets;  // [S+1]
+  std::vector<int64_t> frame_ids;           // [n_img] in layout order
+  std::vector<int32_t> det_start, det_count;  // [n_img * n_classes]
+  std::vector<float> det_box;               // [N,4] x1, y1, x2, y2 rounded to float32 (tracker_sort.py:45)
+  std::vector<int32_t> class_rank;          // [S * n_classes] position of the category in the stream's tracker dict
+};
+
+extern "C" int w2t_json_pack_tracks(const char *path, const double *score_thr, int32_t n_thr, int32_t n_classes,
+                                    const char *segment_id, int32_t block_rank, int32_t block_world,
+                                    w2t_json_tracks_t **out) {
+  if (!path || !score_thr || n_thr < 0 || n_classes < 1 || n_classes > W2T_MAX_CLASSES || !out || block_world < 0 ||
+      (block_world > 1 && (block_rank < 0 || block_rank >= block_world))) {
+    w2t::set_last_error("w2t_json_pack_tracks: bad argument");
+    return W2T_ERR_ARG;
+  }
+  *out = nullptr;
+  Lap lap;
+  std::string error;
+  std::unique_ptr<w2t_json_dets> file(load_file(path, error));
+  if (!file) {
+    w2t::set_last_error("w2t_json_load: %s", error.c_str());
+    return W2T_ERR_ARG;
+  }
+  lap("parse");
+  const w2t_json_dets &d = *file;
+  const int NC = n_classes;
+  const int n_ids = (int)d.image_ids.size();
+  const size_t n = d.score.size();
+  // image id -> (segment, frame, camera); segments and cameras numbered in first-appearance order
+  std::unordered_map<std::string_view, int32_t> seg_index, cam_index;
+  std::vector<std::string_view> segments, cameras;
+  std::vector<int32_t> seg_of((size_t)n_ids), cam_of((size_t)n_ids);
+  std::vector<int64_t> frame_of((size_t)n_ids);
+  for (int i = 0; i < n_ids; i++) {
+    const std::string_view id = d.image_ids[(size_t)i];
+    const size_t a = id.find('/');
+    const size_t b = a == std::string_view::npos ? a : id.find('/', a + 1);
+    if (b == std::string_view::npos || id.find('/', b + 1) != std::string_view::npos ||
+        !plain_int(id.substr(a + 1, b - a - 1), frame_of[(size_t)i])) {
+      w2t::set_last_error("w2t_json_pack_tracks: image id %s is not segment/frame/camera", d.image_ids[(size_t)i].c_str());
+      return W2T_ERR_UNSUPPORTED;  // the general path raises the reference's ValueError (or parses int('1_0'))
+    }
+    const std::string_view seg = id.substr(0, a), cam = id.substr(b + 1);
+    auto si = seg_index.emplace(seg, (int32_t)segments.size());
+    if (si.second) segments.push_back(seg);
+    auto ci = cam_index.emplace(cam, (int32_t)cameras.size());
+    if (ci.second) cameras.push_back(cam);
+    seg_of[(size_t)i] = si.first->second;
+    cam_of[(size_t)i] = ci.first->second;
+  }
+  const int n_cam = std::max<int>((int)cameras.size(), 1);
+  // streams = (segment, camera) pairs in first-appearance order: segment first appearance, then the pair's own
+  // (image ids are interned in first-appearance order, so the smallest image index of a pair is its first image)
+  std::vector<int32_t> pair_first((size_t)segments.size() * n_cam, -1), seg_first(segments.size(), INT32_MAX);
+  for (int i = 0; i < n_ids; i++) {
+    int32_t &pf = pair_first[(size_t)seg_of[(size_t)i] * n_cam + cam_of[(size_t)i]];
+    if (pf < 0) pf = i;
+    seg_first[(size_t)seg_of[(size_t)i]] = std::min(seg_first[(size_t)seg_of[(size_t)i]], (int32_t)i);
+  }
+  std::vector<int32_t> stream_pairs;
+  for (size_t p = 0; p < pair_first.size(); p++)
+    if (pair_first[p] >= 0) stream_pairs.push_back((int32_t)p);
+  std::sort(stream_pairs.begin(), stream_pairs.end(), [&](int32_t x, int32_t y) {
+    const int32_t sx = seg_first[(size_t)(x / n_cam)], sy = seg_first[(size_t)(y / n_cam)];
+    return sx != sy ? sx < sy : pair_first[(size_t)x] < pair_first[(size_t)y];
+  });
+  if (segment_id != nullptr) {  // track.py --segment-id
+    std::vector<int32_t> kept;
+    for (int32_t p : stream_pairs)
+      if (segments[(size_t)(p / n_cam)] == std::string_view(segment_id)) kept.push_back(p);
+    stream_pairs.swap(kept);
+  }
+  if (block_world > 1) {  // this rank's contiguous block of the remaining segments (sharding.block)
+    std::vector<int32_t> seg_order;
+    for (int32_t p : stream_pairs)
+      if (std::find(seg_order.begin(), seg_order.end(), p / n_cam) == seg_order.end()) seg_order.push_back(p / n_cam);
+    const int q = (int)seg_order.size() / block_world, rem = (int)seg_order.size() % block_world;
+    const int lo = block_rank * q + std::min(block_rank, rem), cnt = q + (block_rank < rem ? 1 : 0);
+    std::vector<char> mine(segments.size(), 0);
+    for (int k = lo; k < lo + cnt; k++) mine[(size_t)seg_order[(size_t)k]] = 1;
+    std::vector<int32_t> kept;
+    for (int32_t p : stream_pairs)
+      if (mine[(size_t)(p / n_cam)]) kept.push_back(p);
+    stream_pairs.swap(kept);
+  }
+  const int S = (int)stream_pairs.size();
+  std::vector<int32_t> stream_of_pair(pair_first.size(), -1);
+  for (int sidx = 0; sidx < S; sidx++) stream_of_pair[(size_t)stream_pairs[(size_t)sidx]] = sidx;
+  auto t = std::make_unique<w2t_json_tracks>();
+  for (int sidx = 0; sidx < S; sidx++) {
+    const int32_t p = stream_pairs[(size_t)sidx];
+    t->stream_names.append(segments[(size_t)(p / n_cam)]);
+    t->stream_names += '\t';
+    t->stream_names.append(cameras[(size_t)(p % n_cam)]);
+    t->stream_names += '\n';
+  }
+  // images of each stream in frame order (ties: first appearance), every image of the file whether or not a row
+  // of it survives the filters
+  std::vector<int32_t> img_stream((size_t)n_ids), img_order;
+  for (int i = 0; i < n_ids; i++) {
+    img_stream[(size_t)i] = stream_of_pair[(size_t)seg_of[(size_t)i] * n_cam + cam_of[(size_t)i]];
+    if (img_stream[(size_t)i] >= 0) img_order.push_back(i);
+  }
+  std::stable_sort(img_order.begin(), img_order.end(), [&](int32_t x, int32_t y) {
+    return img_stream[(size_t)x] != img_stream[(size_t)y] ? img_stream[(size_t)x] < img_stream[(size_t)y]
+                                                          : frame_of[(size_t)x] < frame_of[(size_t)y];
+  });
+  const int64_t n_img = (int64_t)img_order.size();
+  std::vector<int32_t> new_img((size_t)n_ids, -1);
+  t->frame_ids.resize((size_t)n_img);
+  t->stream_img_offsets.assign((size_t)S + 1, 0);
+  for (int64_t k = 0; k < n_img; k++) {
+    const int32_t i = img_order[(size_t)k];
+    new_img[(size_t)i] = (int32_t)k;
+    t->frame_ids[(size_t)k] = frame_of[(size_t)i];
+    t->stream_img_offsets[(size_t)img_stream[(size_t)i] + 1]++;
+  }
+  for (int sidx = 0; sidx < S; sidx++) t->stream_img_offsets[(size_t)sidx + 1] += t->stream_img_offsets[(size_t)sidx];
+  if (n_img * NC >= INT32_MAX) { w2t::set_last_error("w2t_json_pack_tracks: too many groups"); return W2T_ERR_UNSUPPORTED; }
+  lap("layout");
+  // filters of read_data_file in its order (utils.py:79-87): box validity, then the category's threshold
+  const int64_t G = n_img * NC;
+  const int cat_hi = std::min(NC, (int)n_thr);
+  t->det_count.assign((size_t)G, 0);
+  std::vector<int32_t> key(n);
+  for (size_t i = 0; i < n; i++) {
+    key[i] = -1;
+    const int32_t img = new_img[(size_t)d.image_index[i]];
+    if (img < 0) continue;
+    if (d.bbox[4 * i + 2] < 1 || d.bbox[4 * i + 3] < 1) continue;
+    const int32_t c = d.category[i];
+    if (c < 1 || c > cat_hi) {
+      w2t::set_last_error("w2t_json_pack_tracks: category_id %d with %d thresholds", (int)c, cat_hi);
+      return W2T_ERR_UNSUPPORTED;  // the general path raises the reference's IndexError
+    }
+    if (d.score[i] < score_thr[c - 1]) continue;
+    key[i] = img * NC + (c - 1);
+    t->det_count[(size_t)key[i]]++;
+  }
+  t->det_start.resize((size_t)G);
+  int64_t total = 0;
+  for (int64_t q = 0; q < G; q++) {
+    t->det_start[(size_t)q] = (int32_t)total;
+    total += t->det_count[(size_t)q];
+    if (total >= INT32_MAX) { w2t::set_last_error("w2t_json_pack_tracks: more than 2^31 rows"); return W2T_ERR_UNSUPPORTED; }
+  }
+  // scatter in file order inside a group; category rank = order of the first surviving row in (image, file) order
+  t->det_box.resize((size_t)total * 4);
+  std::vector<int32_t> cursor(t->det_start);
+  std::vector<int64_t> pos_first((size_t)S * NC, INT64_MAX);
+  for (size_t i = 0; i < n; i++) {
+    const int32_t k = key[i];
+    if (k < 0) continue;
+    float *b = &t->det_box[(size_t)cursor[(size_t)k]++ * 4];
+    const double x = d.bbox[4 * i], y = d.bbox[4 * i + 1];
+    b[0] = (float)x; b[1] = (float)y; b[2] = (float)(x + d.bbox[4 * i + 2]); b[3] = (float)(y + d.bbox[4 * i + 3]);
+    const int32_t img = k / NC;
+    const int32_t sidx = img_stream[(size_t)img_order[(size_t)img]];
+    int64_t &pf = pos_first[(size_t)sidx * NC + (k % NC)];
+    pf = std::min(pf, (int64_t)img * ((int64_t)n + 1) + (int64_t)i);
+  }
+  t->class_rank.resize((size_t)S * NC);
+  for (int sidx = 0; sidx < S; sidx++) {
+    int order[W2T_MAX_CLASSES];
+    for (int c = 0; c < NC; c++) order[c] = c;
+    std::stable_sort(order, order + NC, [&](int x, int y) { return pos_first[(size_t)sidx * NC + x] < pos_first[(size_t)sidx * NC + y]; });
+    for (int r = 0; r < NC; r++) t->class_rank[(size_t)sidx * NC + order[r]] = r;
+  }
+  lap("filter + scatter");
+  *out = t.release();
+  return W2T_OK;
+}
+
+extern "C" int w2t_json_tracks_info(const w2t_json_tracks_t *t, int64_t info[4]) {
+  if (!t || !info) { w2t::set_last_error("w2t_json_tracks_info: null argument"); return W2T_ERR_ARG; }
+  info[0] = (int64_t)t->stream_img_offsets.size() - 1;
+  info[1] = (int64_t)t->frame_ids.size();
+  info[2] = (int64_t)t->det_box.size() / 4;
+  info[3] = (int64_t)t->stream_names.size();
+  return W2T_OK;
+}
+
+extern "C" int w2t_json_tracks_copy(const w2t_json_tracks_t *t, int32_t *stream_img_offsets, int64_t *frame_ids,
+                                    int32_t *det_start, int32_t *det_count, float *det_box, int32_t *class_rank,
+                                    char *stream_names) {
+  if (!t) { w2t::set_last_error("w2t_json_tracks_copy: null handle"); return W2T_ERR_ARG; }
+  auto put = [](auto *dst, const auto &v) {
+    if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+  };
+  put(stream_img_offsets, t->stream_img_offsets);
+  put(frame_ids, t->frame_ids);
+  put(det_start, t->det_start);
+  put(det_count, t->det_count);
+  put(det_box, t->det_box);
+  put(class_rank, t->class_rank);
+  if (stream_names && !t->stream_names.empty()) memcpy(stream_names, t->stream_names.data(), t->stream_names.size());
+  return W2T_OK;
+}
+
+extern "C" void w2t_json_tracks_free(w2t_json_tracks_t *t) { delete t; }
+
 namespace {
 // rows [0, n) formatted by `row(out, i)` on a few host threads (each its own range and buffer), written in order
 template <class ROW>

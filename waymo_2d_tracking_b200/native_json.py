@@ -137,3 +137,40 @@ def group_files(paths, weights, min_score, layout=_abi.W2T_LAYOUT_ENSEMBLE, n_cl
         return out
     finally:
         lib().w2t_json_groups_free(handle)
+
+
+def pack_tracks(path, score_threshold, n_classes, segment_id=None, segment_block=None):
+    """``w2t_json_pack_tracks``: parse one detection file and lay it out for the tracker in one native call.
+    Returns a dict of arrays (``streams``: list of (segment, camera)), or ``None`` when the input needs the general
+    packer (``load`` + ``packing.pack_detections``: odd frame spellings, categories outside the threshold list, more
+    than W2T_MAX_CLASSES categories)."""
+    thr = np.ascontiguousarray(score_threshold, np.float64)
+    if not 1 <= int(n_classes) <= _abi.W2T_MAX_CLASSES:
+        return None
+    rank, world = (0, 0) if segment_block is None else (int(segment_block[0]), int(segment_block[1]))
+    handle = C.c_void_p()
+    status = lib().w2t_json_pack_tracks(os.fsencode(str(path)), thr.ctypes.data_as(C.c_void_p), len(thr), int(n_classes),
+                                        None if segment_id is None else str(segment_id).encode("utf-8"), rank, world,
+                                        C.byref(handle))
+    if status == _abi.W2T_ERR_UNSUPPORTED:
+        lib().w2t_clear_error()
+        return None
+    check(status, "w2t_json_pack_tracks")
+    try:
+        info = (C.c_int64 * 4)()
+        check(lib().w2t_json_tracks_info(handle, info), "w2t_json_tracks_info")
+        S, n_img, n_rows, name_bytes = (int(v) for v in info)
+        G = n_img * int(n_classes)
+        out = {"stream_img_offsets": np.empty(S + 1, np.int32), "frame_ids": np.empty(n_img, np.int64),
+               "det_start": np.empty(G, np.int32), "det_count": np.empty(G, np.int32),
+               "det_box": np.empty((n_rows, 4), np.float32), "class_rank": np.empty(S * int(n_classes), np.int32)}
+        names = C.create_string_buffer(max(name_bytes, 1))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().w2t_json_tracks_copy(handle, vp(out["stream_img_offsets"]), vp(out["frame_ids"]), vp(out["det_start"]),
+                                         vp(out["det_count"]), vp(out["det_box"]), vp(out["class_rank"]),
+                                         C.cast(names, C.c_void_p)), "w2t_json_tracks_copy")
+        text = names.raw[:name_bytes].decode("utf-8")
+        out["streams"] = [tuple(line.split("\t")) for line in text.split("\n")[:-1]] if text else []
+        return out
+    finally:
+        lib().w2t_json_tracks_free(handle)

@@ -447,3 +447,21 @@ def pack_files(paths, weights, min_score):
     if fast is None:
         return pack_detection_files([native_json.load(f) for f in paths], weights, min_score)
     return PackedGroups(fast.image_ids, fast.category_ids, fast.group_offsets, fast.rows, fast.max_group, fast.sub_counts)
+
+
+def pack_track_file(path, score_threshold, n_classes, segment_id=None, segment_block=None):
+    """:func:`pack_detections` straight from the file: one native call parses, filters and lays the rows out
+    (``w2t_json_pack_tracks``); inputs it does not cover go through ``native_json.load`` + :func:`pack_detections`,
+    which reproduces the reference's behaviour or its exception."""
+    from . import native_json
+    fast = native_json.pack_tracks(path, score_threshold, n_classes, segment_id, segment_block)
+    if fast is None:
+        return pack_detections(native_json.load(path), score_threshold, n_classes, segment_id=segment_id,
+                               segment_block=segment_block)
+    streams = fast["streams"]
+    cam_wh = np.asarray([camera_size(c) for _, c in streams], np.float64).reshape(-1, 2)   # KeyError: utils.py:21
+    return PackedTracks(
+        n_streams=len(streams), n_classes=int(n_classes), streams=streams, frame_ids=fast["frame_ids"],
+        stream_img_offsets=fast["stream_img_offsets"], det_start=fast["det_start"], det_count=fast["det_count"],
+        det_box=fast["det_box"], cam_wh=cam_wh, img_exists=None, class_rank=fast["class_rank"],
+        n_rows=int(fast["det_box"].shape[0]))

@@ -51,16 +51,22 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     print(args)
 
-    # native reader: the file goes straight into flat arrays (no per-detection dicts); the grouping,
-    # filters and ordering of read_data_file (utils.py:63-96) are applied by packing.pack_detections
-    dets = native_json.load(args.input)
+    # native reader: the file goes straight into flat arrays (no per-detection dicts); the grouping, filters and
+    # ordering of read_data_file (utils.py:63-96) are applied by packing.pack_track_file (one native call: parse +
+    # pack) or, one process per GPU, by packing.pack_detections on each rank's block of segments
+    multi = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    n_classes = len(args.iou_threshold)
+    if multi:
+        dets = native_json.load(args.input)
+    else:
+        packed = packing.pack_track_file(args.input, args.score_threshold, n_classes, segment_id=args.segment_id or None)
     image_id2path = {}
     ground_truth_dir = dirname(args.ground_truth)
     with open(args.ground_truth) as fp:
         for image in json.load(fp):
             image_id2path[image['id']] = join(ground_truth_dir, image['file_name'])
 
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    if multi:
         # launched by torchrun: one rank per GPU, each packs and tracks its block of segments from the flat arrays,
         # rank 0 gathers ARRAYS and writes the file
         sharding.init_from_env()
@@ -79,8 +85,6 @@ def main(argv=None):
                                  rows["rows_cat"], rows["rows_id"])
         return int(rows["n_rows"])
 
-    n_classes = len(args.iou_threshold)
-    packed = packing.pack_detections(dets, args.score_threshold, n_classes, segment_id=args.segment_id or None)
     start_time = time.time()
     for segment_id in dict.fromkeys(seg for seg, _ in packed.streams):
         print(segment_id)
