@@ -90,7 +90,9 @@ def merge_groups(groups, method, iou_thresh, soft_nms_cut, min_score):
     if method == "weighted_fusion":
         from .nn import fusion
         return fusion.fuse_groups(groups, iou_thresh, min_score)
-    return runtime.softnms_groups(groups.group_offsets, groups.rows, iou_thresh, soft_nms_cut, min_score,
+    # soft-NMS takes the 8-byte rows when the packer proved them exact (5x less to ship, integer ranking keys)
+    rows = groups.packed if (method == "soft_nms" and getattr(groups, "packed", None) is not None) else groups.rows
+    return runtime.softnms_groups(groups.group_offsets, rows, iou_thresh, soft_nms_cut, min_score,
                                   max_group=groups.max_group, want_merged=False, box_format=_abi.W2T_BOX_LTWH,
                                   hard=(method == "nms"))
 

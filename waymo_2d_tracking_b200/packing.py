@@ -215,6 +215,7 @@ class PackedGroups:
     rows: np.ndarray                # [N,5] float64: score*weight, left, top, width, height
     max_group: int = 0
     sub_counts: Optional[np.ndarray] = None   # [G,K] int32: rows of each group per input file (fusion only)
+    packed: Optional[np.ndarray] = None       # [N] uint64: the same rows in 8 bytes each (:func:`packed_rows`) when exact
 
 
 def pack_submissions(input_detections, image_ids, category_ids):
@@ -446,7 +447,8 @@ def pack_files(paths, weights, min_score):
     fast = native_json.group_files(paths, weights, min_score)
     if fast is None:
         return pack_detection_files([native_json.load(f) for f in paths], weights, min_score)
-    return PackedGroups(fast.image_ids, fast.category_ids, fast.group_offsets, fast.rows, fast.max_group, fast.sub_counts)
+    return PackedGroups(fast.image_ids, fast.category_ids, fast.group_offsets, fast.rows, fast.max_group, fast.sub_counts,
+                        fast.packed)
 
 
 def pack_track_file(path, score_threshold, n_classes, segment_id=None, segment_block=None):
