@@ -82,17 +82,18 @@ def ensemble_array_worker(rank, world, port, paths, out_path):
     dist.destroy_process_group()
 
 
-def array_worker(rank, world, port, json_path, out_path):
+def array_worker(rank, world, port, json_path, out_path, from_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from waymo_2d_tracking_b200 import native_json
-    dets = native_json.load(json_path)
+    dets = json_path if from_path else native_json.load(json_path)      # path: the native parse + pack call
     image_ids, rows, nxt = sharding.track_arrays_sharded(dets, helpers.SCORE_THR, helpers.IOU_THR, 2, 0,
                                                          track_fn=oracle_track_packed)
     if rank == 0:
+        assert len(rows["segments"]) == len(set(rows["segments"])) > 1
         native_json.write_tracks(out_path, image_ids, rows["rows_img"], rows["rows_box"], rows["rows_score"],
                                  rows["rows_cat"], rows["rows_id"])
     else:
@@ -152,7 +153,8 @@ def test_world_size_2_sharded_tracking_and_ensemble_equal_single_process(tmp_pat
 
 
 @pytest.mark.timeout(300)
-def test_world_size_2_array_path_of_the_tracking_cli_equals_single_process(tmp_path):
+@pytest.mark.parametrize("from_path", [True, False])
+def test_world_size_2_array_path_of_the_tracking_cli_equals_single_process(tmp_path, from_path):
     """``sharding.track_arrays_sharded`` (what ``tracking/track.py`` runs under torchrun): native reader -> each rank
     packs and tracks its block of segments -> arrays gathered to rank 0 -> native writer; same file as one process."""
     from oracle import sort_port
@@ -160,7 +162,7 @@ def test_world_size_2_array_path_of_the_tracking_cli_equals_single_process(tmp_p
     src = tmp_path / "sub.json"
     src.write_text(json.dumps(subs[0]))
     out = tmp_path / "tracks.json"
-    mp.spawn(array_worker, args=(2, free_port(), str(src), str(out)), nprocs=2, join=True)
+    mp.spawn(array_worker, args=(2, free_port(), str(src), str(out), from_path), nprocs=2, join=True)
     got = json.loads(out.read_text())
     pred = sort_port.group_entries(subs[0], helpers.SCORE_THR)
     want = sort_port.track_all(pred, helpers.IOU_THR, 2, 0, reset_ids=True)

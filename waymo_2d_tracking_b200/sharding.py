@@ -109,24 +109,26 @@ def track_arrays_sharded(dets, score_threshold, iou_thresholds, max_age, min_hit
                          group=None, id_base=0):
     """The tracking CLI's work over all ranks of ``group``, on flat arrays from end to end.
 
-    ``dets``: ``native_json.Detections`` of the whole input file (every rank parses it: the native reader does
-    that at hundreds of MB/s).  Rank r packs and tracks its block of segments
+    ``dets``: the input file's path (every rank parses it and packs its own block in one native call,
+    ``packing.pack_track_file``) or the ``native_json.Detections`` of the whole file (``packing.pack_detections``).
+    Rank r packs and tracks its block of segments
     (``track_fn(packed, iou_thresholds, max_age, min_hits) -> (rows, n_created)``: dense ``rows_*`` arrays with ids
     counted from 1; default: the CUDA path), ids are rebased by the exclusive scan of ``n_created`` and the
     ARRAYS — not lists of dicts — are gathered to rank 0 in rank order.  Returns, on rank 0,
     ``(image_ids, rows, next_id_base)`` with ``rows["rows_img"]`` indexing ``image_ids``; ``(None, None,
-    next_id_base)`` elsewhere.  The rows are identical to a single-process run."""
+    next_id_base)`` elsewhere; ``rows["segments"]`` lists the segments in the order they were tracked.  The rows are
+    identical to a single-process run."""
     import numpy as np
     from . import packing
     if track_fn is None:
         track_fn = _device_track_packed
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    packed = packing.pack_detections(dets, score_threshold, len(iou_thresholds), segment_id=segment_id,
-                                     segment_block=(rank, world))
+    pack = packing.pack_track_file if isinstance(dets, (str, os.PathLike)) else packing.pack_detections
+    packed = pack(dets, score_threshold, len(iou_thresholds), segment_id=segment_id, segment_block=(rank, world))
     res, created = track_fn(packed, iou_thresholds, max_age, min_hits)
     before, total = exclusive_scan_int(created, group)
     n = int(res["n_rows"]) if "n_rows" in res else len(res["rows_id"])
-    part = {"image_ids": packing.image_id_strings(packed),
+    part = {"image_ids": packing.image_id_strings(packed), "segments": list(dict.fromkeys(seg for seg, _ in packed.streams)),
             "rows_img": np.asarray(res["rows_img"][:n], np.int32), "rows_cat": np.asarray(res["rows_cat"][:n], np.int32),
             "rows_box": np.asarray(res["rows_box"][:n], np.float64).reshape(-1, 4),
             "rows_score": np.asarray(res["rows_score"][:n], np.float64),
@@ -142,6 +144,7 @@ def track_arrays_sharded(dets, score_threshold, iou_thresholds, max_age, min_hit
         image_ids += p["image_ids"]
     rows = {k: np.concatenate([p[k] for p in gathered]) for k in ("rows_img", "rows_cat", "rows_box", "rows_score", "rows_id")}
     rows["n_rows"] = len(rows["rows_id"])
+    rows["segments"] = [seg for p in gathered for seg in p["segments"]]
     return image_ids, rows, id_base + total
 
 

@@ -56,9 +56,7 @@ def main(argv=None):
     # pack) or, one process per GPU, by packing.pack_detections on each rank's block of segments
     multi = int(os.environ.get("WORLD_SIZE", "1")) > 1
     n_classes = len(args.iou_threshold)
-    if multi:
-        dets = native_json.load(args.input)
-    else:
+    if not multi:
         packed = packing.pack_track_file(args.input, args.score_threshold, n_classes, segment_id=args.segment_id or None)
     image_id2path = {}
     ground_truth_dir = dirname(args.ground_truth)
@@ -71,15 +69,12 @@ def main(argv=None):
         # rank 0 gathers ARRAYS and writes the file
         sharding.init_from_env()
         start_time = time.time()
-        if sharding.dist.get_rank() == 0:
-            whole = packing.pack_detections(dets, args.score_threshold, len(args.iou_threshold),
-                                            segment_id=args.segment_id or None)
-            for segment_id in dict.fromkeys(seg for seg, _ in whole.streams):
-                print(segment_id)
-        image_ids, rows, _ = sharding.track_arrays_sharded(dets, args.score_threshold, args.iou_threshold, args.max_age,
-                                                           args.min_hits, segment_id=args.segment_id or None)
+        image_ids, rows, _ = sharding.track_arrays_sharded(args.input, args.score_threshold, args.iou_threshold,
+                                                           args.max_age, args.min_hits, segment_id=args.segment_id or None)
         if rows is None:
             return None
+        for segment_id in rows["segments"]:
+            print(segment_id)
         print("duration: %.2fs" % (time.time() - start_time))
         native_json.write_tracks(args.output, image_ids, rows["rows_img"], rows["rows_box"], rows["rows_score"],
                                  rows["rows_cat"], rows["rows_id"])
