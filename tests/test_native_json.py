@@ -316,3 +316,74 @@ def test_native_track_packer_leaves_exceptions_to_the_general_path(tmp_path):
     assert list(packing.pack_track_file(p, thr, 4).frame_ids) == [10]
     with pytest.raises(W2TError):
         packing.pack_track_file(tmp_path / "missing.json", thr, 4)
+
+
+def _random_rows(rng, n, segs, cams, frames, cats, ints=True):
+    rows = []
+    for _ in range(n):
+        box = [float(rng.integers(-50, 1900)), float(rng.integers(-50, 1200)),
+               float(rng.choice([0, 0.5, 1, 2, 30, 250])), float(rng.choice([-3, 0, 0.99, 1, 40, 300]))]
+        if not ints:
+            box = [v + float(rng.choice([0, 0.25])) for v in box]
+        score = float(rng.choice([0.0, 0.005, 0.01, 0.59999, 0.6, 0.94999, 0.95, 0.9, 1.0, float("nan")]))
+        rows.append({'image_id': '%s/%d/%s' % (rng.choice(segs), int(rng.choice(frames)), rng.choice(cams)),
+                     'category_id': int(rng.choice(cats)), 'bbox': box, 'score': score})
+    return rows
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_packers_equal_the_array_packers_on_awkward_inputs(tmp_path, seed):
+    # random small files with the values the filters branch on: zero / negative / fractional sizes, scores on both
+    # sides of every threshold, NaN scores (json.dump writes NaN), images that occur in one file only, unicode ids
+    rng = np.random.default_rng(500 + seed)
+    segs = ["s%d_%s" % (k, "é" if k == 1 else "x") for k in range(3)]
+    cams = ["FRONT", "SIDE_LEFT", "FRONT_RIGHT"]
+    frames = [3, 10, 7, 100, 20]
+    thr = [0.95, 0.6, 1.0, 0.9]
+    files = []
+    for k in range(3):
+        rows = _random_rows(rng, int(rng.integers(0, 60)), segs, cams, frames, [1, 2, 3, 4], ints=(seed % 2 == 0))
+        p = tmp_path / ("f%d.json" % k)
+        p.write_text(json.dumps(rows))
+        files.append(p)
+    weights = [1.0, 0.5, 1.0] if seed % 3 == 0 else [1.0, 1.0, 1.0]
+    for min_score in (0.0, 0.01):
+        want = packing.pack_detection_files([native_json.load(f) for f in files], weights, min_score)
+        got = packing.pack_files(files, weights, min_score)
+        assert got.image_ids == want.image_ids and got.category_ids == want.category_ids and got.max_group == want.max_group
+        np.testing.assert_array_equal(got.group_offsets, want.group_offsets)
+        np.testing.assert_array_equal(got.rows, want.rows)            # NaN == NaN positionally
+        np.testing.assert_array_equal(got.sub_counts, want.sub_counts)
+        packed = packing.packed_rows(want.rows)
+        assert (got.packed is None) == (packed is None)
+        if packed is not None:
+            np.testing.assert_array_equal(got.packed, packed)
+    for f in files:
+        _same_packed(packing.pack_track_file(f, thr, 4), packing.pack_detections(native_json.load(f), thr, 4))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fused_cli_grouping_fast_and_general_paths_agree_on_awkward_inputs(tmp_path, seed):
+    from waymo_2d_tracking_b200 import pipeline
+    rng = np.random.default_rng(900 + seed)
+    segs = ["b_seg", "a_seg", "a_seg_longer"]              # sorted order differs from first appearance
+    cams = ["SIDE_RIGHT", "FRONT", "FRONT_LEFT"]
+    files = []
+    for k in range(2):
+        rows = _random_rows(rng, int(rng.integers(5, 80)), segs, cams, [5, 40, 12, 7], [1, 2, 4])
+        p = tmp_path / ("f%d.json" % k)
+        p.write_text(json.dumps(rows))
+        files.append(p)
+    fast = pipeline.load_groups(files, [1.0, 1.0], 0.01, 4)
+    orig = native_json.group_files
+    try:
+        native_json.group_files = lambda *a, **k: None
+        slow = pipeline.load_groups(files, [1.0, 1.0], 0.01, 4)
+    finally:
+        native_json.group_files = orig
+    assert fast[0] == slow[0] and fast[7] == slow[7]
+    for a, b in zip(fast[1:6], slow[1:6]):
+        np.testing.assert_array_equal(a, b)
+    assert (fast[6] is None) == (slow[6] is None)
+    if fast[6] is not None:
+        np.testing.assert_array_equal(fast[6], slow[6])
