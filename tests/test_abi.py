@@ -156,3 +156,25 @@ def test_compute_entry_points_fail_loudly_without_gpu():
         runtime.softnms_groups(np.array([0, 1], np.int32), np.zeros((1, 5)))
     with pytest.raises(_lib.W2TError):
         runtime.iou_matrix(np.zeros((1, 4), np.float32), np.zeros((1, 4)))
+
+
+def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
+    # include/w2t.h must compile as C99 (the boundary is a C ABI) and every struct of include/w2t_types.h must have
+    # the size its ctypes mirror in _abi.py has: a field added on one side only shows up here, not on the GPU
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    inc = os.path.join(ROOT, "include")
+    pairs = [("w2t_sort_problem_t", _abi.SortProblem), ("w2t_sort_plan_t", _abi.SortPlan),
+             ("w2t_sort_result_t", _abi.SortResult), ("w2t_rows_t", _abi.Rows),
+             ("w2t_nms_problem_t", _abi.NmsProblem), ("w2t_nms_result_t", _abi.NmsResult)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "w2t.h"\nint main(void) {\n' +
+                   "".join('  printf("%%zu\\n", sizeof(%s));\n' % c for c, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    for (cname, mirror), size in zip(pairs, sizes):
+        assert ctypes.sizeof(mirror) == size, cname
